@@ -1,0 +1,48 @@
+// Host-side plumbing shared by all translation units: handle, error reporting, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pgv.h"
+
+struct pgv_handle {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    // cuTensorMapEncodeTiled, resolved through the runtime so that libpgv.so does not link libcuda directly
+    CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+};
+
+namespace pgv {
+
+int set_error(int code, const char* fmt, ...);
+
+#define PGV_CHECK_ARG(cond, ...)                                   \
+    do {                                                           \
+        if (!(cond)) return pgv::set_error(-1, __VA_ARGS__);      \
+    } while (0)
+
+#define PGV_CUDA(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return pgv::set_error(static_cast<int>(e__), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                  __FILE__, __LINE__);                                                      \
+    } while (0)
+
+#define PGV_LAUNCH_CHECK() PGV_CUDA(cudaGetLastError())
+
+// fp32 tensor map, 128-byte swizzle, zero fill out of bounds.  dims[0] is the contiguous dimension; strides_bytes has
+// rank-1 entries (dimension 0 is implicitly 4 bytes).  box[0] must be 32 (128 bytes).
+int make_tmap_f32(const pgv_handle* h, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace pgv

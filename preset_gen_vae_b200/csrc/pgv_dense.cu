@@ -1,0 +1,158 @@
+// Dense layer GEMMs:  C[M,N] = act(A[M,K] * B[N,K]^T + bias)   (nn.Linear layout: B is the [out, in] weight).
+//   pgv_gemm_nt_tf32 : tcgen05 / TMEM / TMA path (1xTF32 or error-compensated 3xTF32)
+//   pgv_gemm_nt_f32  : CUDA-core fp32 path (exact products) for tiny shapes and on-device cross-checks
+#include <string.h>
+
+#include "pgv_common.cuh"
+#include "pgv_gemm.cuh"
+
+namespace pgv {
+
+struct DenseProblem {
+    static constexpr int BLOCK_N = 128, STAGES = 6, ACC_STAGES = 2;
+    struct Params {
+        CUtensorMap a, a_lo, b, b_lo;
+        int m, n, k, m_tiles, n_tiles, kb_per_pass, passes;
+        float* c;
+        int ldc;
+        const float* bias;
+        int act;
+    };
+    __device__ static void prefetch(const Params& p) {
+        tma_prefetch_desc(&p.a); tma_prefetch_desc(&p.b);
+        if (p.passes == 3) { tma_prefetch_desc(&p.a_lo); tma_prefetch_desc(&p.b_lo); }
+    }
+    __device__ static int num_tiles(const Params& p) { return p.m_tiles * p.n_tiles; }
+    __device__ static int num_k_blocks(const Params& p) { return p.passes * p.kb_per_pass; }
+    __device__ static void tile_coords(const Params& p, int tile, int& tm, int& tn) { tm = tile / p.n_tiles; tn = tile % p.n_tiles; }
+    __device__ static void load(const Params& p, int tm, int tn, int kb, void* sA, void* sB, uint64_t* bar) {
+        const int pass = kb / p.kb_per_pass, k0 = (kb % p.kb_per_pass) * GEMM_BLOCK_K;
+        tma_load_2d(sA, pass == 1 ? &p.a_lo : &p.a, bar, k0, tm * GEMM_BLOCK_M);
+        tma_load_2d(sB, pass == 2 ? &p.b_lo : &p.b, bar, k0, tn * BLOCK_N);
+    }
+    __device__ static void epilogue(const Params& p, int tm, int tn, uint32_t taddr, int row) {
+        const int r = tm * GEMM_BLOCK_M + row;
+        const bool row_ok = r < p.m;
+        float* crow = p.c + static_cast<size_t>(r) * p.ldc;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c, v);
+            tmem_ld_wait();
+            const int n0 = tn * BLOCK_N + c;
+            if (!row_ok || n0 >= p.n) continue;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (p.bias != nullptr && n0 + j < p.n) x += p.bias[n0 + j];
+                if (p.act == 1) x = fmaxf(x, 0.0f);
+                o[j] = x;
+            }
+            if (vec_ok && n0 + 16 <= p.n) {
+                float4* d = reinterpret_cast<float4*>(crow + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < p.n) crow[n0 + j] = o[j];
+            }
+        }
+    }
+};
+
+// 64x64 output tile per block, 16x16 threads, 4x4 outputs per thread, K step 16.
+__global__ void __launch_bounds__(256) gemm_nt_f32_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                          float* __restrict__ c, int ldc, int m, int n, int k,
+                                                          const float* __restrict__ bias, int act) {
+    __shared__ float sa[16][64 + 1], sb[16][64 + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < k; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, kk = i & 15;
+            sa[kk][r] = (m0 + r < m && k0 + kk < k) ? a[static_cast<size_t>(m0 + r) * lda + k0 + kk] : 0.0f;
+            sb[kk][r] = (n0 + r < n && k0 + kk < k) ? b[static_cast<size_t>(n0 + r) * ldb + k0 + kk] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { av[i] = sa[kk][ty * 4 + i]; bv[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = m0 + ty * 4 + i, col = n0 + tx * 4 + j;
+            if (r < m && col < n) {
+                float x = acc[i][j] + (bias ? bias[col] : 0.0f);
+                if (act == 1) x = fmaxf(x, 0.0f);
+                c[static_cast<size_t>(r) * ldc + col] = x;
+            }
+        }
+}
+
+}  // namespace pgv
+
+using namespace pgv;
+
+extern "C" {
+
+int pgv_gemm_nt_tf32(pgv_handle* h, const float* a, const float* a_lo, int lda, const float* b, const float* b_lo, int ldb,
+                     float* c, int ldc, int m, int n, int k, const float* bias, int act, int three_pass, pgv_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PGV_CHECK_ARG(h && a && b && c, "pgv_gemm_nt_tf32: NULL argument");
+    PGV_CHECK_ARG(m > 0 && n > 0 && k > 0, "pgv_gemm_nt_tf32: empty problem %dx%dx%d", m, n, k);
+    PGV_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && lda >= k && ldb >= k, "pgv_gemm_nt_tf32: lda/ldb must be >= k and multiples of 4");
+    PGV_CHECK_ARG(!three_pass || (a_lo && b_lo), "pgv_gemm_nt_tf32: three_pass needs a_lo and b_lo");
+    PGV_CHECK_ARG(act == 0 || act == 1, "pgv_gemm_nt_tf32: unknown activation %d", act);
+    DenseProblem::Params p;
+    memset(&p, 0, sizeof(p));
+    const uint64_t ad[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(m)}, as[1] = {static_cast<uint64_t>(lda) * 4};
+    const uint64_t bd[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(n)}, bs[1] = {static_cast<uint64_t>(ldb) * 4};
+    const uint32_t abox[2] = {GEMM_BLOCK_K, GEMM_BLOCK_M}, bbox[2] = {GEMM_BLOCK_K, DenseProblem::BLOCK_N};
+    int rc;
+    if ((rc = make_tmap_f32(h, &p.a, a, 2, ad, as, abox))) return rc;
+    if ((rc = make_tmap_f32(h, &p.b, b, 2, bd, bs, bbox))) return rc;
+    if (three_pass) {
+        if ((rc = make_tmap_f32(h, &p.a_lo, a_lo, 2, ad, as, abox))) return rc;
+        if ((rc = make_tmap_f32(h, &p.b_lo, b_lo, 2, bd, bs, bbox))) return rc;
+    }
+    p.m = m; p.n = n; p.k = k;
+    p.m_tiles = ceil_div(m, GEMM_BLOCK_M); p.n_tiles = ceil_div(n, DenseProblem::BLOCK_N);
+    p.kb_per_pass = ceil_div(k, GEMM_BLOCK_K); p.passes = three_pass ? 3 : 1;
+    p.c = c; p.ldc = ldc; p.bias = bias; p.act = act;
+    static bool configured = false;
+    if (!configured) {
+        PGV_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<DenseProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GemmSmem<DenseProblem>::TOTAL));
+        configured = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    gemm_tf32_kernel<DenseProblem><<<tiles < h->sm_count ? tiles : h->sm_count, GEMM_THREADS, GemmSmem<DenseProblem>::TOTAL, stream>>>(p);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+int pgv_gemm_nt_f32(pgv_handle* h, const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
+                    const float* bias, int act, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && a && b && c, "pgv_gemm_nt_f32: NULL argument");
+    PGV_CHECK_ARG(m > 0 && n > 0 && k > 0, "pgv_gemm_nt_f32: empty problem");
+    dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
+    gemm_nt_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, lda, b, ldb, c, ldc, m, n, k, bias, act);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"
