@@ -26,9 +26,10 @@ struct DenseProblem {
     __device__ static int num_k_blocks(const Params& p) { return p.passes * p.kb_per_pass; }
     __device__ static void tile_coords(const Params& p, int tile, int& tm, int& tn) { tm = tile / p.n_tiles; tn = tile % p.n_tiles; }
     __device__ static void load(const Params& p, int tm, int tn, int kb, void* sA, void* sB, uint64_t* bar) {
-        const int pass = kb / p.kb_per_pass, k0 = (kb % p.kb_per_pass) * GEMM_BLOCK_K;
-        tma_load_2d(sA, pass == 1 ? &p.a_lo : &p.a, bar, k0, tm * GEMM_BLOCK_M);
-        tma_load_2d(sB, pass == 2 ? &p.b_lo : &p.b, bar, k0, tn * BLOCK_N);
+        // 3-pass order: lo*hi, hi*lo, then hi*hi (corrections first, see pgv_gemm.cuh)
+        const int pass = (p.passes == 3) ? kb / p.kb_per_pass : 2, k0 = (kb % p.kb_per_pass) * GEMM_BLOCK_K;
+        tma_load_2d(sA, pass == 0 ? &p.a_lo : &p.a, bar, k0, tm * GEMM_BLOCK_M);
+        tma_load_2d(sB, pass == 1 ? &p.b_lo : &p.b, bar, k0, tn * BLOCK_N);
     }
     __device__ static void epilogue(const Params& p, int tm, int tn, uint32_t taddr, int row) {
         const int r = tm * GEMM_BLOCK_M + row;

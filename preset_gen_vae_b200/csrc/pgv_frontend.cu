@@ -67,10 +67,10 @@ struct DftProblem {
     __device__ static int num_k_blocks(const Params& p) { return 3 * p.kb_per_pass; }
     __device__ static void tile_coords(const Params& p, int tile, int& tm, int& tn) { tm = tile / p.n_tiles; tn = tile % p.n_tiles; }
     __device__ static void load(const Params& p, int tm, int tn, int kb, void* sA, void* sB, uint64_t* bar) {
-        const int pass = kb / p.kb_per_pass, k0 = (kb % p.kb_per_pass) * GEMM_BLOCK_K;   // pass 0: hi*hi, 1: lo*hi, 2: hi*lo
+        const int pass = kb / p.kb_per_pass, k0 = (kb % p.kb_per_pass) * GEMM_BLOCK_K;   // pass 0: lo*hi, 1: hi*lo, 2: hi*hi (see pass order note)
         const int clip = tm / p.m_tiles, mt = tm % p.m_tiles;
-        tma_load_3d(sA, pass == 1 ? &p.x_lo : &p.x_hi, bar, k0 % p.hop, mt * GEMM_BLOCK_M + k0 / p.hop - p.pad_segs, clip);
-        tma_load_2d(sB, pass == 2 ? &p.w_lo : &p.w_hi, bar, k0, tn * BLOCK_N);
+        tma_load_3d(sA, pass == 0 ? &p.x_lo : &p.x_hi, bar, k0 % p.hop, mt * GEMM_BLOCK_M + k0 / p.hop - p.pad_segs, clip);
+        tma_load_2d(sB, pass == 1 ? &p.w_lo : &p.w_hi, bar, k0, tn * BLOCK_N);
     }
     __device__ static void epilogue(const Params& p, int tm, int tn, uint32_t taddr, int row) {
         const int clip = tm / p.m_tiles, t = (tm % p.m_tiles) * GEMM_BLOCK_M + row;
@@ -143,8 +143,8 @@ struct MelProblem {
     __device__ static void tile_coords(const Params& p, int tile, int& tm, int& tn) { tm = tile / p.n_tiles; tn = tile % p.n_tiles; }
     __device__ static void load(const Params& p, int tm, int tn, int kb, void* sA, void* sB, uint64_t* bar) {
         const int pass = kb / p.kb_per_pass, k0 = (kb % p.kb_per_pass) * GEMM_BLOCK_K;
-        tma_load_3d(sA, pass == 1 ? &p.a_lo : &p.a_hi, bar, k0, (tm % p.m_tiles) * GEMM_BLOCK_M, tm / p.m_tiles);
-        tma_load_2d(sB, pass == 2 ? &p.m_lo : &p.m_hi, bar, k0, tn * BLOCK_N);
+        tma_load_3d(sA, pass == 0 ? &p.a_lo : &p.a_hi, bar, k0, (tm % p.m_tiles) * GEMM_BLOCK_M, tm / p.m_tiles);
+        tma_load_2d(sB, pass == 1 ? &p.m_lo : &p.m_hi, bar, k0, tn * BLOCK_N);
     }
     __device__ static void epilogue(const Params& p, int tm, int tn, uint32_t taddr, int row) {
         const int clip = tm / p.m_tiles, t = (tm % p.m_tiles) * GEMM_BLOCK_M + row;

