@@ -98,6 +98,132 @@ PGV_API int pgv_gemm_nt_f32(pgv_handle* h, const float* a, int lda, const float*
 /* hi = round-to-nearest TF32 of x, lo = TF32 of (x - hi); n elements, device pointers. */
 PGV_API int pgv_split_tf32(const float* x, float* hi, float* lo, size_t n, pgv_stream_t stream);
 
+/* General fp32 CUDA-core GEMM: C[M,N] = act(opA(A) * opB(B) + bias[N] + residual[M,N]), row-major.  trans_a = 0: A is
+ * [M,K], 1: A is [K,M]; trans_b = 0: B is [K,N], 1: B is [N,K].  bias / residual may be NULL.  Long-K problems with few
+ * output tiles are split along K (fp32 atomic accumulation).  Linear backward: dX = gemm(0,0,dY,W), dW = gemm(1,0,dY,X). */
+PGV_API int pgv_gemm_f32(pgv_handle* h, int trans_a, int trans_b, const float* a, int lda, const float* b, int ldb, float* c, int ldc,
+                         int m, int n, int k, const float* bias, int act, const float* residual, int ldr, pgv_stream_t stream);
+/* out[f] = sum over rows of x[B,F] (bias gradients). */
+PGV_API int pgv_colsum(const float* x, float* out, int B, int F, pgv_stream_t stream);
+
+/* ------------------------------------------------------------------ convolutions (NCHW fp32)
+ * nn.Conv2d / nn.ConvTranspose2d call sites: model/layer.py:19,38 (blocks of model/encoder.py:233-259 and
+ * model/decoder.py:199-220).  All three take the geometry of the *convolution*: x [B,Cin,H,W], y/dy [B,Cout,Ho,Wo],
+ * w [Cout,Cin,kh,kw].  A ConvTranspose2d with weight [Cin_t,Cout_t,kh,kw] is the data-gradient of the convolution with
+ * that same weight tensor (Cout = Cin_t, Cin = Cout_t, H/W = the transposed conv's OUTPUT size incl. output_padding):
+ *   tconv forward = pgv_conv2d_dgrad (with bias + activation),  tconv dgrad = pgv_conv2d_fwd,  tconv wgrad =
+ *   pgv_conv2d_wgrad(x = tconv grad_output, dy = tconv input).
+ * lrelu_slope < 0 disables the fused LeakyReLU.  kh*kw <= 25. */
+PGV_API int pgv_conv2d_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W, int Cout, int kh,
+                               int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
+PGV_API int pgv_conv2d_dgrad_f32(const float* dy, const float* w, const float* bias, float* dx, int B, int Cin, int H, int W, int Cout,
+                                 int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
+/* dw [Cout,Cin,kh,kw] and (if db != NULL) db [Cout] are overwritten. */
+PGV_API int pgv_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int H, int W, int Cout, int kh,
+                                 int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+
+/* out[c] = sum over (b, h, w) of x[b,c,h,w] (bias gradient of a transposed convolution). */
+PGV_API int pgv_channel_sum(const float* x, float* out, int B, int C, int HW, pgv_stream_t stream);
+
+/* ------------------------------------------------------------------ normalisation
+ * BatchNorm2d after the activation of every conv block (model/layer.py:20-26): training mode uses batch statistics
+ * (biased variance), updates running_mean / running_var (unbiased) with `momentum`, saves mean and 1/sqrt(var+eps).
+ * workspace: 16*C bytes.  The backward optionally continues through the LeakyReLU that produced x (lrelu_slope >= 0). */
+PGV_API int pgv_bn2d_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_rstd,
+                               float* running_mean, float* running_var, float momentum, float eps, int B, int C, int HW, void* workspace,
+                               pgv_stream_t stream);
+PGV_API int pgv_bn2d_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                              float* y, float eps, int B, int C, int HW, pgv_stream_t stream);
+PGV_API int pgv_bn2d_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,
+                               float* dgamma, float* dbeta, float lrelu_slope, int B, int C, int HW, void* workspace, pgv_stream_t stream);
+/* dx = dy * (a > 0 ? 1 : slope): LeakyReLU backward from its OUTPUT a (conv blocks without BatchNorm). */
+PGV_API int pgv_lrelu_bwd(const float* dy, const float* a, float* dx, float slope, size_t n, pgv_stream_t stream);
+/* BatchNorm1d on [B,F] (encoder.py:86-87 and the nflows ResidualBlock): y = mask * relu?(gamma*xhat+beta); mask NULL = none. */
+PGV_API int pgv_bn1d_train_fwd(const float* x, const float* gamma, const float* beta, const float* mask, float* y, float* save_mean,
+                               float* save_rstd, float* running_mean, float* running_var, float momentum, float eps, int relu, int B, int F,
+                               pgv_stream_t stream);
+PGV_API int pgv_bn1d_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                              float* y, float eps, int relu, int B, int F, pgv_stream_t stream);
+PGV_API int pgv_bn1d_train_bwd(const float* dy, const float* x, const float* gamma, const float* beta, const float* save_mean,
+                               const float* save_rstd, const float* mask, float* dx, float* dgamma, float* dbeta, int relu, int B, int F,
+                               pgv_stream_t stream);
+/* nflows transforms.normalization.BatchNorm (model/flows.py:87-88): batch mean / UNBIASED variance, weight =
+ * softplus(u) + eps; logdet_scalar[0] = sum_f(log w_f - 0.5*log(var_f + eps)) is the value added to every row's log|det J|.
+ * grad_logdet_sum[0] = sum over rows of dL/dlogdet. */
+PGV_API int pgv_flowbn_train_fwd(const float* x, const float* unconstrained_weight, const float* bias, float* y, float* save_mean,
+                                 float* save_var, float* running_mean, float* running_var, float* logdet_scalar, float momentum, float eps,
+                                 int B, int F, pgv_stream_t stream);
+PGV_API int pgv_flowbn_eval(const float* x, const float* unconstrained_weight, const float* bias, const float* running_mean,
+                            const float* running_var, float* y, float* logdet_scalar, float eps, int inverse, int B, int F, pgv_stream_t stream);
+PGV_API int pgv_flowbn_train_bwd(const float* dy, const float* x, const float* unconstrained_weight, const float* save_mean,
+                                 const float* save_var, const float* grad_logdet_sum, float* dx, float* d_unconstrained_weight, float* dbias,
+                                 float eps, int B, int F, pgv_stream_t stream);
+
+/* ------------------------------------------------------------------ latent space / flows ([B, D] tensors)
+ * Reparameterisation (model/VAE.py:167-174): z0 = mu + exp(logvar/2)*eps, mu_logvar is [B,2,D]; eps NULL = eval (z0 = mu).
+ * The backward adds d_mu_logvar_add (e.g. the latent-loss gradient) when it is not NULL. */
+PGV_API int pgv_reparam_fwd(const float* mu_logvar, const float* eps, float* z0, int B, int D, pgv_stream_t stream);
+PGV_API int pgv_reparam_bwd(const float* dz0, const float* mu_logvar, const float* eps, const float* d_mu_logvar_add, float* d_mu_logvar,
+                            int B, int D, pgv_stream_t stream);
+PGV_API int pgv_gather_cols(const float* x, const int* idx, float* out, int B, int D, int n, pgv_stream_t stream);
+PGV_API int pgv_scatter_add_cols(float* dst, const int* idx, const float* src, int B, int D, int n, pgv_stream_t stream);
+/* nflows AffineCouplingTransform (via model/flows.py:42-90, model/VAE.py:118-125): params[b, :n_t] = shift,
+ * params[b, n_t:] = unconstrained scale, s = sigmoid(u+2)+1e-3; forward y = x*s+t, logdet_out = logdet_in + sum log s
+ * (logdet_in may be NULL); inverse != 0: y = (x-t)/s, logdet_out = logdet_in - sum log s. */
+PGV_API int pgv_coupling_fwd(const float* x, const float* params, const int* identity_idx, const int* transform_idx, float* y,
+                             const float* logdet_in, float* logdet_out, int B, int D, int n_identity, int n_transform, int inverse,
+                             pgv_stream_t stream);
+PGV_API int pgv_coupling_bwd(const float* dy, const float* dlogdet, const float* x, const float* params, const int* identity_idx,
+                             const int* transform_idx, float* dx, float* dparams, int B, int D, int n_identity, int n_transform,
+                             pgv_stream_t stream);
+/* nn.Hardtanh (decoder.py:98 output activation, regression.py:22 PresetActivation). */
+PGV_API int pgv_hardtanh_fwd(const float* x, float* y, float lo, float hi, size_t n, pgv_stream_t stream);
+PGV_API int pgv_hardtanh_bwd(const float* dy, const float* x, float* dx, float lo, float hi, size_t n, pgv_stream_t stream);
+/* y = x * m (dropout with a pre-scaled keep mask) and y = a + b. */
+PGV_API int pgv_mul(const float* x, const float* m, float* y, size_t n, pgv_stream_t stream);
+PGV_API int pgv_add(const float* a, const float* b, float* y, size_t n, pgv_stream_t stream);
+/* y[i] = a[i] + scalar_dev[0] (a NULL = 0): adds the flow-BatchNorm log-det scalar to every row's log|det J|. */
+PGV_API int pgv_add_scalar(const float* a, const float* scalar_dev, float* y, size_t n, pgv_stream_t stream);
+/* PresetActivation with cat_softmax_activation=True (regression.py:47-50). */
+PGV_API int pgv_preset_act_softmax_fwd(const float* x, float* y, const int* num_cols, int n_num, const int* grp_start, const int* grp_len,
+                                       int n_grp, int B, int D, pgv_stream_t stream);
+PGV_API int pgv_preset_act_softmax_bwd(const float* dy, const float* x, const float* y, float* dx, const int* num_cols, int n_num,
+                                       const int* grp_start, const int* grp_len, int n_grp, int B, int D, pgv_stream_t stream);
+
+/* ------------------------------------------------------------------ losses
+ * Scalars live in device memory: *_fwd writes loss_out[0]; *_bwd reads the upstream gradient from grad_out[0].
+ * pgv_sqerr: loss = scale * sum((a-b)^2)  (nn.MSELoss: scale = 1/n; L2Loss, model/loss.py:15-43: scale = 1/B).  workspace >= 8 B. */
+PGV_API int pgv_sqerr_fwd(const float* a, const float* b, size_t n, double scale, float* loss_out, void* workspace, pgv_stream_t stream);
+PGV_API int pgv_sqerr_bwd(const float* a, const float* b, size_t n, double scale, const float* grad_out, float* da, pgv_stream_t stream);
+/* FlowVAE.latent_loss (model/VAE.py:183-193, utils/probability.py:13-29).  workspace >= 8 B. */
+PGV_API int pgv_latent_loss_fwd(const float* mu_logvar, const float* z0, const float* zk, const float* logdet, int B, int D, int normalize,
+                                float* loss_out, void* workspace, pgv_stream_t stream);
+PGV_API int pgv_latent_loss_bwd(const float* grad_out, const float* mu_logvar, const float* z0, const float* zk, int B, int D, int normalize,
+                                float* d_mu_logvar, float* dz0, float* dzk, float* dlogdet, pgv_stream_t stream);
+/* GaussianDkl (model/loss.py:46-66).  workspace >= 8 B. */
+PGV_API int pgv_dkl_fwd(const float* mu_logvar, int B, int D, int normalize, float* loss_out, void* workspace, pgv_stream_t stream);
+PGV_API int pgv_dkl_bwd(const float* grad_out, const float* mu_logvar, int B, int D, int normalize, float* d_mu_logvar, pgv_stream_t stream);
+/* SynthParamsLoss (model/loss.py:73-183) with the useless-parameter rule of data/preset.py:247-283 evaluated on the
+ * device from v_in: tables as returned by PresetIndexesHelper.device_tables().  cat_softmax != 0 applies
+ * softmax(q / temperature) inside the loss.  The same workspace must be passed to fwd and bwd. */
+PGV_API size_t pgv_synth_loss_workspace_bytes(int n_groups);
+PGV_API int pgv_synth_loss_fwd(const float* v_out, const float* v_in, int B, int L, const int* num_cols, const int* num_vol_col, int n_num,
+                               const int* grp_start, const int* grp_len, const int* grp_vol_col, int n_grp, int normalize,
+                               float cat_loss_factor, int cat_softmax, float softmax_temperature, float* loss_out, void* workspace,
+                               pgv_stream_t stream);
+PGV_API int pgv_synth_loss_bwd(const float* grad_out, const float* v_out, const float* v_in, int B, int L, const int* num_cols,
+                               const int* num_vol_col, int n_num, const int* grp_start, const int* grp_len, const int* grp_vol_col, int n_grp,
+                               int normalize, float cat_loss_factor, int cat_softmax, float softmax_temperature, const void* workspace,
+                               float* d_v_out, pgv_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizer (train.py:165-167)
+ * torch.optim.Adam semantics with L2-in-gradient weight decay on one flat fp32 buffer; `step` counts from 1.
+ * The _dev variant reads {lr, 1-beta1^t, sqrt(1-beta2^t), grad_scale} from device memory (CUDA-graph replay). */
+PGV_API int pgv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float grad_scale, pgv_stream_t stream);
+PGV_API int pgv_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, const float* hyper_dev,
+                              float beta1, float beta2, float eps, float weight_decay, pgv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,19 +64,32 @@ struct DenseProblem {
     }
 };
 
-// 64x64 output tile per block, 16x16 threads, 4x4 outputs per thread, K step 16.
-__global__ void __launch_bounds__(256) gemm_nt_f32_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
-                                                          float* __restrict__ c, int ldc, int m, int n, int k,
-                                                          const float* __restrict__ bias, int act) {
-    __shared__ float sa[16][64 + 1], sb[16][64 + 1];
+// Generic fp32 GEMM on the CUDA cores: C[M,N] = act(opA(A) * opB(B) + bias + residual), row-major storage.
+//   TA = 0: A is [M, K]      TA = 1: A is [K, M]          TB = 0: B is [K, N]      TB = 1: B is [N, K] (nn.Linear weight)
+// 64x64 output tile per block, 16x16 threads, 4x4 outputs per thread, K step 16; grid.z splits K (atomic accumulate).
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                       float* __restrict__ c, int ldc, int m, int n, int k, const float* __restrict__ bias,
+                                                       int act, const float* __restrict__ residual, int ldr, int k_per_split) {
+    __shared__ float sa[16][64 + 4], sb[16][64 + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int kbeg = blockIdx.z * k_per_split, kend = min(k, kbeg + k_per_split);
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < k; k0 += 16) {
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
         for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-            const int r = i >> 4, kk = i & 15;
-            sa[kk][r] = (m0 + r < m && k0 + kk < k) ? a[static_cast<size_t>(m0 + r) * lda + k0 + kk] : 0.0f;
-            sb[kk][r] = (n0 + r < n && k0 + kk < k) ? b[static_cast<size_t>(n0 + r) * ldb + k0 + kk] : 0.0f;
+            {   // A tile: make the contiguous storage dimension the fastest-varying thread index
+                const int r = TA ? (i & 63) : (i >> 4), kk = TA ? (i >> 6) : (i & 15);
+                float v = 0.0f;
+                if (m0 + r < m && k0 + kk < kend) v = TA ? a[static_cast<size_t>(k0 + kk) * lda + m0 + r] : a[static_cast<size_t>(m0 + r) * lda + k0 + kk];
+                sa[kk][r] = v;
+            }
+            {
+                const int r = TB ? (i >> 4) : (i & 63), kk = TB ? (i & 15) : (i >> 6);
+                float v = 0.0f;
+                if (n0 + r < n && k0 + kk < kend) v = TB ? b[static_cast<size_t>(n0 + r) * ldb + k0 + kk] : b[static_cast<size_t>(k0 + kk) * ldb + n0 + r];
+                sb[kk][r] = v;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -97,9 +110,19 @@ __global__ void __launch_bounds__(256) gemm_nt_f32_kernel(const float* __restric
         for (int j = 0; j < 4; ++j) {
             const int r = m0 + ty * 4 + i, col = n0 + tx * 4 + j;
             if (r < m && col < n) {
-                float x = acc[i][j] + (bias ? bias[col] : 0.0f);
-                if (act == 1) x = fmaxf(x, 0.0f);
-                c[static_cast<size_t>(r) * ldc + col] = x;
+                float x = acc[i][j];
+                if (gridDim.z == 1) {
+                    if (bias) x += bias[col];
+                    if (residual) x += residual[static_cast<size_t>(r) * ldr + col];
+                    if (act == 1) x = fmaxf(x, 0.0f);
+                    c[static_cast<size_t>(r) * ldc + col] = x;
+                } else {   // split-K: C was zero-filled; split 0 carries bias and residual
+                    if (blockIdx.z == 0) {
+                        if (bias) x += bias[col];
+                        if (residual) x += residual[static_cast<size_t>(r) * ldr + col];
+                    }
+                    atomicAdd(c + static_cast<size_t>(r) * ldc + col, x);
+                }
             }
         }
 }
@@ -146,14 +169,36 @@ int pgv_gemm_nt_tf32(pgv_handle* h, const float* a, const float* a_lo, int lda, 
     return 0;
 }
 
-int pgv_gemm_nt_f32(pgv_handle* h, const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
-                    const float* bias, int act, pgv_stream_t stream) {
-    PGV_CHECK_ARG(h && a && b && c, "pgv_gemm_nt_f32: NULL argument");
-    PGV_CHECK_ARG(m > 0 && n > 0 && k > 0, "pgv_gemm_nt_f32: empty problem");
-    dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
-    gemm_nt_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, lda, b, ldb, c, ldc, m, n, k, bias, act);
+int pgv_gemm_f32(pgv_handle* h, int trans_a, int trans_b, const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n,
+                 int k, const float* bias, int act, const float* residual, int ldr, pgv_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PGV_CHECK_ARG(h && a && b && c, "pgv_gemm_f32: NULL argument");
+    PGV_CHECK_ARG(m > 0 && n > 0 && k > 0, "pgv_gemm_f32: empty problem");
+    PGV_CHECK_ARG(act == 0 || act == 1, "pgv_gemm_f32: unknown activation %d", act);
+    const int tiles = ceil_div(n, 64) * ceil_div(m, 64);
+    int splits = 1;
+    if (act == 0 && k >= 2048 && tiles < h->sm_count * 2) {   // long-K, few tiles: split K to fill the chip
+        splits = (h->sm_count * 4) / tiles;
+        if (splits > k / 512) splits = k / 512;
+        if (splits < 1) splits = 1;
+    }
+    const int k_per_split = ceil_div(ceil_div(k, splits), 16) * 16;
+    splits = ceil_div(k, k_per_split);
+    if (splits > 1) PGV_CUDA(cudaMemset2DAsync(c, sizeof(float) * ldc, 0, sizeof(float) * n, m, stream));
+    dim3 grid(ceil_div(n, 64), ceil_div(m, 64), splits);
+#define PGV_GEMM_LAUNCH(TA, TB) gemm_f32_kernel<TA, TB><<<grid, 256, 0, stream>>>(a, lda, b, ldb, c, ldc, m, n, k, bias, act, residual, ldr, k_per_split)
+    if (!trans_a && !trans_b) PGV_GEMM_LAUNCH(0, 0);
+    else if (!trans_a && trans_b) PGV_GEMM_LAUNCH(0, 1);
+    else if (trans_a && !trans_b) PGV_GEMM_LAUNCH(1, 0);
+    else PGV_GEMM_LAUNCH(1, 1);
+#undef PGV_GEMM_LAUNCH
     PGV_LAUNCH_CHECK();
     return 0;
+}
+
+int pgv_gemm_nt_f32(pgv_handle* h, const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,
+                    const float* bias, int act, pgv_stream_t stream) {
+    return pgv_gemm_f32(h, 0, 1, a, lda, b, ldb, c, ldc, m, n, k, bias, act, nullptr, 0, stream);
 }
 
 }  // extern "C"

@@ -230,6 +230,38 @@ class PresetIndexesHelper:
                     grp_vol_col=i32(g_vol))
 
 
+class tables_from_foreign_helper:
+    """Adapter giving `device_tables()` to a helper that does not have it (e.g. the reference's own
+    data.preset.PresetIndexesHelper): the operator -> affected-columns map is recovered by probing
+    `get_useless_learned_params_indexes` with one silent operator at a time."""
+
+    def __init__(self, helper):
+        self.helper = helper
+
+    def device_tables(self):
+        h = self.helper
+        num_cols = h.get_numerical_learnable_indexes()
+        groups = h.get_categorical_learnable_indexes()
+        num_vol = {c: -1 for c in num_cols}
+        grp_vol = {g[0]: -1 for g in groups}
+        for op in range(_N_OPS):
+            vst = _OP_FIRST + _OP_STRIDE * op + _OP_OUTPUT_LEVEL
+            vol = h.full_to_learnable[vst] if vst < len(h.full_to_learnable) else None
+            if not isinstance(vol, int):
+                continue
+            probe = torch.ones(h.learnable_preset_size)
+            probe[vol] = 0.0
+            n, c = h.get_useless_learned_params_indexes(probe)
+            for col in n:
+                num_vol[col] = vol
+            for col in c:
+                grp_vol[col] = vol
+        i32 = lambda a: np.asarray(a, dtype=np.int32)
+        return dict(num_cols=i32(num_cols), num_vol_col=i32([num_vol[c] for c in num_cols]),
+                    grp_start=i32([g[0] for g in groups]), grp_len=i32([len(g) for g in groups]),
+                    grp_vol_col=i32([grp_vol[g[0]] for g in groups]))
+
+
 def learnable_to_full_presets(idx_helper, learnable_presets: torch.Tensor, default_values: dict) -> torch.Tensor:
     """Inference tail (data/preset.py:350-369): per-group argmax / (n-1) for categorical groups, copy for
     numerical columns, defaults (else -0.1) for non-learnable VST parameters.  Vectorised, runs on the tensor's device."""

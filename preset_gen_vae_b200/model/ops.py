@@ -1,0 +1,406 @@
+"""Thin Python wrappers over the C ABI (include/pgv.h) for the model path.
+
+Each function allocates its outputs with torch (PyTorch owns all device memory), passes raw pointers, sizes and the
+current CUDA stream to ONE libpgv.so entry point and returns the tensors.  No arithmetic happens in Python and there
+is no fallback: a non-CUDA tensor raises.
+
+`set_precision('tf32' | 'fp32')` selects how GEMM-shaped layers multiply: 'tf32' (default) uses the tcgen05 tensor-core
+kernels (TF32 products, fp32 accumulation, what north_star asks for); 'fp32' routes the same layers to the exact-fp32
+CUDA-core kernels and is what the tight parity tests use.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+LRELU_SLOPE = 0.1
+_precision = 'tf32'
+launches = 0          # kernels launched through this module since the last reset (bench.py's gpu_launches)
+
+
+def set_precision(p):
+    global _precision
+    assert p in ('tf32', 'fp32')
+    _precision = p
+
+
+def get_precision():
+    return _precision
+
+
+def _f(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise _lib.PgvError("pgv kernels need CUDA tensors (got %s): there is no CPU path" % t.device)
+    assert t.dtype in (torch.float32, torch.int32, torch.float64, torch.uint8), t.dtype
+    assert t.is_contiguous()
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _call(name, *args, n=1):
+    global launches
+    launches += n
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def _s(t):
+    return _lib.stream_ptr(t.device)
+
+
+def _h(t):
+    return _lib.handle(t.device)
+
+
+def _empty(ref, *shape):
+    return torch.empty(*shape, dtype=torch.float32, device=ref.device)
+
+
+_scratch = {}
+
+
+def _ws(ref, nbytes):
+    """Small reusable fp64 scratch per device (reduction partials)."""
+    key = (ref.device.index, torch.cuda.current_stream(ref.device).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=ref.device)
+        _scratch[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+def conv_out_size(h, k, stride, pad):
+    return (h + 2 * pad - k) // stride + 1
+
+
+def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None):
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
+    y = _empty(x, B, Cout, Ho, Wo)
+    _call('pgv_conv2d_fwd_f32', _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x))
+    return y
+
+
+def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0):
+    """dx of the convolution with weight w [Cout, Cin, kh, kw]; also the forward of ConvTranspose2d(weight=w)."""
+    B, Cout, Ho, Wo = dy.shape
+    _, Cin, kh, kw = w.shape
+    H, W = in_hw
+    dx = _empty(dy, B, Cin, H, W)
+    _call('pgv_conv2d_dgrad_f32', _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(dy))
+    return dx
+
+
+def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
+    B, Cin, H, W = x.shape
+    _, Cout, Ho, Wo = dy.shape
+    _, _, kh, kw = w_shape
+    dw = _empty(x, *w_shape)
+    db = _empty(x, Cout) if want_bias else None
+    _call('pgv_conv2d_wgrad_f32', _f(x), _f(dy), _f(dw), _f(db), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x),
+          n=4 if want_bias else 2)
+    return dw, db
+
+
+def channel_sum(x):
+    B, C = x.shape[:2]
+    out = _empty(x, C)
+    _call('pgv_channel_sum', _f(x), _f(out), B, C, x[0, 0].numel(), _s(x), n=2)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ normalisation
+def bn2d_train_fwd(x, bn):
+    B, C = x.shape[:2]
+    HW = x[0, 0].numel()
+    y, mean, rstd = torch.empty_like(x), _empty(x, C), _empty(x, C)
+    _call('pgv_bn2d_train_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(y), _f(mean), _f(rstd), _f(bn.running_mean),
+          _f(bn.running_var), bn.momentum, bn.eps, B, C, HW, _f(_ws(x, 16 * C)), _s(x), n=3)
+    return y, mean, rstd
+
+
+def bn2d_eval_fwd(x, bn):
+    B, C = x.shape[:2]
+    y = torch.empty_like(x)
+    _call('pgv_bn2d_eval_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(bn.running_mean), _f(bn.running_var), _f(y), bn.eps, B, C,
+          x[0, 0].numel(), _s(x))
+    return y
+
+
+def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope):
+    B, C = x.shape[:2]
+    dx, dg, db = torch.empty_like(x), _empty(x, C), _empty(x, C)
+    _call('pgv_bn2d_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B, C, x[0, 0].numel(),
+          _f(_ws(x, 16 * C)), _s(x), n=3)
+    return dx, dg, db
+
+
+def lrelu_bwd(dy, a, slope=LRELU_SLOPE):
+    dx = torch.empty_like(a)
+    _call('pgv_lrelu_bwd', _f(dy), _f(a), _f(dx), slope, a.numel(), _s(a))
+    return dx
+
+
+def bn1d_train_fwd(x, bn, relu=False, mask=None):
+    B, F = x.shape
+    y, mean, rstd = torch.empty_like(x), _empty(x, F), _empty(x, F)
+    _call('pgv_bn1d_train_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(mask), _f(y), _f(mean), _f(rstd), _f(bn.running_mean),
+          _f(bn.running_var), bn.momentum, bn.eps, int(relu), B, F, _s(x))
+    return y, mean, rstd
+
+
+def bn1d_eval_fwd(x, bn, relu=False):
+    B, F = x.shape
+    y = torch.empty_like(x)
+    _call('pgv_bn1d_eval_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(bn.running_mean), _f(bn.running_var), _f(y), bn.eps, int(relu), B, F,
+          _s(x))
+    return y
+
+
+def bn1d_train_bwd(dy, x, bn, mean, rstd, relu=False, mask=None):
+    B, F = x.shape
+    dx, dg, db = torch.empty_like(x), _empty(x, F), _empty(x, F)
+    _call('pgv_bn1d_train_bwd', _f(dy), _f(x), _f(bn.weight), _f(bn.bias), _f(mean), _f(rstd), _f(mask), _f(dx), _f(dg), _f(db), int(relu),
+          B, F, _s(x))
+    return dx, dg, db
+
+
+def flowbn_train_fwd(x, t):
+    B, F = x.shape
+    y, mean, var, ld = torch.empty_like(x), _empty(x, F), _empty(x, F), _empty(x, 1)
+    _call('pgv_flowbn_train_fwd', _f(x), _f(t.unconstrained_weight), _f(t.bias), _f(y), _f(mean), _f(var), _f(t.running_mean),
+          _f(t.running_var), _f(ld), t.momentum, t.eps, B, F, _s(x), n=2)
+    return y, mean, var, ld
+
+
+def flowbn_eval(x, t, inverse=False):
+    B, F = x.shape
+    y, ld = torch.empty_like(x), _empty(x, 1)
+    _call('pgv_flowbn_eval', _f(x), _f(t.unconstrained_weight), _f(t.bias), _f(t.running_mean), _f(t.running_var), _f(y), _f(ld), t.eps,
+          int(inverse), B, F, _s(x))
+    return y, ld
+
+
+def flowbn_train_bwd(dy, x, t, mean, var, g_ld_sum):
+    B, F = x.shape
+    dx, du, db = torch.empty_like(x), _empty(x, F), _empty(x, F)
+    _call('pgv_flowbn_train_bwd', _f(dy), _f(x), _f(t.unconstrained_weight), _f(mean), _f(var), _f(g_ld_sum), _f(dx), _f(du), _f(db), t.eps,
+          B, F, _s(x))
+    return dx, du, db
+
+
+# ------------------------------------------------------------------------------------------------ dense layers
+def _tc_ok(*lds):
+    return _precision == 'tf32' and all(ld % 4 == 0 for ld in lds)
+
+
+def linear_fwd(x, w, bias, relu=False, residual=None):
+    """y = act(x @ w.T + bias + residual); x [M,K], w [N,K] (nn.Linear layout)."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = _empty(x, M, N)
+    if residual is None and _tc_ok(K):
+        _call('pgv_gemm_nt_tf32', _h(x), _f(x), None, K, _f(w), None, K, _f(y), N, M, N, K, _f(bias), int(relu), 0, _s(x))
+    else:
+        _call('pgv_gemm_f32', _h(x), 0, 1, _f(x), K, _f(w), K, _f(y), N, M, N, K, _f(bias), int(relu), _f(residual), N, _s(x))
+    return y
+
+
+def linear_dgrad(dy, w):
+    """dx = dy @ w; dy [M,N], w [N,K]."""
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = _empty(dy, M, K)
+    _call('pgv_gemm_f32', _h(dy), 0, 0, _f(dy), N, _f(w), K, _f(dx), K, M, K, N, None, 0, None, 0, _s(dy))
+    return dx
+
+
+def linear_wgrad(dy, x, want_bias=True):
+    """dw = dy.T @ x [N,K]; db = column sums of dy."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = _empty(dy, N, K)
+    _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy))
+    db = None
+    if want_bias:
+        db = _empty(dy, N)
+        _call('pgv_colsum', _f(dy), _f(db), M, N, _s(dy))
+    return dw, db
+
+
+# ------------------------------------------------------------------------------------------------ latent space / flows
+def reparam_fwd(mu_logvar, eps):
+    B, _, D = mu_logvar.shape
+    z = _empty(mu_logvar, B, D)
+    _call('pgv_reparam_fwd', _f(mu_logvar), _f(eps), _f(z), B, D, _s(z))
+    return z
+
+
+def reparam_bwd(dz, mu_logvar, eps, add=None):
+    B, _, D = mu_logvar.shape
+    d = torch.empty_like(mu_logvar)
+    _call('pgv_reparam_bwd', _f(dz), _f(mu_logvar), _f(eps), _f(add), _f(d), B, D, _s(d))
+    return d
+
+
+def gather_cols(x, idx):
+    B, D = x.shape
+    out = _empty(x, B, idx.numel())
+    _call('pgv_gather_cols', _f(x), _f(idx), _f(out), B, D, idx.numel(), _s(x))
+    return out
+
+
+def scatter_add_cols_(dst, idx, src):
+    B, D = dst.shape
+    _call('pgv_scatter_add_cols', _f(dst), _f(idx), _f(src), B, D, idx.numel(), _s(dst))
+    return dst
+
+
+def coupling_fwd(x, params, id_idx, tr_idx, logdet_in, inverse=False):
+    B, D = x.shape
+    y, ld = torch.empty_like(x), _empty(x, B)
+    _call('pgv_coupling_fwd', _f(x), _f(params), _f(id_idx), _f(tr_idx), _f(y), _f(logdet_in), _f(ld), B, D, id_idx.numel(),
+          tr_idx.numel(), int(inverse), _s(x))
+    return y, ld
+
+
+def coupling_bwd(dy, dlogdet, x, params, id_idx, tr_idx):
+    B, D = x.shape
+    dx, dp = torch.empty_like(x), torch.empty_like(params)
+    _call('pgv_coupling_bwd', _f(dy), _f(dlogdet), _f(x), _f(params), _f(id_idx), _f(tr_idx), _f(dx), _f(dp), B, D, id_idx.numel(),
+          tr_idx.numel(), _s(x))
+    return dx, dp
+
+
+def hardtanh_fwd(x, lo, hi):
+    y = torch.empty_like(x)
+    _call('pgv_hardtanh_fwd', _f(x), _f(y), lo, hi, x.numel(), _s(x))
+    return y
+
+
+def hardtanh_bwd(dy, x, lo, hi):
+    dx = torch.empty_like(x)
+    _call('pgv_hardtanh_bwd', _f(dy), _f(x), _f(dx), lo, hi, x.numel(), _s(x))
+    return dx
+
+
+def mul(x, m):
+    y = torch.empty_like(x)
+    _call('pgv_mul', _f(x), _f(m), _f(y), x.numel(), _s(x))
+    return y
+
+
+def add(a, b):
+    y = torch.empty_like(a)
+    _call('pgv_add', _f(a), _f(b), _f(y), a.numel(), _s(a))
+    return y
+
+
+def add_scalar(a, scalar, n, ref):
+    y = _empty(ref, n)
+    _call('pgv_add_scalar', _f(a), _f(scalar), _f(y), n, _s(ref))
+    return y
+
+
+def colsum(x):
+    out = _empty(x, x.shape[1])
+    _call('pgv_colsum', _f(x), _f(out), x.shape[0], x.shape[1], _s(x))
+    return out
+
+
+class DeviceTables:
+    """int32 device copies of PresetIndexesHelper.device_tables() (cached per device)."""
+
+    def __init__(self, idx_helper):
+        self.host = idx_helper.device_tables()
+        self.n_num = len(self.host['num_cols'])
+        self.n_grp = len(self.host['grp_start'])
+        self._dev = {}
+
+    def on(self, device):
+        key = (device.type, device.index)
+        if key not in self._dev:
+            self._dev[key] = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in self.host.items()}
+        return self._dev[key]
+
+
+def preset_act_softmax_fwd(x, tables):
+    t = tables.on(x.device)
+    y = torch.empty_like(x)
+    _call('pgv_preset_act_softmax_fwd', _f(x), _f(y), _f(t['num_cols']), tables.n_num, _f(t['grp_start']), _f(t['grp_len']), tables.n_grp,
+          x.shape[0], x.shape[1], _s(x))
+    return y
+
+
+def preset_act_softmax_bwd(dy, x, y, tables):
+    t = tables.on(x.device)
+    dx = torch.empty_like(x)
+    _call('pgv_preset_act_softmax_bwd', _f(dy), _f(x), _f(y), _f(dx), _f(t['num_cols']), tables.n_num, _f(t['grp_start']), _f(t['grp_len']),
+          tables.n_grp, x.shape[0], x.shape[1], _s(x))
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ losses / optimizer
+def sqerr_fwd(a, b, scale):
+    out = _empty(a, 1)
+    _call('pgv_sqerr_fwd', _f(a), _f(b), a.numel(), float(scale), _f(out), _f(_ws(a, 8)), _s(a), n=3)
+    return out
+
+
+def sqerr_bwd(a, b, scale, gout):
+    da = torch.empty_like(a)
+    _call('pgv_sqerr_bwd', _f(a), _f(b), a.numel(), float(scale), _f(gout), _f(da), _s(a))
+    return da
+
+
+def latent_loss_fwd(ml, z0, zk, logdet, normalize):
+    B, _, D = ml.shape
+    out = _empty(ml, 1)
+    _call('pgv_latent_loss_fwd', _f(ml), _f(z0), _f(zk), _f(logdet), B, D, int(normalize), _f(out), _f(_ws(ml, 8)), _s(ml), n=3)
+    return out
+
+
+def latent_loss_bwd(gout, ml, z0, zk, normalize):
+    B, _, D = ml.shape
+    dml, dz0, dzk, dld = torch.empty_like(ml), torch.empty_like(z0), torch.empty_like(zk), _empty(ml, B)
+    _call('pgv_latent_loss_bwd', _f(gout), _f(ml), _f(z0), _f(zk), B, D, int(normalize), _f(dml), _f(dz0), _f(dzk), _f(dld), _s(ml))
+    return dml, dz0, dzk, dld
+
+
+def dkl_fwd(ml, normalize):
+    B, _, D = ml.shape
+    out = _empty(ml, 1)
+    _call('pgv_dkl_fwd', _f(ml), B, D, int(normalize), _f(out), _f(_ws(ml, 8)), _s(ml), n=3)
+    return out
+
+
+def dkl_bwd(gout, ml, normalize):
+    B, _, D = ml.shape
+    d = torch.empty_like(ml)
+    _call('pgv_dkl_bwd', _f(gout), _f(ml), B, D, int(normalize), _f(d), _s(ml))
+    return d
+
+
+def synth_loss_fwd(v_out, v_in, tables, normalize, factor, cat_softmax, temperature):
+    t = tables.on(v_out.device)
+    B, L = v_out.shape
+    out = _empty(v_out, 1)
+    ws = torch.empty(_lib.lib().pgv_synth_loss_workspace_bytes(tables.n_grp), dtype=torch.uint8, device=v_out.device)
+    _call('pgv_synth_loss_fwd', _f(v_out), _f(v_in), B, L, _f(t['num_cols']), _f(t['num_vol_col']), tables.n_num, _f(t['grp_start']),
+          _f(t['grp_len']), _f(t['grp_vol_col']), tables.n_grp, int(normalize), float(factor), int(cat_softmax), float(temperature),
+          _f(out), _f(ws), _s(v_out), n=3)
+    return out, ws
+
+
+def synth_loss_bwd(gout, v_out, v_in, tables, normalize, factor, cat_softmax, temperature, ws):
+    t = tables.on(v_out.device)
+    B, L = v_out.shape
+    d = torch.empty_like(v_out)
+    _call('pgv_synth_loss_bwd', _f(gout), _f(v_out), _f(v_in), B, L, _f(t['num_cols']), _f(t['num_vol_col']), tables.n_num,
+          _f(t['grp_start']), _f(t['grp_len']), _f(t['grp_vol_col']), tables.n_grp, int(normalize), float(factor), int(cat_softmax),
+          float(temperature), _f(ws), _f(d), _s(v_out))
+    return d
