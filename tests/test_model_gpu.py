@@ -1,12 +1,18 @@
 """GPU: the full ExtendedAE path (this package's modules -> C ABI -> CUDA kernels) against the CPU oracle on identical
 seeded inputs, weights, eps and dropout masks.
 
+The checker is the oracle evaluated in fp64 (same code as the fp32 oracle that tests/test_oracle_model.py pins to the
+reference's golden outputs); measured on B200 (tools/gpu_diag_model.py, B=4) the reference's own fp32 CPU path is
+5.1e-5 global / 7.3e-4 worst-tensor relative-L2 away from it, the CUDA fp32 path 1.9e-5 / 5.5e-5.
+
 Tolerances (north_star: "per-step losses and gradients within a stated fp32/TF32 tolerance"):
-  precision 'fp32' (exact-fp32 products everywhere): outputs 2e-4 relative-L2, losses 2e-5 relative, every parameter
-      gradient 2e-3 relative-L2 (the floor the reference's own fp32-vs-fp64 comparison shows); tensors
-      whose gradient is structurally zero (a bias feeding a train-mode BatchNorm) are compared absolutely.
-  precision 'tf32' (tensor-core layers multiply in TF32): outputs 5e-3, losses 2e-3, global gradient cosine >= 0.999.
+  precision 'fp32' (exact-fp32 products everywhere): outputs 1e-4 relative-L2, losses 1e-5 relative, every parameter
+      gradient 2e-3 relative-L2; tensors whose gradient is structurally zero (a bias feeding a train-mode BatchNorm,
+      SURVEY.md §7) are compared absolutely.
+  precision 'tf32' (tensor-core layers multiply in TF32, operands truncated to 10 mantissa bits by the hardware):
+      outputs 5e-3, losses 2e-3, global gradient cosine >= 0.9999 (measured 0.999985, global rel-L2 5.5e-3).
 """
+import copy
 import numpy as np
 import pytest
 import torch
@@ -48,7 +54,8 @@ def run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, precision):
     noise = synthetic.make_noise(B, m_cfg.dim_z, t_cfg.fc_dropout, t_cfg.reg_fc_dropout, seed=1,
                                  enc_fc_in=orc.ae_model.encoder.mlp[1].in_features)
     orc.train()
-    outs, losses, total = oloss.train_step_losses(orc, x, v_in, info, noise, beta=0.2,
+    noise64 = {k: (v.double() if torch.is_tensor(v) else [[m.double() for m in l] for l in v]) for k, v in noise.items()}
+    outs, losses, total = oloss.train_step_losses(orc, x.double(), v_in.double(), info, noise64, beta=0.2,
                                                   params_reg_softmax=m_cfg.params_reg_softmax)
     total.backward()
     ops.set_precision(precision)
@@ -80,7 +87,7 @@ def check(orc, mine, outs, losses, got, got_losses, out_tol, loss_tol, grad_tol,
         assert g is not None and r is not None, name
         g, r = g.double().cpu(), r.double()
         dot += float((g * r).sum()); n1 += float((g * g).sum()); n2 += float((r * r).sum())
-        if r.norm() < 1e-9 * max(1.0, float(p.detach().norm())):           # structurally zero gradient
+        if r.norm() < 1e-7:                                                  # structurally zero gradient
             assert g.abs().max() < 1e-5, name
             continue
         e = float((g - r).norm() / r.norm())
@@ -100,17 +107,18 @@ def test_train_step_parity_default_config(idx_helper, precision):
     orc, mine, m_cfg, t_cfg = make_pair(idx_helper, B)
     mine.load_state_dict(orc.state_dict())
     mine.cuda()
+    orc = copy.deepcopy(orc).double()
     res = run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, precision)
     if precision == 'fp32':
-        check(orc, mine, *res, out_tol=2e-4, loss_tol=2e-5, grad_tol=2e-3, min_cos=0.99999)
+        check(orc, mine, *res, out_tol=1e-4, loss_tol=1e-5, grad_tol=2e-3, min_cos=0.999999)
     else:
-        check(orc, mine, *res, out_tol=5e-3, loss_tol=2e-3, grad_tol=None, min_cos=0.999)
+        check(orc, mine, *res, out_tol=5e-3, loss_tol=2e-3, grad_tol=None, min_cos=0.9999)
     ops.set_precision('tf32')
     # running statistics after one training forward
     sd_o, sd_m = orc.state_dict(), mine.state_dict()
     for k in sd_o:
         if 'running' in k:
-            assert rel(sd_m[k], sd_o[k]) < 1e-3, k
+            assert rel(sd_m[k], sd_o[k]) < (1e-4 if precision == 'fp32' else 2e-2), k
         if 'num_batches_tracked' in k:
             assert int(sd_m[k]) == int(sd_o[k]), k
 
@@ -152,9 +160,10 @@ def test_stacked_six_channel_config(idx_helper):
     assert m_cfg.input_tensor_size[1] == 6
     mine.load_state_dict(orc.state_dict())
     mine.cuda()
+    orc = copy.deepcopy(orc).double()
     res = run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, 'fp32')
     ops.set_precision('tf32')
-    check(orc, mine, *res, out_tol=2e-4, loss_tol=2e-5, grad_tol=3e-3, min_cos=0.99999)
+    check(orc, mine, *res, out_tol=1e-4, loss_tol=1e-5, grad_tol=2e-3, min_cos=0.999999)
 
 
 def test_midi_concat_and_softmax_head_config(idx_helper):
@@ -165,9 +174,10 @@ def test_midi_concat_and_softmax_head_config(idx_helper):
     assert m_cfg.concat_midi_to_z and m_cfg.input_tensor_size[1] == 1
     mine.load_state_dict(orc.state_dict())
     mine.cuda()
+    orc = copy.deepcopy(orc).double()
     res = run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, 'fp32')
     ops.set_precision('tf32')
-    check(orc, mine, *res, out_tol=2e-4, loss_tol=5e-5, grad_tol=5e-3, min_cos=0.9999)
+    check(orc, mine, *res, out_tol=1e-4, loss_tol=1e-5, grad_tol=2e-3, min_cos=0.999999)
 
 
 def test_reference_checkpoint_layout_round_trip(idx_helper, tmp_path):
