@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the preset-gen-vae hot path on B200 (driver contract: see the task statement / DESIGN.md §6).
+
+    python bench.py --gpus 1 --steps K --warmup W                       # this repo's CUDA path, one JSON line
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      # N ranks, NCCL, weak scaling
+    python bench.py --impl reference ...                                # the reference algorithm on the host CPU
+
+Workloads (BASELINE.json `configs`):
+    train      (default) configs[2]: full ExtendedAE training step from audio - mel front end, conv VAE, latent flow,
+               regression flow, losses, backward, Adam - C=1, per-GPU batch 160 (config.py:80); metric = samples/s
+    frontend   configs[1]: STFT + mel front end alone, 256 clips
+    inference  configs[4]: audio -> latent -> preset parameters, batch 1024
+`value` is timed with inputs resident in HBM; `e2e` goes through the public API with pinned HOST buffers (H2D of
+the step's audio / targets and D2H of the losses inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = {'train': 'train samples/sec', 'frontend': 'front-end clips/sec', 'inference': 'inference samples/sec'}
+FRONTEND_FLOP_PER_CLIP = 820.63e6          # dense DFT (729.13 MFLOP) + dense mel (91.50 MFLOP)
+DFT_FLOP_PER_CLIP, MEL_FLOP_PER_CLIP = 729.13e6, 91.50e6
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p['hbm_gbs'], bf16_burst=p['bf16_tflops'], bf16_sustained=p['bf16_tflops_sustained'], src='measured')
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.rows = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7), ('sw_power_cap', 8)):
+                if len(r) > col and r[col].lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+def default_batch(workload):
+    return {'train': 160, 'frontend': 256, 'inference': 1024}[workload]
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def oracle_step_factory(workload, batch):
+    """The reference algorithm on the host CPU (oracle port: nflows / librosa restated, see oracle/__init__.py).
+    Returns (callable running ONE step on `batch` samples, description)."""
+    from oracle import frontend as ofe, losses as oloss, model as omodel
+    from preset_gen_vae_b200 import config as pcfg, synthetic
+    from preset_gen_vae_b200.data.preset import DexedLearnableLayout
+    helper = DexedLearnableLayout().preset_indexes_helper
+    m_cfg, t_cfg = pcfg.make_default(minibatch_size=batch)
+    pcfg.apply_dataset_dims(m_cfg, helper)
+    audio = synthetic.make_audio(batch, 1, seed=0)
+    st = synthetic.SPEC_STATS
+    if workload == 'frontend':
+        def step():      # one clip at a time, as the reference DataLoader worker does (abstractbasedataset.py:124-134)
+            return ofe.batch_front_end(audio, 1024, 256, -120.0, 257, st['min'], st['max'])
+        return step, 'oracle port of utils/audio.py MelSpectrogram, per-clip loop'
+    torch.manual_seed(0)
+    ext = omodel.build_extended_ae_model(m_cfg, t_cfg, helper)[3]
+    v_in = synthetic.make_preset_targets(helper, batch, seed=0)
+    info = synthetic.make_sample_info(batch)
+    if workload == 'inference':
+        ext.eval()
+
+        def step():
+            with torch.no_grad():
+                x = ofe.batch_front_end(audio, 1024, 256, -120.0, 257, st['min'], st['max'])
+                ml = ext.ae_model.encoder(x)
+                zk, _ = ext.ae_model.flow_transform(ml[:, 0, :])
+                return ext.reg_model(zk)
+        return step, 'oracle port: front end + encoder + flows + regression head (eval)'
+    ext.train()
+    opt = torch.optim.Adam(ext.parameters(), lr=t_cfg.initial_learning_rate, weight_decay=t_cfg.weight_decay, betas=t_cfg.adam_betas)
+
+    def step():          # train.py:204-248 without DataParallel
+        x = ofe.batch_front_end(audio, 1024, 256, -120.0, 257, st['min'], st['max'])
+        opt.zero_grad()
+        _, losses, total = oloss.train_step_losses(ext, x, v_in, info, None, beta=t_cfg.beta)
+        total.backward()
+        opt.step()
+        return total
+    return step, 'oracle port of train.py:204-248 (front end per clip + fwd + losses + bwd + torch Adam)'
+
+
+def run_cpu(workload, batch, budget_s, min_steps=2, max_steps=50):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step, what = oracle_step_factory(workload, batch)
+    step()                                            # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_steps or (time.perf_counter() < t_end and len(times) < max_steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return dict(value=batch / med, unit='samples/s', cores=threads, kind='port',
+                sample='%d steps of batch %d (%s), median %.3f s/step' % (len(times), batch, what, med)), med
+
+
+def main_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    batch = args.batch_per_gpu or default_batch(args.workload)
+    cpu_batch = min(batch, args.cpu_batch)
+    budget = max(10.0, min(150.0, 12.0 * max(args.steps, 1)))
+    cb, med = run_cpu(args.workload, cpu_batch, budget)
+    line = {'impl': 'reference', 'metric': METRIC[args.workload], 'value': cb['value'], 'unit': 'samples/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.workload, cpu_batch), 'note': 'reference algorithm on the host CPU (no GPU)'},
+            'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(workload, batch):
+    return {'train': 'full ExtendedAE train step from audio (mel front end + speccnn8l1_bn conv VAE + realnvp_6l300 latent flow + '
+                     'flow_realnvp_6l300 regression + losses, fwd+bwd+Adam), C=1, dim_z=610, per-GPU batch %d' % batch,
+            'frontend': 'STFT + mel spectrogram front end alone, %d synthetic clips of 88576 samples (n_fft 1024, hop 256, 257 mel)' % batch,
+            'inference': 'batched inference audio -> latent -> Dexed preset parameters, batch %d per GPU' % batch}[workload]
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def main_ours(args):
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+        pg = torch.distributed.group.WORLD
+    from preset_gen_vae_b200 import _lib, config as pcfg, synthetic
+    from preset_gen_vae_b200.data.preset import DexedLearnableLayout
+    from preset_gen_vae_b200.model import ops
+    from preset_gen_vae_b200.train import TrainStep
+    from preset_gen_vae_b200.utils.audio import MelSpectrogram
+    B = args.batch_per_gpu or default_batch(args.workload)
+    helper = DexedLearnableLayout().preset_indexes_helper
+    m_cfg, t_cfg = pcfg.make_default(minibatch_size=B)
+    pcfg.apply_dataset_dims(m_cfg, helper)
+    audio_h = synthetic.make_audio(min(B, 64), 1, seed=rank)                 # CPU synthesis is slow: tile 64 distinct clips
+    audio_h = audio_h.repeat((B + audio_h.shape[0] - 1) // audio_h.shape[0], 1, 1)[:B].contiguous().pin_memory()
+    v_in_h = synthetic.make_preset_targets(helper, B, seed=rank).pin_memory()
+    info_h = synthetic.make_sample_info(B).pin_memory()
+    audio, v_in, info = audio_h.to(dev), v_in_h.to(dev), info_h.to(dev)
+    st = synthetic.SPEC_STATS
+
+    trainer = None
+    if args.workload == 'frontend':
+        mel = MelSpectrogram(1024, 256, -120.0, 257, 22050, device=dev)
+        a2 = audio.view(B, -1)
+        launches = _lib.lib().pgv_frontend_launch_count(257)
+
+        def dev_step():
+            return mel.compute(a2, normalize=(st['min'], st['max']))
+
+        def e2e_step():
+            return mel.compute_host(audio_h.view(B, -1), normalize=(st['min'], st['max']), device=dev)
+        h2d, d2h = audio_h.numel() * 4, B * 257 * 347 * 4
+    else:
+        trainer = TrainStep(m_cfg, t_cfg, helper, device=dev, process_group=pg, use_cuda_graph=not args.no_graph)
+        if args.workload == 'train':
+            def dev_step():
+                return trainer.step(audio, v_in, info)
+
+            def e2e_step():
+                a = audio_h.to(dev, non_blocking=True); v = v_in_h.to(dev, non_blocking=True); i = info_h.to(dev, non_blocking=True)
+                return trainer.step(a, v, i).cpu()
+            h2d, d2h = (audio_h.numel() + v_in_h.numel() + info_h.numel()) * 4, 12
+        else:
+            def dev_step():
+                return trainer.infer(audio)
+
+            def e2e_step():
+                return trainer.infer(audio_h.to(dev, non_blocking=True)).cpu()
+            h2d, d2h = audio_h.numel() * 4, B * 610 * 4
+        launches = None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    before = ops.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(dev_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if launches is None:
+        launches = getattr(trainer, 'launches_per_step', None) or (ops.launches - before) // max(args.steps, 1)
+    ms_per_step = total_ms / args.steps
+    value = world * B / ms_per_step * 1e3
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e = {'value': world * B / e2e_ms * 1e3, 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+           'ms_per_step': e2e_ms}
+
+    # ---- live roofline of the dominant kernel family: eager steps with CUDA events around every C entry point ----
+    pk = peaks()
+    roofline, breakdown = None, None
+    if rank == 0:
+        if args.workload == 'frontend':
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            # the DFT contraction is ~80 % of the front end; time the whole call and attribute by the ncu share in profiles/
+            for a, b in ev:
+                a.record(); dev_step(); b.record()
+            torch.cuda.synchronize(dev)
+            ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            ach = FRONTEND_FLOP_PER_CLIP * B / (ms * 1e-3) / 1e12
+            roofline = {'kernel': 'gemm_tf32_kernel<DftProblem> + <MelProblem> (whole front end)', 'bound': 'tensor', 'achieved': ach,
+                        'peak': pk['bf16_burst'] / 2, 'unit': 'TFLOP/s', 'frac': ach / (pk['bf16_burst'] / 2), 'traffic': None,
+                        'note': 'algorithmic dense flops 820.63 MFLOP/clip; the 3xTF32 split executes 3x that on the tensor pipe; '
+                                'peak = TF32 dense = half of the %s bf16 burst figure' % pk['src']}
+        else:
+            trainer_graph = trainer.use_graph
+            trainer.use_graph = False
+            ops.start_profile()
+            for _ in range(2):
+                dev_step()
+            prof = ops.stop_profile()
+            trainer.use_graph = trainer_graph
+            tot = sum(v['ms'] for v in prof.values())
+            breakdown = {k: round(v['ms'] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:8]}
+            name, top = max(prof.items(), key=lambda kv: kv[1]['ms'])
+            per_ms = top['ms'] / 2
+            if top['flops'] > 0:
+                ach = top['flops'] / 2 / (per_ms * 1e-3) / 1e12
+                tensor = 'tf32' in name
+                peak = pk['bf16_sustained'] / 2
+                roofline = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                            'traffic': None, 'share_of_step': top['ms'] / tot,
+                            'note': ('tcgen05 TF32 kernel' if tensor else 'CUDA-core fp32 kernel (not yet on the tensor pipe)') +
+                                    '; algorithmic flops of all its launches in one step / their summed CUDA-event time; peak = TF32 dense '
+                                    '= half of the %s sustained bf16 figure' % pk['src']}
+            else:
+                ach = top['bytes'] / 2 / (per_ms * 1e-3) / 1e9
+                roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
+                            'traffic': None, 'share_of_step': top['ms'] / tot, 'note': 'peak = %s copy bandwidth' % pk['src']}
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_baseline, _ = run_cpu(args.workload, min(B, args.cpu_batch), budget_s=args.cpu_budget)
+    if rank == 0:
+        line = {'metric': METRIC[args.workload], 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32 storage; tf32 tensor-core products where the layer runs on tcgen05, fp32 elsewhere',
+                'data': 'synthetic', 'config': {'workload': workload_name(args.workload, B), 'global_batch': world * B,
+                                                'parallelism': 'dp%d' % world,
+                                                'l2': 'per-step working set (activations + 241 MB of parameters, > 1 GB) exceeds the 126 MB L2; no flush needed',
+                                                'cuda_graph': bool(trainer is not None and trainer.use_graph)},
+                'e2e': e2e, 'gpu_launches': int(launches * args.steps), 'gpu_launches_per_step': int(launches), 'clocks': clocks,
+                'roofline': roofline, 'cpu_baseline': cpu_baseline}
+        if breakdown is not None:
+            line['ms_by_entry_point_eager'] = breakdown
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='train', choices=['train', 'frontend', 'inference'])
+    ap.add_argument('--batch-per-gpu', type=int, default=0)
+    ap.add_argument('--cpu-batch', type=int, default=160, help='batch of the bounded CPU sample')
+    ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU baseline work')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == '__main__':
+    main()

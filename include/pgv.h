@@ -219,6 +219,9 @@ PGV_API int pgv_synth_loss_bwd(const float* grad_out, const float* v_out, const 
 /* ------------------------------------------------------------------ optimizer (train.py:165-167)
  * torch.optim.Adam semantics with L2-in-gradient weight decay on one flat fp32 buffer; `step` counts from 1.
  * The _dev variant reads {lr, 1-beta1^t, sqrt(1-beta2^t), grad_scale} from device memory (CUDA-graph replay). */
+/* flat[off_i .. off_i+n_i) = scale * src_i for n_tensors tensors in ONE launch; table_dev: device array of 3*n uint64
+ * {source address, destination offset in elements, element count}; max_elems = largest n_i. */
+PGV_API int pgv_multi_pack(const void* table_dev, int n_tensors, size_t max_elems, float* flat, float scale, pgv_stream_t stream);
 PGV_API int pgv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int step, float grad_scale, pgv_stream_t stream);
 PGV_API int pgv_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, const float* hyper_dev,

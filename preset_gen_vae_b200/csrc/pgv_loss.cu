@@ -225,6 +225,16 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Gather many tensors into one flat buffer (gradient bucket for the all-reduce / fused Adam).  table[3*i] = source
+// address, table[3*i+1] = destination offset (elements), table[3*i+2] = element count; gridDim.y = tensors.
+__global__ void multi_pack_kernel(const unsigned long long* __restrict__ table, float* __restrict__ flat, float scale) {
+    const float* src = reinterpret_cast<const float*>(table[3 * blockIdx.y]);
+    float* dst = flat + table[3 * blockIdx.y + 1];
+    const size_t n = table[3 * blockIdx.y + 2];
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = src[i] * scale;
+}
+
 }  // namespace pgv
 
 using namespace pgv;
@@ -328,6 +338,17 @@ int pgv_synth_loss_bwd(const float* grad_out, const float* v_out, const float* v
     synth_loss_bwd_kernel<<<ceil_div(B, 8), 256, 0, PGV_STREAM(stream)>>>(grad_out, v_out, v_in, t, static_cast<const double*>(workspace), d_v_out,
                                                                          static_cast<float>(2.0 * num_scale), static_cast<float>(cat_scale),
                                                                          1.0f / softmax_temperature, cat_softmax, B, L);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+int pgv_multi_pack(const void* table_dev, int n_tensors, size_t max_elems, float* flat, float scale, pgv_stream_t stream) {
+    PGV_CHECK_ARG(table_dev && flat && n_tensors > 0, "pgv_multi_pack: bad argument");
+    size_t bx = (max_elems + 256 * 8 - 1) / (256 * 8);
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    multi_pack_kernel<<<dim3(static_cast<unsigned>(bx), n_tensors), 256, 0, PGV_STREAM(stream)>>>(
+        static_cast<const unsigned long long*>(table_dev), flat, scale);
     PGV_LAUNCH_CHECK();
     return 0;
 }

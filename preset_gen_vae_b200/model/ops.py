@@ -40,10 +40,41 @@ def _f(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _call(name, *args, n=1):
+profile = None        # None, or a dict filled by _call: name -> [calls, flops, bytes, [(start_event, end_event), ...]]
+
+
+def start_profile():
+    """Per-entry-point accounting for bench.py / tools: CUDA events around every C call (eager mode only)."""
+    global profile
+    profile = {}
+
+
+def stop_profile():
+    """Returns {name: dict(calls, ms, flops, bytes)} and disables profiling.  Synchronises the device."""
+    global profile
+    torch.cuda.synchronize()
+    out = {}
+    for name, (calls, flops, nbytes, events) in (profile or {}).items():
+        out[name] = dict(calls=calls, ms=sum(a.elapsed_time(b) for a, b in events), flops=flops, bytes=nbytes)
+    profile = None
+    return out
+
+
+def _call(name, *args, n=1, flops=0, nbytes=0):
     global launches
     launches += n
+    if profile is None:
+        _lib.check(getattr(_lib.lib(), name)(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     _lib.check(getattr(_lib.lib(), name)(*args), name)
+    b.record()
+    rec = profile.setdefault(name, [0, 0, 0, []])
+    rec[0] += 1
+    rec[1] += flops
+    rec[2] += nbytes
+    rec[3].append((a, b))
 
 
 def _s(t):
@@ -81,7 +112,8 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None):
     Cout, _, kh, kw = w.shape
     Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
     y = _empty(x, B, Cout, Ho, Wo)
-    _call('pgv_conv2d_fwd_f32', _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x))
+    _call('pgv_conv2d_fwd_f32', _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x),
+          flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + y.numel() + w.numel()))
     return y
 
 
@@ -91,7 +123,8 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0):
     _, Cin, kh, kw = w.shape
     H, W = in_hw
     dx = _empty(dy, B, Cin, H, W)
-    _call('pgv_conv2d_dgrad_f32', _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(dy))
+    _call('pgv_conv2d_dgrad_f32', _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(dy),
+          flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
     return dx
 
 
@@ -102,7 +135,7 @@ def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
     dw = _empty(x, *w_shape)
     db = _empty(x, Cout) if want_bias else None
     _call('pgv_conv2d_wgrad_f32', _f(x), _f(dy), _f(dw), _f(db), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x),
-          n=4 if want_bias else 2)
+          n=4 if want_bias else 2, flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
     return dw, db
 
 
@@ -119,7 +152,7 @@ def bn2d_train_fwd(x, bn):
     HW = x[0, 0].numel()
     y, mean, rstd = torch.empty_like(x), _empty(x, C), _empty(x, C)
     _call('pgv_bn2d_train_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(y), _f(mean), _f(rstd), _f(bn.running_mean),
-          _f(bn.running_var), bn.momentum, bn.eps, B, C, HW, _f(_ws(x, 16 * C)), _s(x), n=3)
+          _f(bn.running_var), bn.momentum, bn.eps, B, C, HW, _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 3 * x.numel())
     return y, mean, rstd
 
 
@@ -135,7 +168,7 @@ def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope):
     B, C = x.shape[:2]
     dx, dg, db = torch.empty_like(x), _empty(x, C), _empty(x, C)
     _call('pgv_bn2d_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B, C, x[0, 0].numel(),
-          _f(_ws(x, 16 * C)), _s(x), n=3)
+          _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 5 * x.numel())
     return dx, dg, db
 
 
@@ -204,9 +237,11 @@ def linear_fwd(x, w, bias, relu=False, residual=None):
     N = w.shape[0]
     y = _empty(x, M, N)
     if residual is None and _tc_ok(K):
-        _call('pgv_gemm_nt_tf32', _h(x), _f(x), None, K, _f(w), None, K, _f(y), N, M, N, K, _f(bias), int(relu), 0, _s(x))
+        _call('pgv_gemm_nt_tf32', _h(x), _f(x), None, K, _f(w), None, K, _f(y), N, M, N, K, _f(bias), int(relu), 0, _s(x),
+              flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     else:
-        _call('pgv_gemm_f32', _h(x), 0, 1, _f(x), K, _f(w), K, _f(y), N, M, N, K, _f(bias), int(relu), _f(residual), N, _s(x))
+        _call('pgv_gemm_f32', _h(x), 0, 1, _f(x), K, _f(w), K, _f(y), N, M, N, K, _f(bias), int(relu), _f(residual), N, _s(x),
+              flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     return y
 
 
@@ -215,7 +250,8 @@ def linear_dgrad(dy, w):
     M, N = dy.shape
     K = w.shape[1]
     dx = _empty(dy, M, K)
-    _call('pgv_gemm_f32', _h(dy), 0, 0, _f(dy), N, _f(w), K, _f(dx), K, M, K, N, None, 0, None, 0, _s(dy))
+    _call('pgv_gemm_f32', _h(dy), 0, 0, _f(dy), N, _f(w), K, _f(dx), K, M, K, N, None, 0, None, 0, _s(dy),
+          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     return dx
 
 
@@ -224,7 +260,8 @@ def linear_wgrad(dy, x, want_bias=True):
     M, N = dy.shape
     K = x.shape[1]
     dw = _empty(dy, N, K)
-    _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy))
+    _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy),
+          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     db = None
     if want_bias:
         db = _empty(dy, N)

@@ -1,0 +1,175 @@
+"""One data-parallel training step of the hot path, as the reference's loop body does it (train.py:204-248):
+
+    audio -> mel front end (+ min-max) -> ExtendedAE forward -> regression head -> MSE + beta * latent + controls
+          -> backward -> (N > 1: gradient all-reduce, mean over ranks) -> Adam (L2 weight decay)
+
+B200 design: one process per GPU, parameters resident per rank in ONE flat fp32 buffer (module
+parameters are views into it), gradients packed into one flat buffer by a single kernel, one NCCL all-reduce over
+NVLink on that buffer, one fused Adam kernel over the flat buffers, and the whole device-side step replayed from a
+CUDA graph.  BatchNorm statistics are per-rank, as with the reference's nn.DataParallel replicas (train.py:95-97).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, synthetic
+from .model import build, loss as ploss, ops
+from .utils import audio as paudio
+
+
+class TrainStep:
+    def __init__(self, model_config, train_config, idx_helper, device=None, process_group=None, use_cuda_graph=True,
+                 spec_stats=None, beta=None, seed=0):
+        self.mc, self.tc, self.idx_helper = model_config, train_config, idx_helper
+        self.device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.use_graph = use_cuda_graph
+        self.spec_stats = spec_stats or synthetic.SPEC_STATS
+        self.beta = train_config.beta if beta is None else beta
+        torch.manual_seed(seed)                       # same initial weights on every rank
+        with torch.cuda.device(self.device):
+            self.model = build.build_extended_ae_model(model_config, train_config, idx_helper)[3].to(self.device)
+        self.model.train()
+        self.frontend = paudio.build_spectrogram(model_config, device=self.device)
+        self.recons_criterion = ploss.MSELoss() if train_config.normalize_losses else ploss.L2Loss()
+        self.controls_criterion = ploss.SynthParamsLoss(
+            idx_helper, train_config.normalize_losses, cat_bce=train_config.params_cat_bceloss,
+            cat_softmax=(not model_config.params_reg_softmax and not train_config.params_cat_bceloss),
+            cat_softmax_t=train_config.params_cat_softmax_temperature)
+        self._flatten_parameters()
+        self.step_count = 0
+        self.lr = train_config.initial_learning_rate
+        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._graph = None
+        self._static = None
+        self.losses = None
+
+    # ------------------------------------------------------------------ flat parameter / gradient / Adam-state buffers
+    def _flatten_parameters(self):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        sizes = [p.numel() for p in params]
+        offs = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])      # 16-byte aligned slots
+        total = int(offs[-1])
+        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        for p, o, n in zip(params, offs[:-1], sizes):
+            flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = flat[o:o + n].view_as(p.data)
+        self.params, self.flat_params, self._offs, self._sizes = params, flat, offs[:-1], sizes
+        self.flat_grads = torch.zeros_like(flat)
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.n_param_elems = sum(sizes)
+        self._table_host = torch.zeros(len(params) * 3, dtype=torch.int64).pin_memory()
+        self._table_dev = torch.zeros(len(params) * 3, dtype=torch.int64, device=self.device)
+        self._table_host[1::3] = torch.from_numpy(np.asarray(self._offs, dtype=np.int64))
+        self._table_host[2::3] = torch.tensor(sizes, dtype=torch.int64)
+
+    def _pack_grads(self, scale=1.0):
+        self._table_host[0::3] = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
+        self._table_dev.copy_(self._table_host, non_blocking=True)
+        _lib.check(_lib.lib().pgv_multi_pack(_lib.ptr(self._table_dev), len(self.params), max(self._sizes),
+                                             _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
+        ops.launches += 1
+
+    # ------------------------------------------------------------------ one step, eager (also what gets captured)
+    def _device_step(self, audio, v_in, sample_info, with_optimizer):
+        B, C, L = audio.shape
+        x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
+        ops.launches += _lib.lib().pgv_frontend_launch_count(self.mc.mel_bins)
+        x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
+        z0_ml, z0, zk, logdet, x_out = self.model(x_in, sample_info)
+        v_out = self.model.reg_model(zk)
+        recons = self.recons_criterion(x_out, x_in)
+        lat = self.model.latent_loss(z0_ml, z0, zk, logdet)
+        cont = self.controls_criterion(v_out, v_in)
+        total = recons + self.beta * lat + cont
+        for p in self.params:
+            p.grad = None
+        total.backward()
+        self._pack_grads(1.0 / self.world)
+        if with_optimizer:
+            self._adam()
+        return torch.stack([recons.detach(), lat.detach(), cont.detach()])
+
+    def _adam(self):
+        tc = self.tc
+        _lib.check(_lib.lib().pgv_adam_step_dev(
+            _lib.ptr(self.flat_params), _lib.ptr(self.flat_grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+            self.flat_params.numel(), _lib.ptr(self._hyper_dev), tc.adam_betas[0], tc.adam_betas[1], 1e-8, tc.weight_decay,
+            _lib.stream_ptr(self.device)), 'pgv_adam_step_dev')
+        ops.launches += 1
+
+    def _refresh_hyper(self):
+        self.step_count += 1
+        b1, b2 = self.tc.adam_betas
+        self._hyper_host[0] = self.lr
+        self._hyper_host[1] = 1.0 - b1 ** self.step_count
+        self._hyper_host[2] = float(np.sqrt(1.0 - b2 ** self.step_count))
+        self._hyper_host[3] = 1.0
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+
+    def _allreduce(self):
+        torch.distributed.all_reduce(self.flat_grads, group=self.pg)    # sum; the 1/world factor was applied while packing
+
+    def step(self, audio, v_in, sample_info):
+        """audio [B, C, L] fp32, v_in [B, L_params] fp32, sample_info [B, 3] int32: CUDA tensors on this rank's device.
+        Returns a device tensor (recons, latent, controls) of this rank's un-weighted losses."""
+        self._refresh_hyper()
+        fused_opt = self.world == 1
+        if not self.use_graph:
+            losses = self._device_step(audio, v_in, sample_info, with_optimizer=fused_opt)
+        else:
+            if self._graph is None:
+                self._capture(audio, v_in, sample_info, fused_opt)
+            for dst, src in zip(self._static[:3], (audio, v_in, sample_info)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            losses = self._static[3]
+        if not fused_opt:
+            self._allreduce()
+            self._adam()
+        self.losses = losses
+        return losses
+
+    def _capture(self, audio, v_in, sample_info, with_optimizer):
+        static_in = (audio.clone(), v_in.clone(), sample_info.clone())
+        backup = (self.flat_params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+        bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if 'running' in k}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                  # warm-up: lazy init, allocator pools, constants upload
+                self._device_step(*static_in, with_optimizer=with_optimizer)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        # warm-up steps must not count as training: restore parameters, optimizer state and BN statistics
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self.model.load_state_dict(bn_state, strict=False)
+        graph = torch.cuda.CUDAGraph()
+        before = ops.launches
+        with torch.cuda.graph(graph):
+            losses = self._device_step(*static_in, with_optimizer=with_optimizer)
+        self.launches_per_step = ops.launches - before
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self.model.load_state_dict(bn_state, strict=False)
+        self._graph, self._static = graph, (*static_in, losses)
+
+    @torch.no_grad()
+    def infer(self, audio):
+        """Batched inference audio -> latent -> preset parameters (eval.py:161-182, BASELINE config 5): encoder,
+        latent flow and regression flow in eval mode; the decoder is not needed for the parameters and is skipped."""
+        was_training = self.model.training
+        self.model.eval()
+        B, C, L = audio.shape
+        x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
+        x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
+        from .model.VAE import reparametrize
+        z0_ml = self.model.ae_model.encoder(x_in)
+        zk, _ = self.model.ae_model.flow_transform(reparametrize(z0_ml, None))
+        v_out = self.model.reg_model(zk)
+        self.model.train(was_training)
+        return v_out
