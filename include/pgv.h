@@ -122,6 +122,16 @@ PGV_API int pgv_conv2d_dgrad_f32(const float* dy, const float* w, const float* b
 PGV_API int pgv_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, int B, int Cin, int H, int W, int Cout, int kh,
                                  int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
 
+/* The same three operations as implicit GEMMs on the tcgen05 tensor cores (TF32 products with round-to-nearest
+ * operands, fp32 accumulation in TMEM; see csrc/pgv_conv_tc.cu).  Same argument meaning as the _f32 entry points.
+ * dgrad supports stride 1 and 2; wgrad accumulates split-K partial sums with fp32 atomics (dw is zeroed first) and
+ * does not produce db (use pgv_channel_sum). */
+PGV_API int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
+                                int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
+PGV_API int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const float* bias, float* dx, int B, int Cin, int H, int W,
+                                  int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
+PGV_API int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout, int kh,
+                                  int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
 /* out[c] = sum over (b, h, w) of x[b,c,h,w] (bias gradient of a transposed convolution). */
 PGV_API int pgv_channel_sum(const float* x, float* out, int B, int C, int HW, pgv_stream_t stream);
 

@@ -179,17 +179,17 @@ class FlowVAE(nn.Module):                                      # VAE.py:69-193
         if not self.concat_midi_to_z0:
             z0_mu_logvar = enc
         else:                                                  # VAE.py:155-165
-            z0_mu_logvar = torch.empty((B, 2, self.dim_z))
+            z0_mu_logvar = enc.new_empty((B, 2, self.dim_z))
             z0_mu_logvar[:, :, 2:] = enc
             if sample_info is None:
                 z0_mu_logvar[:, :, [0, 1]] = 0.0
             else:
-                z0_mu_logvar[:, 0, [0, 1]] = -1.0 + 2.0 * sample_info[:, [1, 2]].float() / 127.0
+                z0_mu_logvar[:, 0, [0, 1]] = (-1.0 + 2.0 * sample_info[:, [1, 2]].float() / 127.0).to(enc.dtype)
                 z0_mu_logvar[:, 1, [0, 1]] = np.log(4.0 / (127 ** 2))
         mu0 = z0_mu_logvar[:, 0, :]
         sigma0 = torch.exp(z0_mu_logvar[:, 1, :] / 2.0)
         if self.training:
-            eps = torch.normal(torch.zeros(B, self.dim_z), torch.ones(B, self.dim_z)) if noise is None \
+            eps = torch.normal(torch.zeros(B, self.dim_z), torch.ones(B, self.dim_z)).to(mu0.dtype) if noise is None \
                 else noise['eps'].to(mu0.dtype)
             z0 = mu0 + sigma0 * eps
         else:

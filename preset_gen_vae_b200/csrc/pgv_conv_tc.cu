@@ -1,0 +1,462 @@
+// Implicit-GEMM convolutions on the 5th-generation tensor cores (tcgen05, TF32 products, fp32 accumulation in TMEM).
+//
+//   mode FWD    y[b,co,oh,ow]  = act(bias[co] + sum_{ci,r,s} x[b,ci,oh*st-p+r,ow*st-p+s] * w[co,ci,r,s])
+//               GEMM: M = B*Ho*Wo pixels, N = Cout, K = Cin*kh*kw
+//   mode DGRAD  dx[b,ci,ih,iw] = act(bias[ci] + sum_{co,r,s : oh*st-p+r = ih, ...} dy[b,co,oh,ow] * w[co,ci,r,s])
+//               = forward of nn.ConvTranspose2d(weight = w).  One GEMM per input-pixel parity class (st x st classes):
+//               M = B*Hc*Wc pixels of the class, N = Cin, K = Cout * taps (taps = ceil(kh/st)*ceil(kw/st))
+//   mode WGRAD  dw[co,ci,r,s] += sum_{b,oh,ow} dy[b,co,oh,ow] * x[b,ci,oh*st-p+r,ow*st-p+s]
+//               GEMM: M = Cin*kh*kw, N = Cout, K = pixels; split along K across CTAs, fp32 atomic accumulation
+//
+// Neither operand of these GEMMs is a plain matrix in memory (NCHW activations, strided taps, zero padding, weight
+// sub-lattices), so both smem tiles are written by 8 PRODUCER warps: each thread gathers 16-byte chunks (4 consecutive
+// k of one row), rounds them to TF32 (cvt.rna) and stores them at the 128-byte-swizzled position the UMMA descriptor
+// expects, then fence.proxy.async + mbarrier arrive.  One thread issues tcgen05.mma (M=128, N = tile width, K=8);
+// accumulators are double-buffered in TMEM so the 4 epilogue warps drain tile i while tile i+1 is being multiplied.
+#include <string.h>
+
+#include "pgv_common.cuh"
+#include "pgv_tc.cuh"
+
+namespace pgv {
+
+enum { CONV_FWD = 0, CONV_DGRAD = 1, CONV_WGRAD = 2 };
+
+constexpr int CT_BLOCK_M = 128, CT_BLOCK_K = 32, CT_MAX_N = 256, CT_STAGES = 4;
+constexpr int CT_A_BYTES = CT_BLOCK_M * 128, CT_B_BYTES = CT_MAX_N * 128, CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
+constexpr int CT_PRODUCER_WARPS = 8, CT_PRODUCERS = CT_PRODUCER_WARPS * 32;
+constexpr int CT_THREADS = CT_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
+constexpr int CT_SMEM = 1024 + CT_STAGES * CT_STAGE_BYTES + 256;
+
+struct ConvTcParams {
+    const float* x;      // FWD: input x        DGRAD: dy (conv output side)    WGRAD: x
+    const float* w;      // weights [Cout, Cin, kh, kw]                          WGRAD: dy
+    const float* bias;   // FWD: [Cout], DGRAD: [Cin] or NULL
+    float* out;          // FWD: y              DGRAD: dx                        WGRAD: dw (pre-zeroed)
+    int B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo;
+    int n_tile, n_tiles;            // tile width (multiple of 16, <= 256) and count along N
+    int gemm_n, gemm_k;             // logical N and K of one GEMM
+    int kb_total, kb_per_split, k_splits;
+    int classes;                    // DGRAD: stride*stride parity classes, else 1
+    int m_tiles_class[4];           // M tiles per class (FWD / WGRAD use [0])
+    int Hc[4], Wc[4];               // DGRAD: sub-grid size of every class
+    int taps_h, taps_w;             // DGRAD: taps per class along h / w
+    int pix_blocks;                 // WGRAD: k-blocks per image = ceil(Ho*Wo / 32)
+    float slope;
+};
+
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+    return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void st_chunk(uint8_t* tile, int row, int chunk, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(tile + sw128_offset(row, chunk)) = make_float4(to_tf32_rna(a), to_tf32_rna(b), to_tf32_rna(c), to_tf32_rna(d));
+}
+
+struct WorkItem { int cls, tm, tn, kb0, kb1; };
+
+__device__ __forceinline__ int total_m_tiles(const ConvTcParams& p) {
+    int t = 0;
+    for (int c = 0; c < p.classes; ++c) t += p.m_tiles_class[c];
+    return t;
+}
+__device__ __forceinline__ WorkItem decode_item(const ConvTcParams& p, int item) {
+    WorkItem wi;
+    const int split = item % p.k_splits;
+    int t = item / p.k_splits;
+    wi.tn = t % p.n_tiles;
+    t /= p.n_tiles;
+    wi.cls = 0;
+    while (wi.cls < p.classes - 1 && t >= p.m_tiles_class[wi.cls]) { t -= p.m_tiles_class[wi.cls]; ++wi.cls; }
+    wi.tm = t;
+    wi.kb0 = split * p.kb_per_split;
+    wi.kb1 = min(p.kb_total, wi.kb0 + p.kb_per_split);
+    return wi;
+}
+
+// ------------------------------------------------------------------------------------------------ operand gathers
+// Every gather returns 4 consecutive k values of one row (k0 = 4 * global chunk index).
+template <int MODE>
+struct Gather {
+    // ---- A operand -------------------------------------------------------------------------------------------
+    struct RowA { const float* base; int i0, j0; bool ok; };   // meaning depends on MODE
+
+    __device__ static RowA row_a(const ConvTcParams& p, const WorkItem& wi, int row) {
+        RowA r;
+        r.base = nullptr; r.i0 = r.j0 = 0;
+        if (MODE == CONV_FWD) {
+            const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
+            const int HW = p.Ho * p.Wo;
+            r.ok = m < static_cast<long long>(p.B) * HW;
+            if (r.ok) {
+                const int b = static_cast<int>(m / HW), pix = static_cast<int>(m % HW);
+                r.i0 = (pix / p.Wo) * p.stride - p.pad;
+                r.j0 = (pix % p.Wo) * p.stride - p.pad;
+                r.base = p.x + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+            }
+        } else if (MODE == CONV_DGRAD) {
+            const int Hc = p.Hc[wi.cls], Wc = p.Wc[wi.cls];
+            const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
+            r.ok = m < static_cast<long long>(p.B) * Hc * Wc;
+            if (r.ok) {
+                const int b = static_cast<int>(m / (Hc * Wc)), pix = static_cast<int>(m % (Hc * Wc));
+                const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
+                const int ih = (pix / Wc) * p.stride + ph, iw = (pix % Wc) * p.stride + pw;
+                // tap (a, c) of the class reads dy at oh = (ih + pad - r)/stride with r = r0 + a*stride, r0 = (ih + pad) % stride
+                r.i0 = (ih + p.pad) / p.stride;      // oh for a = 0; oh decreases by 1 per tap
+                r.j0 = (iw + p.pad) / p.stride;
+                r.base = p.x + static_cast<size_t>(b) * p.Cout * p.Ho * p.Wo;
+            }
+        } else {   // WGRAD: row = (ci, r, s)
+            const int m = wi.tm * CT_BLOCK_M + row;
+            r.ok = m < p.Cin * p.kh * p.kw;
+            if (r.ok) {
+                const int taps = p.kh * p.kw, ci = m / taps, t = m % taps;
+                r.i0 = t / p.kw - p.pad;             // ih = oh*stride + i0
+                r.j0 = t % p.kw - p.pad;
+                r.base = p.x + static_cast<size_t>(ci) * p.H * p.W;   // + b * Cin*H*W
+            }
+        }
+        return r;
+    }
+
+    __device__ static float4 chunk_a(const ConvTcParams& p, const WorkItem& wi, const RowA& r, int gchunk) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!r.ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k0 = gchunk * 4;
+        if (MODE == CONV_FWD) {
+            const int taps = p.kh * p.kw;
+            if (p.kw == 4 && p.kh == 4) {            // chunk = one (ci, r): 4 consecutive input pixels
+                const int ci = k0 >> 4, rr = (k0 >> 2) & 3, ih = r.i0 + rr;
+                if (ci < p.Cin && ih >= 0 && ih < p.H) {
+                    const float* src = r.base + (static_cast<size_t>(ci) * p.H + ih) * p.W;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) { const int iw = r.j0 + s; if (iw >= 0 && iw < p.W) v[s] = src[iw]; }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = k0 + e;
+                    if (k < p.gemm_k) {
+                        const int ci = k / taps, t = k % taps, ih = r.i0 + t / p.kw, iw = r.j0 + t % p.kw;
+                        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = r.base[(static_cast<size_t>(ci) * p.H + ih) * p.W + iw];
+                    }
+                }
+            }
+        } else if (MODE == CONV_DGRAD) {
+            const int taps = p.taps_h * p.taps_w, HWo = p.Ho * p.Wo;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + e;
+                if (k < p.gemm_k) {
+                    const int co = k / taps, t = k % taps, oh = r.i0 - t / p.taps_w, ow = r.j0 - t % p.taps_w;
+                    if (oh >= 0 && oh < p.Ho && ow >= 0 && ow < p.Wo) v[e] = r.base[static_cast<size_t>(co) * HWo + oh * p.Wo + ow];
+                }
+            }
+        } else {   // WGRAD: k = pixel index inside image b
+            const int kb = gchunk >> 3, b = kb / p.pix_blocks, pix0 = (kb % p.pix_blocks) * CT_BLOCK_K + (gchunk & 7) * 4;
+            const int HWo = p.Ho * p.Wo;
+            const float* src = r.base + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+            int oh = pix0 / p.Wo, ow = pix0 % p.Wo;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (pix0 + e < HWo) {
+                    const int ih = oh * p.stride + r.i0, iw = ow * p.stride + r.j0;
+                    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = src[ih * p.W + iw];
+                }
+                if (++ow == p.Wo) { ow = 0; ++oh; }
+            }
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+
+    // ---- B operand: row = output column n ------------------------------------------------------------------------
+    __device__ static float4 chunk_b(const ConvTcParams& p, const WorkItem& wi, int row, int gchunk) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const int n = wi.tn * p.n_tile + row;
+        if (n >= p.gemm_n) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k0 = gchunk * 4;
+        if (MODE == CONV_FWD) {                      // w[co = n, k] contiguous in k
+            const float* src = p.w + static_cast<size_t>(n) * p.gemm_k + k0;
+            if (k0 + 4 <= p.gemm_k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) return *reinterpret_cast<const float4*>(src);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (k0 + e < p.gemm_k) v[e] = src[e];
+        } else if (MODE == CONV_DGRAD) {             // w[co, ci = n, r0 + a*stride, s0 + c*stride]
+            const int taps = p.taps_h * p.taps_w, khw = p.kh * p.kw;
+            const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
+            const int r0 = (ph + p.pad) % p.stride, s0 = (pw + p.pad) % p.stride;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + e;
+                if (k < p.gemm_k) {
+                    const int co = k / taps, t = k % taps, rr = r0 + (t / p.taps_w) * p.stride, ss = s0 + (t % p.taps_w) * p.stride;
+                    if (rr < p.kh && ss < p.kw) v[e] = p.w[(static_cast<size_t>(co) * p.Cin + n) * khw + rr * p.kw + ss];
+                }
+            }
+        } else {                                     // WGRAD: dy[b, co = n, pixel]
+            const int kb = gchunk >> 3, b = kb / p.pix_blocks, pix0 = (kb % p.pix_blocks) * CT_BLOCK_K + (gchunk & 7) * 4;
+            const int HWo = p.Ho * p.Wo;
+            const float* src = p.w + (static_cast<size_t>(b) * p.Cout + n) * HWo + pix0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (pix0 + e < HWo) v[e] = src[e];
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+__device__ __forceinline__ float act_lrelu(float v, float slope) { return (slope >= 0.0f && v < 0.0f) ? v * slope : v; }
+
+template <int MODE>
+__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE_BYTES);
+    uint64_t* bar_empty = bar_full + CT_STAGES;
+    uint64_t* bar_tfull = bar_empty + CT_STAGES;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int MMA_WARP = CT_PRODUCER_WARPS, EPI_WARP0 = CT_PRODUCER_WARPS + 1;
+
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&bar_full[s], CT_PRODUCERS); mbar_init(&bar_empty[s], 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_items = total_m_tiles(p) * p.n_tiles * p.k_splits;
+
+    if (warp < CT_PRODUCER_WARPS) {
+        // ===================== producers: gather A (128 rows) and B (n_tile rows), 8 chunks per row per k-block
+        const int t = threadIdx.x;                   // 0 .. 255
+        const int a_row = t & 127, a_c0 = t >> 7;    // A: 128 rows x 8 chunks = 1024 chunks -> 4 per thread (chunks a_c0, +2, +4, +6)
+        int stage = 0; uint32_t phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const WorkItem wi = decode_item(p, item);
+            const typename Gather<MODE>::RowA ra = Gather<MODE>::row_a(p, wi, a_row);
+            const int b_chunks = p.n_tile * 8;
+            for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * CT_STAGE_BYTES;
+                uint8_t* sB = sA + CT_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = a_c0 + 2 * j;
+                    const float4 v = Gather<MODE>::chunk_a(p, wi, ra, kb * 8 + c);
+                    st_chunk(sA, a_row, c, v.x, v.y, v.z, v.w);
+                }
+                for (int id = t; id < b_chunks; id += CT_PRODUCERS) {
+                    // FWD weights are contiguous along k: let consecutive threads take consecutive chunks of one row;
+                    // otherwise consecutive threads take consecutive rows (coalesced along n / pixels)
+                    const int row = (MODE == CONV_FWD) ? (id >> 3) : (id % p.n_tile);
+                    const int c = (MODE == CONV_FWD) ? (id & 7) : (id / p.n_tile);
+                    const float4 v = Gather<MODE>::chunk_b(p, wi, row, kb * 8 + c);
+                    st_chunk(sB, row, c, v.x, v.y, v.z, v.w);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar_full[stage]);
+                if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(CT_BLOCK_M, p.n_tile);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const WorkItem wi = decode_item(p, item);
+                mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + acc * CT_MAX_N;
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + stage * CT_STAGE_BYTES);
+                    const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + CT_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CT_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&bar_empty[stage]);
+                    if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&bar_tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global
+        const int quad = warp & 3, row = quad * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const WorkItem wi = decode_item(p, item);
+            // destination of this thread's row
+            float* dst = nullptr;      // address of column n = 0 of the tile; columns are `col_stride` apart
+            size_t col_stride = 0;
+            bool row_ok = false;
+            if (MODE == CONV_FWD) {
+                const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
+                const int HW = p.Ho * p.Wo;
+                row_ok = m < static_cast<long long>(p.B) * HW;
+                if (row_ok) {
+                    const int b = static_cast<int>(m / HW), pix = static_cast<int>(m % HW);
+                    dst = p.out + (static_cast<size_t>(b) * p.Cout + wi.tn * p.n_tile) * HW + pix;
+                    col_stride = HW;
+                }
+            } else if (MODE == CONV_DGRAD) {
+                const int Hc = p.Hc[wi.cls], Wc = p.Wc[wi.cls];
+                const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
+                row_ok = m < static_cast<long long>(p.B) * Hc * Wc;
+                if (row_ok) {
+                    const int b = static_cast<int>(m / (Hc * Wc)), pix = static_cast<int>(m % (Hc * Wc));
+                    const int ih = (pix / Wc) * p.stride + wi.cls / p.stride, iw = (pix % Wc) * p.stride + wi.cls % p.stride;
+                    dst = p.out + ((static_cast<size_t>(b) * p.Cin + wi.tn * p.n_tile) * p.H + ih) * p.W + iw;
+                    col_stride = static_cast<size_t>(p.H) * p.W;
+                }
+            } else {
+                const int m = wi.tm * CT_BLOCK_M + row, Kc = p.Cin * p.kh * p.kw;
+                row_ok = m < Kc;
+                if (row_ok) { dst = p.out + static_cast<size_t>(wi.tn * p.n_tile) * Kc + m; col_stride = Kc; }
+            }
+            mbar_wait(&bar_tfull[acc], acc_phase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + acc * CT_MAX_N + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < p.n_tile; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = wi.tn * p.n_tile + c + j;
+                    if (n < p.gemm_n) {
+                        float val = __uint_as_float(v[j]);
+                        if (MODE == CONV_WGRAD) {
+                            atomicAdd(dst + static_cast<size_t>(c + j) * col_stride, val);
+                        } else {
+                            if (p.bias != nullptr) val += p.bias[n];
+                            dst[static_cast<size_t>(c + j) * col_stride] = act_lrelu(val, p.slope);
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
+static int pick_n_tile(int n) {
+    int t = (n + 15) / 16 * 16;
+    if (t > CT_MAX_N) {
+        // split evenly into tiles of at most 256 columns, multiples of 16
+        const int parts = ceil_div(n, CT_MAX_N);
+        t = ceil_div(ceil_div(n, parts), 16) * 16;
+    }
+    return t;
+}
+
+template <int MODE>
+static int launch_conv_tc(const pgv_handle* h, ConvTcParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        PGV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+        configured = true;
+    }
+    int m_tiles = 0;
+    for (int c = 0; c < p.classes; ++c) m_tiles += p.m_tiles_class[c];
+    const long long items = static_cast<long long>(m_tiles) * p.n_tiles * p.k_splits;
+    const int grid = static_cast<int>(items < h->sm_count ? items : h->sm_count);
+    conv_tc_kernel<MODE><<<grid, CT_THREADS, CT_SMEM, stream>>>(p);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+static int fill_common(ConvTcParams& p, const char* who, int B, int Cin, int H, int W, int Cout, int kh, int kw, int stride, int pad,
+                       int Ho, int Wo) {
+    if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0)
+        return set_error(-1, "%s: bad geometry", who);
+    if ((Ho - 1) * stride - 2 * pad + kh > H || (Wo - 1) * stride - 2 * pad + kw > W)
+        return set_error(-1, "%s: output %dx%d does not fit input %dx%d", who, Ho, Wo, H, W);
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.Ho = Ho; p.Wo = Wo;
+    p.classes = 1; p.k_splits = 1;
+    return 0;
+}
+
+}  // namespace pgv
+
+using namespace pgv;
+
+extern "C" {
+
+int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int H, int W,
+                        int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && x && w && y, "pgv_conv2d_fwd_tf32: NULL argument");
+    ConvTcParams p;
+    if (int rc = fill_common(p, "pgv_conv2d_fwd_tf32", B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo)) return rc;
+    p.x = x; p.w = w; p.bias = bias; p.out = y; p.slope = lrelu_slope;
+    p.gemm_n = Cout; p.gemm_k = Cin * kh * kw;
+    p.n_tile = pick_n_tile(Cout); p.n_tiles = ceil_div(Cout, p.n_tile);
+    p.kb_total = ceil_div(p.gemm_k, CT_BLOCK_K); p.kb_per_split = p.kb_total;
+    p.m_tiles_class[0] = static_cast<int>((static_cast<long long>(B) * Ho * Wo + CT_BLOCK_M - 1) / CT_BLOCK_M);
+    return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const float* bias, float* dx, int B, int Cin, int H, int W,
+                          int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && dy && w && dx, "pgv_conv2d_dgrad_tf32: NULL argument");
+    PGV_CHECK_ARG(stride == 1 || stride == 2, "pgv_conv2d_dgrad_tf32: stride %d unsupported", stride);
+    ConvTcParams p;
+    if (int rc = fill_common(p, "pgv_conv2d_dgrad_tf32", B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo)) return rc;
+    p.x = dy; p.w = w; p.bias = bias; p.out = dx; p.slope = lrelu_slope;
+    p.taps_h = ceil_div(kh, stride); p.taps_w = ceil_div(kw, stride);
+    p.gemm_n = Cin; p.gemm_k = Cout * p.taps_h * p.taps_w;
+    p.n_tile = pick_n_tile(Cin); p.n_tiles = ceil_div(Cin, p.n_tile);
+    p.kb_total = ceil_div(p.gemm_k, CT_BLOCK_K); p.kb_per_split = p.kb_total;
+    p.classes = stride * stride;
+    for (int c = 0; c < p.classes; ++c) {
+        const int ph = c / stride, pw = c % stride;
+        p.Hc[c] = (H - ph + stride - 1) / stride;
+        p.Wc[c] = (W - pw + stride - 1) / stride;
+        p.m_tiles_class[c] = static_cast<int>((static_cast<long long>(B) * p.Hc[c] * p.Wc[c] + CT_BLOCK_M - 1) / CT_BLOCK_M);
+    }
+    return launch_conv_tc<CONV_DGRAD>(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout, int kh,
+                          int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PGV_CHECK_ARG(h && x && dy && dw, "pgv_conv2d_wgrad_tf32: NULL argument");
+    ConvTcParams p;
+    if (int rc = fill_common(p, "pgv_conv2d_wgrad_tf32", B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo)) return rc;
+    p.x = x; p.w = dy; p.out = dw; p.slope = -1.0f;
+    const int Kc = Cin * kh * kw;
+    p.gemm_n = Cout; p.gemm_k = 0;
+    p.n_tile = pick_n_tile(Cout); p.n_tiles = ceil_div(Cout, p.n_tile);
+    p.pix_blocks = ceil_div(Ho * Wo, CT_BLOCK_K);
+    p.kb_total = B * p.pix_blocks;
+    p.m_tiles_class[0] = ceil_div(Kc, CT_BLOCK_M);
+    const int tiles = p.m_tiles_class[0] * p.n_tiles;
+    int splits = ceil_div(h->sm_count * 2, tiles);          // ~2 work items per SM
+    if (splits > p.kb_total / 4) splits = p.kb_total / 4;    // at least 4 k-blocks per item
+    if (splits < 1) splits = 1;
+    p.kb_per_split = ceil_div(p.kb_total, splits);
+    p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    PGV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * static_cast<size_t>(Cout) * Kc, stream));
+    return launch_conv_tc<CONV_WGRAD>(h, p, stream);
+}
+
+}  // extern "C"

@@ -112,6 +112,10 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None):
     Cout, _, kh, kw = w.shape
     Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
     y = _empty(x, B, Cout, Ho, Wo)
+    if _precision == 'tf32':
+        _call('pgv_conv2d_fwd_tf32', _h(x), _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x),
+              flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + y.numel() + w.numel()))
+        return y
     _call('pgv_conv2d_fwd_f32', _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x),
           flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + y.numel() + w.numel()))
     return y
@@ -123,6 +127,10 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0):
     _, Cin, kh, kw = w.shape
     H, W = in_hw
     dx = _empty(dy, B, Cin, H, W)
+    if _precision == 'tf32' and stride <= 2:
+        _call('pgv_conv2d_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope,
+              _s(dy), flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
+        return dx
     _call('pgv_conv2d_dgrad_f32', _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(dy),
           flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
     return dx
@@ -133,6 +141,10 @@ def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
     _, Cout, Ho, Wo = dy.shape
     _, _, kh, kw = w_shape
     dw = _empty(x, *w_shape)
+    if _precision == 'tf32':
+        _call('pgv_conv2d_wgrad_tf32', _h(x), _f(x), _f(dy), _f(dw), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
+              flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
+        return dw, (channel_sum(dy) if want_bias else None)
     db = _empty(x, Cout) if want_bias else None
     _call('pgv_conv2d_wgrad_f32', _f(x), _f(dy), _f(dw), _f(db), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x),
           n=4 if want_bias else 2, flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))

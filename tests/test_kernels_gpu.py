@@ -30,6 +30,7 @@ ENC_LAYERS = [(1, 8, 5, 2, 2, 257, 347), (8, 16, 4, 2, 2, 129, 174), (16, 32, 4,
 @pytest.mark.parametrize("cin,cout,k,s,p,H,W", ENC_LAYERS)
 def test_conv_fwd_dgrad_wgrad(cin, cout, k, s, p, H, W):
     B = 2
+    ops.set_precision('fp32')
     x, w, b = rnd(B, cin, H, W, seed=1), rnd(cout, cin, k, k, seed=2, scale=0.1), rnd(cout, seed=3)
     y = ops.conv2d_fwd(x, w, b, s, p, slope=0.1)
     xd, wd, bd = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
@@ -40,6 +41,7 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, s, p, H, W):
     gx, gw, gb = torch.autograd.grad(pre, (xd, wd, bd), dy.double())
     assert rel(ops.conv2d_dgrad(dy, w, (H, W), s, p), gx) < 2e-6
     dw, db = ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=True)
+    ops.set_precision('tf32')
     assert rel(dw, gw) < 5e-6 and rel(db, gb) < 5e-6
 
 
@@ -52,6 +54,7 @@ DEC_LAYERS = [(2048, 512, 1, (0, 0), 1, 3, 4), (512, 256, 4, (1, 1), 2, 3, 4), (
 @pytest.mark.parametrize("cin,cout,k,op,s,H,W", DEC_LAYERS)
 def test_transposed_conv_via_conv_gradients(cin, cout, k, op, s, H, W):
     from preset_gen_vae_b200.model import layer
+    ops.set_precision('fp32')
     B, p = 2, (2 if k > 1 else 0)
     conv = torch.nn.ConvTranspose2d(cin, cout, k, s, p, op).to(DEV)
     x = rnd(B, cin, H, W, seed=5)
@@ -64,8 +67,39 @@ def test_transposed_conv_via_conv_gradients(cin, cout, k, op, s, H, W):
     gx, gw, gb = torch.autograd.grad(pre, (xd, wd, bd), dz.double())
     grads = {}
     dx = layer.tconv_bwd(dz, x, conv, grads, True)
+    ops.set_precision('tf32')
     assert rel(dx, gx) < 2e-6 and rel(grads[id(conv.weight)], gw) < 5e-6 and rel(grads[id(conv.bias)], gb) < 5e-6
     expected = {1: (3, 4), 4: None}   # output sizes of decoder.py:199-220 are checked in the model test
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,H,W", ENC_LAYERS + [(8, 1, 5, 2, 2, 257, 347), (16, 8, 4, 2, 2, 129, 174)])
+def test_tensor_core_convs_against_fp64(cin, cout, k, s, p, H, W):
+    """tcgen05 implicit-GEMM conv fwd / dgrad / wgrad (TF32 products, operands rounded to nearest) for every layer
+    geometry, incl. the decoder's last two transposed convs viewed as conv data-gradients.  TF32 tolerance: relative-L2
+    error of a K-term dot product of operands with 2^-11 relative rounding ~ 2^-11 * sqrt(2) = 7e-4; gate 2e-3."""
+    B = 3
+    Ho, Wo = ops.conv_out_size(H, k, s, p), ops.conv_out_size(W, k, s, p)
+    if (cin, cout, k) == (16, 8, 4):            # dec7 geometry: odd output_padding makes H one larger than the conv's natural input
+        H, W = 129, 174
+        Ho, Wo = 65, 88
+    x, w, b = rnd(B, cin, H, W, seed=1), rnd(cout, cin, k, k, seed=2, scale=0.1), rnd(cout, seed=3)
+    dy = rnd(B, cout, Ho, Wo, seed=4)
+    xd, wd, bd = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    pre = F.conv2d(xd, wd, bd, s, p)[:, :, :Ho, :Wo]
+    gx, gw, gb = torch.autograd.grad(pre, (xd, wd, bd), dy.double())
+    ops.set_precision('tf32')
+    try:
+        y = ops.conv2d_fwd(x, w, b, s, p, slope=0.1, out_hw=(Ho, Wo))
+        dx = ops.conv2d_dgrad(dy, w, (H, W), s, p)
+        dw, db = ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=True)
+        bias_in = rnd(cin, seed=5)
+        dx_act = ops.conv2d_dgrad(dy, w, (H, W), s, p, bias=bias_in, slope=0.1)     # transposed-conv forward form
+    finally:
+        ops.set_precision('tf32')
+    errs = (rel(y, F.leaky_relu(pre, 0.1)), rel(dx, gx), rel(dw, gw), rel(db, gb),
+            rel(dx_act, F.leaky_relu(gx + bias_in.double()[None, :, None, None], 0.1)))
+    print("tc conv", (cin, cout, k, s, p, H, W), "rel-L2 fwd %.2e dgrad %.2e wgrad %.2e db %.2e tconv-fwd %.2e" % errs)
+    assert max(errs) < 2e-3
 
 
 def test_batchnorm2d_train_eval_backward():
@@ -197,7 +231,7 @@ def test_reparam_hardtanh_elementwise():
 
 
 def test_gemm_f32_all_transposes_and_split_k():
-    h = None
+    ops.set_precision('fp32')
     for (m, n, k) in [(37, 50, 19), (160, 1220, 4096), (160, 300, 305)]:
         a, b, bias, res = rnd(m, k, seed=29), rnd(n, k, seed=30), rnd(n, seed=31), rnd(m, n, seed=32)
         y = ops.linear_fwd(a, b, bias, relu=False, residual=res)
@@ -207,6 +241,7 @@ def test_gemm_f32_all_transposes_and_split_k():
         assert rel(ops.linear_dgrad(dy, b), dy.double() @ b.double()) < 2e-6
         dw, db = ops.linear_wgrad(dy, a)
         assert rel(dw, dy.double().T @ a.double()) < 2e-6 and rel(db, dy.double().sum(0)) < 2e-6
+    ops.set_precision('tf32')
 
 
 def test_losses_match_oracle(idx_helper):

@@ -12,8 +12,11 @@ from preset_gen_vae_b200.data.preset import DexedLearnableLayout  # noqa: E402
 from preset_gen_vae_b200.model import build, loss as ploss, ops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+MODE = sys.argv[2] if len(sys.argv) > 2 else 'c1'           # c1 | c6 | c1fe (real front-end input)
+SIX = ((40, 85), (50, 85), (60, 42), (60, 85), (60, 127), (70, 85))
 h = DexedLearnableLayout().preset_indexes_helper
-m_cfg, t_cfg = pcfg.make_default(minibatch_size=B)
+m_cfg, t_cfg = pcfg.make_default(minibatch_size=B, midi_notes=SIX if MODE == 'c6' else None, stack_spectrograms=(MODE == 'c6'))
+print("##### B=%d mode=%s" % (B, MODE))
 pcfg.apply_dataset_dims(m_cfg, h)
 torch.manual_seed(0)
 orc = omodel.build_extended_ae_model(m_cfg, t_cfg, h)[3]
@@ -22,10 +25,14 @@ torch.manual_seed(0)
 mine = build.build_extended_ae_model(m_cfg, t_cfg, h)[3]
 mine.load_state_dict(orc.state_dict())
 mine.cuda()
-x = synthetic.make_spectrogram_like(B, 1, seed=0)
+C = m_cfg.input_tensor_size[1]
+x = synthetic.make_spectrogram_like(B, C, seed=0)
+if MODE == 'c1fe':
+    from oracle import frontend as ofe
+    x = ofe.batch_front_end(synthetic.make_audio(B, 1, seed=0), 1024, 256, -120.0, 257, -120.0, 0.0)
 v_in = synthetic.make_preset_targets(h, B, seed=0)
 info = synthetic.make_sample_info(B)
-noise = synthetic.make_noise(B, 610, t_cfg.fc_dropout, t_cfg.reg_fc_dropout, seed=1)
+noise = synthetic.make_noise(B, 610, t_cfg.fc_dropout, t_cfg.reg_fc_dropout, seed=1, enc_fc_in=orc.ae_model.encoder.mlp[1].in_features)
 noise64 = {k: (v.double() if torch.is_tensor(v) else [[m.double() for m in l] for l in v]) for k, v in noise.items()}
 
 
