@@ -132,6 +132,12 @@ PGV_API int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w
                                   int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
 PGV_API int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout, int kh,
                                   int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+/* nn.Linear on the same tensor-core kernel (any K, no alignment requirement): x [M,K], w [N,K], y [M,N] = act(x w^T +
+ * bias + residual) (bias / residual may be NULL, relu != 0 fuses a ReLU); dx [M,K] = dy w; dw [N,K] = dy^T x. */
+PGV_API int pgv_linear_fwd_tf32(pgv_handle* h, const float* x, const float* w, const float* bias, const float* residual, float* y, int M,
+                                int N, int K, int relu, pgv_stream_t stream);
+PGV_API int pgv_linear_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, float* dx, int M, int N, int K, pgv_stream_t stream);
+PGV_API int pgv_linear_wgrad_tf32(pgv_handle* h, const float* dy, const float* x, float* dw, int M, int N, int K, pgv_stream_t stream);
 /* out[c] = sum over (b, h, w) of x[b,c,h,w] (bias gradient of a transposed convolution). */
 PGV_API int pgv_channel_sum(const float* x, float* out, int B, int C, int HW, pgv_stream_t stream);
 

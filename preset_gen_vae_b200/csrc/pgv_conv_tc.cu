@@ -20,7 +20,7 @@
 
 namespace pgv {
 
-enum { CONV_FWD = 0, CONV_DGRAD = 1, CONV_WGRAD = 2 };
+enum { CONV_FWD = 0, CONV_DGRAD = 1, CONV_WGRAD = 2, DENSE_WGRAD = 3 };
 
 constexpr int CT_BLOCK_M = 128, CT_BLOCK_K = 32, CT_MAX_N = 256, CT_STAGES = 4;
 constexpr int CT_A_BYTES = CT_BLOCK_M * 128, CT_B_BYTES = CT_MAX_N * 128, CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
@@ -28,10 +28,24 @@ constexpr int CT_PRODUCER_WARPS = 8, CT_PRODUCERS = CT_PRODUCER_WARPS * 32;
 constexpr int CT_THREADS = CT_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
 constexpr int CT_SMEM = 1024 + CT_STAGES * CT_STAGE_BYTES + 256;
 
+// n / d and n % d for 0 <= n < 2^31 without a hardware divide (Granlund-Montgomery round-up method).
+struct FastDiv {
+    uint32_t d, m, l;
+    __host__ void init(uint32_t div) {
+        d = div < 1 ? 1 : div;
+        l = 0;
+        while ((1u << l) < d) ++l;
+        m = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << l) - d)) / d + 1);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, m) + n) >> l; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 struct ConvTcParams {
     const float* x;      // FWD: input x        DGRAD: dy (conv output side)    WGRAD: x
     const float* w;      // weights [Cout, Cin, kh, kw]                          WGRAD: dy
     const float* bias;   // FWD: [Cout], DGRAD: [Cin] or NULL
+    const float* residual;   // FWD only: same shape as out, added before the activation (or NULL)
     float* out;          // FWD: y              DGRAD: dx                        WGRAD: dw (pre-zeroed)
     int B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo;
     int n_tile, n_tiles;            // tile width (multiple of 16, <= 256) and count along N
@@ -42,14 +56,17 @@ struct ConvTcParams {
     int Hc[4], Wc[4];               // DGRAD: sub-grid size of every class
     int taps_h, taps_w;             // DGRAD: taps per class along h / w
     int pix_blocks;                 // WGRAD: k-blocks per image = ceil(Ho*Wo / 32)
+    int fast;                       // 1: 4x4 kernel (FWD) / 2x2 taps (DGRAD); 2: 1x1 kernel; 0: generic
     float slope;
+    FastDiv fd_HWo, fd_Wo, fd_taps, fd_kw, fd_dtaps, fd_dtapsw, fd_pixblocks, fd_ntile, fd_HcWc[4], fd_Wc[4];
 };
 
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
     return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
-__device__ __forceinline__ void st_chunk(uint8_t* tile, int row, int chunk, float a, float b, float c, float d) {
-    *reinterpret_cast<float4*>(tile + sw128_offset(row, chunk)) = make_float4(to_tf32_rna(a), to_tf32_rna(b), to_tf32_rna(c), to_tf32_rna(d));
+__device__ __forceinline__ void st_chunk(uint8_t* tile, int row, int chunk, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(tile + sw128_offset(row, chunk)) =
+        make_float4(to_tf32_rna(v[0]), to_tf32_rna(v[1]), to_tf32_rna(v[2]), to_tf32_rna(v[3]));
 }
 
 struct WorkItem { int cls, tm, tn, kb0, kb1; };
@@ -74,134 +91,213 @@ __device__ __forceinline__ WorkItem decode_item(const ConvTcParams& p, int item)
 }
 
 // ------------------------------------------------------------------------------------------------ operand gathers
-// Every gather returns 4 consecutive k values of one row (k0 = 4 * global chunk index).
+// Every gather produces 4 consecutive k values of one row (k0 = 4 * global chunk index).  The per-row state is computed
+// once per tile (each producer thread owns one A row), so the per-chunk work is a few integer ops and predicated loads.
+struct RowA {
+    const float* base;
+    int i0, j0;          // FWD: ih0, iw0   DGRAD: oh, ow of tap 0   WGRAD: r - pad, s - pad
+    uint32_t hmask, wmask;   // validity of tap rows / columns
+    bool ok;
+};
+
 template <int MODE>
-struct Gather {
-    // ---- A operand -------------------------------------------------------------------------------------------
-    struct RowA { const float* base; int i0, j0; bool ok; };   // meaning depends on MODE
-
-    __device__ static RowA row_a(const ConvTcParams& p, const WorkItem& wi, int row) {
-        RowA r;
-        r.base = nullptr; r.i0 = r.j0 = 0;
-        if (MODE == CONV_FWD) {
-            const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
-            const int HW = p.Ho * p.Wo;
-            r.ok = m < static_cast<long long>(p.B) * HW;
-            if (r.ok) {
-                const int b = static_cast<int>(m / HW), pix = static_cast<int>(m % HW);
-                r.i0 = (pix / p.Wo) * p.stride - p.pad;
-                r.j0 = (pix % p.Wo) * p.stride - p.pad;
-                r.base = p.x + static_cast<size_t>(b) * p.Cin * p.H * p.W;
-            }
-        } else if (MODE == CONV_DGRAD) {
-            const int Hc = p.Hc[wi.cls], Wc = p.Wc[wi.cls];
-            const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
-            r.ok = m < static_cast<long long>(p.B) * Hc * Wc;
-            if (r.ok) {
-                const int b = static_cast<int>(m / (Hc * Wc)), pix = static_cast<int>(m % (Hc * Wc));
-                const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
-                const int ih = (pix / Wc) * p.stride + ph, iw = (pix % Wc) * p.stride + pw;
-                // tap (a, c) of the class reads dy at oh = (ih + pad - r)/stride with r = r0 + a*stride, r0 = (ih + pad) % stride
-                r.i0 = (ih + p.pad) / p.stride;      // oh for a = 0; oh decreases by 1 per tap
-                r.j0 = (iw + p.pad) / p.stride;
-                r.base = p.x + static_cast<size_t>(b) * p.Cout * p.Ho * p.Wo;
-            }
-        } else {   // WGRAD: row = (ci, r, s)
-            const int m = wi.tm * CT_BLOCK_M + row;
-            r.ok = m < p.Cin * p.kh * p.kw;
-            if (r.ok) {
-                const int taps = p.kh * p.kw, ci = m / taps, t = m % taps;
-                r.i0 = t / p.kw - p.pad;             // ih = oh*stride + i0
-                r.j0 = t % p.kw - p.pad;
-                r.base = p.x + static_cast<size_t>(ci) * p.H * p.W;   // + b * Cin*H*W
-            }
+__device__ __forceinline__ RowA row_a(const ConvTcParams& p, const WorkItem& wi, int row) {
+    RowA r;
+    r.base = nullptr; r.i0 = r.j0 = 0; r.hmask = r.wmask = 0; r.ok = false;
+    if (MODE == CONV_FWD) {
+        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
+        uint32_t b, pix, oh, ow;
+        p.fd_HWo.divmod(m, b, pix);
+        r.ok = b < static_cast<uint32_t>(p.B);
+        if (r.ok) {
+            p.fd_Wo.divmod(pix, oh, ow);
+            r.i0 = static_cast<int>(oh) * p.stride - p.pad;
+            r.j0 = static_cast<int>(ow) * p.stride - p.pad;
+            r.base = p.x + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+            for (int t = 0; t < p.kh; ++t) if (r.i0 + t >= 0 && r.i0 + t < p.H) r.hmask |= 1u << t;
+            for (int t = 0; t < p.kw; ++t) if (r.j0 + t >= 0 && r.j0 + t < p.W) r.wmask |= 1u << t;
         }
-        return r;
-    }
-
-    __device__ static float4 chunk_a(const ConvTcParams& p, const WorkItem& wi, const RowA& r, int gchunk) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!r.ok) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const int k0 = gchunk * 4;
-        if (MODE == CONV_FWD) {
-            const int taps = p.kh * p.kw;
-            if (p.kw == 4 && p.kh == 4) {            // chunk = one (ci, r): 4 consecutive input pixels
-                const int ci = k0 >> 4, rr = (k0 >> 2) & 3, ih = r.i0 + rr;
-                if (ci < p.Cin && ih >= 0 && ih < p.H) {
-                    const float* src = r.base + (static_cast<size_t>(ci) * p.H + ih) * p.W;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) { const int iw = r.j0 + s; if (iw >= 0 && iw < p.W) v[s] = src[iw]; }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k0 + e;
-                    if (k < p.gemm_k) {
-                        const int ci = k / taps, t = k % taps, ih = r.i0 + t / p.kw, iw = r.j0 + t % p.kw;
-                        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = r.base[(static_cast<size_t>(ci) * p.H + ih) * p.W + iw];
-                    }
-                }
-            }
-        } else if (MODE == CONV_DGRAD) {
-            const int taps = p.taps_h * p.taps_w, HWo = p.Ho * p.Wo;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = k0 + e;
-                if (k < p.gemm_k) {
-                    const int co = k / taps, t = k % taps, oh = r.i0 - t / p.taps_w, ow = r.j0 - t % p.taps_w;
-                    if (oh >= 0 && oh < p.Ho && ow >= 0 && ow < p.Wo) v[e] = r.base[static_cast<size_t>(co) * HWo + oh * p.Wo + ow];
-                }
-            }
-        } else {   // WGRAD: k = pixel index inside image b
-            const int kb = gchunk >> 3, b = kb / p.pix_blocks, pix0 = (kb % p.pix_blocks) * CT_BLOCK_K + (gchunk & 7) * 4;
-            const int HWo = p.Ho * p.Wo;
-            const float* src = r.base + static_cast<size_t>(b) * p.Cin * p.H * p.W;
-            int oh = pix0 / p.Wo, ow = pix0 % p.Wo;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (pix0 + e < HWo) {
-                    const int ih = oh * p.stride + r.i0, iw = ow * p.stride + r.j0;
-                    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = src[ih * p.W + iw];
-                }
-                if (++ow == p.Wo) { ow = 0; ++oh; }
-            }
-        }
-        return make_float4(v[0], v[1], v[2], v[3]);
-    }
-
-    // ---- B operand: row = output column n ------------------------------------------------------------------------
-    __device__ static float4 chunk_b(const ConvTcParams& p, const WorkItem& wi, int row, int gchunk) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        const int n = wi.tn * p.n_tile + row;
-        if (n >= p.gemm_n) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const int k0 = gchunk * 4;
-        if (MODE == CONV_FWD) {                      // w[co = n, k] contiguous in k
-            const float* src = p.w + static_cast<size_t>(n) * p.gemm_k + k0;
-            if (k0 + 4 <= p.gemm_k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) return *reinterpret_cast<const float4*>(src);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (k0 + e < p.gemm_k) v[e] = src[e];
-        } else if (MODE == CONV_DGRAD) {             // w[co, ci = n, r0 + a*stride, s0 + c*stride]
-            const int taps = p.taps_h * p.taps_w, khw = p.kh * p.kw;
+    } else if (MODE == CONV_DGRAD) {
+        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
+        uint32_t b, pix, i, j;
+        p.fd_HcWc[wi.cls].divmod(m, b, pix);
+        r.ok = b < static_cast<uint32_t>(p.B);
+        if (r.ok) {
+            p.fd_Wc[wi.cls].divmod(pix, i, j);
             const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
-            const int r0 = (ph + p.pad) % p.stride, s0 = (pw + p.pad) % p.stride;
+            const int ih = static_cast<int>(i) * p.stride + ph, iw = static_cast<int>(j) * p.stride + pw;
+            // tap (a, c) reads dy at oh = (ih + pad)/stride - a, kernel row r0 + a*stride with r0 = (ih + pad) % stride
+            r.i0 = (ih + p.pad) / p.stride;
+            r.j0 = (iw + p.pad) / p.stride;
+            r.base = p.x + static_cast<size_t>(b) * p.Cout * p.Ho * p.Wo;
+            for (int t = 0; t < p.taps_h; ++t) if (r.i0 - t >= 0 && r.i0 - t < p.Ho) r.hmask |= 1u << t;
+            for (int t = 0; t < p.taps_w; ++t) if (r.j0 - t >= 0 && r.j0 - t < p.Wo) r.wmask |= 1u << t;
+        }
+    } else if (MODE == CONV_WGRAD) {   // row = (ci, r, s)
+        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
+        r.ok = m < static_cast<uint32_t>(p.Cin * p.kh * p.kw);
+        if (r.ok) {
+            uint32_t ci, t, rr, ss;
+            p.fd_taps.divmod(m, ci, t);
+            p.fd_kw.divmod(t, rr, ss);
+            r.i0 = static_cast<int>(rr) - p.pad;
+            r.j0 = static_cast<int>(ss) - p.pad;
+            r.base = p.x + static_cast<size_t>(ci) * p.H * p.W;
+        }
+    } else {                            // DENSE_WGRAD: row = input feature ci
+        const int m = wi.tm * CT_BLOCK_M + row;
+        r.ok = m < p.Cin;
+        r.base = p.x + m;
+    }
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ void chunk_a(const ConvTcParams& p, const WorkItem& wi, const RowA& r, int gchunk, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (!r.ok) return;
+    const int k0 = gchunk * 4;
+    if (MODE == CONV_FWD) {
+        if (p.fast == 1) {                           // 4x4 kernel: chunk = one (ci, r), 4 consecutive input pixels
+            const int ci = k0 >> 4, rr = (k0 >> 2) & 3;
+            if (ci < p.Cin && ((r.hmask >> rr) & 1u)) {
+                const float* src = r.base + (static_cast<size_t>(ci) * p.H + (r.i0 + rr)) * p.W + r.j0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) if ((r.wmask >> s) & 1u) v[s] = src[s];
+            }
+        } else if (p.fast == 2) {                    // 1x1 kernel: chunk = 4 consecutive input channels of one pixel
+            if (r.hmask & r.wmask & 1u) {
+                const size_t hw = static_cast<size_t>(p.H) * p.W;
+                const float* src = r.base + static_cast<size_t>(r.i0) * p.W + r.j0 + static_cast<size_t>(k0) * hw;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (k0 + e < p.Cin) v[e] = src[e * hw];
+            }
+        } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int k = k0 + e;
-                if (k < p.gemm_k) {
-                    const int co = k / taps, t = k % taps, rr = r0 + (t / p.taps_w) * p.stride, ss = s0 + (t % p.taps_w) * p.stride;
-                    if (rr < p.kh && ss < p.kw) v[e] = p.w[(static_cast<size_t>(co) * p.Cin + n) * khw + rr * p.kw + ss];
+                const uint32_t k = k0 + e;
+                if (k < static_cast<uint32_t>(p.gemm_k)) {
+                    uint32_t ci, t, rr, ss;
+                    p.fd_taps.divmod(k, ci, t);
+                    p.fd_kw.divmod(t, rr, ss);
+                    if (((r.hmask >> rr) & 1u) && ((r.wmask >> ss) & 1u))
+                        v[e] = r.base[(static_cast<size_t>(ci) * p.H + (r.i0 + rr)) * p.W + r.j0 + ss];
                 }
             }
-        } else {                                     // WGRAD: dy[b, co = n, pixel]
-            const int kb = gchunk >> 3, b = kb / p.pix_blocks, pix0 = (kb % p.pix_blocks) * CT_BLOCK_K + (gchunk & 7) * 4;
-            const int HWo = p.Ho * p.Wo;
-            const float* src = p.w + (static_cast<size_t>(b) * p.Cout + n) * HWo + pix0;
+        }
+    } else if (MODE == CONV_DGRAD) {
+        const int HWo = p.Ho * p.Wo;
+        if (p.fast == 1) {                           // 2x2 taps: chunk = one output channel co
+            const int co = k0 >> 2;
+            if (co < p.Cout) {
+                const float* src = r.base + static_cast<size_t>(co) * HWo + r.i0 * p.Wo + r.j0;
+                const bool h0 = r.hmask & 1u, h1 = r.hmask & 2u, w0 = r.wmask & 1u, w1 = r.wmask & 2u;
+                if (h0 && w0) v[0] = src[0];
+                if (h0 && w1) v[1] = src[-1];
+                if (h1 && w0) v[2] = src[-p.Wo];
+                if (h1 && w1) v[3] = src[-p.Wo - 1];
+            }
+        } else if (p.fast == 2) {                    // single tap: chunk = 4 consecutive output channels
+            if (r.hmask & r.wmask & 1u) {
+                const float* src = r.base + static_cast<size_t>(k0) * HWo + r.i0 * p.Wo + r.j0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (k0 + e < p.Cout) v[e] = src[static_cast<size_t>(e) * HWo];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t k = k0 + e;
+                if (k < static_cast<uint32_t>(p.gemm_k)) {
+                    uint32_t co, t, a, c;
+                    p.fd_dtaps.divmod(k, co, t);
+                    p.fd_dtapsw.divmod(t, a, c);
+                    if (((r.hmask >> a) & 1u) && ((r.wmask >> c) & 1u))
+                        v[e] = r.base[static_cast<size_t>(co) * HWo + (r.i0 - static_cast<int>(a)) * p.Wo + r.j0 - static_cast<int>(c)];
+                }
+            }
+        }
+    } else if (MODE == CONV_WGRAD) {   // k = pixel index inside image b
+        uint32_t b, pb, oh, ow;
+        p.fd_pixblocks.divmod(static_cast<uint32_t>(gchunk >> 3), b, pb);
+        const int pix0 = static_cast<int>(pb) * CT_BLOCK_K + (gchunk & 7) * 4, HWo = p.Ho * p.Wo;
+        if (pix0 >= HWo) return;
+        const float* src = r.base + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+        p.fd_Wo.divmod(static_cast<uint32_t>(pix0), oh, ow);
+        int ih = static_cast<int>(oh) * p.stride + r.i0, iw = static_cast<int>(ow) * p.stride + r.j0, col = static_cast<int>(ow);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (pix0 + e < HWo && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = src[ih * p.W + iw];
+            iw += p.stride;
+            if (++col == p.Wo) { col = 0; ih += p.stride; iw = r.j0; }
+        }
+    } else {                            // DENSE_WGRAD: k = batch row
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (k0 + e < p.B) v[e] = r.base[static_cast<size_t>(k0 + e) * p.Cin];
+    }
+}
+
+// B operand: row = output column n
+template <int MODE>
+__device__ __forceinline__ void chunk_b(const ConvTcParams& p, const WorkItem& wi, int row, int gchunk, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    const int n = wi.tn * p.n_tile + row;
+    if (n >= p.gemm_n) return;
+    const int k0 = gchunk * 4;
+    if (MODE == CONV_FWD) {                          // w[co = n, k] contiguous in k
+        const float* src = p.w + static_cast<size_t>(n) * p.gemm_k + k0;
+        if (k0 + 4 <= p.gemm_k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (k0 + e < p.gemm_k) v[e] = __ldg(src + e);
+        }
+    } else if (MODE == CONV_DGRAD) {                 // w[co, ci = n, r0 + a*stride, s0 + c*stride]
+        const int khw = p.kh * p.kw;
+        const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
+        const int r0 = (ph + p.pad) % p.stride, s0 = (pw + p.pad) % p.stride;
+        if (p.fast == 1) {
+            const int co = k0 >> 2;
+            if (co < p.Cout) {
+                const float* src = p.w + (static_cast<size_t>(co) * p.Cin + n) * khw + r0 * p.kw + s0;
+                v[0] = __ldg(src); v[1] = __ldg(src + p.stride);
+                v[2] = __ldg(src + p.stride * p.kw); v[3] = __ldg(src + p.stride * p.kw + p.stride);
+            }
+        } else if (p.fast == 2) {
+            const float* src = p.w + static_cast<size_t>(k0) * p.Cin + n;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (k0 + e < p.Cout) v[e] = __ldg(src + static_cast<size_t>(e) * p.Cin);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t k = k0 + e;
+                if (k < static_cast<uint32_t>(p.gemm_k)) {
+                    uint32_t co, t, a, c;
+                    p.fd_dtaps.divmod(k, co, t);
+                    p.fd_dtapsw.divmod(t, a, c);
+                    const int rr = r0 + static_cast<int>(a) * p.stride, ss = s0 + static_cast<int>(c) * p.stride;
+                    if (rr < p.kh && ss < p.kw) v[e] = __ldg(p.w + (static_cast<size_t>(co) * p.Cin + n) * khw + rr * p.kw + ss);
+                }
+            }
+        }
+    } else if (MODE == CONV_WGRAD) {                 // dy[b, co = n, pixel]
+        uint32_t b, pb;
+        p.fd_pixblocks.divmod(static_cast<uint32_t>(gchunk >> 3), b, pb);
+        const int pix0 = static_cast<int>(pb) * CT_BLOCK_K + (gchunk & 7) * 4, HWo = p.Ho * p.Wo;
+        if (pix0 >= HWo) return;
+        const float* src = p.w + (static_cast<size_t>(b) * p.Cout + n) * HWo + pix0;
+        if (pix0 + 4 <= HWo && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const float4 q = *reinterpret_cast<const float4*>(src);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) if (pix0 + e < HWo) v[e] = src[e];
         }
-        return make_float4(v[0], v[1], v[2], v[3]);
+    } else {                                         // DENSE_WGRAD: dy[b, co = n]
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (k0 + e < p.B) v[e] = p.w[static_cast<size_t>(k0 + e) * p.Cout + n];
     }
-};
+}
 
 __device__ __forceinline__ float act_lrelu(float v, float slope) { return (slope >= 0.0f && v < 0.0f) ? v * slope : v; }
 
@@ -240,7 +336,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         int stage = 0; uint32_t phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const WorkItem wi = decode_item(p, item);
-            const typename Gather<MODE>::RowA ra = Gather<MODE>::row_a(p, wi, a_row);
+            const RowA ra = row_a<MODE>(p, wi, a_row);
             const int b_chunks = p.n_tile * 8;
             for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                 mbar_wait(&bar_empty[stage], phase ^ 1);
@@ -249,16 +345,19 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int c = a_c0 + 2 * j;
-                    const float4 v = Gather<MODE>::chunk_a(p, wi, ra, kb * 8 + c);
-                    st_chunk(sA, a_row, c, v.x, v.y, v.z, v.w);
+                    float v[4];
+                    chunk_a<MODE>(p, wi, ra, kb * 8 + c, v);
+                    st_chunk(sA, a_row, c, v);
                 }
                 for (int id = t; id < b_chunks; id += CT_PRODUCERS) {
                     // FWD weights are contiguous along k: let consecutive threads take consecutive chunks of one row;
                     // otherwise consecutive threads take consecutive rows (coalesced along n / pixels)
-                    const int row = (MODE == CONV_FWD) ? (id >> 3) : (id % p.n_tile);
-                    const int c = (MODE == CONV_FWD) ? (id & 7) : (id / p.n_tile);
-                    const float4 v = Gather<MODE>::chunk_b(p, wi, row, kb * 8 + c);
-                    st_chunk(sB, row, c, v.x, v.y, v.z, v.w);
+                    int row, c;
+                    if (MODE == CONV_FWD) { row = id >> 3; c = id & 7; }
+                    else { uint32_t q, rem; p.fd_ntile.divmod(static_cast<uint32_t>(id), q, rem); row = static_cast<int>(rem); c = static_cast<int>(q); }
+                    float v[4];
+                    chunk_b<MODE>(p, wi, row, kb * 8 + c, v);
+                    st_chunk(sB, row, c, v);
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_full[stage]);
@@ -300,21 +399,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             size_t col_stride = 0;
             bool row_ok = false;
             if (MODE == CONV_FWD) {
-                const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
+                const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
                 const int HW = p.Ho * p.Wo;
-                row_ok = m < static_cast<long long>(p.B) * HW;
+                uint32_t b, pix;
+                p.fd_HWo.divmod(m, b, pix);
+                row_ok = b < static_cast<uint32_t>(p.B);
                 if (row_ok) {
-                    const int b = static_cast<int>(m / HW), pix = static_cast<int>(m % HW);
                     dst = p.out + (static_cast<size_t>(b) * p.Cout + wi.tn * p.n_tile) * HW + pix;
                     col_stride = HW;
                 }
             } else if (MODE == CONV_DGRAD) {
-                const int Hc = p.Hc[wi.cls], Wc = p.Wc[wi.cls];
-                const long long m = static_cast<long long>(wi.tm) * CT_BLOCK_M + row;
-                row_ok = m < static_cast<long long>(p.B) * Hc * Wc;
+                const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
+                uint32_t b, pix, i, j;
+                p.fd_HcWc[wi.cls].divmod(m, b, pix);
+                row_ok = b < static_cast<uint32_t>(p.B);
                 if (row_ok) {
-                    const int b = static_cast<int>(m / (Hc * Wc)), pix = static_cast<int>(m % (Hc * Wc));
-                    const int ih = (pix / Wc) * p.stride + wi.cls / p.stride, iw = (pix % Wc) * p.stride + wi.cls % p.stride;
+                    p.fd_Wc[wi.cls].divmod(pix, i, j);
+                    const int ih = static_cast<int>(i) * p.stride + wi.cls / p.stride, iw = static_cast<int>(j) * p.stride + wi.cls % p.stride;
                     dst = p.out + ((static_cast<size_t>(b) * p.Cin + wi.tn * p.n_tile) * p.H + ih) * p.W + iw;
                     col_stride = static_cast<size_t>(p.H) * p.W;
                 }
@@ -339,8 +440,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                         float val = __uint_as_float(v[j]);
                         if (MODE == CONV_WGRAD) {
                             atomicAdd(dst + static_cast<size_t>(c + j) * col_stride, val);
+                        } else if (MODE == DENSE_WGRAD) {
+                            dst[static_cast<size_t>(c + j) * col_stride] = val;
                         } else {
                             if (p.bias != nullptr) val += p.bias[n];
+                            if (MODE == CONV_FWD && p.residual != nullptr) val += p.residual[(dst - p.out) + static_cast<size_t>(c + j) * col_stride];
                             dst[static_cast<size_t>(c + j) * col_stride] = act_lrelu(val, p.slope);
                         }
                     }
@@ -393,6 +497,9 @@ static int fill_common(ConvTcParams& p, const char* who, int B, int Cin, int H, 
     memset(&p, 0, sizeof(p));
     p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.Ho = Ho; p.Wo = Wo;
     p.classes = 1; p.k_splits = 1;
+    p.fd_HWo.init(Ho * Wo); p.fd_Wo.init(Wo); p.fd_taps.init(kh * kw); p.fd_kw.init(kw);
+    p.fd_dtaps.init(1); p.fd_dtapsw.init(1); p.fd_pixblocks.init(1); p.fd_ntile.init(1);
+    for (int c = 0; c < 4; ++c) { p.fd_HcWc[c].init(1); p.fd_Wc[c].init(1); }
     return 0;
 }
 
@@ -412,6 +519,8 @@ int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.n_tile = pick_n_tile(Cout); p.n_tiles = ceil_div(Cout, p.n_tile);
     p.kb_total = ceil_div(p.gemm_k, CT_BLOCK_K); p.kb_per_split = p.kb_total;
     p.m_tiles_class[0] = static_cast<int>((static_cast<long long>(B) * Ho * Wo + CT_BLOCK_M - 1) / CT_BLOCK_M);
+    p.fast = (kh == 4 && kw == 4) ? 1 : ((kh == 1 && kw == 1) ? 2 : 0);
+    p.fd_ntile.init(p.n_tile);
     return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -432,7 +541,11 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
         p.Hc[c] = (H - ph + stride - 1) / stride;
         p.Wc[c] = (W - pw + stride - 1) / stride;
         p.m_tiles_class[c] = static_cast<int>((static_cast<long long>(B) * p.Hc[c] * p.Wc[c] + CT_BLOCK_M - 1) / CT_BLOCK_M);
+        p.fd_HcWc[c].init(p.Hc[c] * p.Wc[c]);
+        p.fd_Wc[c].init(p.Wc[c]);
     }
+    p.fast = (p.taps_h == 2 && p.taps_w == 2) ? 1 : ((p.taps_h == 1 && p.taps_w == 1) ? 2 : 0);
+    p.fd_dtaps.init(p.taps_h * p.taps_w); p.fd_dtapsw.init(p.taps_w); p.fd_ntile.init(p.n_tile);
     return launch_conv_tc<CONV_DGRAD>(h, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -455,8 +568,42 @@ int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float*
     if (splits < 1) splits = 1;
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    p.fd_pixblocks.init(p.pix_blocks); p.fd_ntile.init(p.n_tile);
     PGV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * static_cast<size_t>(Cout) * Kc, stream));
     return launch_conv_tc<CONV_WGRAD>(h, p, stream);
+}
+
+/* Linear layers on the same kernel (no alignment requirement on K): x [M, K], w [N, K] (nn.Linear), y [M, N]. */
+int pgv_linear_fwd_tf32(pgv_handle* h, const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
+                        int K, int relu, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && x && w && y && M > 0 && N > 0 && K > 0, "pgv_linear_fwd_tf32: bad argument");
+    ConvTcParams p;
+    if (int rc = fill_common(p, "pgv_linear_fwd_tf32", M, K, 1, 1, N, 1, 1, 1, 0, 1, 1)) return rc;
+    p.x = x; p.w = w; p.bias = bias; p.residual = residual; p.out = y; p.slope = relu ? 0.0f : -1.0f;
+    p.gemm_n = N; p.gemm_k = K;
+    p.n_tile = pick_n_tile(N); p.n_tiles = ceil_div(N, p.n_tile);
+    p.kb_total = ceil_div(K, CT_BLOCK_K); p.kb_per_split = p.kb_total;
+    p.m_tiles_class[0] = ceil_div(M, CT_BLOCK_M);
+    p.fast = 2;
+    p.fd_ntile.init(p.n_tile);
+    return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_linear_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, float* dx, int M, int N, int K, pgv_stream_t stream) {
+    return pgv_conv2d_dgrad_tf32(h, dy, w, nullptr, dx, M, K, 1, 1, N, 1, 1, 1, 0, 1, 1, -1.0f, stream);
+}
+
+int pgv_linear_wgrad_tf32(pgv_handle* h, const float* dy, const float* x, float* dw, int M, int N, int K, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && dy && x && dw && M > 0 && N > 0 && K > 0, "pgv_linear_wgrad_tf32: bad argument");
+    ConvTcParams p;
+    if (int rc = fill_common(p, "pgv_linear_wgrad_tf32", M, K, 1, 1, N, 1, 1, 1, 0, 1, 1)) return rc;
+    p.x = x; p.w = dy; p.out = dw; p.slope = -1.0f;
+    p.gemm_n = N; p.gemm_k = M;
+    p.n_tile = pick_n_tile(N); p.n_tiles = ceil_div(N, p.n_tile);
+    p.kb_total = ceil_div(M, CT_BLOCK_K); p.kb_per_split = p.kb_total;
+    p.m_tiles_class[0] = ceil_div(K, CT_BLOCK_M);
+    p.fd_ntile.init(p.n_tile);
+    return launch_conv_tc<DENSE_WGRAD>(h, p, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

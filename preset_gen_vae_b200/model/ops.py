@@ -239,21 +239,16 @@ def flowbn_train_bwd(dy, x, t, mean, var, g_ld_sum):
 
 
 # ------------------------------------------------------------------------------------------------ dense layers
-def _tc_ok(*lds):
-    return _precision == 'tf32' and all(ld % 4 == 0 for ld in lds)
-
-
 def linear_fwd(x, w, bias, relu=False, residual=None):
     """y = act(x @ w.T + bias + residual); x [M,K], w [N,K] (nn.Linear layout)."""
     M, K = x.shape
     N = w.shape[0]
     y = _empty(x, M, N)
-    if residual is None and _tc_ok(K):
-        _call('pgv_gemm_nt_tf32', _h(x), _f(x), None, K, _f(w), None, K, _f(y), N, M, N, K, _f(bias), int(relu), 0, _s(x),
-              flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    if _precision == 'tf32':
+        _call('pgv_linear_fwd_tf32', _h(x), _f(x), _f(w), _f(bias), _f(residual), _f(y), M, N, K, int(relu), _s(x), **acct)
     else:
-        _call('pgv_gemm_f32', _h(x), 0, 1, _f(x), K, _f(w), K, _f(y), N, M, N, K, _f(bias), int(relu), _f(residual), N, _s(x),
-              flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+        _call('pgv_gemm_f32', _h(x), 0, 1, _f(x), K, _f(w), K, _f(y), N, M, N, K, _f(bias), int(relu), _f(residual), N, _s(x), **acct)
     return y
 
 
@@ -262,8 +257,11 @@ def linear_dgrad(dy, w):
     M, N = dy.shape
     K = w.shape[1]
     dx = _empty(dy, M, K)
-    _call('pgv_gemm_f32', _h(dy), 0, 0, _f(dy), N, _f(w), K, _f(dx), K, M, K, N, None, 0, None, 0, _s(dy),
-          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    if _precision == 'tf32':
+        _call('pgv_linear_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(dx), M, N, K, _s(dy), **acct)
+    else:
+        _call('pgv_gemm_f32', _h(dy), 0, 0, _f(dy), N, _f(w), K, _f(dx), K, M, K, N, None, 0, None, 0, _s(dy), **acct)
     return dx
 
 
@@ -272,8 +270,11 @@ def linear_wgrad(dy, x, want_bias=True):
     M, N = dy.shape
     K = x.shape[1]
     dw = _empty(dy, N, K)
-    _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy),
-          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    if _precision == 'tf32':
+        _call('pgv_linear_wgrad_tf32', _h(dy), _f(dy), _f(x), _f(dw), M, N, K, _s(dy), **acct)
+    else:
+        _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy), **acct)
     db = None
     if want_bias:
         db = _empty(dy, N)

@@ -244,6 +244,21 @@ def test_gemm_f32_all_transposes_and_split_k():
     ops.set_precision('tf32')
 
 
+@pytest.mark.parametrize("m,n,k", [(160, 1220, 24576), (160, 24576, 610), (160, 300, 305), (160, 610, 300), (5, 17, 9)])
+def test_tensor_core_linear_layers(m, n, k):
+    """nn.Linear forward / dgrad / wgrad on the tcgen05 gather kernel, incl. the unaligned K = 610 / 305 layers."""
+    ops.set_precision('tf32')
+    a, w, bias, res = rnd(m, k, seed=50), rnd(n, k, seed=51, scale=0.05), rnd(n, seed=52), rnd(m, n, seed=53)
+    dy = rnd(m, n, seed=54)
+    y = ops.linear_fwd(a, w, bias, relu=True, residual=res)
+    want = torch.relu(a.double() @ w.double().T + bias.double() + res.double())
+    dx = ops.linear_dgrad(dy, w)
+    dw, db = ops.linear_wgrad(dy, a)
+    errs = (rel(y, want), rel(dx, dy.double() @ w.double()), rel(dw, dy.double().T @ a.double()), rel(db, dy.double().sum(0)))
+    print("tc linear", (m, n, k), "rel-L2 fwd %.2e dgrad %.2e wgrad %.2e db %.2e" % errs)
+    assert max(errs) < 2e-3
+
+
 def test_losses_match_oracle(idx_helper):
     from preset_gen_vae_b200 import synthetic
     B, D = 16, 610
