@@ -132,6 +132,17 @@ PGV_API int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w
                                   int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
 PGV_API int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout, int kh,
                                   int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+/* Direct streaming kernels (exact fp32) for the two thin full-resolution layers, enc1 = Conv2d(1,8,5,2,2)
+ * (encoder.py:241) and dec8 = ConvTranspose2d(8,1,5,2,2) (decoder.py:218), which are HBM-bound (8 flop/byte).  Conv-view
+ * geometry: x [B,1,H,W], y [B,C<=8,Ho,Wo], w [C,1,5,5], stride 2, pad 2.  _dgrad is the transposed convolution and
+ * clamps its result to [clamp_lo, clamp_hi] (the decoder's Hardtanh; pass -INF/+INF for none). */
+PGV_API int pgv_conv5x5s2_c1_supported(int Cin, int Cout, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo);
+PGV_API int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int C, int H, int W, int Ho, int Wo,
+                                 float lrelu_slope, pgv_stream_t stream);
+PGV_API int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, float* x, int B, int C, int H, int W, int Ho, int Wo,
+                                   float clamp_lo, float clamp_hi, pgv_stream_t stream);
+PGV_API int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo,
+                                   pgv_stream_t stream);
 /* nn.Linear on the same tensor-core kernel (any K, no alignment requirement): x [M,K], w [N,K], y [M,N] = act(x w^T +
  * bias + residual) (bias / residual may be NULL, relu != 0 fuses a ReLU); dx [M,K] = dy w; dw [N,K] = dy^T x. */
 PGV_API int pgv_linear_fwd_tf32(pgv_handle* h, const float* x, const float* w, const float* bias, const float* residual, float* y, int M,

@@ -57,6 +57,8 @@ struct ConvTcParams {
     int taps_h, taps_w;             // DGRAD: taps per class along h / w
     int pix_blocks;                 // WGRAD: k-blocks per image = ceil(Ho*Wo / 32)
     int fast;                       // 1: 4x4 kernel (FWD) / 2x2 taps (DGRAD); 2: 1x1 kernel; 0: generic
+    int atomic_out;                 // FWD / DGRAD with k_splits > 1: accumulate into a pre-zeroed output, split 0 adds the bias
+    int a_dense;                    // A is a plain row-major [M, K] matrix (Linear layers): K-contiguous vector loads
     float slope;
     FastDiv fd_HWo, fd_Wo, fd_taps, fd_kw, fd_dtaps, fd_dtapsw, fd_pixblocks, fd_ntile, fd_HcWc[4], fd_Wc[4];
 };
@@ -163,14 +165,14 @@ __device__ __forceinline__ void chunk_a(const ConvTcParams& p, const WorkItem& w
             if (ci < p.Cin && ((r.hmask >> rr) & 1u)) {
                 const float* src = r.base + (static_cast<size_t>(ci) * p.H + (r.i0 + rr)) * p.W + r.j0;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) if ((r.wmask >> s) & 1u) v[s] = src[s];
+                for (int s = 0; s < 4; ++s) if ((r.wmask >> s) & 1u) v[s] = __ldg(src + s);
             }
         } else if (p.fast == 2) {                    // 1x1 kernel: chunk = 4 consecutive input channels of one pixel
             if (r.hmask & r.wmask & 1u) {
                 const size_t hw = static_cast<size_t>(p.H) * p.W;
                 const float* src = r.base + static_cast<size_t>(r.i0) * p.W + r.j0 + static_cast<size_t>(k0) * hw;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (k0 + e < p.Cin) v[e] = src[e * hw];
+                for (int e = 0; e < 4; ++e) if (k0 + e < p.Cin) v[e] = __ldg(src + e * hw);
             }
         } else {
 #pragma unroll
@@ -192,16 +194,16 @@ __device__ __forceinline__ void chunk_a(const ConvTcParams& p, const WorkItem& w
             if (co < p.Cout) {
                 const float* src = r.base + static_cast<size_t>(co) * HWo + r.i0 * p.Wo + r.j0;
                 const bool h0 = r.hmask & 1u, h1 = r.hmask & 2u, w0 = r.wmask & 1u, w1 = r.wmask & 2u;
-                if (h0 && w0) v[0] = src[0];
-                if (h0 && w1) v[1] = src[-1];
-                if (h1 && w0) v[2] = src[-p.Wo];
-                if (h1 && w1) v[3] = src[-p.Wo - 1];
+                if (h0 && w0) v[0] = __ldg(src);
+                if (h0 && w1) v[1] = __ldg(src - 1);
+                if (h1 && w0) v[2] = __ldg(src - p.Wo);
+                if (h1 && w1) v[3] = __ldg(src - p.Wo - 1);
             }
         } else if (p.fast == 2) {                    // single tap: chunk = 4 consecutive output channels
             if (r.hmask & r.wmask & 1u) {
                 const float* src = r.base + static_cast<size_t>(k0) * HWo + r.i0 * p.Wo + r.j0;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (k0 + e < p.Cout) v[e] = src[static_cast<size_t>(e) * HWo];
+                for (int e = 0; e < 4; ++e) if (k0 + e < p.Cout) v[e] = __ldg(src + static_cast<size_t>(e) * HWo);
             }
         } else {
 #pragma unroll
@@ -226,13 +228,13 @@ __device__ __forceinline__ void chunk_a(const ConvTcParams& p, const WorkItem& w
         int ih = static_cast<int>(oh) * p.stride + r.i0, iw = static_cast<int>(ow) * p.stride + r.j0, col = static_cast<int>(ow);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            if (pix0 + e < HWo && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = src[ih * p.W + iw];
+            if (pix0 + e < HWo && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v[e] = __ldg(src + ih * p.W + iw);
             iw += p.stride;
             if (++col == p.Wo) { col = 0; ih += p.stride; iw = r.j0; }
         }
     } else {                            // DENSE_WGRAD: k = batch row
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (k0 + e < p.B) v[e] = r.base[static_cast<size_t>(k0 + e) * p.Cin];
+        for (int e = 0; e < 4; ++e) if (k0 + e < p.B) v[e] = __ldg(r.base + static_cast<size_t>(k0 + e) * p.Cin);
     }
 }
 
@@ -287,15 +289,15 @@ __device__ __forceinline__ void chunk_b(const ConvTcParams& p, const WorkItem& w
         if (pix0 >= HWo) return;
         const float* src = p.w + (static_cast<size_t>(b) * p.Cout + n) * HWo + pix0;
         if (pix0 + 4 <= HWo && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            const float4 q = *reinterpret_cast<const float4*>(src);
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src));
             v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (pix0 + e < HWo) v[e] = src[e];
+            for (int e = 0; e < 4; ++e) if (pix0 + e < HWo) v[e] = __ldg(src + e);
         }
     } else {                                         // DENSE_WGRAD: dy[b, co = n]
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (k0 + e < p.B) v[e] = p.w[static_cast<size_t>(k0 + e) * p.Cout + n];
+        for (int e = 0; e < 4; ++e) if (k0 + e < p.B) v[e] = __ldg(p.w + static_cast<size_t>(k0 + e) * p.Cout + n);
     }
 }
 
@@ -339,26 +341,58 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             const RowA ra = row_a<MODE>(p, wi, a_row);
             const int b_chunks = p.n_tile * 8;
             for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                // Phase 1: issue EVERY global load of this k-block into registers.  Nothing here touches shared memory,
+                // so the loads are independent and overlap (and they overlap the wait for the smem slot below).
+                float va[4][4], vb[8][4];
+                int a_rows[4], a_cs[4], b_rows[8], b_cs[8];
+                if ((MODE == CONV_FWD || MODE == CONV_DGRAD) && p.a_dense) {
+                    // Linear layers: 8 consecutive threads read one 128-byte row segment (coalesced), 4 rows per thread
+                    const int rows_total = p.B, kdim = p.gemm_k;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int id = t + j * CT_PRODUCERS, row = id >> 3, c = id & 7, m = wi.tm * CT_BLOCK_M + row, k0 = (kb * 8 + c) * 4;
+                        a_rows[j] = row; a_cs[j] = c;
+                        va[j][0] = va[j][1] = va[j][2] = va[j][3] = 0.f;
+                        if (m < rows_total && k0 < kdim) {
+                            const float* src = p.x + static_cast<size_t>(m) * kdim + k0;
+                            if (k0 + 4 <= kdim && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+                                va[j][0] = q.x; va[j][1] = q.y; va[j][2] = q.z; va[j][3] = q.w;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (k0 + e < kdim) va[j][e] = __ldg(src + e);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a_rows[j] = a_row; a_cs[j] = a_c0 + 2 * j;
+                        chunk_a<MODE>(p, wi, ra, kb * 8 + a_cs[j], va[j]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int id = t + q * CT_PRODUCERS;
+                    b_rows[q] = -1; b_cs[q] = 0;
+                    if (id < b_chunks) {
+                        // FWD weights are contiguous along k: consecutive threads take consecutive chunks of one row;
+                        // otherwise consecutive threads take consecutive rows (coalesced along n / pixels)
+                        int row, c;
+                        if (MODE == CONV_FWD) { row = id >> 3; c = id & 7; }
+                        else { uint32_t qq, rem; p.fd_ntile.divmod(static_cast<uint32_t>(id), qq, rem); row = static_cast<int>(rem); c = static_cast<int>(qq); }
+                        b_rows[q] = row; b_cs[q] = c;
+                        chunk_b<MODE>(p, wi, row, kb * 8 + c, vb[q]);
+                    }
+                }
+                // Phase 2: wait for the slot, convert to TF32 and store at the swizzled positions
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * CT_STAGE_BYTES;
                 uint8_t* sB = sA + CT_A_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = a_c0 + 2 * j;
-                    float v[4];
-                    chunk_a<MODE>(p, wi, ra, kb * 8 + c, v);
-                    st_chunk(sA, a_row, c, v);
-                }
-                for (int id = t; id < b_chunks; id += CT_PRODUCERS) {
-                    // FWD weights are contiguous along k: let consecutive threads take consecutive chunks of one row;
-                    // otherwise consecutive threads take consecutive rows (coalesced along n / pixels)
-                    int row, c;
-                    if (MODE == CONV_FWD) { row = id >> 3; c = id & 7; }
-                    else { uint32_t q, rem; p.fd_ntile.divmod(static_cast<uint32_t>(id), q, rem); row = static_cast<int>(rem); c = static_cast<int>(q); }
-                    float v[4];
-                    chunk_b<MODE>(p, wi, row, kb * 8 + c, v);
-                    st_chunk(sB, row, c, v);
-                }
+                for (int j = 0; j < 4; ++j) st_chunk(sA, a_rows[j], a_cs[j], va[j]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (b_rows[q] >= 0) st_chunk(sB, b_rows[q], b_cs[q], vb[q]);
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_full[stage]);
                 if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
@@ -442,6 +476,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                             atomicAdd(dst + static_cast<size_t>(c + j) * col_stride, val);
                         } else if (MODE == DENSE_WGRAD) {
                             dst[static_cast<size_t>(c + j) * col_stride] = val;
+                        } else if (p.atomic_out) {
+                            if (p.bias != nullptr && wi.kb0 == 0) val += p.bias[n];
+                            atomicAdd(dst + static_cast<size_t>(c + j) * col_stride, val);
                         } else {
                             if (p.bias != nullptr) val += p.bias[n];
                             if (MODE == CONV_FWD && p.residual != nullptr) val += p.residual[(dst - p.out) + static_cast<size_t>(c + j) * col_stride];
@@ -470,6 +507,23 @@ static int pick_n_tile(int n) {
         t = ceil_div(ceil_div(n, parts), 16) * 16;
     }
     return t;
+}
+
+// Long-K problems with few output tiles (deep conv layers, the two big FC layers): split K across CTAs when the epilogue is
+// linear (no activation, no residual); partial sums are accumulated with fp32 atomics into a zero-filled output.
+static int maybe_split_k(const pgv_handle* h, ConvTcParams& p, size_t out_elems, cudaStream_t stream) {
+    int m_tiles = 0;
+    for (int c = 0; c < p.classes; ++c) m_tiles += p.m_tiles_class[c];
+    const long long tiles = static_cast<long long>(m_tiles) * p.n_tiles;
+    if (p.slope >= 0.0f || p.residual != nullptr || tiles >= h->sm_count || p.kb_total < 16) return 0;
+    int splits = static_cast<int>((h->sm_count * 2) / tiles);
+    if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+    if (splits <= 1) return 0;
+    p.kb_per_split = ceil_div(p.kb_total, splits);
+    p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    p.atomic_out = 1;
+    PGV_CUDA(cudaMemsetAsync(p.out, 0, sizeof(float) * out_elems, stream));
+    return 0;
 }
 
 template <int MODE>
@@ -521,6 +575,7 @@ int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.m_tiles_class[0] = static_cast<int>((static_cast<long long>(B) * Ho * Wo + CT_BLOCK_M - 1) / CT_BLOCK_M);
     p.fast = (kh == 4 && kw == 4) ? 1 : ((kh == 1 && kw == 1) ? 2 : 0);
     p.fd_ntile.init(p.n_tile);
+    if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cout * Ho * Wo, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -546,6 +601,8 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
     }
     p.fast = (p.taps_h == 2 && p.taps_w == 2) ? 1 : ((p.taps_h == 1 && p.taps_w == 1) ? 2 : 0);
     p.fd_dtaps.init(p.taps_h * p.taps_w); p.fd_dtapsw.init(p.taps_w); p.fd_ntile.init(p.n_tile);
+    p.a_dense = (H == 1 && W == 1 && Ho == 1 && Wo == 1 && kh == 1 && kw == 1) ? 1 : 0;   // Linear dgrad: A = dy [M, N] row-major
+    if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cin * H * W, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_DGRAD>(h, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -584,8 +641,9 @@ int pgv_linear_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.n_tile = pick_n_tile(N); p.n_tiles = ceil_div(N, p.n_tile);
     p.kb_total = ceil_div(K, CT_BLOCK_K); p.kb_per_split = p.kb_total;
     p.m_tiles_class[0] = ceil_div(M, CT_BLOCK_M);
-    p.fast = 2;
+    p.fast = 2; p.a_dense = 1;
     p.fd_ntile.init(p.n_tile);
+    if (int rc = maybe_split_k(h, p, static_cast<size_t>(M) * N, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,0 +1,170 @@
+// Direct kernels for the two thin 5x5 / stride-2 layers that touch the full-resolution spectrogram:
+//   enc1  nn.Conv2d(1, 8, 5, 2, 2)            model/encoder.py:241      (1 x 257 x 347 -> 8 x 129 x 174)
+//   dec8  nn.ConvTranspose2d(8, 1, 5, 2, 2)   model/decoder.py:218      (8 x 129 x 174 -> 1 x 257 x 347) + Hardtanh
+// With one channel on one side these are 8-25 flop/byte: HBM-bound, so they are written as coalesced
+// streaming kernels with the 200 weights in shared memory instead of 128-row tensor-core tiles with 1 useful column.
+// Exact fp32 arithmetic.  "Conv view" geometry for all three: x [B,1,H,W], y [B,C,Ho,Wo], w [C,1,5,5], stride 2, pad 2.
+#include <algorithm>
+
+#include "pgv_common.cuh"
+
+namespace pgv {
+
+constexpr int THIN_K = 5, THIN_TAPS = 25, THIN_MAXC = 8;
+
+// y[b,c,oh,ow] = act(bias[c] + sum_{r,s} x[b,0,2oh-2+r,2ow-2+s] * w[c,0,r,s]).  One thread per output pixel, all C channels.
+__global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int B, int C, int H,
+                                                            int W, int Ho, int Wo, float slope) {
+    __shared__ float sw[THIN_MAXC * THIN_TAPS], sb[THIN_MAXC];
+    for (int i = threadIdx.x; i < C * THIN_TAPS; i += 256) sw[i] = w[i];
+    if (threadIdx.x < C) sb[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.0f;
+    __syncthreads();
+    const int HWo = Ho * Wo;
+    const long long total = static_cast<long long>(B) * HWo;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int b = static_cast<int>(i / HWo), pix = static_cast<int>(i % HWo), oh = pix / Wo, ow = pix % Wo;
+        const float* xb = x + static_cast<size_t>(b) * H * W;
+        float in[THIN_TAPS];
+#pragma unroll
+        for (int r = 0; r < THIN_K; ++r) {
+            const int ih = 2 * oh - 2 + r;
+#pragma unroll
+            for (int s = 0; s < THIN_K; ++s) {
+                const int iw = 2 * ow - 2 + s;
+                in[r * THIN_K + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
+            }
+        }
+        float* yb = y + static_cast<size_t>(b) * C * HWo + pix;
+        for (int c = 0; c < C; ++c) {
+            float acc = sb[c];
+#pragma unroll
+            for (int t = 0; t < THIN_TAPS; ++t) acc = fmaf(in[t], sw[c * THIN_TAPS + t], acc);
+            yb[static_cast<size_t>(c) * HWo] = (slope >= 0.0f && acc < 0.0f) ? acc * slope : acc;
+        }
+    }
+}
+
+// Transposed form: x[b,0,ih,iw] = clamp(bias + sum_{c,r,s: 2oh-2+r = ih, 2ow-2+s = iw} y[b,c,oh,ow] * w[c,0,r,s], lo, hi).
+// One thread per full-resolution pixel; taps r = (ih & 1) + 2a.
+__global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float* __restrict__ y, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ x, int B, int C, int H,
+                                                              int W, int Ho, int Wo, float lo, float hi) {
+    __shared__ float sw[THIN_MAXC * THIN_TAPS];
+    for (int i = threadIdx.x; i < C * THIN_TAPS; i += 256) sw[i] = w[i];
+    __syncthreads();
+    const float b0 = bias != nullptr ? bias[0] : 0.0f;
+    const int HW = H * W, HWo = Ho * Wo;
+    const long long total = static_cast<long long>(B) * HW;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int b = static_cast<int>(i / HW), pix = static_cast<int>(i % HW), ih = pix / W, iw = pix % W;
+        const float* yb = y + static_cast<size_t>(b) * C * HWo;
+        const int r0 = ih & 1, s0 = iw & 1, oh0 = (ih + 2) >> 1, ow0 = (iw + 2) >> 1;   // tap a: r = r0 + 2a, oh = oh0 - a
+        float acc = b0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int r = r0 + 2 * a, oh = oh0 - a;
+            if (r >= THIN_K || oh < 0 || oh >= Ho) continue;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int s = s0 + 2 * d, ow = ow0 - d;
+                if (s >= THIN_K || ow < 0 || ow >= Wo) continue;
+                const float* src = yb + oh * Wo + ow;
+                for (int c = 0; c < C; ++c) acc = fmaf(__ldg(src + static_cast<size_t>(c) * HWo), sw[c * THIN_TAPS + r * THIN_K + s], acc);
+            }
+        }
+        x[i] = fminf(fmaxf(acc, lo), hi);
+    }
+}
+
+// dw[c,0,r,s] = sum_{b,oh,ow} dy[b,c,oh,ow] * x[b,0,2oh-2+r,2ow-2+s].  One block per image slice: thread (c, tap) walks
+// shared-memory tiles of dy (C x 8 x 32) and of the matching input patch (19 x 67); one atomicAdd per thread at the end.
+constexpr int TW_TH = 8, TW_TW = 32, TW_PH = 2 * TW_TH + 3, TW_PW = 2 * TW_TW + 3;
+__global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ dw, int B, int C, int H, int W, int Ho, int Wo,
+                                                              int tiles_per_block) {
+    __shared__ float sdy[THIN_MAXC][TW_TH * TW_TW];
+    __shared__ float sx[TW_PH * TW_PW];
+    const int tiles_h = (Ho + TW_TH - 1) / TW_TH, tiles_w = (Wo + TW_TW - 1) / TW_TW, tiles_img = tiles_h * tiles_w;
+    const long long n_tiles = static_cast<long long>(B) * tiles_img;
+    const int c = threadIdx.x / THIN_TAPS, tap = threadIdx.x % THIN_TAPS, r = tap / THIN_K, s = tap % THIN_K;
+    const bool worker = threadIdx.x < C * THIN_TAPS;
+    float acc = 0.0f;
+    const long long t0 = static_cast<long long>(blockIdx.x) * tiles_per_block;
+    for (long long t = t0; t < t0 + tiles_per_block && t < n_tiles; ++t) {
+        const int b = static_cast<int>(t / tiles_img), ti = static_cast<int>(t % tiles_img), oh0 = (ti / tiles_w) * TW_TH,
+                  ow0 = (ti % tiles_w) * TW_TW;
+        const float* xb = x + static_cast<size_t>(b) * H * W;
+        const float* dyb = dy + static_cast<size_t>(b) * C * Ho * Wo;
+        __syncthreads();
+        for (int i = threadIdx.x; i < TW_PH * TW_PW; i += 256) {
+            const int ih = 2 * oh0 - 2 + i / TW_PW, iw = 2 * ow0 - 2 + i % TW_PW;
+            sx[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
+        }
+        for (int i = threadIdx.x; i < C * TW_TH * TW_TW; i += 256) {
+            const int cc = i / (TW_TH * TW_TW), p = i % (TW_TH * TW_TW), oh = oh0 + p / TW_TW, ow = ow0 + p % TW_TW;
+            sdy[cc][p] = (oh < Ho && ow < Wo) ? __ldg(dyb + (static_cast<size_t>(cc) * Ho + oh) * Wo + ow) : 0.0f;
+        }
+        __syncthreads();
+        if (worker) {
+            const float* px = sx + r * TW_PW + s;
+#pragma unroll
+            for (int py = 0; py < TW_TH; ++py)
+#pragma unroll 8
+                for (int qx = 0; qx < TW_TW; ++qx) acc = fmaf(sdy[c][py * TW_TW + qx], px[2 * py * TW_PW + 2 * qx], acc);
+        }
+    }
+    if (worker) atomicAdd(dw + c * THIN_TAPS + tap, acc);
+}
+
+static bool thin_geometry(int C, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo) {
+    return C >= 1 && C <= THIN_MAXC && kh == 5 && kw == 5 && stride == 2 && pad == 2 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1;
+}
+
+}  // namespace pgv
+
+using namespace pgv;
+
+extern "C" {
+
+int pgv_conv5x5s2_c1_supported(int Cin, int Cout, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo) {
+    return Cin == 1 && thin_geometry(Cout, kh, kw, stride, pad, H, W, Ho, Wo);
+}
+
+int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int C, int H, int W, int Ho, int Wo,
+                         float lrelu_slope, pgv_stream_t stream) {
+    PGV_CHECK_ARG(x && w && y, "pgv_conv5x5s2_c1_fwd: NULL argument");
+    PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_fwd: unsupported geometry");
+    const long long total = static_cast<long long>(B) * Ho * Wo;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    thin_conv_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, B, C, H, W, Ho, Wo, lrelu_slope);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, float* x, int B, int C, int H, int W, int Ho, int Wo,
+                           float clamp_lo, float clamp_hi, pgv_stream_t stream) {
+    PGV_CHECK_ARG(y && w && x, "pgv_conv5x5s2_c1_dgrad: NULL argument");
+    PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_dgrad: unsupported geometry");
+    const long long total = static_cast<long long>(B) * H * W;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    thin_conv_dgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo, pgv_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PGV_CHECK_ARG(x && dy && dw, "pgv_conv5x5s2_c1_wgrad: NULL argument");
+    PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_wgrad: unsupported geometry");
+    PGV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C * THIN_TAPS, stream));
+    const long long n_tiles = static_cast<long long>(B) * ((Ho + TW_TH - 1) / TW_TH) * ((Wo + TW_TW - 1) / TW_TW);
+    int per_block = static_cast<int>((n_tiles + 148 * 4 - 1) / (148 * 4));
+    if (per_block < 1) per_block = 1;
+    const int grid = static_cast<int>((n_tiles + per_block - 1) / per_block);
+    thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -51,8 +51,14 @@ class SpectrogramCNN(nn.Module):
         for blk in self.blocks():
             h, c = blk.fwd(h, training)
             ctxs.append(c)
+        lo, hi = self.out_act.min_val, self.out_act.max_val
+        if layer.tconv_clamp_fusable(h, self.last_tconv):
+            # Hardtanh fused into the thin transposed-conv kernel; y in (lo, hi) <=> the pre-activation is, so the
+            # backward mask can be taken from y itself
+            y = layer.tconv_fwd(h, self.last_tconv, clamp=(lo, hi))
+            return y, (ctxs, h, y)
         pre = layer.tconv_fwd(h, self.last_tconv)
-        y = ops.hardtanh_fwd(pre, self.out_act.min_val, self.out_act.max_val)
+        y = ops.hardtanh_fwd(pre, lo, hi)
         return y, (ctxs, h, pre)
 
     def bwd(self, dy, ctx, grads):

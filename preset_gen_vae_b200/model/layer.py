@@ -156,10 +156,17 @@ def tconv_out_hw(conv, h, w):
     return (h - 1) * s - 2 * p + k[0] + op[0], (w - 1) * s - 2 * p + k[1] + op[1]
 
 
-def tconv_fwd(x, conv, slope=-1.0):
-    """ConvTranspose2d forward (+bias, optional fused LeakyReLU) = conv data-gradient."""
+def tconv_fwd(x, conv, slope=-1.0, clamp=None):
+    """ConvTranspose2d forward (+bias, optional fused LeakyReLU or Hardtanh clamp) = conv data-gradient."""
     return ops.conv2d_dgrad(x, conv.weight, tconv_out_hw(conv, x.shape[2], x.shape[3]), conv.stride[0], conv.padding[0],
-                            bias=conv.bias, slope=slope)
+                            bias=conv.bias, slope=slope, clamp=clamp)
+
+
+def tconv_clamp_fusable(x, conv):
+    """True when the transposed convolution is the thin 5x5 / one-output-channel layer whose kernel fuses the Hardtanh."""
+    cin_t, cout_t, kh, kw = conv.weight.shape
+    H, W = tconv_out_hw(conv, x.shape[2], x.shape[3])
+    return ops.use_thin and ops._thin(cout_t, cin_t, kh, kw, conv.stride[0], conv.padding[0], H, W, x.shape[2], x.shape[3])
 
 
 def tconv_bwd(dz, x, conv, grads, need_dx=True):

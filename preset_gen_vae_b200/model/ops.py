@@ -16,6 +16,7 @@ import torch
 from .. import _lib
 
 LRELU_SLOPE = 0.1
+use_thin = True       # route the 5x5 / one-channel layers (enc1, dec8) to the direct streaming kernels (exact fp32)
 _precision = 'tf32'
 launches = 0          # kernels launched through this module since the last reset (bench.py's gpu_launches)
 
@@ -112,6 +113,10 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None):
     Cout, _, kh, kw = w.shape
     Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
     y = _empty(x, B, Cout, Ho, Wo)
+    if use_thin and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+        _call('pgv_conv5x5s2_c1_fwd', _f(x), _f(w), _f(bias), _f(y), B, Cout, H, W, Ho, Wo, slope, _s(x),
+              flops=2 * B * Ho * Wo * Cout * 25, nbytes=4 * (x.numel() + y.numel()))
+        return y
     if _precision == 'tf32':
         _call('pgv_conv2d_fwd_tf32', _h(x), _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x),
               flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + y.numel() + w.numel()))
@@ -121,12 +126,23 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None):
     return y
 
 
-def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0):
-    """dx of the convolution with weight w [Cout, Cin, kh, kw]; also the forward of ConvTranspose2d(weight=w)."""
+def _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+    return bool(_lib.lib().pgv_conv5x5s2_c1_supported(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo))
+
+
+def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None):
+    """dx of the convolution with weight w [Cout, Cin, kh, kw]; also the forward of ConvTranspose2d(weight=w).
+    clamp=(lo, hi) fuses a Hardtanh (only available on the thin-layer kernel; callers check `thin_dgrad_available`)."""
     B, Cout, Ho, Wo = dy.shape
     _, Cin, kh, kw = w.shape
     H, W = in_hw
     dx = _empty(dy, B, Cin, H, W)
+    if use_thin and slope < 0 and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+        lo, hi = clamp if clamp is not None else (-float('inf'), float('inf'))
+        _call('pgv_conv5x5s2_c1_dgrad', _f(dy), _f(w), _f(bias), _f(dx), B, Cout, H, W, Ho, Wo, lo, hi, _s(dy),
+              flops=2 * B * Ho * Wo * Cout * 25, nbytes=4 * (dx.numel() + dy.numel()))
+        return dx
+    assert clamp is None, "fused clamp needs the thin-layer kernel"
     if _precision == 'tf32' and stride <= 2:
         _call('pgv_conv2d_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope,
               _s(dy), flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
@@ -141,6 +157,10 @@ def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
     _, Cout, Ho, Wo = dy.shape
     _, _, kh, kw = w_shape
     dw = _empty(x, *w_shape)
+    if use_thin and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+        _call('pgv_conv5x5s2_c1_wgrad', _f(x), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, _s(x), n=2,
+              flops=2 * B * Ho * Wo * Cout * 25, nbytes=4 * (x.numel() + dy.numel()))
+        return dw, (channel_sum(dy) if want_bias else None)
     if _precision == 'tf32':
         _call('pgv_conv2d_wgrad_tf32', _h(x), _f(x), _f(dy), _f(dw), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
               flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))

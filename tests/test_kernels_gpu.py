@@ -31,6 +31,7 @@ ENC_LAYERS = [(1, 8, 5, 2, 2, 257, 347), (8, 16, 4, 2, 2, 129, 174), (16, 32, 4,
 def test_conv_fwd_dgrad_wgrad(cin, cout, k, s, p, H, W):
     B = 2
     ops.set_precision('fp32')
+    ops.use_thin = False          # this test covers the generic exact-fp32 kernels; the thin kernels have their own test
     x, w, b = rnd(B, cin, H, W, seed=1), rnd(cout, cin, k, k, seed=2, scale=0.1), rnd(cout, seed=3)
     y = ops.conv2d_fwd(x, w, b, s, p, slope=0.1)
     xd, wd, bd = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
@@ -42,7 +43,28 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, s, p, H, W):
     assert rel(ops.conv2d_dgrad(dy, w, (H, W), s, p), gx) < 2e-6
     dw, db = ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=True)
     ops.set_precision('tf32')
+    ops.use_thin = True
     assert rel(dw, gw) < 5e-6 and rel(db, gb) < 5e-6
+
+
+def test_thin_layer_kernels():
+    """enc1 = Conv2d(1,8,5,2,2) and dec8 = ConvTranspose2d(8,1,5,2,2)+Hardtanh on the direct streaming kernels."""
+    B, H, W, C = 3, 257, 347, 8
+    x, w, b = rnd(B, 1, H, W, seed=60), rnd(C, 1, 5, 5, seed=61, scale=0.2), rnd(C, seed=62)
+    assert ops.use_thin and ops._thin(1, C, 5, 5, 2, 2, H, W, 129, 174)
+    y = ops.conv2d_fwd(x, w, b, 2, 2, slope=0.1)
+    xd, wd, bd = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    pre = F.conv2d(xd, wd, bd, 2, 2)
+    assert y.shape == (B, C, 129, 174) and rel(y, F.leaky_relu(pre, 0.1)) < 2e-6
+    dy = rnd(B, C, 129, 174, seed=63)
+    gx, gw, gb = torch.autograd.grad(pre, (xd, wd, bd), dy.double())
+    dw, db = ops.conv2d_wgrad(x, dy, w.shape, 2, 2, want_bias=True)
+    assert rel(dw, gw) < 5e-6 and rel(db, gb) < 5e-6
+    bias1 = rnd(1, seed=64)
+    t = ops.conv2d_dgrad(dy, w, (H, W), 2, 2, bias=bias1, clamp=(-1.0, 1.0))      # dec8 forward + Hardtanh
+    want = F.hardtanh(gx + bias1.double())
+    assert rel(t, want) < 2e-6
+    assert rel(ops.conv2d_dgrad(dy, w, (H, W), 2, 2), gx) < 2e-6
 
 
 # (Cin, Cout, k, output_padding, Hin, Win): every transposed conv of the decoder (decoder.py:72-75, 205-218)

@@ -1,0 +1,63 @@
+"""Per-layer timing of the tensor-core conv / linear kernels at the training batch (CUDA events, 5 reps after warm-up)."""
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from preset_gen_vae_b200.model import ops  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 160
+dev = 'cuda'
+ops.set_precision('tf32')
+# conv geometry (Cin, Cout, k, s, p, H, W, Ho, Wo) of the convolution whose fwd/dgrad/wgrad each layer uses
+ENC = [('enc1', 1, 8, 5, 257, 347), ('enc2', 8, 16, 4, 129, 174), ('enc3', 16, 32, 4, 65, 88), ('enc4', 32, 64, 4, 33, 45),
+       ('enc5', 64, 128, 4, 17, 23), ('enc6', 128, 256, 4, 9, 12), ('enc7', 256, 512, 4, 5, 7)]
+DEC = [('dec2', 256, 512, 4, 5, 7), ('dec3', 128, 256, 4, 9, 12), ('dec4', 64, 128, 4, 17, 23), ('dec5', 32, 64, 4, 33, 45),
+       ('dec6', 16, 32, 4, 65, 88), ('dec7', 8, 16, 4, 129, 174), ('dec8', 1, 8, 5, 257, 347)]
+
+
+def timeit(fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+tot = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
+print("layer        flops(G)  fwd ms (TF/s)      dgrad ms (TF/s)    wgrad ms (TF/s)   act MB")
+for name, cin, cout, k, H, W in ENC + DEC:
+    s, p = 2, 2
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    x = torch.randn(B, cin, H, W, device=dev)
+    w = torch.randn(cout, cin, k, k, device=dev) * 0.1
+    b = torch.randn(cout, device=dev)
+    dy = torch.randn(B, cout, Ho, Wo, device=dev)
+    fl = 2 * B * Ho * Wo * cout * cin * k * k / 1e9
+    t_f = timeit(lambda: ops.conv2d_fwd(x, w, b, s, p, 0.1))
+    t_d = timeit(lambda: ops.conv2d_dgrad(dy, w, (H, W), s, p))
+    t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=False))
+    tot['fwd'] += t_f; tot['dgrad'] += t_d; tot['wgrad'] += t_w
+    mb = 4 * (x.numel() + dy.numel()) / 1e6
+    print("%-10s %8.2f   %7.3f (%6.1f)   %7.3f (%6.1f)   %7.3f (%6.1f)   %7.1f" %
+          (name, fl, t_f, fl / t_f, t_d, fl / t_d, t_w, fl / t_w, mb))
+for name, cin, cout, H, W in [('enc8 1x1', 512, 2048, 3, 4), ('dec1 1x1', 512, 2048, 3, 4)]:
+    x = torch.randn(B, cin, H, W, device=dev); w = torch.randn(cout, cin, 1, 1, device=dev) * 0.05; b = torch.randn(cout, device=dev)
+    dy = torch.randn(B, cout, H, W, device=dev)
+    fl = 2 * B * H * W * cout * cin / 1e9
+    t_f = timeit(lambda: ops.conv2d_fwd(x, w, b, 1, 0, 0.1)); t_d = timeit(lambda: ops.conv2d_dgrad(dy, w, (H, W), 1, 0))
+    t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, w.shape, 1, 0, want_bias=False))
+    tot['fwd'] += t_f; tot['dgrad'] += t_d; tot['wgrad'] += t_w
+    print("%-10s %8.2f   %7.3f (%6.1f)   %7.3f (%6.1f)   %7.3f (%6.1f)" % (name, fl, t_f, fl / t_f, t_d, fl / t_d, t_w, fl / t_w))
+for name, M, N, K in [('enc FC', B, 1220, 24576), ('dec FC', B, 24576, 610), ('flow 300x300', B, 300, 300), ('flow 305->300', B, 300, 305),
+                      ('flow 300->610', B, 610, 300)]:
+    a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; bias = torch.randn(N, device=dev); dy = torch.randn(M, N, device=dev)
+    fl = 2 * M * N * K / 1e9
+    t_f = timeit(lambda: ops.linear_fwd(a, w, bias)); t_d = timeit(lambda: ops.linear_dgrad(dy, w)); t_w = timeit(lambda: ops.linear_wgrad(dy, a))
+    print("%-14s %6.2f   %7.3f (%6.1f)   %7.3f (%6.1f)   %7.3f (%6.1f)" % (name, fl, t_f, fl / t_f, t_d, fl / t_d, t_w, fl / t_w))
+print("conv totals (ms): fwd %.2f dgrad %.2f wgrad %.2f" % (tot['fwd'], tot['dgrad'], tot['wgrad']))
