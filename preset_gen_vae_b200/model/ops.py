@@ -259,13 +259,23 @@ def flowbn_train_bwd(dy, x, t, mean, var, g_ld_sum):
 
 
 # ------------------------------------------------------------------------------------------------ dense layers
+# Below this many multiply-accumulates a dense layer is latency-bound (a 160x300x300 flow conditioner layer is 14 M): the
+# persistent tensor-core kernel's fixed cost (TMEM allocation, barrier set-up, pipeline fill) exceeds the whole job, so
+# such layers run on the exact-fp32 CUDA-core GEMM instead.
+SMALL_GEMM_MACS = 48_000_000
+
+
+def _use_tc(M, N, K):
+    return _precision == 'tf32' and M * N * K >= SMALL_GEMM_MACS
+
+
 def linear_fwd(x, w, bias, relu=False, residual=None):
     """y = act(x @ w.T + bias + residual); x [M,K], w [N,K] (nn.Linear layout)."""
     M, K = x.shape
     N = w.shape[0]
     y = _empty(x, M, N)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    if _precision == 'tf32':
+    if _use_tc(M, N, K):
         _call('pgv_linear_fwd_tf32', _h(x), _f(x), _f(w), _f(bias), _f(residual), _f(y), M, N, K, int(relu), _s(x), **acct)
     else:
         _call('pgv_gemm_f32', _h(x), 0, 1, _f(x), K, _f(w), K, _f(y), N, M, N, K, _f(bias), int(relu), _f(residual), N, _s(x), **acct)
@@ -278,7 +288,7 @@ def linear_dgrad(dy, w):
     K = w.shape[1]
     dx = _empty(dy, M, K)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    if _precision == 'tf32':
+    if _use_tc(M, N, K):
         _call('pgv_linear_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(dx), M, N, K, _s(dy), **acct)
     else:
         _call('pgv_gemm_f32', _h(dy), 0, 0, _f(dy), N, _f(w), K, _f(dx), K, M, K, N, None, 0, None, 0, _s(dy), **acct)
@@ -291,7 +301,7 @@ def linear_wgrad(dy, x, want_bias=True):
     K = x.shape[1]
     dw = _empty(dy, N, K)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    if _precision == 'tf32':
+    if _use_tc(M, N, K):
         _call('pgv_linear_wgrad_tf32', _h(dy), _f(dy), _f(x), _f(dw), M, N, K, _s(dy), **acct)
     else:
         _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy), **acct)
