@@ -22,7 +22,7 @@ namespace pgv {
 
 enum { CONV_FWD = 0, CONV_DGRAD = 1, CONV_WGRAD = 2, DENSE_WGRAD = 3 };
 
-constexpr int CT_BLOCK_M = 128, CT_BLOCK_K = 32, CT_MAX_N = 256, CT_STAGES = 4;
+constexpr int CT_BLOCK_M = 128, CT_BLOCK_K = 32, CT_MAX_N = 128, CT_STAGES = 6;
 constexpr int CT_A_BYTES = CT_BLOCK_M * 128, CT_B_BYTES = CT_MAX_N * 128, CT_STAGE_BYTES = CT_A_BYTES + CT_B_BYTES;
 constexpr int CT_PRODUCER_WARPS = 8, CT_PRODUCERS = CT_PRODUCER_WARPS * 32;
 constexpr int CT_THREADS = CT_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
@@ -57,6 +57,10 @@ struct ConvTcParams {
     int taps_h, taps_w;             // DGRAD: taps per class along h / w
     int pix_blocks;                 // WGRAD: k-blocks per image = ceil(Ho*Wo / 32)
     int fast;                       // 1: 4x4 kernel (FWD) / 2x2 taps (DGRAD); 2: 1x1 kernel; 0: generic
+    // slot model (see Producer): element e of a chunk is at ptr + off[e-1]; ptr advances by step per k-block
+    int slot_a, slot_b;             // 1: operand uses the slot model, 0: generic chunk_a / chunk_b gathers
+    int a_off[3], b_off[3], a_vec, b_vec, a_kdim, b_kdim;   // kdim: valid length along k (tail masking)
+    long long a_step, b_step;
     int atomic_out;                 // FWD / DGRAD with k_splits > 1: accumulate into a pre-zeroed output, split 0 adds the bias
     int a_dense;                    // A is a plain row-major [M, K] matrix (Linear layers): K-contiguous vector loads
     float slope;
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_ptr, 512);
+        tmem_alloc(tmem_ptr, 2 * CT_MAX_N);
         tmem_relinquish();
     }
     tc_fence_before_sync();
@@ -332,70 +336,195 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     const int n_items = total_m_tiles(p) * p.n_tiles * p.k_splits;
 
     if (warp < CT_PRODUCER_WARPS) {
-        // ===================== producers: gather A (128 rows) and B (n_tile rows), 8 chunks per row per k-block
+        // ===================== producers: gather A (128 rows) and B (n_tile <= 128 rows), 8 chunks per row per k-block.
+        // Each thread owns 4 A slots and up to 4 B slots (a slot = one 16-byte chunk position of the tile).  For the
+        // common layer shapes a slot is {pointer, validity mask, swizzled smem offset}, set up once per tile; a
+        // k-block then costs predicated loads + one pointer increment.  The loads of k-block i+1 are issued into a
+        // second register set before k-block i is converted and stored, and the (tile, k-block) sequence is
+        // flattened so the prefetch runs across tile boundaries.
         const int t = threadIdx.x;                   // 0 .. 255
-        const int a_row = t & 127, a_c0 = t >> 7;    // A: 128 rows x 8 chunks = 1024 chunks -> 4 per thread (chunks a_c0, +2, +4, +6)
-        int stage = 0; uint32_t phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const WorkItem wi = decode_item(p, item);
-            const RowA ra = row_a<MODE>(p, wi, a_row);
-            const int b_chunks = p.n_tile * 8;
-            for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-                // Phase 1: issue EVERY global load of this k-block into registers.  Nothing here touches shared memory,
-                // so the loads are independent and overlap (and they overlap the wait for the smem slot below).
-                float va[4][4], vb[8][4];
-                int a_rows[4], a_cs[4], b_rows[8], b_cs[8];
-                if ((MODE == CONV_FWD || MODE == CONV_DGRAD) && p.a_dense) {
-                    // Linear layers: 8 consecutive threads read one 128-byte row segment (coalesced), 4 rows per thread
-                    const int rows_total = p.B, kdim = p.gemm_k;
+        const float* ap[4]; uint32_t am[4];          // am / bm: mask (bits 0-3) | chunk (bits 4-6) | smem offset << 8
+        const float* bp[4]; uint32_t bm[4];
+        RowA ra;                                      // generic-gather state
+        int b_row[4];
+
+        auto init_slots = [&](const WorkItem& wi) {
+            const int a_row = t & 127, a_c0 = t >> 7;
+            if (!p.slot_a) ra = row_a<MODE>(p, wi, a_row);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int id = t + j * CT_PRODUCERS, row = id >> 3, c = id & 7, m = wi.tm * CT_BLOCK_M + row, k0 = (kb * 8 + c) * 4;
-                        a_rows[j] = row; a_cs[j] = c;
-                        va[j][0] = va[j][1] = va[j][2] = va[j][3] = 0.f;
-                        if (m < rows_total && k0 < kdim) {
-                            const float* src = p.x + static_cast<size_t>(m) * kdim + k0;
-                            if (k0 + 4 <= kdim && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-                                const float4 q = __ldg(reinterpret_cast<const float4*>(src));
-                                va[j][0] = q.x; va[j][1] = q.y; va[j][2] = q.z; va[j][3] = q.w;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) if (k0 + e < kdim) va[j][e] = __ldg(src + e);
+            for (int j = 0; j < 4; ++j) {
+                int row = a_row, c = a_c0 + 2 * j;
+                if (p.a_dense) { const int id = t + j * CT_PRODUCERS; row = id >> 3; c = id & 7; }
+                uint32_t mask = 0;
+                const float* ptr = p.x;
+                if (p.slot_a) {
+                    const int g0 = wi.kb0 * 8 + c;                 // first global chunk of this slot
+                    if (MODE == CONV_FWD && p.a_dense) {
+                        const int m = wi.tm * CT_BLOCK_M + row;
+                        if (m < p.B) { mask = 15; ptr = p.x + static_cast<size_t>(m) * p.gemm_k + g0 * 4; }
+                    } else if (MODE == CONV_DGRAD && p.a_dense) {
+                        const int m = wi.tm * CT_BLOCK_M + row;
+                        if (m < p.B) { mask = 15; ptr = p.x + static_cast<size_t>(m) * p.gemm_k + g0 * 4; }
+                    } else if (MODE == CONV_FWD) {
+                        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
+                        uint32_t b, pix, oh, ow;
+                        p.fd_HWo.divmod(m, b, pix);
+                        if (b < static_cast<uint32_t>(p.B)) {
+                            p.fd_Wo.divmod(pix, oh, ow);
+                            const int ih0 = static_cast<int>(oh) * p.stride - p.pad, iw0 = static_cast<int>(ow) * p.stride - p.pad;
+                            const float* xb = p.x + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+                            if (p.fast == 1) {                      // 4x4: chunk = (ci, r); elements = 4 consecutive iw
+                                const int ci = g0 >> 2, r = g0 & 3, ih = ih0 + r;
+                                if (ih >= 0 && ih < p.H)
+                                    for (int e = 0; e < 4; ++e) if (iw0 + e >= 0 && iw0 + e < p.W) mask |= 1u << e;
+                                ptr = xb + (static_cast<long long>(ci) * p.H + ih) * p.W + iw0;
+                            } else {                                // 1x1: chunk = 4 consecutive ci at one pixel
+                                mask = 15;
+                                ptr = xb + static_cast<size_t>(g0) * 4 * p.H * p.W + ih0 * p.W + iw0;
                             }
                         }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a_rows[j] = a_row; a_cs[j] = a_c0 + 2 * j;
-                        chunk_a<MODE>(p, wi, ra, kb * 8 + a_cs[j], va[j]);
+                    } else if (MODE == CONV_DGRAD) {
+                        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
+                        uint32_t b, pix, i, jj;
+                        p.fd_HcWc[wi.cls].divmod(m, b, pix);
+                        if (b < static_cast<uint32_t>(p.B)) {
+                            p.fd_Wc[wi.cls].divmod(pix, i, jj);
+                            const int ih = static_cast<int>(i) * p.stride + wi.cls / p.stride, iw = static_cast<int>(jj) * p.stride + wi.cls % p.stride;
+                            const int oh0 = (ih + p.pad) / p.stride, ow0 = (iw + p.pad) / p.stride;
+                            const float* yb = p.x + static_cast<size_t>(b) * p.Cout * p.Ho * p.Wo;
+                            if (p.fast == 1) {                      // 2x2 taps: chunk = co; elements (oh0,ow0), (oh0,ow0-1), (oh0-1,ow0), (oh0-1,ow0-1)
+                                const bool h0 = oh0 >= 0 && oh0 < p.Ho, h1 = oh0 - 1 >= 0 && oh0 - 1 < p.Ho;
+                                const bool w0 = ow0 >= 0 && ow0 < p.Wo, w1 = ow0 - 1 >= 0 && ow0 - 1 < p.Wo;
+                                mask = (h0 && w0 ? 1u : 0u) | (h0 && w1 ? 2u : 0u) | (h1 && w0 ? 4u : 0u) | (h1 && w1 ? 8u : 0u);
+                                ptr = yb + static_cast<long long>(g0) * p.Ho * p.Wo + oh0 * p.Wo + ow0;
+                            } else {                                // single tap: chunk = 4 consecutive co
+                                if (oh0 >= 0 && oh0 < p.Ho && ow0 >= 0 && ow0 < p.Wo) mask = 15;
+                                ptr = yb + static_cast<long long>(g0) * 4 * p.Ho * p.Wo + oh0 * p.Wo + ow0;
+                            }
+                        }
+                    } else if (MODE == DENSE_WGRAD) {
+                        const int ci = wi.tm * CT_BLOCK_M + row;
+                        if (ci < p.Cin) { mask = 15; ptr = p.x + ci + static_cast<size_t>(g0) * 4 * p.Cin; }
                     }
                 }
+                ap[j] = ptr;
+                am[j] = mask | (static_cast<uint32_t>(c) << 4) | (sw128_offset(row, c) << 8);
+            }
+            const int b_chunks = p.n_tile * 8;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int id = t + q * CT_PRODUCERS;
-                    b_rows[q] = -1; b_cs[q] = 0;
-                    if (id < b_chunks) {
-                        // FWD weights are contiguous along k: consecutive threads take consecutive chunks of one row;
-                        // otherwise consecutive threads take consecutive rows (coalesced along n / pixels)
-                        int row, c;
-                        if (MODE == CONV_FWD) { row = id >> 3; c = id & 7; }
-                        else { uint32_t qq, rem; p.fd_ntile.divmod(static_cast<uint32_t>(id), qq, rem); row = static_cast<int>(rem); c = static_cast<int>(qq); }
-                        b_rows[q] = row; b_cs[q] = c;
-                        chunk_b<MODE>(p, wi, row, kb * 8 + c, vb[q]);
+            for (int q = 0; q < 4; ++q) {
+                const int id = t + q * CT_PRODUCERS;
+                uint32_t mask = 0; int row = -1, c = 0;
+                const float* ptr = p.w;
+                if (id < b_chunks) {
+                    if (MODE == CONV_FWD) { row = id >> 3; c = id & 7; }
+                    else { uint32_t qq, rem; p.fd_ntile.divmod(static_cast<uint32_t>(id), qq, rem); row = static_cast<int>(rem); c = static_cast<int>(qq); }
+                    const int n = wi.tn * p.n_tile + row, g0 = wi.kb0 * 8 + c;
+                    if (p.slot_b && n < p.gemm_n) {
+                        mask = 15;
+                        if (MODE == CONV_FWD) ptr = p.w + static_cast<size_t>(n) * p.gemm_k + g0 * 4;
+                        else if (MODE == CONV_DGRAD) {
+                            const int khw = p.kh * p.kw;
+                            if (p.fast == 1) {
+                                const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
+                                const int r0 = (ph + p.pad) % p.stride, s0 = (pw + p.pad) % p.stride;
+                                ptr = p.w + (static_cast<size_t>(g0) * p.Cin + n) * khw + r0 * p.kw + s0;
+                            } else ptr = p.w + static_cast<size_t>(g0) * 4 * p.Cin + n;
+                        } else if (MODE == DENSE_WGRAD) ptr = p.w + n + static_cast<size_t>(g0) * 4 * p.Cout;
                     }
                 }
-                // Phase 2: wait for the slot, convert to TF32 and store at the swizzled positions
+                b_row[q] = row;
+                bp[q] = ptr;
+                bm[q] = mask | (static_cast<uint32_t>(c) << 4) | ((row >= 0 ? sw128_offset(row, c) : 0u) << 8);
+            }
+        };
+
+        // one slot: predicated loads of the 4 elements (vector load when contiguous, aligned and fully valid)
+        auto load_slot = [&](const float*& ptr, uint32_t meta, int kb, const int (&off)[3], int vec, int kdim, long long step, float (&v)[4]) {
+            uint32_t mask = meta & 15u;
+            const int rem = kdim - (kb * 8 + static_cast<int>((meta >> 4) & 7u)) * 4;     // valid elements left along k
+            if (rem < 4) mask &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+            v[0] = v[1] = v[2] = v[3] = 0.f;
+            if (vec && mask == 15u && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(ptr));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
+                if (mask & 1u) v[0] = __ldg(ptr);
+                if (mask & 2u) v[1] = __ldg(ptr + off[0]);
+                if (mask & 4u) v[2] = __ldg(ptr + off[1]);
+                if (mask & 8u) v[3] = __ldg(ptr + off[2]);
+            }
+            ptr += step;
+        };
+        auto load_kb = [&](const WorkItem& wi, int kb, float (&va)[4][4], float (&vb)[4][4]) {
+            if (p.slot_a) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_slot(ap[j], am[j], kb, p.a_off, p.a_vec, p.a_kdim, p.a_step, va[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) chunk_a<MODE>(p, wi, ra, kb * 8 + static_cast<int>((am[j] >> 4) & 7u), va[j]);
+            }
+            if (p.slot_b) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (b_row[q] >= 0) load_slot(bp[q], bm[q], kb, p.b_off, p.b_vec, p.b_kdim, p.b_step, vb[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (b_row[q] >= 0) chunk_b<MODE>(p, wi, b_row[q], kb * 8 + static_cast<int>((bm[q] >> 4) & 7u), vb[q]);
+            }
+        };
+
+        int stage = 0; uint32_t phase = 0;
+        int item = blockIdx.x;
+        if (item < n_items) {
+            WorkItem wi = decode_item(p, item);
+            int kb = wi.kb0;
+            init_slots(wi);
+            float va[4][4], vb[4][4], na[4][4], nb[4][4];
+            uint32_t cur_am[4], cur_bm[4];
+            load_kb(wi, kb, va, vb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { cur_am[j] = am[j]; cur_bm[j] = bm[j]; }
+            bool cur_b_valid[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cur_b_valid[q] = b_row[q] >= 0;
+            while (true) {
+                // advance the issue cursor and prefetch the next k-block (possibly of the next tile)
+                bool have_next = true;
+                int nkb = kb + 1;
+                WorkItem nwi = wi;
+                if (nkb >= wi.kb1) {
+                    item += gridDim.x;
+                    if (item < n_items) { nwi = decode_item(p, item); nkb = nwi.kb0; init_slots(nwi); }
+                    else have_next = false;
+                }
+                if (have_next) load_kb(nwi, nkb, na, nb);
+                // store the current k-block
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 uint8_t* sA = smem + stage * CT_STAGE_BYTES;
                 uint8_t* sB = sA + CT_A_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) st_chunk(sA, a_rows[j], a_cs[j], va[j]);
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(sA + (cur_am[j] >> 8)) =
+                        make_float4(to_tf32_rna(va[j][0]), to_tf32_rna(va[j][1]), to_tf32_rna(va[j][2]), to_tf32_rna(va[j][3]));
 #pragma unroll
-                for (int q = 0; q < 8; ++q) if (b_rows[q] >= 0) st_chunk(sB, b_rows[q], b_cs[q], vb[q]);
+                for (int q = 0; q < 4; ++q)
+                    if (cur_b_valid[q])
+                        *reinterpret_cast<float4*>(sB + (cur_bm[q] >> 8)) =
+                            make_float4(to_tf32_rna(vb[q][0]), to_tf32_rna(vb[q][1]), to_tf32_rna(vb[q][2]), to_tf32_rna(vb[q][3]));
                 fence_proxy_async_smem();
                 mbar_arrive(&bar_full[stage]);
                 if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+                if (!have_next) break;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cur_am[j] = am[j]; cur_bm[j] = bm[j]; cur_b_valid[j] = b_row[j] >= 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { va[j][e] = na[j][e]; vb[j][e] = nb[j][e]; }
+                }
+                wi = nwi; kb = nkb;
             }
         }
     } else if (warp == MMA_WARP) {
@@ -496,7 +625,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * CT_MAX_N);
 }
 
 static int pick_n_tile(int n) {
@@ -575,6 +704,9 @@ int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.m_tiles_class[0] = static_cast<int>((static_cast<long long>(B) * Ho * Wo + CT_BLOCK_M - 1) / CT_BLOCK_M);
     p.fast = (kh == 4 && kw == 4) ? 1 : ((kh == 1 && kw == 1) ? 2 : 0);
     p.fd_ntile.init(p.n_tile);
+    if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 2LL * H * W; p.a_kdim = p.gemm_k; }
+    if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = H * W; p.a_off[1] = 2 * H * W; p.a_off[2] = 3 * H * W; p.a_step = 32LL * H * W; p.a_kdim = p.gemm_k; }
+    p.slot_b = 1; p.b_off[0] = 1; p.b_off[1] = 2; p.b_off[2] = 3; p.b_step = 32; p.b_kdim = p.gemm_k; p.b_vec = (p.gemm_k % 4 == 0);
     if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cout * Ho * Wo, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
 }
@@ -602,6 +734,12 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
     p.fast = (p.taps_h == 2 && p.taps_w == 2) ? 1 : ((p.taps_h == 1 && p.taps_w == 1) ? 2 : 0);
     p.fd_dtaps.init(p.taps_h * p.taps_w); p.fd_dtapsw.init(p.taps_w); p.fd_ntile.init(p.n_tile);
     p.a_dense = (H == 1 && W == 1 && Ho == 1 && Wo == 1 && kh == 1 && kw == 1) ? 1 : 0;   // Linear dgrad: A = dy [M, N] row-major
+    const int HWo = Ho * Wo, khw = kh * kw;
+    if (p.a_dense) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 32; p.a_kdim = p.gemm_k; p.a_vec = (p.gemm_k % 4 == 0); }
+    else if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = -1; p.a_off[1] = -Wo; p.a_off[2] = -Wo - 1; p.a_step = 8LL * HWo; p.a_kdim = p.gemm_k; }
+    else if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = HWo; p.a_off[1] = 2 * HWo; p.a_off[2] = 3 * HWo; p.a_step = 32LL * HWo; p.a_kdim = p.gemm_k; }
+    if (p.fast == 1) { p.slot_b = 1; p.b_off[0] = stride; p.b_off[1] = stride * kw; p.b_off[2] = stride * kw + stride; p.b_step = 8LL * Cin * khw; p.b_kdim = p.gemm_k; }
+    else if (p.fast == 2) { p.slot_b = 1; p.b_off[0] = Cin; p.b_off[1] = 2 * Cin; p.b_off[2] = 3 * Cin; p.b_step = 32LL * Cin; p.b_kdim = p.gemm_k; }
     if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cin * H * W, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_DGRAD>(h, p, static_cast<cudaStream_t>(stream));
 }
@@ -643,6 +781,8 @@ int pgv_linear_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.m_tiles_class[0] = ceil_div(M, CT_BLOCK_M);
     p.fast = 2; p.a_dense = 1;
     p.fd_ntile.init(p.n_tile);
+    p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 32; p.a_kdim = K; p.a_vec = (K % 4 == 0);
+    p.slot_b = 1; p.b_off[0] = 1; p.b_off[1] = 2; p.b_off[2] = 3; p.b_step = 32; p.b_kdim = K; p.b_vec = (K % 4 == 0);
     if (int rc = maybe_split_k(h, p, static_cast<size_t>(M) * N, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_FWD>(h, p, static_cast<cudaStream_t>(stream));
 }
@@ -661,6 +801,8 @@ int pgv_linear_wgrad_tf32(pgv_handle* h, const float* dy, const float* x, float*
     p.kb_total = ceil_div(M, CT_BLOCK_K); p.kb_per_split = p.kb_total;
     p.m_tiles_class[0] = ceil_div(K, CT_BLOCK_M);
     p.fd_ntile.init(p.n_tile);
+    p.slot_a = 1; p.a_off[0] = K; p.a_off[1] = 2 * K; p.a_off[2] = 3 * K; p.a_step = 32LL * K; p.a_kdim = M;
+    p.slot_b = 1; p.b_off[0] = N; p.b_off[1] = 2 * N; p.b_off[2] = 3 * N; p.b_step = 32LL * N; p.b_kdim = M;
     return launch_conv_tc<DENSE_WGRAD>(h, p, static_cast<cudaStream_t>(stream));
 }
 
