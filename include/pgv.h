@@ -132,6 +132,9 @@ PGV_API int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w
                                   int Cout, int kh, int kw, int stride, int pad, int Ho, int Wo, float lrelu_slope, pgv_stream_t stream);
 PGV_API int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout, int kh,
                                   int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+/* Debug: subsequent pgv_conv2d_*_tf32 / pgv_linear_*_tf32 launches record pipeline timestamps of CTA 0 into trace_dev
+ * (3 x 64 x 8 int64, device memory); NULL disables.  Used by tools/gpu_trace_conv.py only. */
+PGV_API int pgv_debug_set_conv_trace(void* trace_dev);
 /* Direct streaming kernels (exact fp32) for the two thin full-resolution layers, enc1 = Conv2d(1,8,5,2,2)
  * (encoder.py:241) and dec8 = ConvTranspose2d(8,1,5,2,2) (decoder.py:218), which are HBM-bound (8 flop/byte).  Conv-view
  * geometry: x [B,1,H,W], y [B,C<=8,Ho,Wo], w [C,1,5,5], stride 2, pad 2.  _dgrad is the transposed convolution and

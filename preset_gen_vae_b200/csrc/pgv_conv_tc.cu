@@ -61,6 +61,7 @@ struct ConvTcParams {
     int slot_a, slot_b;             // 1: operand uses the slot model, 0: generic chunk_a / chunk_b gathers
     int a_off[3], b_off[3], a_vec, b_vec, a_kdim, b_kdim;   // kdim: valid length along k (tail masking)
     long long a_step, b_step;
+    long long* trace;               // debug: clock64 timestamps of CTA 0 (NULL in production)
     int atomic_out;                 // FWD / DGRAD with k_splits > 1: accumulate into a pre-zeroed output, split 0 adds the bias
     int a_dense;                    // A is a plain row-major [M, K] matrix (Linear layers): K-contiguous vector loads
     float slope;
@@ -305,6 +306,11 @@ __device__ __forceinline__ void chunk_b(const ConvTcParams& p, const WorkItem& w
     }
 }
 
+// trace layout: [role][event_index][field]; role 0 producer thread 0, 1 MMA thread, 2 epilogue thread
+__device__ __forceinline__ void trace_evt(const ConvTcParams& p, int role, int& n, int field, long long v) {
+    if (p.trace != nullptr && blockIdx.x == 0 && n < 64) p.trace[(role * 64 + n) * 8 + field] = v;
+}
+
 __device__ __forceinline__ float act_lrelu(float v, float slope) { return (slope >= 0.0f && v < 0.0f) ? v * slope : v; }
 
 template <int MODE>
@@ -478,6 +484,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
 
         int stage = 0; uint32_t phase = 0;
         int item = blockIdx.x;
+        int trace_n = 0;
         if (item < n_items) {
             WorkItem wi = decode_item(p, item);
             int kb = wi.kb0;
@@ -500,9 +507,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (item < n_items) { nwi = decode_item(p, item); nkb = nwi.kb0; init_slots(nwi); }
                     else have_next = false;
                 }
+                long long t_a = 0, t_b = 0, t_c = 0, t_d = 0, t_e = 0;
+                if (p.trace && t == 0) t_a = clock64();
                 if (have_next) load_kb(nwi, nkb, na, nb);
+                if (p.trace && t == 0) t_b = clock64();
                 // store the current k-block
                 mbar_wait(&bar_empty[stage], phase ^ 1);
+                if (p.trace && t == 0) t_c = clock64();
                 uint8_t* sA = smem + stage * CT_STAGE_BYTES;
                 uint8_t* sB = sA + CT_A_BYTES;
 #pragma unroll
@@ -514,8 +525,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (cur_b_valid[q])
                         *reinterpret_cast<float4*>(sB + (cur_bm[q] >> 8)) =
                             make_float4(to_tf32_rna(vb[q][0]), to_tf32_rna(vb[q][1]), to_tf32_rna(vb[q][2]), to_tf32_rna(vb[q][3]));
+                if (p.trace && t == 0) t_d = clock64();
                 fence_proxy_async_smem();
+                if (p.trace && t == 0) t_e = clock64();
                 mbar_arrive(&bar_full[stage]);
+                if (p.trace && t == 0) {
+                    trace_evt(p, 0, trace_n, 0, t_a); trace_evt(p, 0, trace_n, 1, t_b); trace_evt(p, 0, trace_n, 2, t_c);
+                    trace_evt(p, 0, trace_n, 3, t_d); trace_evt(p, 0, trace_n, 4, t_e); trace_evt(p, 0, trace_n, 5, clock64());
+                    trace_evt(p, 0, trace_n, 6, kb); ++trace_n;
+                }
                 if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
                 if (!have_next) break;
 #pragma unroll
@@ -531,19 +549,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(CT_BLOCK_M, p.n_tile);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            int trace_n = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const WorkItem wi = decode_item(p, item);
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * CT_MAX_N;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    const long long t_a = p.trace ? clock64() : 0;
                     mbar_wait(&bar_full[stage], phase);
+                    if (p.trace) { trace_evt(p, 1, trace_n, 0, t_a); trace_evt(p, 1, trace_n, 1, clock64()); trace_evt(p, 1, trace_n, 6, kb); }
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(smem + stage * CT_STAGE_BYTES);
                     const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + CT_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < CT_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
                     umma_commit(&bar_empty[stage]);
+                    if (p.trace) { trace_evt(p, 1, trace_n, 2, clock64()); ++trace_n; }
                     if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&bar_tfull[acc]);
@@ -555,6 +577,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===================== epilogue: TMEM -> registers -> global
         const int quad = warp & 3, row = quad * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
+        int etrace_n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const WorkItem wi = decode_item(p, item);
             // destination of this thread's row
@@ -587,7 +610,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 row_ok = m < Kc;
                 if (row_ok) { dst = p.out + static_cast<size_t>(wi.tn * p.n_tile) * Kc + m; col_stride = Kc; }
             }
+            const long long te_a = p.trace ? clock64() : 0;
             mbar_wait(&bar_tfull[acc], acc_phase);
+            const long long te_b = p.trace ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * CT_MAX_N + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
@@ -619,6 +644,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            if (p.trace && warp == EPI_WARP0 && lane == 0) {
+                trace_evt(p, 2, etrace_n, 0, te_a); trace_evt(p, 2, etrace_n, 1, te_b); trace_evt(p, 2, etrace_n, 2, clock64()); ++etrace_n;
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -628,6 +656,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * CT_MAX_N);
 }
 
+extern long long* g_conv_trace_ptr;
 static int pick_n_tile(int n) {
     int t = (n + 15) / 16 * 16;
     if (t > CT_MAX_N) {
@@ -666,6 +695,7 @@ static int launch_conv_tc(const pgv_handle* h, ConvTcParams& p, cudaStream_t str
     for (int c = 0; c < p.classes; ++c) m_tiles += p.m_tiles_class[c];
     const long long items = static_cast<long long>(m_tiles) * p.n_tiles * p.k_splits;
     const int grid = static_cast<int>(items < h->sm_count ? items : h->sm_count);
+    p.trace = g_conv_trace_ptr;
     conv_tc_kernel<MODE><<<grid, CT_THREADS, CT_SMEM, stream>>>(p);
     PGV_LAUNCH_CHECK();
     return 0;
@@ -685,6 +715,8 @@ static int fill_common(ConvTcParams& p, const char* who, int B, int Cin, int H, 
     for (int c = 0; c < 4; ++c) { p.fd_HcWc[c].init(1); p.fd_Wc[c].init(1); }
     return 0;
 }
+
+long long* g_conv_trace_ptr = nullptr;
 
 }  // namespace pgv
 
@@ -743,6 +775,10 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
     if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cin * H * W, static_cast<cudaStream_t>(stream))) return rc;
     return launch_conv_tc<CONV_DGRAD>(h, p, static_cast<cudaStream_t>(stream));
 }
+
+/* Debug hook (tools/gpu_trace_conv.py): the next pgv_conv2d_*_tf32 launches record CTA 0's pipeline timestamps into
+ * `trace_dev` (3 roles x 64 events x 8 int64).  Pass NULL to disable. */
+int pgv_debug_set_conv_trace(void* trace_dev) { pgv::g_conv_trace_ptr = static_cast<long long*>(trace_dev); return 0; }
 
 int pgv_conv2d_wgrad_tf32(pgv_handle* h, const float* x, const float* dy, float* dw, int B, int Cin, int H, int W, int Cout, int kh,
                           int kw, int stride, int pad, int Ho, int Wo, pgv_stream_t stream_) {

@@ -22,7 +22,9 @@ class TrainStep:
     def __init__(self, model_config, train_config, idx_helper, device=None, process_group=None, use_cuda_graph=True,
                  spec_stats=None, beta=None, seed=0):
         self.mc, self.tc, self.idx_helper = model_config, train_config, idx_helper
-        self.device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.use_graph = use_cuda_graph
