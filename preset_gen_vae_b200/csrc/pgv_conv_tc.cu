@@ -61,6 +61,7 @@ struct ConvTcParams {
     int slot_a, slot_b;             // 1: operand uses the slot model, 0: generic chunk_a / chunk_b gathers
     int a_off[3], b_off[3], a_vec, b_vec, a_kdim, b_kdim;   // kdim: valid length along k (tail masking)
     long long a_step, b_step;
+    int sshift;                     // log2(stride) (stride is 1 or 2 on every tensor-core path)
     long long* trace;               // debug: clock64 timestamps of CTA 0 (NULL in production)
     int atomic_out;                 // FWD / DGRAD with k_splits > 1: accumulate into a pre-zeroed output, split 0 adds the bias
     int a_dense;                    // A is a plain row-major [M, K] matrix (Linear layers): K-contiguous vector loads
@@ -356,7 +357,42 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
 
         auto init_slots = [&](const WorkItem& wi) {
             const int a_row = t & 127, a_c0 = t >> 7;
-            if (!p.slot_a) ra = row_a<MODE>(p, wi, a_row);
+            const int smask = p.stride - 1;            // stride is a power of two: divisions become shifts / masks
+            // ---- row-level state, shared by the 4 A slots of this thread (non-dense operands) ----
+            bool row_ok = false;
+            const float* rbase = p.x;
+            int r_i = 0, r_j = 0;                       // FWD: ih0, iw0      DGRAD: oh0, ow0
+            uint32_t hm = 0, wm = 0;
+            if (!p.slot_a) {
+                ra = row_a<MODE>(p, wi, a_row);
+            } else if (!p.a_dense && (MODE == CONV_FWD || MODE == CONV_DGRAD)) {
+                const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + a_row;
+                uint32_t b, pix, i, jj;
+                if (MODE == CONV_FWD) {
+                    p.fd_HWo.divmod(m, b, pix);
+                    row_ok = b < static_cast<uint32_t>(p.B);
+                    p.fd_Wo.divmod(pix, i, jj);
+                    r_i = (static_cast<int>(i) << p.sshift) - p.pad;
+                    r_j = (static_cast<int>(jj) << p.sshift) - p.pad;
+                    rbase = p.x + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+                    for (int e = 0; e < 4; ++e) {
+                        if (r_i + e >= 0 && r_i + e < p.H) hm |= 1u << e;
+                        if (r_j + e >= 0 && r_j + e < p.W) wm |= 1u << e;
+                    }
+                } else {
+                    p.fd_HcWc[wi.cls].divmod(m, b, pix);
+                    row_ok = b < static_cast<uint32_t>(p.B);
+                    p.fd_Wc[wi.cls].divmod(pix, i, jj);
+                    const int ih = (static_cast<int>(i) << p.sshift) + (wi.cls >> p.sshift), iw = (static_cast<int>(jj) << p.sshift) + (wi.cls & smask);
+                    r_i = (ih + p.pad) >> p.sshift;
+                    r_j = (iw + p.pad) >> p.sshift;
+                    rbase = p.x + static_cast<size_t>(b) * p.Cout * p.Ho * p.Wo;
+                    for (int e = 0; e < 2; ++e) {
+                        if (r_i - e >= 0 && r_i - e < p.Ho) hm |= 1u << e;
+                        if (r_j - e >= 0 && r_j - e < p.Wo) wm |= 1u << e;
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int row = a_row, c = a_c0 + 2 * j;
@@ -365,47 +401,29 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 const float* ptr = p.x;
                 if (p.slot_a) {
                     const int g0 = wi.kb0 * 8 + c;                 // first global chunk of this slot
-                    if (MODE == CONV_FWD && p.a_dense) {
-                        const int m = wi.tm * CT_BLOCK_M + row;
-                        if (m < p.B) { mask = 15; ptr = p.x + static_cast<size_t>(m) * p.gemm_k + g0 * 4; }
-                    } else if (MODE == CONV_DGRAD && p.a_dense) {
+                    if ((MODE == CONV_FWD || MODE == CONV_DGRAD) && p.a_dense) {
                         const int m = wi.tm * CT_BLOCK_M + row;
                         if (m < p.B) { mask = 15; ptr = p.x + static_cast<size_t>(m) * p.gemm_k + g0 * 4; }
                     } else if (MODE == CONV_FWD) {
-                        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
-                        uint32_t b, pix, oh, ow;
-                        p.fd_HWo.divmod(m, b, pix);
-                        if (b < static_cast<uint32_t>(p.B)) {
-                            p.fd_Wo.divmod(pix, oh, ow);
-                            const int ih0 = static_cast<int>(oh) * p.stride - p.pad, iw0 = static_cast<int>(ow) * p.stride - p.pad;
-                            const float* xb = p.x + static_cast<size_t>(b) * p.Cin * p.H * p.W;
+                        if (row_ok) {
                             if (p.fast == 1) {                      // 4x4: chunk = (ci, r); elements = 4 consecutive iw
-                                const int ci = g0 >> 2, r = g0 & 3, ih = ih0 + r;
-                                if (ih >= 0 && ih < p.H)
-                                    for (int e = 0; e < 4; ++e) if (iw0 + e >= 0 && iw0 + e < p.W) mask |= 1u << e;
-                                ptr = xb + (static_cast<long long>(ci) * p.H + ih) * p.W + iw0;
+                                const int ci = g0 >> 2, r = g0 & 3;
+                                if ((hm >> r) & 1u) mask = wm;
+                                ptr = rbase + (static_cast<long long>(ci) * p.H + r_i + r) * p.W + r_j;
                             } else {                                // 1x1: chunk = 4 consecutive ci at one pixel
                                 mask = 15;
-                                ptr = xb + static_cast<size_t>(g0) * 4 * p.H * p.W + ih0 * p.W + iw0;
+                                ptr = rbase + static_cast<size_t>(g0) * 4 * p.H * p.W + r_i * p.W + r_j;
                             }
                         }
                     } else if (MODE == CONV_DGRAD) {
-                        const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
-                        uint32_t b, pix, i, jj;
-                        p.fd_HcWc[wi.cls].divmod(m, b, pix);
-                        if (b < static_cast<uint32_t>(p.B)) {
-                            p.fd_Wc[wi.cls].divmod(pix, i, jj);
-                            const int ih = static_cast<int>(i) * p.stride + wi.cls / p.stride, iw = static_cast<int>(jj) * p.stride + wi.cls % p.stride;
-                            const int oh0 = (ih + p.pad) / p.stride, ow0 = (iw + p.pad) / p.stride;
-                            const float* yb = p.x + static_cast<size_t>(b) * p.Cout * p.Ho * p.Wo;
-                            if (p.fast == 1) {                      // 2x2 taps: chunk = co; elements (oh0,ow0), (oh0,ow0-1), (oh0-1,ow0), (oh0-1,ow0-1)
-                                const bool h0 = oh0 >= 0 && oh0 < p.Ho, h1 = oh0 - 1 >= 0 && oh0 - 1 < p.Ho;
-                                const bool w0 = ow0 >= 0 && ow0 < p.Wo, w1 = ow0 - 1 >= 0 && ow0 - 1 < p.Wo;
+                        if (row_ok) {
+                            if (p.fast == 1) {                      // 2x2 taps: (oh0,ow0), (oh0,ow0-1), (oh0-1,ow0), (oh0-1,ow0-1)
+                                const bool h0 = hm & 1u, h1 = hm & 2u, w0 = wm & 1u, w1 = wm & 2u;
                                 mask = (h0 && w0 ? 1u : 0u) | (h0 && w1 ? 2u : 0u) | (h1 && w0 ? 4u : 0u) | (h1 && w1 ? 8u : 0u);
-                                ptr = yb + static_cast<long long>(g0) * p.Ho * p.Wo + oh0 * p.Wo + ow0;
+                                ptr = rbase + static_cast<long long>(g0) * p.Ho * p.Wo + r_i * p.Wo + r_j;
                             } else {                                // single tap: chunk = 4 consecutive co
-                                if (oh0 >= 0 && oh0 < p.Ho && ow0 >= 0 && ow0 < p.Wo) mask = 15;
-                                ptr = yb + static_cast<long long>(g0) * 4 * p.Ho * p.Wo + oh0 * p.Wo + ow0;
+                                if ((hm & 1u) && (wm & 1u)) mask = 15;
+                                ptr = rbase + static_cast<long long>(g0) * 4 * p.Ho * p.Wo + r_i * p.Wo + r_j;
                             }
                         }
                     } else if (MODE == DENSE_WGRAD) {
@@ -417,6 +435,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 am[j] = mask | (static_cast<uint32_t>(c) << 4) | (sw128_offset(row, c) << 8);
             }
             const int b_chunks = p.n_tile * 8;
+            const int r0s0 = (MODE == CONV_DGRAD) ? ((((wi.cls >> p.sshift) + p.pad) & smask) * p.kw + (((wi.cls & smask) + p.pad) & smask)) : 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int id = t + q * CT_PRODUCERS;
@@ -430,12 +449,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                         mask = 15;
                         if (MODE == CONV_FWD) ptr = p.w + static_cast<size_t>(n) * p.gemm_k + g0 * 4;
                         else if (MODE == CONV_DGRAD) {
-                            const int khw = p.kh * p.kw;
-                            if (p.fast == 1) {
-                                const int ph = wi.cls / p.stride, pw = wi.cls % p.stride;
-                                const int r0 = (ph + p.pad) % p.stride, s0 = (pw + p.pad) % p.stride;
-                                ptr = p.w + (static_cast<size_t>(g0) * p.Cin + n) * khw + r0 * p.kw + s0;
-                            } else ptr = p.w + static_cast<size_t>(g0) * 4 * p.Cin + n;
+                            if (p.fast == 1) ptr = p.w + (static_cast<size_t>(g0) * p.Cin + n) * (p.kh * p.kw) + r0s0;
+                            else ptr = p.w + static_cast<size_t>(g0) * 4 * p.Cin + n;
                         } else if (MODE == DENSE_WGRAD) ptr = p.w + n + static_cast<size_t>(g0) * 4 * p.Cout;
                     }
                 }
@@ -601,7 +616,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 row_ok = b < static_cast<uint32_t>(p.B);
                 if (row_ok) {
                     p.fd_Wc[wi.cls].divmod(pix, i, j);
-                    const int ih = static_cast<int>(i) * p.stride + wi.cls / p.stride, iw = static_cast<int>(j) * p.stride + wi.cls % p.stride;
+                    const int ih = (static_cast<int>(i) << p.sshift) + (wi.cls >> p.sshift), iw = (static_cast<int>(j) << p.sshift) + (wi.cls & (p.stride - 1));
                     dst = p.out + ((static_cast<size_t>(b) * p.Cin + wi.tn * p.n_tile) * p.H + ih) * p.W + iw;
                     col_stride = static_cast<size_t>(p.H) * p.W;
                 }
@@ -619,24 +634,29 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c = 0; c < p.n_tile; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c, v);
+                float bv[16];
+                const int nbase = wi.tn * p.n_tile + c;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)   // all bias loads first: independent of the stores below
+                    bv[j] = (MODE != CONV_WGRAD && MODE != DENSE_WGRAD && p.bias != nullptr && nbase + j < p.gemm_n &&
+                             (!p.atomic_out || wi.kb0 == 0)) ? __ldg(p.bias + nbase + j) : 0.0f;
                 tmem_ld_wait();
                 if (!row_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int n = wi.tn * p.n_tile + c + j;
+                    const int n = nbase + j;
                     if (n < p.gemm_n) {
-                        float val = __uint_as_float(v[j]);
+                        float val = __uint_as_float(v[j]) + bv[j];
+                        float* o = dst + static_cast<size_t>(c + j) * col_stride;
                         if (MODE == CONV_WGRAD) {
-                            atomicAdd(dst + static_cast<size_t>(c + j) * col_stride, val);
+                            atomicAdd(o, val);
                         } else if (MODE == DENSE_WGRAD) {
-                            dst[static_cast<size_t>(c + j) * col_stride] = val;
+                            *o = val;
                         } else if (p.atomic_out) {
-                            if (p.bias != nullptr && wi.kb0 == 0) val += p.bias[n];
-                            atomicAdd(dst + static_cast<size_t>(c + j) * col_stride, val);
+                            atomicAdd(o, val);
                         } else {
-                            if (p.bias != nullptr) val += p.bias[n];
-                            if (MODE == CONV_FWD && p.residual != nullptr) val += p.residual[(dst - p.out) + static_cast<size_t>(c + j) * col_stride];
-                            dst[static_cast<size_t>(c + j) * col_stride] = act_lrelu(val, p.slope);
+                            if (MODE == CONV_FWD && p.residual != nullptr) val += __ldg(p.residual + (o - p.out));
+                            *o = act_lrelu(val, p.slope);
                         }
                     }
                 }
@@ -709,7 +729,7 @@ static int fill_common(ConvTcParams& p, const char* who, int B, int Cin, int H, 
         return set_error(-1, "%s: output %dx%d does not fit input %dx%d", who, Ho, Wo, H, W);
     memset(&p, 0, sizeof(p));
     p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.Ho = Ho; p.Wo = Wo;
-    p.classes = 1; p.k_splits = 1;
+    p.classes = 1; p.k_splits = 1; p.sshift = (stride == 2) ? 1 : 0;
     p.fd_HWo.init(Ho * Wo); p.fd_Wo.init(Wo); p.fd_taps.init(kh * kw); p.fd_kw.init(kw);
     p.fd_dtaps.init(1); p.fd_dtapsw.init(1); p.fd_pixblocks.init(1); p.fd_ntile.init(1);
     for (int c = 0; c < 4; ++c) { p.fd_HcWc[c].init(1); p.fd_Wc[c].init(1); }
@@ -735,6 +755,7 @@ int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.kb_total = ceil_div(p.gemm_k, CT_BLOCK_K); p.kb_per_split = p.kb_total;
     p.m_tiles_class[0] = static_cast<int>((static_cast<long long>(B) * Ho * Wo + CT_BLOCK_M - 1) / CT_BLOCK_M);
     p.fast = (kh == 4 && kw == 4) ? 1 : ((kh == 1 && kw == 1) ? 2 : 0);
+    if (stride != 1 && stride != 2) p.fast = 0;      // the slot fast paths use shift arithmetic for the stride
     p.fd_ntile.init(p.n_tile);
     if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 2LL * H * W; p.a_kdim = p.gemm_k; }
     if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = H * W; p.a_off[1] = 2 * H * W; p.a_off[2] = 3 * H * W; p.a_step = 32LL * H * W; p.a_kdim = p.gemm_k; }

@@ -127,6 +127,69 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
         }
 }
 
+// Small-problem variant (flow conditioner layers: M = batch <= ~1k, N, K ~ 300-610): 32x32 output tile per block, 256
+// threads with 2x2 outputs each, K step 32, next k-chunk prefetched into registers while the current one is multiplied.
+// A 160x300x300 layer becomes 50 blocks of 10 short iterations instead of 15 blocks of 19 long ones.
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_f32_small_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                             float* __restrict__ c, int ldc, int m, int n, int k,
+                                                             const float* __restrict__ bias, int act, const float* __restrict__ residual, int ldr) {
+    __shared__ float sa[32][33], sb[32][33];          // [k][row]
+    const int t = threadIdx.x, m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = t & 15, ty = t >> 4;               // outputs (ty*2 + i, tx*2 + j)
+    // loader mapping: 1024 elements per operand per chunk -> 4 per thread; contiguous storage dimension fastest
+    int ar[4], ak[4], br[4], bk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int id = t + q * 256;
+        ar[q] = TA ? (id & 31) : (id >> 5); ak[q] = TA ? (id >> 5) : (id & 31);
+        br[q] = TB ? (id >> 5) : (id & 31); bk[q] = TB ? (id & 31) : (id >> 5);
+    }
+    auto lda_ = [&](int q, int k0) -> float {
+        const int r = m0 + ar[q], kk = k0 + ak[q];
+        if (r >= m || kk >= k) return 0.0f;
+        return TA ? __ldg(a + static_cast<size_t>(kk) * lda + r) : __ldg(a + static_cast<size_t>(r) * lda + kk);
+    };
+    auto ldb_ = [&](int q, int k0) -> float {
+        const int r = n0 + br[q], kk = k0 + bk[q];
+        if (r >= n || kk >= k) return 0.0f;
+        return TB ? __ldg(b + static_cast<size_t>(r) * ldb + kk) : __ldg(b + static_cast<size_t>(kk) * ldb + r);
+    };
+    float pa[4], pb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { pa[q] = lda_(q, 0); pb[q] = ldb_(q, 0); }
+    float acc[2][2] = {};
+    for (int k0 = 0; k0 < k; k0 += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sa[ak[q]][ar[q]] = pa[q]; sb[bk[q]][br[q]] = pb[q]; }
+        __syncthreads();
+        if (k0 + 32 < k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { pa[q] = lda_(q, k0 + 32); pb[q] = ldb_(q, k0 + 32); }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+            const float a0 = sa[kk][ty * 2], a1 = sa[kk][ty * 2 + 1], b0 = sb[kk][tx * 2], b1 = sb[kk][tx * 2 + 1];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = m0 + ty * 2 + i, col = n0 + tx * 2 + j;
+            if (r < m && col < n) {
+                float x = acc[i][j];
+                if (bias) x += bias[col];
+                if (residual) x += residual[static_cast<size_t>(r) * ldr + col];
+                if (act == 1) x = fmaxf(x, 0.0f);
+                c[static_cast<size_t>(r) * ldc + col] = x;
+            }
+        }
+}
+
 }  // namespace pgv
 
 using namespace pgv;
@@ -175,6 +238,17 @@ int pgv_gemm_f32(pgv_handle* h, int trans_a, int trans_b, const float* a, int ld
     PGV_CHECK_ARG(h && a && b && c, "pgv_gemm_f32: NULL argument");
     PGV_CHECK_ARG(m > 0 && n > 0 && k > 0, "pgv_gemm_f32: empty problem");
     PGV_CHECK_ARG(act == 0 || act == 1, "pgv_gemm_f32: unknown activation %d", act);
+    if (static_cast<long long>(m) * n <= 1024LL * 1024 && k <= 4096) {   // small problem: many small tiles beat few big ones
+        dim3 g(ceil_div(n, 32), ceil_div(m, 32));
+#define PGV_SMALL_LAUNCH(TA, TB) gemm_f32_small_kernel<TA, TB><<<g, 256, 0, stream>>>(a, lda, b, ldb, c, ldc, m, n, k, bias, act, residual, ldr)
+        if (!trans_a && !trans_b) PGV_SMALL_LAUNCH(0, 0);
+        else if (!trans_a && trans_b) PGV_SMALL_LAUNCH(0, 1);
+        else if (trans_a && !trans_b) PGV_SMALL_LAUNCH(1, 0);
+        else PGV_SMALL_LAUNCH(1, 1);
+#undef PGV_SMALL_LAUNCH
+        PGV_LAUNCH_CHECK();
+        return 0;
+    }
     const int tiles = ceil_div(n, 64) * ceil_div(m, 64);
     int splits = 1;
     if (act == 0 && k >= 2048 && tiles < h->sm_count * 2) {   // long-K, few tiles: split K to fill the chip

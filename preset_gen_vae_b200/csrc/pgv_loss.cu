@@ -344,9 +344,9 @@ int pgv_synth_loss_bwd(const float* grad_out, const float* v_out, const float* v
 
 int pgv_multi_pack(const void* table_dev, int n_tensors, size_t max_elems, float* flat, float scale, pgv_stream_t stream) {
     PGV_CHECK_ARG(table_dev && flat && n_tensors > 0, "pgv_multi_pack: bad argument");
-    size_t bx = (max_elems + 256 * 8 - 1) / (256 * 8);
+    size_t bx = (max_elems + 256 * 16 - 1) / (256 * 16);     // blocks beyond a tensor's size exit at once
     if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
+    if (bx > 2048) bx = 2048;
     multi_pack_kernel<<<dim3(static_cast<unsigned>(bx), n_tensors), 256, 0, PGV_STREAM(stream)>>>(
         static_cast<const unsigned long long*>(table_dev), flat, scale);
     PGV_LAUNCH_CHECK();
