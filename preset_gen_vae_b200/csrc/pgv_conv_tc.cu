@@ -61,11 +61,14 @@ struct ConvTcParams {
     int slot_a, slot_b;             // 1: operand uses the slot model, 0: generic chunk_a / chunk_b gathers
     int a_off[3], b_off[3], a_vec, b_vec, a_kdim, b_kdim;   // kdim: valid length along k (tail masking)
     long long a_step, b_step;
+    int quad;                       // DGRAD 4x4 / stride 2 / even pad: the 4 parity classes of a 2x2 pixel quad share one A row
+                                    // (same 2x2 dy patch) and are stacked along N: column n = class * Cin + ci
     int sshift;                     // log2(stride) (stride is 1 or 2 on every tensor-core path)
     long long* trace;               // debug: clock64 timestamps of CTA 0 (NULL in production)
     int atomic_out;                 // FWD / DGRAD with k_splits > 1: accumulate into a pre-zeroed output, split 0 adds the bias
     int a_dense;                    // A is a plain row-major [M, K] matrix (Linear layers): K-contiguous vector loads
     float slope;
+    FastDiv fd_Cin;
     FastDiv fd_HWo, fd_Wo, fd_taps, fd_kw, fd_dtaps, fd_dtapsw, fd_pixblocks, fd_ntile, fd_HcWc[4], fd_Wc[4];
 };
 
@@ -449,7 +452,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                         mask = 15;
                         if (MODE == CONV_FWD) ptr = p.w + static_cast<size_t>(n) * p.gemm_k + g0 * 4;
                         else if (MODE == CONV_DGRAD) {
-                            if (p.fast == 1) ptr = p.w + (static_cast<size_t>(g0) * p.Cin + n) * (p.kh * p.kw) + r0s0;
+                            if (p.quad) {              // n = class * Cin + ci ; class (ph, pw) uses kernel rows ph, ph+2 and columns pw, pw+2
+                                uint32_t cls, ci;
+                                p.fd_Cin.divmod(static_cast<uint32_t>(n), cls, ci);
+                                ptr = p.w + (static_cast<size_t>(g0) * p.Cin + ci) * (p.kh * p.kw) + (cls >> 1) * p.kw + (cls & 1);
+                            } else if (p.fast == 1) ptr = p.w + (static_cast<size_t>(g0) * p.Cin + n) * (p.kh * p.kw) + r0s0;
                             else ptr = p.w + static_cast<size_t>(g0) * 4 * p.Cin + n;
                         } else if (MODE == DENSE_WGRAD) ptr = p.w + n + static_cast<size_t>(g0) * 4 * p.Cout;
                     }
@@ -598,7 +605,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             // destination of this thread's row
             float* dst = nullptr;      // address of column n = 0 of the tile; columns are `col_stride` apart
             size_t col_stride = 0;
-            bool row_ok = false;
+            bool row_ok = false, q_h1 = false, q_w1 = false;
             if (MODE == CONV_FWD) {
                 const uint32_t m = static_cast<uint32_t>(wi.tm) * CT_BLOCK_M + row;
                 const int HW = p.Ho * p.Wo;
@@ -617,7 +624,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (row_ok) {
                     p.fd_Wc[wi.cls].divmod(pix, i, j);
                     const int ih = (static_cast<int>(i) << p.sshift) + (wi.cls >> p.sshift), iw = (static_cast<int>(j) << p.sshift) + (wi.cls & (p.stride - 1));
-                    dst = p.out + ((static_cast<size_t>(b) * p.Cin + wi.tn * p.n_tile) * p.H + ih) * p.W + iw;
+                    if (p.quad) {                  // dst = pixel (2i, 2j) of channel 0; class / channel offsets are added per column
+                        dst = p.out + (static_cast<size_t>(b) * p.Cin * p.H + ih) * p.W + iw;
+                        q_h1 = ih + 1 < p.H; q_w1 = iw + 1 < p.W;
+                    } else {
+                        dst = p.out + ((static_cast<size_t>(b) * p.Cin + wi.tn * p.n_tile) * p.H + ih) * p.W + iw;
+                    }
                     col_stride = static_cast<size_t>(p.H) * p.W;
                 }
             } else {
@@ -637,9 +649,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 float bv[16];
                 const int nbase = wi.tn * p.n_tile + c;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)   // all bias loads first: independent of the stores below
+                for (int j = 0; j < 16; ++j) {  // all bias loads first: independent of the stores below
+                    int bidx = nbase + j;
+                    if (MODE == CONV_DGRAD && p.quad) bidx -= static_cast<int>(p.fd_Cin.div(static_cast<uint32_t>(bidx))) * p.Cin;
                     bv[j] = (MODE != CONV_WGRAD && MODE != DENSE_WGRAD && p.bias != nullptr && nbase + j < p.gemm_n &&
-                             (!p.atomic_out || wi.kb0 == 0)) ? __ldg(p.bias + nbase + j) : 0.0f;
+                             (!p.atomic_out || wi.kb0 == 0)) ? __ldg(p.bias + bidx) : 0.0f;
+                }
                 tmem_ld_wait();
                 if (!row_ok) continue;
 #pragma unroll
@@ -648,6 +663,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (n < p.gemm_n) {
                         float val = __uint_as_float(v[j]) + bv[j];
                         float* o = dst + static_cast<size_t>(c + j) * col_stride;
+                        if (MODE == CONV_DGRAD && p.quad) {
+                            uint32_t cls, ci;
+                            p.fd_Cin.divmod(static_cast<uint32_t>(n), cls, ci);
+                            if (((cls & 2u) && !q_h1) || ((cls & 1u) && !q_w1)) continue;       // odd H / W: last row / column has no partner
+                            o = dst + static_cast<size_t>(ci) * col_stride + (cls >> 1) * p.W + (cls & 1u);
+                        }
                         if (MODE == CONV_WGRAD) {
                             atomicAdd(o, val);
                         } else if (MODE == DENSE_WGRAD) {
@@ -772,12 +793,14 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
     if (int rc = fill_common(p, "pgv_conv2d_dgrad_tf32", B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo)) return rc;
     p.x = dy; p.w = w; p.bias = bias; p.out = dx; p.slope = lrelu_slope;
     p.taps_h = ceil_div(kh, stride); p.taps_w = ceil_div(kw, stride);
-    p.gemm_n = Cin; p.gemm_k = Cout * p.taps_h * p.taps_w;
-    p.n_tile = pick_n_tile(Cin); p.n_tiles = ceil_div(Cin, p.n_tile);
+    p.quad = (stride == 2 && kh == 4 && kw == 4 && pad % 2 == 0) ? 1 : 0;
+    p.fd_Cin.init(Cin);
+    p.gemm_n = p.quad ? 4 * Cin : Cin; p.gemm_k = Cout * p.taps_h * p.taps_w;
+    p.n_tile = pick_n_tile(p.gemm_n); p.n_tiles = ceil_div(p.gemm_n, p.n_tile);
     p.kb_total = ceil_div(p.gemm_k, CT_BLOCK_K); p.kb_per_split = p.kb_total;
-    p.classes = stride * stride;
+    p.classes = p.quad ? 1 : stride * stride;
     for (int c = 0; c < p.classes; ++c) {
-        const int ph = c / stride, pw = c % stride;
+        const int ph = c / stride, pw = c % stride;     // quad mode: the single "class" enumerates the 2x2 quads (ph = pw = 0)
         p.Hc[c] = (H - ph + stride - 1) / stride;
         p.Wc[c] = (W - pw + stride - 1) / stride;
         p.m_tiles_class[c] = static_cast<int>((static_cast<long long>(B) * p.Hc[c] * p.Wc[c] + CT_BLOCK_M - 1) / CT_BLOCK_M);
