@@ -58,6 +58,7 @@ struct ConvTcParams {
     int pix_blocks;                 // WGRAD: k-blocks per image = ceil(Ho*Wo / 32)
     int fast;                       // 1: 4x4 kernel (FWD) / 2x2 taps (DGRAD); 2: 1x1 kernel; 0: generic
     // slot model (see Producer): element e of a chunk is at ptr + off[e-1]; ptr advances by step per k-block
+    int a_pair;                     // 1: FWD 4x4/s2, 2: quad DGRAD -> adjacent lanes share two of the four chunk elements
     int slot_a, slot_b;             // 1: operand uses the slot model, 0: generic chunk_a / chunk_b gathers
     int a_off[3], b_off[3], a_vec, b_vec, a_kdim, b_kdim;   // kdim: valid length along k (tail masking)
     long long a_step, b_step;
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         const float* bp[4]; uint32_t bm[4];
         RowA ra;                                      // generic-gather state
         int b_row[4];
+        bool has_left = false;                       // lane-1 holds the horizontally preceding pixel / quad of the same image row
 
         auto init_slots = [&](const WorkItem& wi) {
             const int a_row = t & 127, a_c0 = t >> 7;
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                         if (r_i + e >= 0 && r_i + e < p.H) hm |= 1u << e;
                         if (r_j + e >= 0 && r_j + e < p.W) wm |= 1u << e;
                     }
+                    has_left = row_ok && jj > 0 && (t & 31) != 0;
                 } else {
                     p.fd_HcWc[wi.cls].divmod(m, b, pix);
                     row_ok = b < static_cast<uint32_t>(p.B);
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                         if (r_i - e >= 0 && r_i - e < p.Ho) hm |= 1u << e;
                         if (r_j - e >= 0 && r_j - e < p.Wo) wm |= 1u << e;
                     }
+                    has_left = row_ok && jj > 0 && (t & 31) != 0 && p.quad;
                 }
             }
 #pragma unroll
@@ -445,7 +449,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
                 uint32_t mask = 0; int row = -1, c = 0;
                 const float* ptr = p.w;
                 if (id < b_chunks) {
-                    if (MODE == CONV_FWD) { row = id >> 3; c = id & 7; }
+                    // operands that are contiguous along k (FWD weights, WGRAD dy): 8 consecutive threads read one 128-byte row
+                    // segment; otherwise consecutive threads take consecutive rows (contiguous along n)
+                    if (MODE == CONV_FWD || MODE == CONV_WGRAD) { row = id >> 3; c = id & 7; }
                     else { uint32_t qq, rem; p.fd_ntile.divmod(static_cast<uint32_t>(id), qq, rem); row = static_cast<int>(rem); c = static_cast<int>(qq); }
                     const int n = wi.tn * p.n_tile + row, g0 = wi.kb0 * 8 + c;
                     if (p.slot_b && n < p.gemm_n) {
@@ -485,7 +491,34 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             ptr += step;
         };
         auto load_kb = [&](const WorkItem& wi, int kb, float (&va)[4][4], float (&vb)[4][4]) {
-            if (p.slot_a) {
+            if (p.slot_a && p.a_pair) {
+                // 4x4 / stride-2 windows of horizontally adjacent pixels overlap by two elements: every lane loads only
+                // its two NEW elements and takes the other two from lane-1 (warp shuffle); lanes without a left
+                // neighbour in the same image row load all four.  Halves the LSU work of the A gather.
+                const uint32_t own = (p.a_pair == 1) ? 0xCu : 0x5u;      // FWD: elements 2,3   DGRAD: elements 0,2
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t mask = am[j] & 15u;
+                    const int rem = p.a_kdim - (kb * 8 + static_cast<int>((am[j] >> 4) & 7u)) * 4;
+                    if (rem < 4) mask &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+                    const uint32_t ld = has_left ? (mask & own) : mask;
+                    const float* ptr = ap[j];
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+                    if (ld & 1u) v0 = __ldg(ptr);
+                    if (ld & 2u) v1 = __ldg(ptr + p.a_off[0]);
+                    if (ld & 4u) v2 = __ldg(ptr + p.a_off[1]);
+                    if (ld & 8u) v3 = __ldg(ptr + p.a_off[2]);
+                    if (p.a_pair == 1) {       // FWD: my (e0, e1) = left neighbour's (e2, e3)
+                        const float n2 = __shfl_up_sync(0xffffffffu, v2, 1), n3 = __shfl_up_sync(0xffffffffu, v3, 1);
+                        if (has_left) { v0 = n2; v1 = n3; }
+                    } else {                   // quad DGRAD: my (e1, e3) = left neighbour's (e0, e2)
+                        const float n0 = __shfl_up_sync(0xffffffffu, v0, 1), n2 = __shfl_up_sync(0xffffffffu, v2, 1);
+                        if (has_left) { v1 = n0; v3 = n2; }
+                    }
+                    va[j][0] = v0; va[j][1] = v1; va[j][2] = v2; va[j][3] = v3;
+                    ap[j] = ptr + p.a_step;
+                }
+            } else if (p.slot_a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) load_slot(ap[j], am[j], kb, p.a_off, p.a_vec, p.a_kdim, p.a_step, va[j]);
             } else {
@@ -778,7 +811,7 @@ int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.fast = (kh == 4 && kw == 4) ? 1 : ((kh == 1 && kw == 1) ? 2 : 0);
     if (stride != 1 && stride != 2) p.fast = 0;      // the slot fast paths use shift arithmetic for the stride
     p.fd_ntile.init(p.n_tile);
-    if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 2LL * H * W; p.a_kdim = p.gemm_k; }
+    if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 2LL * H * W; p.a_kdim = p.gemm_k; p.a_pair = (stride == 2) ? 1 : 0; }
     if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = H * W; p.a_off[1] = 2 * H * W; p.a_off[2] = 3 * H * W; p.a_step = 32LL * H * W; p.a_kdim = p.gemm_k; }
     p.slot_b = 1; p.b_off[0] = 1; p.b_off[1] = 2; p.b_off[2] = 3; p.b_step = 32; p.b_kdim = p.gemm_k; p.b_vec = (p.gemm_k % 4 == 0);
     if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cout * Ho * Wo, static_cast<cudaStream_t>(stream))) return rc;
@@ -812,7 +845,7 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
     p.a_dense = (H == 1 && W == 1 && Ho == 1 && Wo == 1 && kh == 1 && kw == 1) ? 1 : 0;   // Linear dgrad: A = dy [M, N] row-major
     const int HWo = Ho * Wo, khw = kh * kw;
     if (p.a_dense) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 32; p.a_kdim = p.gemm_k; p.a_vec = (p.gemm_k % 4 == 0); }
-    else if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = -1; p.a_off[1] = -Wo; p.a_off[2] = -Wo - 1; p.a_step = 8LL * HWo; p.a_kdim = p.gemm_k; }
+    else if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = -1; p.a_off[1] = -Wo; p.a_off[2] = -Wo - 1; p.a_step = 8LL * HWo; p.a_kdim = p.gemm_k; p.a_pair = p.quad ? 2 : 0; }
     else if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = HWo; p.a_off[1] = 2 * HWo; p.a_off[2] = 3 * HWo; p.a_step = 32LL * HWo; p.a_kdim = p.gemm_k; }
     if (p.fast == 1) { p.slot_b = 1; p.b_off[0] = stride; p.b_off[1] = stride * kw; p.b_off[2] = stride * kw + stride; p.b_step = 8LL * Cin * khw; p.b_kdim = p.gemm_k; }
     else if (p.fast == 2) { p.slot_b = 1; p.b_off[0] = Cin; p.b_off[1] = 2 * Cin; p.b_off[2] = 3 * Cin; p.b_step = 32LL * Cin; p.b_kdim = p.gemm_k; }
