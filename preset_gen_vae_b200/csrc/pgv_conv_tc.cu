@@ -811,7 +811,7 @@ int pgv_conv2d_fwd_tf32(pgv_handle* h, const float* x, const float* w, const flo
     p.fast = (kh == 4 && kw == 4) ? 1 : ((kh == 1 && kw == 1) ? 2 : 0);
     if (stride != 1 && stride != 2) p.fast = 0;      // the slot fast paths use shift arithmetic for the stride
     p.fd_ntile.init(p.n_tile);
-    if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 2LL * H * W; p.a_kdim = p.gemm_k; p.a_pair = (stride == 2) ? 1 : 0; }
+    if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 2LL * H * W; p.a_kdim = p.gemm_k; p.a_pair = 0; /* neighbour-shuffle reuse measured slower on B200 (layers6 vs layers5) */ }
     if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = H * W; p.a_off[1] = 2 * H * W; p.a_off[2] = 3 * H * W; p.a_step = 32LL * H * W; p.a_kdim = p.gemm_k; }
     p.slot_b = 1; p.b_off[0] = 1; p.b_off[1] = 2; p.b_off[2] = 3; p.b_step = 32; p.b_kdim = p.gemm_k; p.b_vec = (p.gemm_k % 4 == 0);
     if (int rc = maybe_split_k(h, p, static_cast<size_t>(B) * Cout * Ho * Wo, static_cast<cudaStream_t>(stream))) return rc;
@@ -845,7 +845,7 @@ int pgv_conv2d_dgrad_tf32(pgv_handle* h, const float* dy, const float* w, const 
     p.a_dense = (H == 1 && W == 1 && Ho == 1 && Wo == 1 && kh == 1 && kw == 1) ? 1 : 0;   // Linear dgrad: A = dy [M, N] row-major
     const int HWo = Ho * Wo, khw = kh * kw;
     if (p.a_dense) { p.slot_a = 1; p.a_off[0] = 1; p.a_off[1] = 2; p.a_off[2] = 3; p.a_step = 32; p.a_kdim = p.gemm_k; p.a_vec = (p.gemm_k % 4 == 0); }
-    else if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = -1; p.a_off[1] = -Wo; p.a_off[2] = -Wo - 1; p.a_step = 8LL * HWo; p.a_kdim = p.gemm_k; p.a_pair = p.quad ? 2 : 0; }
+    else if (p.fast == 1) { p.slot_a = 1; p.a_off[0] = -1; p.a_off[1] = -Wo; p.a_off[2] = -Wo - 1; p.a_step = 8LL * HWo; p.a_kdim = p.gemm_k; p.a_pair = 0; }
     else if (p.fast == 2) { p.slot_a = 1; p.a_off[0] = HWo; p.a_off[1] = 2 * HWo; p.a_off[2] = 3 * HWo; p.a_step = 32LL * HWo; p.a_kdim = p.gemm_k; }
     if (p.fast == 1) { p.slot_b = 1; p.b_off[0] = stride; p.b_off[1] = stride * kw; p.b_off[2] = stride * kw + stride; p.b_step = 8LL * Cin * khw; p.b_kdim = p.gemm_k; }
     else if (p.fast == 2) { p.slot_b = 1; p.b_off[0] = Cin; p.b_off[1] = 2 * Cin; p.b_off[2] = 3 * Cin; p.b_step = 32LL * Cin; p.b_kdim = p.gemm_k; }
