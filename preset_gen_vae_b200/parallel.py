@@ -1,0 +1,69 @@
+"""Host-side data-parallel plumbing (one process per GPU, torch.distributed; NCCL on the B200 box, gloo in CPU tests).
+
+The reference trains with single-process nn.DataParallel (train.py:95-97): every step it scatters the batch, re-broadcasts
+all 241.5 MB of parameters, gathers the outputs and reduces the gradients onto the main device.  Here every rank keeps
+its parameters resident, processes its own shard of the global batch with per-rank BatchNorm statistics (the semantics
+of DataParallel replicas) and the only exchange is ONE all-reduce (sum, fp32) of a flat gradient buffer, pre-scaled by
+1/world so that equal shards reproduce the full-batch mean gradient.
+
+Caveat: SynthParamsLoss normalises each categorical group by the number of useful rows of the batch it
+sees (loss.py:172).  With equal shards this equals the global normalisation only when every shard has the same count;
+`global_useful_counts` all-reduces the 54 counts so a caller can rescale, and the difference is otherwise documented.
+"""
+from typing import List, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Contiguous, equal shards (the training DataLoader drops the last incomplete batch, data/build.py:64-67)."""
+    if global_batch % world != 0:
+        raise ValueError("global batch %d is not divisible by the world size %d" % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+class FlatLayout:
+    """Offsets of many tensors inside one flat fp32 buffer; every slot starts on a 16-byte boundary."""
+
+    def __init__(self, sizes: Sequence[int], align_elems: int = 4):
+        self.sizes = [int(s) for s in sizes]
+        padded = [(s + align_elems - 1) // align_elems * align_elems for s in self.sizes]
+        self.offsets = np.concatenate([[0], np.cumsum(padded)])[:-1].astype(np.int64)
+        self.total = int(sum(padded))
+
+    def views(self, flat: torch.Tensor, shapes: Sequence[torch.Size]) -> List[torch.Tensor]:
+        return [flat[o:o + n].view(shape) for o, n, shape in zip(self.offsets, self.sizes, shapes)]
+
+    def pack_(self, flat: torch.Tensor, tensors: Sequence[torch.Tensor], scale: float = 1.0):
+        """Reference (torch) implementation of pgv_multi_pack, for CPU tests and non-CUDA tensors."""
+        for o, n, t in zip(self.offsets, self.sizes, tensors):
+            flat[o:o + n].copy_(t.reshape(-1))
+        if scale != 1.0:
+            flat.mul_(scale)
+        return flat
+
+
+def allreduce_mean_(flat_grads_prescaled: torch.Tensor, group=None):
+    """Sum over ranks of a buffer every rank already scaled by 1/world  ==  mean gradient."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grads_prescaled, op=dist.ReduceOp.SUM, group=group)
+    return flat_grads_prescaled
+
+
+def global_useful_counts(local_counts: torch.Tensor, group=None) -> torch.Tensor:
+    """All-reduce of the per-categorical-group useful-row counts (they depend on the targets only)."""
+    out = local_counts.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def max_over_ranks(value: float, device, group=None) -> float:
+    """Timing helper: the slowest rank defines the step time."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

@@ -13,7 +13,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib, synthetic
+from . import _lib, parallel, synthetic
 from .model import build, loss as ploss, ops
 from .utils import audio as paudio
 
@@ -53,13 +53,12 @@ class TrainStep:
     def _flatten_parameters(self):
         params = [p for p in self.model.parameters() if p.requires_grad]
         sizes = [p.numel() for p in params]
-        offs = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])      # 16-byte aligned slots
-        total = int(offs[-1])
-        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        for p, o, n in zip(params, offs[:-1], sizes):
-            flat[o:o + n].copy_(p.data.reshape(-1))
-            p.data = flat[o:o + n].view_as(p.data)
-        self.params, self.flat_params, self._offs, self._sizes = params, flat, offs[:-1], sizes
+        self.layout = parallel.FlatLayout(sizes)                                         # 16-byte aligned slots
+        flat = torch.zeros(self.layout.total, dtype=torch.float32, device=self.device)
+        for p, view in zip(params, self.layout.views(flat, [p.shape for p in params])):
+            view.copy_(p.data)
+            p.data = view
+        self.params, self.flat_params, self._offs, self._sizes = params, flat, self.layout.offsets, sizes
         self.flat_grads = torch.zeros_like(flat)
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
@@ -114,7 +113,7 @@ class TrainStep:
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
     def _allreduce(self):
-        torch.distributed.all_reduce(self.flat_grads, group=self.pg)    # sum; the 1/world factor was applied while packing
+        parallel.allreduce_mean_(self.flat_grads, self.pg)              # sum; the 1/world factor was applied while packing
 
     def step(self, audio, v_in, sample_info):
         """audio [B, C, L] fp32, v_in [B, L_params] fp32, sample_info [B, 3] int32: CUDA tensors on this rank's device.

@@ -1,0 +1,72 @@
+"""CPU: the data-parallel host logic with two gloo ranks (the N > 1 path without GPUs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from preset_gen_vae_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                                     # identical initial weights on every rank
+        model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(8, 7, generator=g), torch.randn(8, 3, generator=g)
+        lo, hi = parallel.shard_range(8, rank, world)
+        loss = torch.nn.functional.mse_loss(model(x[lo:hi]), y[lo:hi])       # per-rank mean loss on the shard
+        loss.backward()
+        params = list(model.parameters())
+        layout = parallel.FlatLayout([p.numel() for p in params])
+        flat = torch.zeros(layout.total)
+        layout.pack_(flat, [p.grad for p in params], scale=1.0 / world)
+        parallel.allreduce_mean_(flat)
+        # full-batch reference on every rank
+        ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        ref.load_state_dict(model.state_dict())
+        torch.nn.functional.mse_loss(ref(x), y).backward()
+        err = max(float((v - p.grad).abs().max()) for v, p in zip(layout.views(flat, [p.shape for p in params]), ref.parameters()))
+        counts = parallel.global_useful_counts(torch.tensor([3.0 + rank, 4.0]))
+        slow = parallel.max_over_ranks(1.0 + rank, 'cpu')
+        ret[rank] = (err, counts.tolist(), slow, layout.offsets.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_full_batch():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert len(ret) == 2
+        for rank in range(world):
+            err, counts, slow, offsets = ret[rank]
+            assert err < 1e-6                                    # equal shards: mean of shard means == full-batch mean
+            assert counts == [7.0, 8.0] and slow == 2.0
+            assert all(o % 4 == 0 for o in offsets)              # 16-byte aligned slots
+
+
+def test_shard_range_and_layout():
+    assert parallel.shard_range(160, 3, 8) == (60, 80)
+    with pytest.raises(ValueError):
+        parallel.shard_range(161, 0, 8)
+    lay = parallel.FlatLayout([5, 8, 1])
+    assert lay.offsets.tolist() == [0, 8, 16] and lay.total == 20
+    flat = torch.zeros(lay.total)
+    ts = [torch.arange(5.0), torch.ones(8), torch.tensor([7.0])]
+    lay.pack_(flat, ts, scale=0.5)
+    v = lay.views(flat, [t.shape for t in ts])
+    assert torch.equal(v[0], torch.arange(5.0) * 0.5) and float(v[2]) == 3.5
