@@ -45,8 +45,11 @@ def test_eager_step_matches_manual_forward_backward_and_torch_adam(idx_helper):
     for a, b in zip(got, (rec.item(), lat.item(), con.item())):
         assert abs(a - b) <= 2e-5 * abs(b) + 1e-6       # atomics in wgrad / split-K make runs non bit-identical
     # gradients landed in the flat buffer, Adam matches torch.optim.Adam
+    # two runs of the same kernels are not bit-identical: split-K / thin weight-gradient kernels accumulate with fp32
+    # atomics, and heavily cancelling sums (enc1conv.weight.grad) are order dependent at the 1e-4..1e-3 level
     for p, q in list(zip(tr.params, ref_model.parameters()))[::17]:
-        assert torch.allclose(p.grad, q.grad, rtol=2e-3, atol=1e-6)
+        gn = float(q.grad.norm())
+        assert float((p.grad - q.grad).norm()) <= 3e-3 * gn + 1e-7
     worst = max(float((p.data - q.data).abs().max()) for p, q in zip(tr.params, ref_model.parameters()))
     assert worst < 5e-6                                   # one Adam step moves weights by <= lr = 2e-4
 
