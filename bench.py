@@ -267,10 +267,9 @@ def main_ours(args):
     # ---- live roofline of the dominant kernel family: eager steps with CUDA events around every C entry point ----
     pk = peaks()
     roofline, breakdown = None, None
-    if rank == 0:
-        if args.workload == 'frontend':
+    if args.workload == 'frontend':
+        if rank == 0:
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            # the DFT contraction is ~80 % of the front end; time the whole call and attribute by the ncu share in profiles/
             for a, b in ev:
                 a.record(); dev_step(); b.record()
             torch.cuda.synchronize(dev)
@@ -280,24 +279,26 @@ def main_ours(args):
                         'peak': pk['bf16_burst'] / 2, 'unit': 'TFLOP/s', 'frac': ach / (pk['bf16_burst'] / 2), 'traffic': None,
                         'note': 'algorithmic dense flops 820.63 MFLOP/clip; the 3xTF32 split executes 3x that on the tensor pipe; '
                                 'peak = TF32 dense = half of the %s bf16 burst figure' % pk['src']}
-        else:
-            trainer_graph = trainer.use_graph
-            trainer.use_graph = False
+    else:
+        # EVERY rank runs the instrumented eager steps (they contain the gradient all-reduce); rank 0 reports.
+        trainer_graph = trainer.use_graph
+        trainer.use_graph = False
+        dev_step()
+        torch.cuda.synchronize(dev)
+        # keep the GPU busy while the CPU enqueues the instrumented steps, so that the CUDA events around each entry
+        # point measure device execution only (without this, short kernels are dominated by CPU launch gaps)
+        blocker = torch.empty(16384, 16384, device=dev)
+        for _ in range(6):
+            torch.mm(blocker, blocker)
+        ops.start_profile()
+        for _ in range(2):
             dev_step()
-            torch.cuda.synchronize(dev)
-            # keep the GPU busy while the CPU enqueues the instrumented steps, so that the CUDA events around each entry
-            # point measure device execution only (without this, short kernels are dominated by CPU launch gaps)
-            blocker = torch.empty(16384, 16384, device=dev)
-            for _ in range(6):
-                torch.mm(blocker, blocker)
-            ops.start_profile()
-            for _ in range(2):
-                dev_step()
-            prof = ops.stop_profile()
-            del blocker
-            trainer.use_graph = trainer_graph
+        prof = ops.stop_profile()
+        del blocker
+        trainer.use_graph = trainer_graph
+        if rank == 0:
             tot = sum(v['ms'] for v in prof.values())
-            breakdown = {k: round(v['ms'] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:8]}
+            breakdown = {k: round(v['ms'] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:10]}
             name, top = max(prof.items(), key=lambda kv: kv[1]['ms'])
             per_ms = top['ms'] / 2
             if top['flops'] > 0:
@@ -306,7 +307,7 @@ def main_ours(args):
                 peak = pk['bf16_sustained'] / 2
                 roofline = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                             'traffic': None, 'share_of_step': top['ms'] / tot,
-                            'note': ('tcgen05 TF32 kernel' if tensor else 'CUDA-core fp32 kernel (not yet on the tensor pipe)') +
+                            'note': ('tcgen05 TF32 kernel' if tensor else 'CUDA-core fp32 kernel (not on the tensor pipe)') +
                                     '; algorithmic flops of all its launches in one step / their summed CUDA-event time; peak = TF32 dense '
                                     '= half of the %s sustained bf16 figure' % pk['src']}
             else:
