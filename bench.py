@@ -179,6 +179,8 @@ def main_ours(args):
     dev = torch.device('cuda', local_rank)
     pg = None
     if world > 1:
+        # NCCL prints its version banner to stdout when NCCL_DEBUG is set; keep stdout to the single JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/pgv_nccl_debug.%h.%p')
         torch.distributed.init_process_group('nccl', device_id=dev)
         pg = torch.distributed.group.WORLD
     from preset_gen_vae_b200 import _lib, config as pcfg, synthetic
