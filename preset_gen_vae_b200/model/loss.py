@@ -148,3 +148,24 @@ def _tables_for(idx_helper):
         return ops.DeviceTables(idx_helper)
     from ..data.preset import tables_from_foreign_helper
     return ops.DeviceTables(tables_from_foreign_helper(idx_helper))
+
+
+class _Total:
+    """recons + beta * latent + controls (train.py:228) with beta read from DEVICE memory, so that the beta warm-up
+    schedule (train.py:122-124) reaches a captured CUDA graph."""
+
+    def prog_fwd(self, inputs, training, extra):
+        recons, lat, cont, beta = (t.reshape(1) for t in inputs)
+        return ops.add(ops.add(recons, ops.mul(lat, beta)), cont).view(()), beta
+
+    def prog_bwd(self, dout, ctx, grads, needs):
+        g = dout.reshape(1)
+        return g.view(()), ops.mul(g, ctx).view(()), g.view(()), None
+
+
+_TOTAL = _Total()
+
+
+def total_loss(recons, latent, controls, beta_dev):
+    """beta_dev: 1-element float32 device tensor."""
+    return run_program(_TOTAL, (recons, latent, controls, beta_dev), [], True)

@@ -43,8 +43,8 @@ class TrainStep:
         self._flatten_parameters()
         self.step_count = 0
         self.lr = train_config.initial_learning_rate
-        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
-        self._hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(5, dtype=torch.float32).pin_memory()         # lr, bias corrections, grad scale, beta
+        self._hyper_dev = torch.zeros(5, dtype=torch.float32, device=self.device)
         self._graph = None
         self._static = None
         self.losses = None
@@ -86,7 +86,7 @@ class TrainStep:
         recons = self.recons_criterion(x_out, x_in)
         lat = self.model.latent_loss(z0_ml, z0, zk, logdet)
         cont = self.controls_criterion(v_out, v_in)
-        total = recons + self.beta * lat + cont
+        total = ploss.total_loss(recons, lat, cont, self._hyper_dev[4:5])
         for p in self.params:
             p.grad = None
         total.backward()
@@ -110,6 +110,7 @@ class TrainStep:
         self._hyper_host[1] = 1.0 - b1 ** self.step_count
         self._hyper_host[2] = float(np.sqrt(1.0 - b2 ** self.step_count))
         self._hyper_host[3] = 1.0
+        self._hyper_host[4] = self.beta
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
     def _allreduce(self):

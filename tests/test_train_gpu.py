@@ -72,3 +72,21 @@ def test_cuda_graph_steps_train(idx_helper):
     # batched inference tail: audio -> preset parameters in [0, 1]
     v = tr.infer(audio)
     assert v.shape == (B, 610) and float(v.min()) >= 0.0 and float(v.max()) <= 1.0 and tr.model.training
+    # schedules reach the captured graph through device memory: lr = 0 must freeze the weights
+    tr.lr = 0.0
+    snap = tr.flat_params.clone()
+    tr.step(audio, v_in, info)
+    torch.cuda.synchronize()
+    assert torch.equal(snap, tr.flat_params)
+
+
+def test_total_loss_reads_beta_from_device():
+    """train.py:228 with the beta warm-up value living in device memory (so a captured graph sees schedule updates)."""
+    r, l, c = (torch.tensor(v, device='cuda', requires_grad=True) for v in (1.5, 2.0, 0.25))
+    beta = torch.tensor([0.2], device='cuda')
+    t = ploss.total_loss(r, l, c, beta)
+    t.backward()
+    assert abs(t.item() - 2.15) < 1e-6
+    assert abs(r.grad.item() - 1.0) < 1e-7 and abs(l.grad.item() - 0.2) < 1e-7 and abs(c.grad.item() - 1.0) < 1e-7
+    beta.fill_(0.5)
+    assert abs(ploss.total_loss(r, l, c, beta).item() - 2.75) < 1e-6
