@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PGV_VERSION 100
+#define PGV_VERSION 101
 #if defined(__GNUC__)
 #define PGV_API __attribute__((visibility("default")))
 #else
@@ -138,14 +138,58 @@ PGV_API int pgv_debug_set_conv_trace(void* trace_dev);
 /* Direct streaming kernels (exact fp32) for the two thin full-resolution layers, enc1 = Conv2d(1,8,5,2,2)
  * (encoder.py:241) and dec8 = ConvTranspose2d(8,1,5,2,2) (decoder.py:218), which are HBM-bound (8 flop/byte).  Conv-view
  * geometry: x [B,1,H,W], y [B,C<=8,Ho,Wo], w [C,1,5,5], stride 2, pad 2.  _dgrad is the transposed convolution and
- * clamps its result to [clamp_lo, clamp_hi] (the decoder's Hardtanh; pass -INF/+INF for none). */
+ * clamps its result to [clamp_lo, clamp_hi] (the decoder's Hardtanh; pass -INF/+INF for none).  channels_last != 0: the
+ * C-channel tensor (y / dy) is stored [B, Ho, Wo, C] instead of [B, C, Ho, Wo]; round_out rounds y to TF32 (nearest). */
 PGV_API int pgv_conv5x5s2_c1_supported(int Cin, int Cout, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo);
 PGV_API int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int C, int H, int W, int Ho, int Wo,
-                                 float lrelu_slope, pgv_stream_t stream);
+                                 float lrelu_slope, int channels_last, int round_out, pgv_stream_t stream);
 PGV_API int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, float* x, int B, int C, int H, int W, int Ho, int Wo,
-                                   float clamp_lo, float clamp_hi, pgv_stream_t stream);
+                                   float clamp_lo, float clamp_hi, int channels_last, pgv_stream_t stream);
 PGV_API int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo,
-                                   pgv_stream_t stream);
+                                   int channels_last, pgv_stream_t stream);
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Channels-last (NHWC) convolution path: the default 'tf32' route of the Conv2D / TConv2D blocks (model/layer.py:10-46,
+ * encoder.py:233-259, decoder.py:190-221).  Activations are [B, H, W, C]; the reduction index is (kh, kw, c), so every
+ * operand tile is filled with 16-byte cp.async copies (no register staging) and multiplied by tcgen05.mma kind::tf32.
+ * Operands are consumed as stored: callers pass TF32-rounded activations (the *_cl producers below have a round_out
+ * flag) and the weight matrices made by pgv_conv_cl_prep_weights.  Supported: 4x4 / stride 2 / pad 2 and 1x1 / stride 1
+ * (pgv_conv_cl_supported); channel counts multiples of 8 (4x4) or 32 (1x1); all pointers 16-byte aligned. */
+PGV_API int pgv_conv_cl_supported(int Cin, int Cout, int KH, int KW, int stride, int pad);
+/* w [Cout, Cin, KH, KW] (PyTorch) -> wf [Cout][(kh, kw, ci)] (forward operand) and / or wq (data-gradient operand:
+ * [(ph, pw, ci)][(a, b, co)] = w[co, ci, ph + 2(1-a), pw + 2(1-b)] for 4x4/s2/p2, [ci][co] for 1x1); either may be NULL. */
+PGV_API int pgv_conv_cl_prep_weights(const float* w, float* wf, float* wq, int Cout, int Cin, int KH, int KW, int stride, int pad,
+                                     pgv_stream_t stream);
+/* y [B, Ho, Wo, Cout] = lrelu(bias + conv(x [B, H, W, Cin], w)); lrelu_slope < 0: no activation. */
+PGV_API int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin,
+                            int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
+                            pgv_stream_t stream);
+/* dx [B, H, W, Cin] = lrelu(bias + conv_transpose(dy [B, Ho, Wo, Cout], w)): data gradient of the convolution above and
+ * forward of nn.ConvTranspose2d(weight = w) (bias has Cin entries or is NULL). */
+PGV_API int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin,
+                              int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
+                              pgv_stream_t stream);
+/* dwcl [Cout][(kh, kw, ci)] = sum over pixels of dy x patch(x) (split over CTAs, fp32 atomics; zero-filled by the call);
+ * pgv_conv_cl_unpack_dw converts it to the PyTorch layout [Cout, Cin, KH, KW]. */
+PGV_API int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH,
+                              int KW, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+PGV_API int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Cin, int KH, int KW, pgv_stream_t stream);
+/* BatchNorm2d on channels-last tensors viewed as [P = B*H*W, C] (same semantics as pgv_bn2d_*; C % 4 == 0).
+ * workspace: 16*C bytes. */
+PGV_API int pgv_bn_cl_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_rstd,
+                                float* running_mean, float* running_var, float momentum, float eps, size_t P, int C, int round_out,
+                                void* workspace, pgv_stream_t stream);
+PGV_API int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                               float* y, float eps, size_t P, int C, int round_out, pgv_stream_t stream);
+PGV_API int pgv_bn_cl_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd,
+                                float* dx, float* dgamma, float* dbeta, float lrelu_slope, size_t P, int C, int round_out, void* workspace,
+                                pgv_stream_t stream);
+/* out[c] = sum over rows of x [P, C] (bias gradient).  workspace: 16*C bytes. */
+PGV_API int pgv_colsum_cl(const float* x, float* out, size_t P, int C, void* workspace, pgv_stream_t stream);
+/* dx = dy * (a > 0 ? 1 : slope), flat arrays of n elements (n % 4 == 0), optionally rounded to TF32. */
+PGV_API int pgv_lrelu_bwd_round(const float* dy, const float* a, float* dx, float slope, size_t n, int round_out, pgv_stream_t stream);
+/* src [batch, R, S] -> dst [batch, S, R] (NCHW -> NHWC: R = C, S = H*W; NHWC -> NCHW: R = H*W, S = C). */
+PGV_API int pgv_transpose_inner(const float* src, float* dst, int batch, int R, int S, int round_out, pgv_stream_t stream);
+
 /* nn.Linear on the same tensor-core kernel (any K, no alignment requirement): x [M,K], w [N,K], y [M,N] = act(x w^T +
  * bias + residual) (bias / residual may be NULL, relu != 0 fuses a ReLU); dx [M,K] = dy w; dw [N,K] = dy^T x. */
 PGV_API int pgv_linear_fwd_tf32(pgv_handle* h, const float* x, const float* w, const float* bias, const float* residual, float* y, int M,

@@ -1,0 +1,545 @@
+// Channels-last (NHWC) implicit-GEMM convolutions on tcgen05 (TF32 products, fp32 accumulation in TMEM) fed by cp.async.
+//
+// With activations stored [B, H, W, C] (C a multiple of 4) and the reduction index ordered (kh, kw, c), every 16-byte
+// chunk of every operand tile is 16 contiguous, 16-byte-aligned bytes of global memory:
+//
+//   GEMM mode  (convolution forward, and data-gradient / ConvTranspose2d forward through a re-packed weight matrix)
+//       out[m, n] = act(bias[n] + sum_k A[m, k] * Bw[n, k])
+//       m = (b, oh, ow) output pixel (or 2x2 pixel quad), k = (kh, kw, c): A[m, k] = in[b, oh*st-p+kh, ow*st-p+kw, c]
+//       (for one kh the KW*C values are ONE contiguous run of memory); Bw = prepared weights [N][K], K contiguous.
+//       Both tiles are K-major, 128-byte rows, SWIZZLE_128B.
+//   WGRAD mode dWcl[n, m] += sum_k A[m, k] * Bd[n, k],  m = (kh, kw, ci), n = co, k = pixel:
+//       A[m, k] = x[pixel k shifted by tap (kh, kw), ci] and Bd[n, k] = dy[pixel k, co] are contiguous along m / n for one
+//       pixel, so both tiles are MN-major (atoms of 4 pixels x 128 bytes, SWIZZLE_128B_BASE32B).  The reduction runs over
+//       (oh, ow, b) with b fastest, so that the 32 pixels of a k-block share their tap geometry.
+//
+// Nothing goes through registers: 8 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
+// the swizzled tile and hand completion to the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so up to CL_STAGES
+// k-blocks (192 KB) are in flight per SM.  The operands are therefore NOT rounded on the way in: activations are
+// rounded to TF32 (round-to-nearest) by the kernels that write them (BatchNorm apply, thin-layer kernels, layout
+// converters: `round_out` flags) and weights by pgv_conv_cl_prep_weights, which is numerically identical to rounding
+// in the gather and keeps the tensor core's own truncation out of the picture.
+// One thread issues tcgen05.mma (M = 128, N = tile width, K = 8); accumulators are double-buffered in TMEM; 4 epilogue
+// warps drain them (bias, LeakyReLU, optional TF32 rounding, float4 stores along the channel dimension).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "pgv_common.cuh"
+#include "pgv_tc.cuh"
+
+namespace pgv {
+
+enum { CL_GEMM = 0, CL_WGRAD = 1 };
+enum { CL_EPI_ROWS = 0, CL_EPI_QUAD = 1 };
+
+constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_STAGES = 6;
+constexpr int CL_A_BYTES = CL_BLOCK_M * 128, CL_B_BYTES = CL_MAX_N * 128, CL_STAGE_BYTES = CL_A_BYTES + CL_B_BYTES;
+constexpr int CL_PRODUCER_WARPS = 8, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
+constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
+constexpr int CL_SMEM = 1024 + CL_STAGES * CL_STAGE_BYTES + 256;
+
+struct ConvClParams {
+    const float* a;      // GEMM: gathered activations [B, H, W, C]      WGRAD: x [B, H, W, C]
+    const float* b;      // GEMM: prepared weights [gemm_n][gemm_k]      WGRAD: dy [B, Hg, Wg, gemm_n]
+    const float* bias;   // GEMM: per output channel (or NULL)
+    float* out;
+    int B, H, W, C, KH, KW, stride, pad, Hg, Wg;     // gather geometry: window KH x KW over [H, W, C], output grid Hg x Wg
+    int gemm_m, gemm_n, gemm_k;
+    int n_tile, n_tiles, m_tiles, kb_total, kb_per_split, k_splits;
+    int epi, ldo;        // CL_EPI_ROWS: out[m * ldo + n]
+    int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
+    int bblocks;         // WGRAD: ceil(B / 32) k-blocks per output position
+    int round_out, atomic_out;
+    int variant;         // debug (PGV_WGRAD_VARIANT): 1 swaps LBO / SBO of the MN-major descriptors
+    float slope;
+    FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC;
+};
+
+__device__ __forceinline__ uint32_t cl_sw128(int row, int chunk) {
+    return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// MN-major fp32 / TF32 operands must use the "128-byte swizzle with 32-byte atomicity" layout (the only MN-major layout the
+// tensor core accepts for 32-bit types): atoms of 4 k-rows x 128 bytes in which the 32-byte unit index is XORed with the row
+// index (byte-address bits [5,7) ^= bits [7,9)).  Offset of 16-byte chunk `c16` (0..7) inside row `row` of a 128-byte-row block:
+__device__ __forceinline__ uint32_t cl_sw32(int c16, int row) {
+    return static_cast<uint32_t>(((((c16 >> 1) ^ (row & 3)) << 1) | (c16 & 1)) << 4);
+}
+
+struct ClItem { int tm, tn, kb0, kb1; };
+__device__ __forceinline__ ClItem cl_decode(const ConvClParams& p, int item) {
+    ClItem wi;
+    const int split = item % p.k_splits;
+    int t = item / p.k_splits;
+    wi.tn = t % p.n_tiles;
+    wi.tm = t / p.n_tiles;
+    wi.kb0 = split * p.kb_per_split;
+    wi.kb1 = min(p.kb_total, wi.kb0 + p.kb_per_split);
+    return wi;
+}
+
+__device__ __forceinline__ float cl_act(float v, float slope, int round_out) {
+    if (slope >= 0.0f && v < 0.0f) v *= slope;
+    return round_out ? to_tf32_rna(v) : v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_constant__ ConvClParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + CL_STAGES * CL_STAGE_BYTES);
+    uint64_t* bar_empty = bar_full + CL_STAGES;
+    uint64_t* bar_tfull = bar_empty + CL_STAGES;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int MMA_WARP = CL_PRODUCER_WARPS, EPI_WARP0 = CL_PRODUCER_WARPS + 1;
+
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&bar_full[s], CL_PRODUCERS); mbar_init(&bar_empty[s], 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 2 * CL_MAX_N);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_items = p.m_tiles * p.n_tiles * p.k_splits;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp < CL_PRODUCER_WARPS) {
+        // ================================================================== producers
+        const int t = threadIdx.x;
+        int stage = 0; uint32_t phase = 0;
+        if (MODE == CL_GEMM) {
+            // thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows r0 + 32 i
+            const int j = t & 7, r0 = t >> 3;
+            const uint32_t dst0 = cl_sw128(r0, j);                    // rows r0 + 32 i: + i * 4096 (same row & 7)
+            const long long row_pitch = static_cast<long long>(p.W) * p.C;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ClItem wi = cl_decode(p, item);
+                long long a_base[4]; uint32_t a_msk[4];             // mask: bits 0-7 valid kh, bits 8-15 valid kw
+                const float* b_ptr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + r0 + 32 * i;
+                    uint32_t b, rem, oh, ow;
+                    p.fd_HgWg.divmod(m, b, rem);
+                    p.fd_Wg.divmod(rem, oh, ow);
+                    const int ih0 = static_cast<int>(oh) * p.stride - p.pad, iw0 = static_cast<int>(ow) * p.stride - p.pad;
+                    a_base[i] = ((static_cast<long long>(b) * p.H + ih0) * p.W + iw0) * p.C;
+                    uint32_t hm = 0, wm = 0;
+                    for (int e = 0; e < p.KH; ++e) if (ih0 + e >= 0 && ih0 + e < p.H) hm |= 1u << e;
+                    for (int e = 0; e < p.KW; ++e) if (iw0 + e >= 0 && iw0 + e < p.W) wm |= 1u << e;
+                    a_msk[i] = (m < static_cast<uint32_t>(p.gemm_m)) ? (hm | (wm << 8)) : 0u;
+                    const int row = r0 + 32 * i, n = wi.tn * p.n_tile + row;
+                    b_ptr[i] = (row < p.n_tile && n < p.gemm_n) ? p.b + static_cast<size_t>(n) * p.gemm_k + 4 * j : nullptr;
+                }
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    const uint32_t k = static_cast<uint32_t>(kb) * CL_BLOCK_K + 4 * j;
+                    uint32_t kh, rem;
+                    p.fd_span.divmod(k, kh, rem);
+                    const uint32_t kw = p.fd_C.div(rem);
+                    const long long koff = static_cast<long long>(kh) * row_pitch + rem;
+                    const uint32_t sel = (1u << kh) | (1u << (8 + kw));
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    const uint32_t sA = smem_base + stage * CL_STAGE_BYTES + dst0, sB = sA + CL_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const bool ok = (a_msk[i] & sel) == sel;
+                        cp_async16_ca(sA + i * 4096, ok ? p.a + a_base[i] + koff : p.a, ok ? 16u : 0u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (r0 + 32 * i < p.n_tile) {
+                            const bool ok = b_ptr[i] != nullptr;
+                            cp_async16_cg(sB + i * 4096, ok ? b_ptr[i] + static_cast<size_t>(kb) * CL_BLOCK_K : p.b, ok ? 16u : 0u);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&bar_full[stage]);
+                    if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else {
+            // WGRAD.  A tile: pixel kk = (t / 32) + 8 i (i = k-group), 16-byte chunk cc = t % 32 along the 128 m of the tile:
+            // a warp copies 512 contiguous bytes of one pixel.  B tile: n_tile / 4 chunks per pixel, same idea.
+            const int cc = t & 31, kq = t >> 5;                      // kq = kk & 7 for all four slots
+            const uint32_t a_dst0 = static_cast<uint32_t>((cc >> 3) * 1024 + kq * 128) + cl_sw32(cc & 7, kq);   // + i * 4096
+            const int cpp = p.n_tile >> 2;                            // B chunks per pixel: 8, 16 or 32
+            const int cpp_shift = (cpp == 8) ? 3 : ((cpp == 16) ? 4 : 5);
+            const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;    // one 8-pixel group of the B tile
+            const long long img_a = static_cast<long long>(p.H) * p.W * p.C, img_b = static_cast<long long>(p.Hg) * p.Wg * p.gemm_n;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ClItem wi = cl_decode(p, item);
+                // this thread's 4 consecutive m (fixed for the tile): tap (kh, kw) and channel
+                const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + 4 * cc;
+                uint32_t kh, rem;
+                p.fd_span.divmod(m, kh, rem);
+                const uint32_t kw = p.fd_C.div(rem);
+                const bool m_ok = m < static_cast<uint32_t>(p.gemm_m);
+                const long long m_off = static_cast<long long>(kh) * p.W * p.C + rem;
+                // B slots: id = t + 256 s -> (pixel, chunk)
+                int b_kk[4], b_nc[4]; uint32_t b_dst[4]; bool b_on[4], b_ok[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int id = t + CL_PRODUCERS * s;
+                    b_on[s] = id < 32 * cpp;
+                    b_kk[s] = id >> cpp_shift;
+                    b_nc[s] = id & (cpp - 1);
+                    const int kk = b_kk[s], nc = b_nc[s];
+                    b_dst[s] = static_cast<uint32_t>((kk >> 3) * b_group_bytes + (nc >> 3) * 1024 + (kk & 7) * 128) + cl_sw32(nc & 7, kk & 7);
+                    b_ok[s] = b_on[s] && (wi.tn * p.n_tile + 4 * nc) < p.gemm_n;
+                }
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    uint32_t pos, bb, oh, ow;
+                    p.fd_bblocks.divmod(static_cast<uint32_t>(kb), pos, bb);
+                    p.fd_Wg.divmod(pos, oh, ow);
+                    const int ih = static_cast<int>(oh) * p.stride - p.pad + static_cast<int>(kh);
+                    const int iw = static_cast<int>(ow) * p.stride - p.pad + static_cast<int>(kw);
+                    const bool tap_ok = m_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                    const long long a_off = (static_cast<long long>(oh) * p.stride - p.pad) * p.W * p.C +
+                                            (static_cast<long long>(ow) * p.stride - p.pad) * p.C + m_off;
+                    const long long b_off = static_cast<long long>(pos) * p.gemm_n + wi.tn * p.n_tile;
+                    const int img0 = static_cast<int>(bb) * 32;
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    const uint32_t sA = smem_base + stage * CL_STAGE_BYTES, sB = sA + CL_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int img = img0 + kq + 8 * i;
+                        const bool ok = tap_ok && img < p.B;
+                        cp_async16_ca(sA + a_dst0 + i * 4096, ok ? p.a + img * img_a + a_off : p.a, ok ? 16u : 0u);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (b_on[s]) {
+                            const int img = img0 + b_kk[s];
+                            const bool ok = b_ok[s] && img < p.B;
+                            cp_async16_cg(sB + b_dst[s], ok ? p.b + img * img_b + b_off + 4 * b_nc[s] : p.b, ok ? 16u : 0u);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&bar_full[stage]);
+                    if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(CL_BLOCK_M, p.n_tile) | (MODE == CL_WGRAD ? (UMMA_IDESC_A_MN | UMMA_IDESC_B_MN) : 0u);
+            const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ClItem wi = cl_decode(p, item);
+                mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + acc * CL_MAX_N;
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    fence_proxy_async_smem();          // cp.async wrote through the generic proxy; tcgen05.mma reads through the async proxy
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_base + stage * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
+                    if (MODE == CL_GEMM) {
+                        const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
+#pragma unroll
+                        for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
+                            // one MMA = 8 pixels = two 4-row atoms 512 bytes apart (SBO); 32-element groups along M / N are 1024 bytes apart (LBO)
+                            const uint32_t lbo = p.variant == 1 ? 512u : 1024u, sbo = p.variant == 1 ? 1024u : 512u;
+                            const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, lbo, sbo);
+                            const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, lbo, sbo);
+                            umma_tf32(tmem_d, da, db, idesc, (kb > wi.kb0 || g > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&bar_empty[stage]);
+                    if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&bar_tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ================================================================== epilogue: TMEM -> registers -> global
+        const int quad = warp & 3, row = quad * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const ClItem wi = cl_decode(p, item);
+            const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + row;
+            const bool row_ok = m < static_cast<uint32_t>(p.gemm_m);
+            float* dst = p.out;
+            int qi = 0, qj = 0;
+            if (MODE == CL_WGRAD) {
+                dst = p.out + m;                                             // dWcl[n][m]: lanes write consecutive m
+            } else if (p.epi == CL_EPI_ROWS) {
+                dst = p.out + static_cast<size_t>(m) * p.ldo;
+            } else {
+                uint32_t b, rem, i, j;
+                p.fd_HgWg.divmod(m, b, rem);
+                p.fd_Wg.divmod(rem, i, j);
+                qi = 2 * static_cast<int>(i); qj = 2 * static_cast<int>(j);
+                dst = p.out + ((static_cast<size_t>(b) * p.qH + qi) * p.qW + qj) * p.qC;
+            }
+            const bool add_bias = p.bias != nullptr && (!p.atomic_out || wi.kb0 == 0);
+            mbar_wait(&bar_tfull[acc], acc_phase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + acc * CL_MAX_N + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < p.n_tile; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                const int nbase = wi.tn * p.n_tile + c;
+                if (MODE == CL_WGRAD) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (nbase + e < p.gemm_n) atomicAdd(dst + static_cast<size_t>(nbase + e) * p.gemm_m, __uint_as_float(v[e]));
+                    continue;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int n = nbase + 4 * g;
+                    if (n >= p.gemm_n) break;
+                    float* o;
+                    int bidx = n;
+                    if (p.epi == CL_EPI_ROWS) {
+                        o = dst + n;
+                    } else {
+                        uint32_t cls, ch;
+                        p.fd_qC.divmod(static_cast<uint32_t>(n), cls, ch);
+                        const int ih = qi + static_cast<int>(cls >> 1), iw = qj + static_cast<int>(cls & 1u);
+                        if (ih >= p.qH || iw >= p.qW) continue;              // odd H / W: the last row / column has no partner
+                        o = dst + (static_cast<size_t>(cls >> 1) * p.qW + (cls & 1u)) * p.qC + ch;
+                        bidx = static_cast<int>(ch);
+                    }
+                    float4 r = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                           __uint_as_float(v[4 * g + 3]));
+                    if (add_bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + bidx));
+                        r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
+                    }
+                    if (p.atomic_out) {
+                        atomicAdd(o, r.x); atomicAdd(o + 1, r.y); atomicAdd(o + 2, r.z); atomicAdd(o + 3, r.w);
+                    } else {
+                        r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
+                        r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
+                        *reinterpret_cast<float4*>(o) = r;
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * CL_MAX_N);
+}
+
+// ------------------------------------------------------------------------------------------------ weight re-packing
+// PyTorch conv weight w[co][ci][kh][kw]  ->  TF32-rounded operand matrices:
+//   wf[co][(kh, kw, ci)]                          forward  (K = KH*KW*Cin)
+//   wq[(ph, pw, ci)][(a, bb, co)]                 data gradient of a 4x4 / stride 2 / even-pad convolution: output pixel parity
+//                                                 (ph, pw), tap (a, bb) reads dy at (i + a, j + bb) and kernel element
+//                                                 (ph + 2 (1 - a), pw + 2 (1 - bb));  K = 4 * Cout
+//   wt[ci][co]                                    data gradient of a 1x1 convolution
+__global__ void __launch_bounds__(256) cl_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wq,
+                                                             int Cout, int Cin, int KH, int KW, int quad) {
+    const int taps = KH * KW;
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        // i enumerates the DESTINATION wf index (co, kh, kw, ci) so that writes are coalesced
+        const int ci = static_cast<int>(i % Cin);
+        long long r = i / Cin;
+        const int tap = static_cast<int>(r % taps), co = static_cast<int>(r / taps);
+        const float v = to_tf32_rna(__ldg(w + (static_cast<long long>(co) * Cin + ci) * taps + tap));
+        if (wf != nullptr) wf[i] = v;
+        if (wq != nullptr) {
+            if (quad) {
+                const int kh = tap / KW, kw = tap % KW;
+                const int ph = kh & 1, a = 1 - (kh >> 1), pw = kw & 1, bb = 1 - (kw >> 1);
+                wq[(static_cast<long long>((ph * 2 + pw) * Cin + ci)) * (4LL * Cout) + (a * 2 + bb) * Cout + co] = v;
+            } else {
+                wq[static_cast<long long>(ci) * Cout + co] = v;          // 1x1: transpose
+            }
+        }
+    }
+}
+
+// dWcl[co][(kh, kw, ci)] -> PyTorch layout dw[co][ci][kh][kw]
+__global__ void __launch_bounds__(256) cl_unpack_dw_kernel(const float* __restrict__ dwcl, float* __restrict__ dw, int Cout, int Cin, int taps) {
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int tap = static_cast<int>(i % taps);
+        long long r = i / taps;
+        const int ci = static_cast<int>(r % Cin), co = static_cast<int>(r / Cin);
+        dw[i] = __ldg(dwcl + (static_cast<long long>(co) * taps + tap) * Cin + ci);
+    }
+}
+
+template <int MODE>
+static int launch_conv_cl(const pgv_handle* h, const ConvClParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        PGV_CUDA(cudaFuncSetAttribute(conv_cl_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+        configured = true;
+    }
+    const long long items = static_cast<long long>(p.m_tiles) * p.n_tiles * p.k_splits;
+    const int grid = static_cast<int>(items < h->sm_count ? items : h->sm_count);
+    conv_cl_kernel<MODE><<<grid, CL_THREADS, CL_SMEM, stream>>>(p);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+static int cl_pick_n_tile(int n, int granule) {
+    int t = (n + granule - 1) / granule * granule;
+    if (t > CL_MAX_N) {
+        const int parts = ceil_div(n, CL_MAX_N);
+        t = ceil_div(ceil_div(n, parts), granule) * granule;
+    }
+    return t;
+}
+
+// Shared by forward and data gradient: out = act(bias + gather(in) * Bw^T).
+static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, const float* bw, const float* bias, float* out, int B, int H,
+                        int W, int C, int KH, int KW, int stride, int pad, int Hg, int Wg, int N, int epi, int qH, int qW, int qC, float slope,
+                        int round_out, size_t out_elems, cudaStream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || N <= 0 || Hg <= 0 || Wg <= 0 || KH <= 0 || KH > 8 || KW <= 0 || KW > 8 || stride <= 0 || pad < 0)
+        return set_error(-1, "%s: bad geometry", who);
+    if (C % 4 != 0 || (KH * KW * C) % CL_BLOCK_K != 0 || N % 4 != 0)
+        return set_error(-1, "%s: channels-last kernels need C %% 4 == 0, K %% 32 == 0 and N %% 4 == 0 (C=%d, K=%d, N=%d)", who, C, KH * KW * C, N);
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(bw) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15)
+        return set_error(-1, "%s: pointers must be 16-byte aligned", who);
+    const long long m = static_cast<long long>(B) * Hg * Wg;
+    if (m >= (1LL << 31) - CL_BLOCK_M) return set_error(-1, "%s: too many output pixels", who);
+    ConvClParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = in; p.b = bw; p.bias = bias; p.out = out;
+    p.B = B; p.H = H; p.W = W; p.C = C; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.Hg = Hg; p.Wg = Wg;
+    p.gemm_m = static_cast<int>(m); p.gemm_n = N; p.gemm_k = KH * KW * C;
+    p.n_tile = cl_pick_n_tile(N, 16); p.n_tiles = ceil_div(N, p.n_tile);
+    p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
+    p.kb_total = p.gemm_k / CL_BLOCK_K; p.kb_per_split = p.kb_total; p.k_splits = 1;
+    p.epi = epi; p.ldo = N; p.qH = qH; p.qW = qW; p.qC = qC;
+    p.slope = slope; p.round_out = round_out;
+    p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1);
+    // long-K problems with few tiles and a linear epilogue: split K across CTAs, fp32 atomics into a zero-filled output
+    const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+    if (slope < 0.0f && !round_out && tiles < h->sm_count && p.kb_total >= 16) {
+        int splits = static_cast<int>((h->sm_count * 2) / tiles);
+        if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+        if (splits > 1) {
+            p.kb_per_split = ceil_div(p.kb_total, splits);
+            p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+            p.atomic_out = 1;
+            PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems, stream));
+        }
+    }
+    return launch_conv_cl<CL_GEMM>(h, p, stream);
+}
+
+}  // namespace pgv
+
+using namespace pgv;
+
+extern "C" {
+
+int pgv_conv_cl_prep_weights(const float* w, float* wf, float* wq, int Cout, int Cin, int KH, int KW, int stride, int pad, pgv_stream_t stream) {
+    PGV_CHECK_ARG(w && (wf || wq) && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "pgv_conv_cl_prep_weights: bad argument");
+    const int quad = (KH == 4 && KW == 4 && stride == 2 && pad == 2) ? 1 : 0;
+    PGV_CHECK_ARG(wq == nullptr || quad || (KH == 1 && KW == 1 && stride == 1 && pad == 0),
+                  "pgv_conv_cl_prep_weights: the data-gradient matrix exists for 4x4/stride 2/pad 2 and 1x1/stride 1 only");
+    const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+    cl_prep_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wf, wq, Cout, Cin, KH, KW, quad);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+int pgv_conv_cl_supported(int Cin, int Cout, int KH, int KW, int stride, int pad) {
+    if (Cin % 4 != 0 || Cout % 4 != 0 || (KH * KW * Cin) % 32 != 0) return 0;
+    if (KH == 4 && KW == 4 && stride == 2 && pad == 2) return (Cout % 8 == 0 && Cin % 8 == 0) ? 1 : 0;
+    if (KH == 1 && KW == 1 && stride == 1 && pad == 0) return (Cout % 32 == 0 && Cin % 32 == 0) ? 1 : 0;
+    return 0;
+}
+
+int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
+                    int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && x && wf && y, "pgv_conv_cl_fwd: NULL argument");
+    PGV_CHECK_ARG((Ho - 1) * stride - 2 * pad + KH <= H + stride && (Wo - 1) * stride - 2 * pad + KW <= W + stride,
+                  "pgv_conv_cl_fwd: output %dx%d does not fit input %dx%d", Ho, Wo, H, W);
+    return conv_cl_gemm(h, "pgv_conv_cl_fwd", x, wf, bias, y, B, H, W, Cin, KH, KW, stride, pad, Ho, Wo, Cout, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
+                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
+                      int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && dy && wq && dx, "pgv_conv_cl_dgrad: NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t out_elems = static_cast<size_t>(B) * H * W * Cin;
+    if (KH == 1 && KW == 1 && stride == 1 && pad == 0) {
+        PGV_CHECK_ARG(H == Ho && W == Wo, "pgv_conv_cl_dgrad: 1x1 geometry mismatch");
+        return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 1, 1, 1, 0, Ho, Wo, Cin, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
+                            round_out, out_elems, s);
+    }
+    PGV_CHECK_ARG(KH == 4 && KW == 4 && stride == 2, "pgv_conv_cl_dgrad: only 4x4/stride 2/pad 2 and 1x1/stride 1");
+    // pad = 2: the four pixels (2i + ph, 2j + pw) of a quad all read the 2x2 patch of dy whose corner is (i, j)
+    PGV_CHECK_ARG(pad == 2, "pgv_conv_cl_dgrad: pad %d not implemented", pad);
+    const int Hq = (H + 1) / 2, Wq = (W + 1) / 2;
+    return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 2, 2, 1, 0, Hq, Wq, 4 * Cin, CL_EPI_QUAD, H, W, Cin, lrelu_slope,
+                        round_out, out_elems, s);
+}
+
+int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH, int KW,
+                      int stride, int pad, int Ho, int Wo, pgv_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PGV_CHECK_ARG(h && x && dy && dwcl, "pgv_conv_cl_wgrad: NULL argument");
+    PGV_CHECK_ARG(B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "pgv_conv_cl_wgrad: bad geometry");
+    PGV_CHECK_ARG(Cin % 4 == 0 && Cout % 4 == 0 && (KW * Cin) % 32 == 0, "pgv_conv_cl_wgrad: needs Cin %% 4 == 0, Cout %% 4 == 0, KW*Cin %% 32 == 0");
+    PGV_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dwcl)) & 15) == 0,
+                  "pgv_conv_cl_wgrad: pointers must be 16-byte aligned");
+    ConvClParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = x; p.b = dy; p.out = dwcl;
+    p.B = B; p.H = H; p.W = W; p.C = Cin; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.Hg = Ho; p.Wg = Wo;
+    p.gemm_m = KH * KW * Cin; p.gemm_n = Cout;
+    p.n_tile = cl_pick_n_tile(Cout, 32); p.n_tiles = ceil_div(Cout, p.n_tile);
+    if (p.n_tile != 32 && p.n_tile != 64 && p.n_tile != 128) { p.n_tile = p.n_tile <= 64 ? 64 : 128; p.n_tiles = ceil_div(Cout, p.n_tile); }
+    p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
+    p.bblocks = ceil_div(B, 32);
+    p.kb_total = Ho * Wo * p.bblocks;
+    const int tiles = p.m_tiles * p.n_tiles;
+    int splits = ceil_div(h->sm_count * 2, tiles);
+    if (splits > p.kb_total / 4) splits = p.kb_total / 4;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = ceil_div(p.kb_total, splits);
+    p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    p.slope = -1.0f;
+    p.fd_HgWg.init(Ho * Wo); p.fd_Wg.init(Wo); p.fd_span.init(KW * Cin); p.fd_C.init(Cin); p.fd_bblocks.init(p.bblocks); p.fd_qC.init(1);
+    if (const char* v = getenv("PGV_WGRAD_VARIANT")) p.variant = atoi(v);
+    PGV_CUDA(cudaMemsetAsync(dwcl, 0, sizeof(float) * static_cast<size_t>(Cout) * p.gemm_m, stream));
+    return launch_conv_cl<CL_WGRAD>(h, p, stream);
+}
+
+int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Cin, int KH, int KW, pgv_stream_t stream) {
+    PGV_CHECK_ARG(dwcl && dw && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "pgv_conv_cl_unpack_dw: bad argument");
+    const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+    cl_unpack_dw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dwcl, dw, Cout, Cin, KH * KW);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

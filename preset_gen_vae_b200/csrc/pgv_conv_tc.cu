@@ -28,19 +28,6 @@ constexpr int CT_PRODUCER_WARPS = 8, CT_PRODUCERS = CT_PRODUCER_WARPS * 32;
 constexpr int CT_THREADS = CT_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
 constexpr int CT_SMEM = 1024 + CT_STAGES * CT_STAGE_BYTES + 256;
 
-// n / d and n % d for 0 <= n < 2^31 without a hardware divide (Granlund-Montgomery round-up method).
-struct FastDiv {
-    uint32_t d, m, l;
-    __host__ void init(uint32_t div) {
-        d = div < 1 ? 1 : div;
-        l = 0;
-        while ((1u << l) < d) ++l;
-        m = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << l) - d)) / d + 1);
-    }
-    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, m) + n) >> l; }
-    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
-};
-
 struct ConvTcParams {
     const float* x;      // FWD: input x        DGRAD: dy (conv output side)    WGRAD: x
     const float* w;      // weights [Cout, Cin, kh, kw]                          WGRAD: dy

@@ -12,10 +12,19 @@ namespace pgv {
 
 constexpr int THIN_K = 5, THIN_TAPS = 25, THIN_MAXC = 8;
 
+__device__ __forceinline__ float thin_round(float v, int round_out) {
+    if (!round_out) return v;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 // y[b,c,oh,ow] = act(bias[c] + sum_{r,s} x[b,0,2oh-2+r,2ow-2+s] * w[c,0,r,s]).  One thread per output pixel, all C channels.
+// CL: y is channels-last [B, Ho, Wo, C] (C == 8: two float4 stores per pixel), optionally rounded to TF32.
+template <bool CL>
 __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ y, int B, int C, int H,
-                                                            int W, int Ho, int Wo, float slope) {
+                                                            int W, int Ho, int Wo, float slope, int round_out) {
     __shared__ float sw[THIN_MAXC * THIN_TAPS], sb[THIN_MAXC];
     for (int i = threadIdx.x; i < C * THIN_TAPS; i += 256) sw[i] = w[i];
     if (threadIdx.x < C) sb[threadIdx.x] = bias != nullptr ? bias[threadIdx.x] : 0.0f;
@@ -35,18 +44,34 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const float* __restr
                 in[r * THIN_K + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
             }
         }
-        float* yb = y + static_cast<size_t>(b) * C * HWo + pix;
+        if (CL && C == THIN_MAXC) {
+            float o[THIN_MAXC];
+#pragma unroll
+            for (int c = 0; c < THIN_MAXC; ++c) {
+                float acc = sb[c];
+#pragma unroll
+                for (int t = 0; t < THIN_TAPS; ++t) acc = fmaf(in[t], sw[c * THIN_TAPS + t], acc);
+                o[c] = thin_round((slope >= 0.0f && acc < 0.0f) ? acc * slope : acc, round_out);
+            }
+            float4* yo = reinterpret_cast<float4*>(y + static_cast<size_t>(i) * THIN_MAXC);
+            yo[0] = make_float4(o[0], o[1], o[2], o[3]);
+            yo[1] = make_float4(o[4], o[5], o[6], o[7]);
+            continue;
+        }
+        float* yb = CL ? y + static_cast<size_t>(i) * C : y + static_cast<size_t>(b) * C * HWo + pix;
+        const size_t cs = CL ? 1 : static_cast<size_t>(HWo);
         for (int c = 0; c < C; ++c) {
             float acc = sb[c];
 #pragma unroll
             for (int t = 0; t < THIN_TAPS; ++t) acc = fmaf(in[t], sw[c * THIN_TAPS + t], acc);
-            yb[static_cast<size_t>(c) * HWo] = (slope >= 0.0f && acc < 0.0f) ? acc * slope : acc;
+            yb[c * cs] = thin_round((slope >= 0.0f && acc < 0.0f) ? acc * slope : acc, round_out);
         }
     }
 }
 
 // Transposed form: x[b,0,ih,iw] = clamp(bias + sum_{c,r,s: 2oh-2+r = ih, 2ow-2+s = iw} y[b,c,oh,ow] * w[c,0,r,s], lo, hi).
 // One thread per full-resolution pixel; taps r = (ih & 1) + 2a.
+template <bool CL>
 __global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float* __restrict__ y, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ x, int B, int C, int H,
                                                               int W, int Ho, int Wo, float lo, float hi) {
@@ -69,8 +94,20 @@ __global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float* __res
             for (int d = 0; d < 3; ++d) {
                 const int s = s0 + 2 * d, ow = ow0 - d;
                 if (s >= THIN_K || ow < 0 || ow >= Wo) continue;
-                const float* src = yb + oh * Wo + ow;
-                for (int c = 0; c < C; ++c) acc = fmaf(__ldg(src + static_cast<size_t>(c) * HWo), sw[c * THIN_TAPS + r * THIN_K + s], acc);
+                if (CL) {                                    // y is [B, Ho, Wo, C]
+                    const float* src = yb + (static_cast<size_t>(oh) * Wo + ow) * C;
+                    if (C == THIN_MAXC) {
+                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        const float vs[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                        for (int c = 0; c < THIN_MAXC; ++c) acc = fmaf(vs[c], sw[c * THIN_TAPS + r * THIN_K + s], acc);
+                    } else {
+                        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(src + c), sw[c * THIN_TAPS + r * THIN_K + s], acc);
+                    }
+                } else {
+                    const float* src = yb + oh * Wo + ow;
+                    for (int c = 0; c < C; ++c) acc = fmaf(__ldg(src + static_cast<size_t>(c) * HWo), sw[c * THIN_TAPS + r * THIN_K + s], acc);
+                }
             }
         }
         x[i] = fminf(fmaxf(acc, lo), hi);
@@ -82,7 +119,7 @@ __global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float* __res
 constexpr int TW_TH = 8, TW_TW = 32, TW_PH = 2 * TW_TH + 3, TW_PW = 2 * TW_TW + 3;
 __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                               float* __restrict__ dw, int B, int C, int H, int W, int Ho, int Wo,
-                                                              int tiles_per_block) {
+                                                              int tiles_per_block, int channels_last) {
     __shared__ float sdy[THIN_MAXC][TW_TH * TW_TW];
     __shared__ float sx[TW_PH * TW_PW];
     const int tiles_h = (Ho + TW_TH - 1) / TW_TH, tiles_w = (Wo + TW_TW - 1) / TW_TW, tiles_img = tiles_h * tiles_w;
@@ -101,9 +138,16 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __res
             const int ih = 2 * oh0 - 2 + i / TW_PW, iw = 2 * ow0 - 2 + i % TW_PW;
             sx[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
         }
-        for (int i = threadIdx.x; i < C * TW_TH * TW_TW; i += 256) {
-            const int cc = i / (TW_TH * TW_TW), p = i % (TW_TH * TW_TW), oh = oh0 + p / TW_TW, ow = ow0 + p % TW_TW;
-            sdy[cc][p] = (oh < Ho && ow < Wo) ? __ldg(dyb + (static_cast<size_t>(cc) * Ho + oh) * Wo + ow) : 0.0f;
+        if (channels_last) {                             // dy is [B, Ho, Wo, C]: channel fastest
+            for (int i = threadIdx.x; i < C * TW_TH * TW_TW; i += 256) {
+                const int cc = i % C, p = i / C, oh = oh0 + p / TW_TW, ow = ow0 + p % TW_TW;
+                sdy[cc][p] = (oh < Ho && ow < Wo) ? __ldg(dyb + (static_cast<size_t>(oh) * Wo + ow) * C + cc) : 0.0f;
+            }
+        } else {
+            for (int i = threadIdx.x; i < C * TW_TH * TW_TW; i += 256) {
+                const int cc = i / (TW_TH * TW_TW), p = i % (TW_TH * TW_TW), oh = oh0 + p / TW_TW, ow = ow0 + p % TW_TW;
+                sdy[cc][p] = (oh < Ho && ow < Wo) ? __ldg(dyb + (static_cast<size_t>(cc) * Ho + oh) * Wo + ow) : 0.0f;
+            }
         }
         __syncthreads();
         if (worker) {
@@ -132,28 +176,35 @@ int pgv_conv5x5s2_c1_supported(int Cin, int Cout, int kh, int kw, int stride, in
 }
 
 int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int C, int H, int W, int Ho, int Wo,
-                         float lrelu_slope, pgv_stream_t stream) {
+                         float lrelu_slope, int channels_last, int round_out, pgv_stream_t stream) {
     PGV_CHECK_ARG(x && w && y, "pgv_conv5x5s2_c1_fwd: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_fwd: unsupported geometry");
     const long long total = static_cast<long long>(B) * Ho * Wo;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-    thin_conv_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, B, C, H, W, Ho, Wo, lrelu_slope);
+    if (channels_last)
+        thin_conv_fwd_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, B, C, H, W, Ho, Wo, lrelu_slope, round_out);
+    else
+        thin_conv_fwd_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, B, C, H, W, Ho, Wo, lrelu_slope, round_out);
     PGV_LAUNCH_CHECK();
     return 0;
 }
 
 int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, float* x, int B, int C, int H, int W, int Ho, int Wo,
-                           float clamp_lo, float clamp_hi, pgv_stream_t stream) {
+                           float clamp_lo, float clamp_hi, int channels_last, pgv_stream_t stream) {
     PGV_CHECK_ARG(y && w && x, "pgv_conv5x5s2_c1_dgrad: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_dgrad: unsupported geometry");
     const long long total = static_cast<long long>(B) * H * W;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-    thin_conv_dgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);
+    if (channels_last)
+        thin_conv_dgrad_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);
+    else
+        thin_conv_dgrad_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);
     PGV_LAUNCH_CHECK();
     return 0;
 }
 
-int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo, pgv_stream_t stream_) {
+int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo, int channels_last,
+                           pgv_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PGV_CHECK_ARG(x && dy && dw, "pgv_conv5x5s2_c1_wgrad: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_wgrad: unsupported geometry");
@@ -162,7 +213,7 @@ int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, in
     int per_block = static_cast<int>((n_tiles + 148 * 4 - 1) / (148 * 4));
     if (per_block < 1) per_block = 1;
     const int grid = static_cast<int>((n_tiles + per_block - 1) / per_block);
-    thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block);
+    thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block, channels_last);
     PGV_LAUNCH_CHECK();
     return 0;
 }

@@ -128,4 +128,44 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// n / d and n % d for 0 <= n < 2^31 without a hardware divide (Granlund-Montgomery round-up method).
+struct FastDiv {
+    uint32_t d, m, l;
+    __host__ void init(uint32_t div) {
+        d = div < 1 ? 1 : div;
+        l = 0;
+        while ((1u << l) < d) ++l;
+        m = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << l) - d)) / d + 1);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, m) + n) >> l; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
+// ---------------------------------------------------------------- cp.async (LDGSTS) with zero fill + mbarrier completion
+// 16-byte asynchronous global -> shared copy; `bytes` (0 or 16) of the source are read, the rest of the 16 bytes is zero-filled.
+__device__ __forceinline__ void cp_async16_ca(uint32_t smem_dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
+}
+// The mbarrier receives ONE arrival (counted in its expected-arrival count) once all cp.async issued so far by this thread have landed.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// MN-major operand tile of a 32-bit type: layout type 1 = SWIZZLE_128B_BASE32B (128-byte rows, 32-byte swizzle units, atoms of 4
+// k-rows).  `lbo_bytes` = distance between consecutive 32-element groups along M/N, `sbo_bytes` = distance between consecutive
+// 4-row groups along K.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128_32b(uint32_t smem_addr_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;          // version
+    d |= static_cast<uint64_t>(1) << 61;          // SWIZZLE_128B_BASE32B
+    return d;
+}
+constexpr uint32_t UMMA_IDESC_A_MN = 1u << 15, UMMA_IDESC_B_MN = 1u << 16;      // operand is MN-major instead of K-major
+
 }  // namespace pgv

@@ -125,7 +125,7 @@ class SpectrogramDecoder(nn.Module):
         C = self.spectrogram_channels
         outs, ctxs = [], []
         for ch in range(C):                              # shared CNN, once per 512-channel slice (decoder.py:89-91)
-            part = h if C == 1 else h[:, ch * self.last_4x4conv_ch:(ch + 1) * self.last_4x4conv_ch].contiguous()
+            part = h if C == 1 else ops.slice_channels(h, ch * self.last_4x4conv_ch, (ch + 1) * self.last_4x4conv_ch)
             y, c = self.single_ch_cnn.fwd(part, training)
             outs.append(y)
             ctxs.append(c)
@@ -142,9 +142,9 @@ class SpectrogramDecoder(nn.Module):
             dparts.append(self.single_ch_cnn.bwd(d, ctxs[ch], local))
             for k, v in local.items():
                 grads[k] = v if k not in grads else ops.add(grads[k], v)
-        dh = dparts[0] if C == 1 else torch.cat(dparts, dim=1)
+        dh = dparts[0] if C == 1 else ops.cat_channels(dparts)
         dh = self.features_unmixer_cnn.bwd(dh, un_ctx, grads, True)
-        dflat = dh.reshape(dh.shape[0], -1)
+        dflat = ops.to_nchw(dh).reshape(dh.shape[0], -1)
         if drop_mask is not None:
             dflat = ops.mul(dflat, drop_mask)
         lin = self.mlp[0]

@@ -72,6 +72,8 @@ def _constructor_side_effect(single_blocks, mixer_blocks, input_tensor_size):
         bn.running_var.copy_(shadow.running_var)
         bn.num_batches_tracked += 1
         return y
+    precision = ops.get_precision()
+    ops.set_precision('fp32')            # one tiny forward: exact arithmetic, so the statistics match the reference's to fp32 rounding
     with torch.no_grad():
         x = torch.zeros(1, C, input_tensor_size[2], input_tensor_size[3], device=dev)
         feats = []
@@ -80,9 +82,10 @@ def _constructor_side_effect(single_blocks, mixer_blocks, input_tensor_size):
             for blk in single_blocks:
                 h = run(blk, h)
             feats.append(h)
-        h = feats[0] if C == 1 else torch.cat(feats, dim=1)
+        h = feats[0] if C == 1 else ops.cat_channels(feats)
         for blk in mixer_blocks:
             h = run(blk, h)
+    ops.set_precision(precision)
     return True
 
 
@@ -162,13 +165,13 @@ class SpectrogramEncoder(nn.Module):
                 ctxs.append(c)
             ch_ctx.append(ctxs)
             feats.append(h)
-        h = feats[0] if C == 1 else torch.cat(feats, dim=1)
+        h = feats[0] if C == 1 else ops.cat_channels(feats)
         mix_ctx = []
         for blk in self._mixer_blocks():
             h, c = blk.fwd(h, training)
             mix_ctx.append(c)
         cnn_shape = h.shape
-        flat = h.reshape(B, -1)
+        flat = ops.to_nchw(h).reshape(B, -1)          # nn.Linear expects the (c, h, w) flattening order
         fc_in = ops.mul(flat, drop_mask) if (training and drop_mask is not None) else flat
         lin = self.mlp[1]
         y = ops.linear_fwd(fc_in, lin.weight, lin.bias)
@@ -205,7 +208,7 @@ class SpectrogramEncoder(nn.Module):
         per = dh.shape[1] // C
         blocks = self.single_ch_cnn.blocks()
         for ch in range(C):
-            d = dh if C == 1 else dh[:, ch * per:(ch + 1) * per].contiguous()
+            d = dh if C == 1 else ops.slice_channels(dh, ch * per, (ch + 1) * per)
             local = {}
             for i in range(len(blocks) - 1, -1, -1):
                 d = blocks[i].bwd(d, ch_ctx[ch][i], local, need_dx or i > 0)

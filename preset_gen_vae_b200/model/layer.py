@@ -107,21 +107,32 @@ class Conv2D(_BlockBase):
         k, s, p = self.conv.kernel_size, self.conv.stride[0], self.conv.padding[0]
         return ops.conv_out_size(h, k[0], s, p), ops.conv_out_size(w, k[1], s, p)
 
+    def _route(self, x):
+        c = self.conv
+        Ho, Wo = self.out_hw(x.shape[2], x.shape[3])
+        return ops.conv_route(c.in_channels, c.out_channels, c.kernel_size[0], c.kernel_size[1], c.stride[0], c.padding[0],
+                              x.shape[2], x.shape[3], Ho, Wo)
+
     def fwd(self, x, training):
         c = self.conv
-        a = ops.conv2d_fwd(x, c.weight, c.bias, c.stride[0], c.padding[0], self.slope)
+        wf = wq = None
+        if self._route(x) == 'cl':         # channels-last tensor-core route: TF32-rounded input and re-packed weights
+            x = ops.to_cl(x, round_out=True)
+            wf, wq = ops.prep_conv_weights(c.weight, c.stride[0], c.padding[0], dgrad=training)
+        # without a BatchNorm behind it, the activation itself is the next tensor-core operand
+        a = ops.conv2d_fwd(x, c.weight, c.bias, c.stride[0], c.padding[0], self.slope, wf=wf, round_out=self.bn is None)
         y, mean, rstd = self._post(a, training)
-        return y, (x, a, mean, rstd)
+        return y, (x, a, mean, rstd, wq)
 
     def bwd(self, dy, ctx, grads, need_dx=True):
-        x, a, mean, rstd = ctx
+        x, a, mean, rstd, wq = ctx
         c = self.conv
         dz = self._pre_bwd(dy, a, mean, rstd, grads)
         dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True)
         grads[id(c.weight)], grads[id(c.bias)] = dw, db
         if not need_dx:
             return None
-        return ops.conv2d_dgrad(dz, c.weight, x.shape[2:], c.stride[0], c.padding[0])
+        return ops.conv2d_dgrad(dz, c.weight, x.shape[2:], c.stride[0], c.padding[0], wq=wq)
 
 
 class TConv2D(_BlockBase):
@@ -141,14 +152,19 @@ class TConv2D(_BlockBase):
         return tconv_out_hw(self.conv, h, w)
 
     def fwd(self, x, training):
-        a = tconv_fwd(x, self.conv, self.slope)
+        c = self.conv
+        wf = wq = None
+        if tconv_route(x, c) == 'cl':
+            x = ops.to_cl(x, round_out=True)
+            wf, wq = ops.prep_conv_weights(c.weight, c.stride[0], c.padding[0], fwd=training)
+        a = tconv_fwd(x, c, self.slope, wq=wq, round_out=self.bn is None)
         y, mean, rstd = self._post(a, training)
-        return y, (x, a, mean, rstd)
+        return y, (x, a, mean, rstd, wf)
 
     def bwd(self, dy, ctx, grads, need_dx=True):
-        x, a, mean, rstd = ctx
+        x, a, mean, rstd, wf = ctx
         dz = self._pre_bwd(dy, a, mean, rstd, grads)
-        return tconv_bwd(dz, x, self.conv, grads, need_dx)
+        return tconv_bwd(dz, x, self.conv, grads, need_dx, wf=wf)
 
 
 def tconv_out_hw(conv, h, w):
@@ -156,10 +172,17 @@ def tconv_out_hw(conv, h, w):
     return (h - 1) * s - 2 * p + k[0] + op[0], (w - 1) * s - 2 * p + k[1] + op[1]
 
 
-def tconv_fwd(x, conv, slope=-1.0, clamp=None):
+def tconv_route(x, conv):
+    """Kernel family of the transposed convolution = that of the convolution with the same weight tensor [Cin_t, Cout_t, kh, kw]."""
+    cin_t, cout_t, kh, kw = conv.weight.shape
+    H, W = tconv_out_hw(conv, x.shape[2], x.shape[3])
+    return ops.conv_route(cout_t, cin_t, kh, kw, conv.stride[0], conv.padding[0], H, W, x.shape[2], x.shape[3])
+
+
+def tconv_fwd(x, conv, slope=-1.0, clamp=None, wq=None, round_out=False):
     """ConvTranspose2d forward (+bias, optional fused LeakyReLU or Hardtanh clamp) = conv data-gradient."""
     return ops.conv2d_dgrad(x, conv.weight, tconv_out_hw(conv, x.shape[2], x.shape[3]), conv.stride[0], conv.padding[0],
-                            bias=conv.bias, slope=slope, clamp=clamp)
+                            bias=conv.bias, slope=slope, clamp=clamp, wq=wq, round_out=round_out)
 
 
 def tconv_clamp_fusable(x, conv):
@@ -169,11 +192,11 @@ def tconv_clamp_fusable(x, conv):
     return ops.use_thin and ops._thin(cout_t, cin_t, kh, kw, conv.stride[0], conv.padding[0], H, W, x.shape[2], x.shape[3])
 
 
-def tconv_bwd(dz, x, conv, grads, need_dx=True):
+def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None):
     """dz: gradient w.r.t. the transposed convolution's (pre-activation) output."""
     dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False)
     grads[id(conv.weight)] = dw
     grads[id(conv.bias)] = ops.channel_sum(dz)
     if not need_dx:
         return None
-    return ops.conv2d_fwd(dz, conv.weight, None, conv.stride[0], conv.padding[0], -1.0, out_hw=x.shape[2:])
+    return ops.conv2d_fwd(dz, conv.weight, None, conv.stride[0], conv.padding[0], -1.0, out_hw=x.shape[2:], wf=wf)

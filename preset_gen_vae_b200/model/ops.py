@@ -17,6 +17,7 @@ from .. import _lib
 
 LRELU_SLOPE = 0.1
 use_thin = True       # route the 5x5 / one-channel layers (enc1, dec8) to the direct streaming kernels (exact fp32)
+use_cl = True         # 'tf32' precision: run the 4x4 / 1x1 conv blocks channels-last on the cp.async-fed tcgen05 kernels
 _precision = 'tf32'
 launches = 0          # kernels launched through this module since the last reset (bench.py's gpu_launches)
 
@@ -37,8 +38,63 @@ def _f(t):
     if not t.is_cuda:
         raise _lib.PgvError("pgv kernels need CUDA tensors (got %s): there is no CPU path" % t.device)
     assert t.dtype in (torch.float32, torch.int32, torch.float64, torch.uint8), t.dtype
-    assert t.is_contiguous()
+    assert t.is_contiguous() or is_cl(t), "pgv kernels take dense NCHW or channels-last tensors"
     return ctypes.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------------ layouts
+# Channels-last activations are ordinary torch tensors of logical shape [B, C, H, W] with torch.channels_last strides, so
+# shapes read the same everywhere in Python and only the kernels see the physical [B, H, W, C] order.
+def cl_mode():
+    return _precision == 'tf32' and use_cl
+
+
+def is_cl(t):
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _empty_cl(ref, B, C, H, W):
+    return torch.empty((B, C, H, W), dtype=torch.float32, device=ref.device, memory_format=torch.channels_last)
+
+
+def to_cl(x, round_out=False):
+    """[B, C, H, W] (NCHW memory) -> the same logical tensor in channels-last memory, optionally rounded to TF32."""
+    if is_cl(x):
+        return x
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    y = _empty_cl(x, B, C, H, W)
+    _call('pgv_transpose_inner', _f(x), _f(y), B, C, H * W, int(round_out), _s(x), nbytes=8 * x.numel())
+    return y
+
+
+def to_nchw(x):
+    """Channels-last memory -> NCHW memory (no-op for tensors that already are)."""
+    if x.is_contiguous():
+        return x
+    if not is_cl(x):
+        return x.contiguous()
+    B, C, H, W = x.shape
+    y = _empty(x, B, C, H, W)
+    _call('pgv_transpose_inner', _f(x), _f(y), B, H * W, C, 0, _s(x), nbytes=8 * x.numel())
+    return y
+
+
+def slice_channels(x, lo, hi):
+    """x[:, lo:hi] as a dense tensor in x's own memory layout."""
+    part = x[:, lo:hi]
+    return part.contiguous(memory_format=torch.channels_last) if is_cl(x) else part.contiguous()
+
+
+def cat_channels(parts):
+    """Concatenation along the channel dimension, keeping a channels-last layout when the parts have one."""
+    out = torch.cat(parts, dim=1)
+    return to_cl(out) if (is_cl(parts[0]) and not is_cl(out)) else out
+
+
+def same_layout(t, like):
+    """`t` in the memory layout of `like` (both logically [B, C, H, W])."""
+    return to_cl(t) if is_cl(like) else to_nchw(t)
 
 
 profile = None        # None, or a dict filled by _call: name -> [calls, flops, bytes, [(start_event, end_event), ...]]
@@ -108,21 +164,51 @@ def conv_out_size(h, k, stride, pad):
     return (h + 2 * pad - k) // stride + 1
 
 
-def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None):
+def conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+    """Which kernel family runs a convolution of this geometry: 'thin' (direct 5x5, one channel), 'cl' (channels-last
+    tcgen05 + cp.async), 'tc' (NCHW tcgen05, register-staged gathers) or 'f32' (exact CUDA-core)."""
+    if use_thin and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+        return 'thin'
+    if cl_mode() and _lib.lib().pgv_conv_cl_supported(Cin, Cout, kh, kw, stride, pad):
+        return 'cl'
+    return 'tc' if _precision == 'tf32' else 'f32'
+
+
+def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True):
+    """TF32-rounded operand matrices of the channels-last kernels for weight w [Cout, Cin, kh, kw]: (wf, wq)."""
+    Cout, Cin, kh, kw = w.shape
+    K = Cin * kh * kw
+    wf = _empty(w, Cout, K) if fwd else None
+    wq = (_empty(w, 4 * Cin, 4 * Cout) if kh == 4 else _empty(w, Cin, Cout)) if dgrad else None
+    _call('pgv_conv_cl_prep_weights', _f(w), _f(wf), _f(wq), Cout, Cin, kh, kw, stride, pad, _s(w), nbytes=12 * w.numel())
+    return wf, wq
+
+
+def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_out=False):
+    """round_out: round the result to TF32 (set when it feeds a channels-last tensor-core kernel directly)."""
     B, Cin, H, W = x.shape
     Cout, _, kh, kw = w.shape
     Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
+    route = conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo)
+    flops = 2 * B * Ho * Wo * Cout * Cin * kh * kw
+    if route == 'thin':
+        cl = cl_mode()
+        y = _empty_cl(x, B, Cout, Ho, Wo) if cl else _empty(x, B, Cout, Ho, Wo)
+        _call('pgv_conv5x5s2_c1_fwd', _f(to_nchw(x)), _f(w), _f(bias), _f(y), B, Cout, H, W, Ho, Wo, slope, int(cl), int(cl and round_out),
+              _s(x), flops=flops, nbytes=4 * (x.numel() + y.numel()))
+        return y
+    if route == 'cl':
+        x = to_cl(x, round_out=True)
+        if wf is None:
+            wf, _ = prep_conv_weights(w, stride, pad, dgrad=False)
+        y = _empty_cl(x, B, Cout, Ho, Wo)
+        _call('pgv_conv_cl_fwd', _h(x), _f(x), _f(wf), _f(bias), _f(y), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope, int(round_out),
+              _s(x), flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
+        return y
+    x = to_nchw(x)
     y = _empty(x, B, Cout, Ho, Wo)
-    if use_thin and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
-        _call('pgv_conv5x5s2_c1_fwd', _f(x), _f(w), _f(bias), _f(y), B, Cout, H, W, Ho, Wo, slope, _s(x),
-              flops=2 * B * Ho * Wo * Cout * 25, nbytes=4 * (x.numel() + y.numel()))
-        return y
-    if _precision == 'tf32':
-        _call('pgv_conv2d_fwd_tf32', _h(x), _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x),
-              flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + y.numel() + w.numel()))
-        return y
-    _call('pgv_conv2d_fwd_f32', _f(x), _f(w), _f(bias), _f(y), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x),
-          flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + y.numel() + w.numel()))
+    _call('pgv_conv2d_fwd_tf32' if route == 'tc' else 'pgv_conv2d_fwd_f32', *((_h(x),) if route == 'tc' else ()), _f(x), _f(w), _f(bias), _f(y),
+          B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x), flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
     return y
 
 
@@ -130,25 +216,37 @@ def _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
     return bool(_lib.lib().pgv_conv5x5s2_c1_supported(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo))
 
 
-def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None):
+def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, wq=None, round_out=False):
     """dx of the convolution with weight w [Cout, Cin, kh, kw]; also the forward of ConvTranspose2d(weight=w).
-    clamp=(lo, hi) fuses a Hardtanh (only available on the thin-layer kernel; callers check `thin_dgrad_available`)."""
+    clamp=(lo, hi) fuses a Hardtanh (only available on the thin-layer kernel; callers check `tconv_clamp_fusable`)."""
     B, Cout, Ho, Wo = dy.shape
     _, Cin, kh, kw = w.shape
     H, W = in_hw
-    dx = _empty(dy, B, Cin, H, W)
-    if use_thin and slope < 0 and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
+    route = conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo)
+    flops = 2 * B * Ho * Wo * Cout * Cin * kh * kw
+    if route == 'thin' and slope < 0:
         lo, hi = clamp if clamp is not None else (-float('inf'), float('inf'))
-        _call('pgv_conv5x5s2_c1_dgrad', _f(dy), _f(w), _f(bias), _f(dx), B, Cout, H, W, Ho, Wo, lo, hi, _s(dy),
-              flops=2 * B * Ho * Wo * Cout * 25, nbytes=4 * (dx.numel() + dy.numel()))
+        dx = _empty(dy, B, Cin, H, W)
+        _call('pgv_conv5x5s2_c1_dgrad', _f(dy), _f(w), _f(bias), _f(dx), B, Cout, H, W, Ho, Wo, lo, hi, int(is_cl(dy)), _s(dy),
+              flops=flops, nbytes=4 * (dx.numel() + dy.numel()))
         return dx
     assert clamp is None, "fused clamp needs the thin-layer kernel"
+    if route == 'cl':
+        dy = to_cl(dy, round_out=True)
+        if wq is None:
+            _, wq = prep_conv_weights(w, stride, pad, fwd=False)
+        dx = _empty_cl(dy, B, Cin, H, W)
+        _call('pgv_conv_cl_dgrad', _h(dy), _f(dy), _f(wq), _f(bias), _f(dx), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope,
+              int(round_out), _s(dy), flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
+        return dx
+    dy = to_nchw(dy)
+    dx = _empty(dy, B, Cin, H, W)
     if _precision == 'tf32' and stride <= 2:
         _call('pgv_conv2d_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope,
-              _s(dy), flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
+              _s(dy), flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
         return dx
     _call('pgv_conv2d_dgrad_f32', _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(dy),
-          flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
+          flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
     return dx
 
 
@@ -156,25 +254,38 @@ def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
     B, Cin, H, W = x.shape
     _, Cout, Ho, Wo = dy.shape
     _, _, kh, kw = w_shape
+    route = conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo)
+    flops = 2 * B * Ho * Wo * Cout * Cin * kh * kw
     dw = _empty(x, *w_shape)
-    if use_thin and _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
-        _call('pgv_conv5x5s2_c1_wgrad', _f(x), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, _s(x), n=2,
-              flops=2 * B * Ho * Wo * Cout * 25, nbytes=4 * (x.numel() + dy.numel()))
+    if route == 'thin':
+        _call('pgv_conv5x5s2_c1_wgrad', _f(to_nchw(x)), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, int(is_cl(dy)), _s(x), n=2,
+              flops=flops, nbytes=4 * (x.numel() + dy.numel()))
         return dw, (channel_sum(dy) if want_bias else None)
-    if _precision == 'tf32':
+    if route == 'cl':
+        x, dy = to_cl(x, round_out=True), to_cl(dy, round_out=True)
+        dwcl = _empty(x, Cout, kh * kw * Cin)
+        _call('pgv_conv_cl_wgrad', _h(x), _f(x), _f(dy), _f(dwcl), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
+              flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
+        _call('pgv_conv_cl_unpack_dw', _f(dwcl), _f(dw), Cout, Cin, kh, kw, _s(x), nbytes=8 * dw.numel())
+        return dw, (channel_sum(dy) if want_bias else None)
+    x, dy = to_nchw(x), to_nchw(dy)
+    if route == 'tc':
         _call('pgv_conv2d_wgrad_tf32', _h(x), _f(x), _f(dy), _f(dw), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
-              flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
+              flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
         return dw, (channel_sum(dy) if want_bias else None)
     db = _empty(x, Cout) if want_bias else None
     _call('pgv_conv2d_wgrad_f32', _f(x), _f(dy), _f(dw), _f(db), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x),
-          n=4 if want_bias else 2, flops=2 * B * Ho * Wo * Cout * Cin * kh * kw, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
+          n=4 if want_bias else 2, flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
     return dw, db
 
 
 def channel_sum(x):
-    B, C = x.shape[:2]
+    B, C, H, W = x.shape
     out = _empty(x, C)
-    _call('pgv_channel_sum', _f(x), _f(out), B, C, x[0, 0].numel(), _s(x), n=2)
+    if is_cl(x):
+        _call('pgv_colsum_cl', _f(x), _f(out), B * H * W, C, _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * x.numel())
+    else:
+        _call('pgv_channel_sum', _f(x), _f(out), B, C, H * W, _s(x), n=2, nbytes=4 * x.numel())
     return out
 
 
@@ -183,6 +294,10 @@ def bn2d_train_fwd(x, bn):
     B, C = x.shape[:2]
     HW = x[0, 0].numel()
     y, mean, rstd = torch.empty_like(x), _empty(x, C), _empty(x, C)
+    if is_cl(x):        # result rounded to TF32: its consumers are the cp.async-fed tensor-core kernels
+        _call('pgv_bn_cl_train_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(y), _f(mean), _f(rstd), _f(bn.running_mean), _f(bn.running_var),
+              bn.momentum, bn.eps, B * HW, C, 1, _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 3 * x.numel())
+        return y, mean, rstd
     _call('pgv_bn2d_train_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(y), _f(mean), _f(rstd), _f(bn.running_mean),
           _f(bn.running_var), bn.momentum, bn.eps, B, C, HW, _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 3 * x.numel())
     return y, mean, rstd
@@ -191,6 +306,10 @@ def bn2d_train_fwd(x, bn):
 def bn2d_eval_fwd(x, bn):
     B, C = x.shape[:2]
     y = torch.empty_like(x)
+    if is_cl(x):
+        _call('pgv_bn_cl_eval_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(bn.running_mean), _f(bn.running_var), _f(y), bn.eps,
+              B * x[0, 0].numel(), C, 1, _s(x), nbytes=8 * x.numel())
+        return y
     _call('pgv_bn2d_eval_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(bn.running_mean), _f(bn.running_var), _f(y), bn.eps, B, C,
           x[0, 0].numel(), _s(x))
     return y
@@ -198,7 +317,12 @@ def bn2d_eval_fwd(x, bn):
 
 def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope):
     B, C = x.shape[:2]
+    dy = same_layout(dy, x)
     dx, dg, db = torch.empty_like(x), _empty(x, C), _empty(x, C)
+    if is_cl(x):
+        _call('pgv_bn_cl_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B * x[0, 0].numel(), C, 1,
+              _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 5 * x.numel())
+        return dx, dg, db
     _call('pgv_bn2d_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B, C, x[0, 0].numel(),
           _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 5 * x.numel())
     return dx, dg, db
@@ -206,6 +330,11 @@ def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope):
 
 def lrelu_bwd(dy, a, slope=LRELU_SLOPE):
     dx = torch.empty_like(a)
+    if a.dim() == 4:
+        dy = same_layout(dy, a)
+    if is_cl(a):
+        _call('pgv_lrelu_bwd_round', _f(dy), _f(a), _f(dx), slope, a.numel(), 1, _s(a), nbytes=12 * a.numel())
+        return dx
     _call('pgv_lrelu_bwd', _f(dy), _f(a), _f(dx), slope, a.numel(), _s(a))
     return dx
 

@@ -1,0 +1,143 @@
+"""GPU: the channels-last companions of the tensor-core convolution path (BatchNorm2d on [P, C], per-channel sums,
+layout converters, weight re-packing, thin-layer kernels with channels-last operands), each against an fp64 PyTorch
+evaluation.  The channels-last convolutions themselves are covered for every layer geometry by
+test_kernels_gpu.py::test_tensor_core_convs_against_fp64[use_cl=True]."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from preset_gen_vae_b200.model import layer, ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(*shape, device=DEV, generator=g) * scale
+
+
+def tf32_rna(x):
+    """Round-to-nearest (ties away) to 10 mantissa bits, like cvt.rna.tf32.f32."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def test_layout_converters_round_trip_and_rounding():
+    x = rnd(3, 24, 5, 7, seed=1)
+    cl = ops.to_cl(x)
+    assert ops.is_cl(cl) and torch.equal(cl, x) and cl.data_ptr() != x.data_ptr()
+    assert torch.equal(cl.permute(0, 2, 3, 1).contiguous().view(-1), cl.as_strided((cl.numel(),), (1,)))   # physically NHWC
+    back = ops.to_nchw(cl)
+    assert back.is_contiguous() and torch.equal(back, x)
+    r = ops.to_cl(x, round_out=True)
+    assert torch.equal(r, tf32_rna(x))
+    assert ops.to_cl(cl) is cl and ops.to_nchw(x) is x
+
+
+@pytest.mark.parametrize("cout,cin,k", [(16, 8, 4), (64, 32, 4), (2048, 512, 1)])
+def test_weight_repacking(cout, cin, k):
+    w = rnd(cout, cin, k, k, seed=2)
+    s, p = (2, 2) if k == 4 else (1, 0)
+    wf, wq = ops.prep_conv_weights(w, s, p)
+    wr = tf32_rna(w)
+    assert torch.equal(wf, wr.permute(0, 2, 3, 1).reshape(cout, -1))
+    if k == 1:
+        assert torch.equal(wq, wr.view(cout, cin).t())
+    else:
+        # wq[(ph, pw, ci)][(a, b, co)] = w[co, ci, ph + 2(1-a), pw + 2(1-b)]
+        want = torch.empty(2, 2, cin, 2, 2, cout, device=DEV)
+        for ph in range(2):
+            for pw in range(2):
+                for a in range(2):
+                    for b in range(2):
+                        want[ph, pw, :, a, b, :] = wr[:, :, ph + 2 * (1 - a), pw + 2 * (1 - b)].t()
+        assert torch.equal(wq, want.view(4 * cin, 4 * cout))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 16, 33, 45), (2, 8, 129, 174), (5, 512, 3, 4), (2, 24, 7, 5)])
+def test_batchnorm2d_channels_last(B, C, H, W):
+    a = ops.to_cl(F.leaky_relu(rnd(B, C, H, W, seed=7) * 2 + 0.5, 0.1))
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(rnd(C, seed=8) * 0.3 + 1)
+        bn.bias.copy_(rnd(C, seed=9) * 0.2)
+    ref_bn = torch.nn.BatchNorm2d(C).to(DEV).double()
+    ref_bn.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    y, mean, rstd = ops.bn2d_train_fwd(a, bn)
+    ref = ref_bn(a.double())
+    assert ops.is_cl(y)
+    assert torch.equal(y, tf32_rna(y))                       # the channels-last route hands TF32-rounded operands to the next conv
+    assert rel(y, ref) < 4e-4                                  # 2^-11 rounding
+    assert rel(bn.running_mean, ref_bn.running_mean) < 1e-6 and rel(bn.running_var, ref_bn.running_var) < 1e-6
+    assert rel(mean, a.double().mean((0, 2, 3))) < 1e-6
+    dy = rnd(B, C, H, W, seed=10)                              # NCHW on purpose: the op converts to the layout of `a`
+    z = (a / torch.where(a > 0, torch.ones_like(a), torch.full_like(a, 0.1))).double().requires_grad_()
+    out = ref_bn.train()(F.leaky_relu(z, 0.1))
+    gz, gg, gb = torch.autograd.grad(out, (z, ref_bn.weight, ref_bn.bias), dy.double())
+    dz, dg, db = ops.bn2d_train_bwd(dy, a, bn.weight, mean, rstd, 0.1)
+    assert ops.is_cl(dz) and rel(dz, gz) < 4e-4 and rel(dg, gg) < 5e-6 and rel(db, gb) < 5e-6
+    bn.eval()
+    ref_bn.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    ref_bn.eval()
+    assert rel(ops.bn2d_eval_fwd(a, bn), ref_bn(a.double())) < 4e-4
+    assert rel(ops.lrelu_bwd(dy, a, 0.1), dy * torch.where(a > 0, 1.0, 0.1)) < 4e-4
+    assert rel(ops.channel_sum(ops.to_cl(dy)), dy.double().sum((0, 2, 3))) < 1e-6
+
+
+def test_thin_layer_kernels_with_channels_last_operands():
+    """enc1 writes / dec8 reads the 8-channel tensor in channels-last order on the default route."""
+    B, H, W, C = 3, 257, 347, 8
+    assert ops.cl_mode()
+    x, w, b = rnd(B, 1, H, W, seed=60), rnd(C, 1, 5, 5, seed=61, scale=0.2), rnd(C, seed=62)
+    xd, wd, bd = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    pre = F.conv2d(xd, wd, bd, 2, 2)
+    y = ops.conv2d_fwd(x, w, b, 2, 2, slope=0.1)
+    assert ops.is_cl(y) and rel(y, F.leaky_relu(pre, 0.1)) < 2e-6
+    yr = ops.conv2d_fwd(x, w, b, 2, 2, slope=0.1, round_out=True)
+    assert torch.equal(yr, tf32_rna(y))
+    dy = ops.to_cl(rnd(B, C, 129, 174, seed=63))
+    gx, gw, gb = torch.autograd.grad(pre, (xd, wd, bd), dy.double())
+    dw, db = ops.conv2d_wgrad(x, dy, w.shape, 2, 2, want_bias=True)
+    assert rel(dw, gw) < 5e-6 and rel(db, gb) < 5e-6
+    bias1 = rnd(1, seed=64)
+    t = ops.conv2d_dgrad(dy, w, (H, W), 2, 2, bias=bias1, clamp=(-1.0, 1.0))      # dec8 forward + Hardtanh
+    assert t.is_contiguous() and rel(t, F.hardtanh(gx + bias1.double())) < 2e-6
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_block_forward_backward_on_the_channels_last_route(transposed):
+    """A whole Conv2D / TConv2D block (conv -> LeakyReLU -> BatchNorm2d, weight re-packing, rounding flags, layout
+    conversion of an NCHW input and of the NCHW upstream gradient) against torch's own modules in fp64."""
+    torch.manual_seed(5)
+    B = 4
+    if transposed:
+        blk = layer.TConv2D(64, 32, [4, 4], [2, 2], 2, output_padding=[1, 1], activation=torch.nn.LeakyReLU(0.1), name_prefix='t').to(DEV)
+        x = rnd(B, 64, 17, 23, seed=1)
+        ref_conv = torch.nn.ConvTranspose2d(64, 32, 4, 2, 2, output_padding=1).to(DEV).double()
+    else:
+        blk = layer.Conv2D(32, 64, [4, 4], [2, 2], 2, [1, 1], activation=torch.nn.LeakyReLU(0.1), name_prefix='c').to(DEV)
+        x = rnd(B, 32, 33, 45, seed=1)
+        ref_conv = torch.nn.Conv2d(32, 64, 4, 2, 2).to(DEV).double()
+    ref_bn = torch.nn.BatchNorm2d(blk.bn.num_features).to(DEV).double()
+    with torch.no_grad():
+        ref_conv.weight.copy_(blk.conv.weight.double()); ref_conv.bias.copy_(blk.conv.bias.double())
+    blk.train()
+    xg = x.clone().requires_grad_()
+    y = blk(xg)
+    xd = x.double().requires_grad_()
+    ref = ref_bn(F.leaky_relu(ref_conv(xd), 0.1))
+    assert y.shape == ref.shape and rel(y, ref) < 2e-3
+    # Gradient gate: TF32 noise (3e-4) in the pre-activation flips the LeakyReLU branch of the ~3e-4 fraction of elements that
+    # lie that close to zero; each flip is an O(1) relative error on that element, i.e. ~sqrt(3e-4) * 0.9 = 1.5e-2 in L2.
+    dy = rnd(*y.shape, seed=3)
+    y.backward(dy)
+    ref.backward(dy.double())
+    assert rel(xg.grad, xd.grad) < 3e-2
+    assert rel(blk.conv.weight.grad, ref_conv.weight.grad) < 3e-2
+    assert rel(blk.bn.weight.grad, ref_bn.weight.grad) < 3e-2 and rel(blk.bn.bias.grad, ref_bn.bias.grad) < 3e-2
+    assert rel(blk.conv.bias.grad, ref_conv.bias.grad) < 3e-2

@@ -94,12 +94,15 @@ def test_transposed_conv_via_conv_gradients(cin, cout, k, op, s, H, W):
     expected = {1: (3, 4), 4: None}   # output sizes of decoder.py:199-220 are checked in the model test
 
 
+@pytest.mark.parametrize("use_cl", [True, False])
 @pytest.mark.parametrize("cin,cout,k,s,p,H,W", ENC_LAYERS + [(8, 1, 5, 2, 2, 257, 347), (16, 8, 4, 2, 2, 129, 174)])
-def test_tensor_core_convs_against_fp64(cin, cout, k, s, p, H, W):
+def test_tensor_core_convs_against_fp64(cin, cout, k, s, p, H, W, use_cl):
     """tcgen05 implicit-GEMM conv fwd / dgrad / wgrad (TF32 products, operands rounded to nearest) for every layer
-    geometry, incl. the decoder's last two transposed convs viewed as conv data-gradients.  TF32 tolerance: relative-L2
+    geometry, incl. the decoder's last two transposed convs viewed as conv data-gradients, on both tensor-core routes:
+    channels-last + cp.async (use_cl, the default) and NCHW with register-staged gathers.  TF32 tolerance: relative-L2
     error of a K-term dot product of operands with 2^-11 relative rounding ~ 2^-11 * sqrt(2) = 7e-4; gate 2e-3."""
     B = 3
+    ops.use_cl = use_cl
     Ho, Wo = ops.conv_out_size(H, k, s, p), ops.conv_out_size(W, k, s, p)
     if (cin, cout, k) == (16, 8, 4):            # dec7 geometry: odd output_padding makes H one larger than the conv's natural input
         H, W = 129, 174
@@ -116,11 +119,15 @@ def test_tensor_core_convs_against_fp64(cin, cout, k, s, p, H, W):
         dw, db = ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=True)
         bias_in = rnd(cin, seed=5)
         dx_act = ops.conv2d_dgrad(dy, w, (H, W), s, p, bias=bias_in, slope=0.1)     # transposed-conv forward form
+        route = ops.conv_route(cin, cout, k, k, s, p, H, W, Ho, Wo)
     finally:
         ops.set_precision('tf32')
+        ops.use_cl = True
+    assert route == ('thin' if (cin == 1 and k == 5) else ('cl' if (use_cl and k != 5) else 'tc'))
+    assert ops.is_cl(y) == (use_cl and route in ('thin', 'cl')) and ops.is_cl(dx) == (route == 'cl')
     errs = (rel(y, F.leaky_relu(pre, 0.1)), rel(dx, gx), rel(dw, gw), rel(db, gb),
             rel(dx_act, F.leaky_relu(gx + bias_in.double()[None, :, None, None], 0.1)))
-    print("tc conv", (cin, cout, k, s, p, H, W), "rel-L2 fwd %.2e dgrad %.2e wgrad %.2e db %.2e tconv-fwd %.2e" % errs)
+    print("tc conv", route, (cin, cout, k, s, p, H, W), "rel-L2 fwd %.2e dgrad %.2e wgrad %.2e db %.2e tconv-fwd %.2e" % errs)
     assert max(errs) < 2e-3
 
 

@@ -9,6 +9,8 @@ from preset_gen_vae_b200.model import ops  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 dev = 'cuda'
 ops.set_precision('tf32')
+ops.use_cl = not (len(sys.argv) > 2 and sys.argv[2] == 'nchw')
+print('route:', 'channels-last + cp.async' if ops.use_cl else 'NCHW register-staged')
 # conv geometry (Cin, Cout, k, s, p, H, W, Ho, Wo) of the convolution whose fwd/dgrad/wgrad each layer uses
 ENC = [('enc1', 1, 8, 5, 257, 347), ('enc2', 8, 16, 4, 129, 174), ('enc3', 16, 32, 4, 65, 88), ('enc4', 32, 64, 4, 33, 45),
        ('enc5', 64, 128, 4, 17, 23), ('enc6', 128, 256, 4, 9, 12), ('enc7', 256, 512, 4, 5, 7)]
@@ -39,8 +41,14 @@ for name, cin, cout, k, H, W in ENC + DEC:
     b = torch.randn(cout, device=dev)
     dy = torch.randn(B, cout, Ho, Wo, device=dev)
     fl = 2 * B * Ho * Wo * cout * cin * k * k / 1e9
-    t_f = timeit(lambda: ops.conv2d_fwd(x, w, b, s, p, 0.1))
-    t_d = timeit(lambda: ops.conv2d_dgrad(dy, w, (H, W), s, p))
+    wf = wq = None
+    if ops.conv_route(cin, cout, k, k, s, p, H, W, Ho, Wo) == 'cl':       # operands as the model holds them: channels-last, pre-rounded
+        x, dy = ops.to_cl(x, True), ops.to_cl(dy, True)
+        wf, wq = ops.prep_conv_weights(w, s, p)
+    elif ops.cl_mode() and cin == 1:
+        dy = ops.to_cl(dy, True)
+    t_f = timeit(lambda: ops.conv2d_fwd(x, w, b, s, p, 0.1, wf=wf))
+    t_d = timeit(lambda: ops.conv2d_dgrad(dy, w, (H, W), s, p, wq=wq))
     t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=False))
     tot['fwd'] += t_f; tot['dgrad'] += t_d; tot['wgrad'] += t_w
     mb = 4 * (x.numel() + dy.numel()) / 1e6
@@ -50,7 +58,11 @@ for name, cin, cout, H, W in [('enc8 1x1', 512, 2048, 3, 4), ('dec1 1x1', 512, 2
     x = torch.randn(B, cin, H, W, device=dev); w = torch.randn(cout, cin, 1, 1, device=dev) * 0.05; b = torch.randn(cout, device=dev)
     dy = torch.randn(B, cout, H, W, device=dev)
     fl = 2 * B * H * W * cout * cin / 1e9
-    t_f = timeit(lambda: ops.conv2d_fwd(x, w, b, 1, 0, 0.1)); t_d = timeit(lambda: ops.conv2d_dgrad(dy, w, (H, W), 1, 0))
+    wf = wq = None
+    if ops.conv_route(cin, cout, 1, 1, 1, 0, H, W, H, W) == 'cl':
+        x, dy = ops.to_cl(x, True), ops.to_cl(dy, True)
+        wf, wq = ops.prep_conv_weights(w, 1, 0)
+    t_f = timeit(lambda: ops.conv2d_fwd(x, w, b, 1, 0, 0.1, wf=wf)); t_d = timeit(lambda: ops.conv2d_dgrad(dy, w, (H, W), 1, 0, wq=wq))
     t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, w.shape, 1, 0, want_bias=False))
     tot['fwd'] += t_f; tot['dgrad'] += t_d; tot['wgrad'] += t_w
     print("%-10s %8.2f   %7.3f (%6.1f)   %7.3f (%6.1f)   %7.3f (%6.1f)" % (name, fl, t_f, fl / t_f, t_d, fl / t_d, t_w, fl / t_w))
