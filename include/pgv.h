@@ -105,6 +105,30 @@ PGV_API int pgv_gemm_f32(pgv_handle* h, int trans_a, int trans_b, const float* a
                          int m, int n, int k, const float* bias, int act, const float* residual, int ldr, pgv_stream_t stream);
 /* out[f] = sum over rows of x[B,F] (bias gradients). */
 PGV_API int pgv_colsum(const float* x, float* out, int B, int F, pgv_stream_t stream);
+/* Linear-layer gradients in exact fp32 (nflows ResidualNet conditioners, VAE.py:118-125, flows.py:42-90): dw [N, K] = dy^T x,
+ * db [N] = column sums of dy [M, N] (NULL to skip); the flow-sized problems get db from the GEMM kernel itself. */
+PGV_API int pgv_linear_wgrad_f32(pgv_handle* h, const float* dy, const float* x, float* dw, float* db, int M, int N, int K,
+                                 pgv_stream_t stream);
+
+/* Column-slice GEMM family for the flow conditioners (nflows ResidualNet / ResidualBlock: VAE.py:118-125, flows.py:42-90,
+ * regression.py:142-148): one block owns 16 output columns for all M <= pgv_colslice_max_rows() rows, so BatchNorm1d batch
+ * statistics are block-local and the normalisation is fused into the GEMM.  Exact fp32.  x [M, K], w [N, K] (nn.Linear).
+ *   pgv_linear_cs_fwd       y = act(x w^T + bias + residual)
+ *   pgv_linear_cs_dgrad     dx [M, K] = dy [M, N] w
+ *   pgv_linear_bn_fwd       y_pre = x w^T + bias + residual (stored if non-NULL); out = mask * relu(BN(y_pre)) with batch
+ *                           statistics (saved in save_mean / save_rstd) and running-stat update: Linear -> BatchNorm1d -> ReLU -> Dropout
+ *   pgv_linear_dgrad_bn_bwd dt = dy w; dx = backward of mask * relu(BN(bn_x)) at dt, + add_post; dgamma / dbeta of that BatchNorm */
+PGV_API int pgv_colslice_max_rows(void);
+PGV_API int pgv_linear_cs_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N, int K,
+                              int relu, pgv_stream_t stream);
+PGV_API int pgv_linear_cs_dgrad(const float* dy, const float* w, float* dx, int M, int N, int K, pgv_stream_t stream);
+PGV_API int pgv_linear_bn_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y_pre, float* out,
+                              const float* gamma, const float* beta, const float* mask, float* save_mean, float* save_rstd,
+                              float* running_mean, float* running_var, float momentum, float eps, int M, int N, int K,
+                              pgv_stream_t stream);
+PGV_API int pgv_linear_dgrad_bn_bwd(const float* dy, const float* w, const float* bn_x, const float* gamma, const float* beta,
+                                    const float* mean, const float* rstd, const float* mask, const float* add_post, float* dx,
+                                    float* dgamma, float* dbeta, int M, int N, int K, pgv_stream_t stream);
 
 /* ------------------------------------------------------------------ convolutions (NCHW fp32)
  * nn.Conv2d / nn.ConvTranspose2d call sites: model/layer.py:19,38 (blocks of model/encoder.py:233-259 and

@@ -161,6 +161,62 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __res
     if (worker) atomicAdd(dw + c * THIN_TAPS + tap, acc);
 }
 
+// Channels-last, C == 8 variant: lane = tap (25 of 32 lanes), 8 channel accumulators per lane, warp w walks row w of the 8 x 32
+// pixel tile.  Per pixel a lane reads its patch element (1 LDS) and the pixel's 8 dy values (2 broadcast LDS.128) for 8 FMAs:
+// 0.4 shared-memory reads per FMA instead of 2, which is what bounds the generic kernel above.
+__global__ void __launch_bounds__(256) thin_conv_wgrad_cl8_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
+                                                                  int tiles_per_block) {
+    __shared__ float4 sdy[TW_TH * TW_TW * 2];            // [pixel][2] : 8 channels
+    __shared__ float sx[TW_PH * TW_PW];
+    __shared__ float sred[8][THIN_TAPS][THIN_MAXC];
+    const int tiles_h = (Ho + TW_TH - 1) / TW_TH, tiles_w = (Wo + TW_TW - 1) / TW_TW, tiles_img = tiles_h * tiles_w;
+    const long long n_tiles = static_cast<long long>(B) * tiles_img;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool worker = lane < THIN_TAPS;
+    const int r = lane / THIN_K, s = lane % THIN_K;
+    float acc[THIN_MAXC] = {};
+    const long long t0 = static_cast<long long>(blockIdx.x) * tiles_per_block;
+    for (long long t = t0; t < t0 + tiles_per_block && t < n_tiles; ++t) {
+        const int b = static_cast<int>(t / tiles_img), ti = static_cast<int>(t % tiles_img), oh0 = (ti / tiles_w) * TW_TH,
+                  ow0 = (ti % tiles_w) * TW_TW;
+        const float* xb = x + static_cast<size_t>(b) * H * W;
+        const float4* dyb = reinterpret_cast<const float4*>(dy) + static_cast<size_t>(b) * Ho * Wo * 2;
+        __syncthreads();
+        for (int i = threadIdx.x; i < TW_PH * TW_PW; i += 256) {
+            const int ih = 2 * oh0 - 2 + i / TW_PW, iw = 2 * ow0 - 2 + i % TW_PW;
+            sx[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
+        }
+        for (int i = threadIdx.x; i < TW_TH * TW_TW * 2; i += 256) {
+            const int p = i >> 1, oh = oh0 + p / TW_TW, ow = ow0 + p % TW_TW;
+            sdy[i] = (oh < Ho && ow < Wo) ? __ldg(dyb + (static_cast<size_t>(oh) * Wo + ow) * 2 + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (worker) {
+            const float* px = sx + (2 * warp + r) * TW_PW + s;
+            const float4* pd = sdy + warp * TW_TW * 2;
+#pragma unroll 8
+            for (int qx = 0; qx < TW_TW; ++qx) {
+                const float xv = px[2 * qx];
+                const float4 d0 = pd[2 * qx], d1 = pd[2 * qx + 1];
+                acc[0] = fmaf(d0.x, xv, acc[0]); acc[1] = fmaf(d0.y, xv, acc[1]); acc[2] = fmaf(d0.z, xv, acc[2]); acc[3] = fmaf(d0.w, xv, acc[3]);
+                acc[4] = fmaf(d1.x, xv, acc[4]); acc[5] = fmaf(d1.y, xv, acc[5]); acc[6] = fmaf(d1.z, xv, acc[6]); acc[7] = fmaf(d1.w, xv, acc[7]);
+            }
+        }
+    }
+    if (worker)
+#pragma unroll
+        for (int c = 0; c < THIN_MAXC; ++c) sred[warp][lane][c] = acc[c];
+    __syncthreads();
+    if (threadIdx.x < THIN_TAPS * THIN_MAXC) {
+        const int c = threadIdx.x / THIN_TAPS, tap = threadIdx.x % THIN_TAPS;
+        float v = 0.0f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) v += sred[w8][tap][c];
+        atomicAdd(dw + c * THIN_TAPS + tap, v);
+    }
+}
+
 static bool thin_geometry(int C, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo) {
     return C >= 1 && C <= THIN_MAXC && kh == 5 && kw == 5 && stride == 2 && pad == 2 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1;
 }
@@ -213,7 +269,10 @@ int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, in
     int per_block = static_cast<int>((n_tiles + 148 * 4 - 1) / (148 * 4));
     if (per_block < 1) per_block = 1;
     const int grid = static_cast<int>((n_tiles + per_block - 1) / per_block);
-    thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block, channels_last);
+    if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)
+        thin_conv_wgrad_cl8_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, H, W, Ho, Wo, per_block);
+    else
+        thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block, channels_last);
     PGV_LAUNCH_CHECK();
     return 0;
 }

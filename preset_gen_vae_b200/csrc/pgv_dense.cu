@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_f32_small_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
                                                              float* __restrict__ c, int ldc, int m, int n, int k,
-                                                             const float* __restrict__ bias, int act, const float* __restrict__ residual, int ldr) {
+                                                             const float* __restrict__ bias, int act, const float* __restrict__ residual, int ldr,
+                                                             float* __restrict__ a_colsum) {
+    // a_colsum (optional, TA only): out[r] = sum_k A[k][r], r < m: the bias gradient of a Linear layer, for free next to dW = dY^T X
     __shared__ float sa[32][33], sb[32][33];          // [k][row]
     const int t = threadIdx.x, m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = t & 15, ty = t >> 4;               // outputs (ty*2 + i, tx*2 + j)
@@ -159,6 +161,8 @@ __global__ void __launch_bounds__(256) gemm_f32_small_kernel(const float* __rest
 #pragma unroll
     for (int q = 0; q < 4; ++q) { pa[q] = lda_(q, 0); pb[q] = ldb_(q, 0); }
     float acc[2][2] = {};
+    float cs0 = 0.0f, cs1 = 0.0f;
+    const bool do_colsum = TA && a_colsum != nullptr && blockIdx.x == 0 && tx == 0;
     for (int k0 = 0; k0 < k; k0 += 32) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { sa[ak[q]][ar[q]] = pa[q]; sb[bk[q]][br[q]] = pb[q]; }
@@ -172,8 +176,13 @@ __global__ void __launch_bounds__(256) gemm_f32_small_kernel(const float* __rest
             const float a0 = sa[kk][ty * 2], a1 = sa[kk][ty * 2 + 1], b0 = sb[kk][tx * 2], b1 = sb[kk][tx * 2 + 1];
             acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
             acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+            if (do_colsum) { cs0 += a0; cs1 += a1; }
         }
         __syncthreads();
+    }
+    if (do_colsum) {
+        if (m0 + ty * 2 < m) a_colsum[m0 + ty * 2] = cs0;
+        if (m0 + ty * 2 + 1 < m) a_colsum[m0 + ty * 2 + 1] = cs1;
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -240,7 +249,7 @@ int pgv_gemm_f32(pgv_handle* h, int trans_a, int trans_b, const float* a, int ld
     PGV_CHECK_ARG(act == 0 || act == 1, "pgv_gemm_f32: unknown activation %d", act);
     if (static_cast<long long>(m) * n <= 1024LL * 1024 && k <= 4096) {   // small problem: many small tiles beat few big ones
         dim3 g(ceil_div(n, 32), ceil_div(m, 32));
-#define PGV_SMALL_LAUNCH(TA, TB) gemm_f32_small_kernel<TA, TB><<<g, 256, 0, stream>>>(a, lda, b, ldb, c, ldc, m, n, k, bias, act, residual, ldr)
+#define PGV_SMALL_LAUNCH(TA, TB) gemm_f32_small_kernel<TA, TB><<<g, 256, 0, stream>>>(a, lda, b, ldb, c, ldc, m, n, k, bias, act, residual, ldr, nullptr)
         if (!trans_a && !trans_b) PGV_SMALL_LAUNCH(0, 0);
         else if (!trans_a && trans_b) PGV_SMALL_LAUNCH(0, 1);
         else if (trans_a && !trans_b) PGV_SMALL_LAUNCH(1, 0);
@@ -268,6 +277,21 @@ int pgv_gemm_f32(pgv_handle* h, int trans_a, int trans_b, const float* a, int ld
 #undef PGV_GEMM_LAUNCH
     PGV_LAUNCH_CHECK();
     return 0;
+}
+
+/* Linear-layer weight and bias gradients in exact fp32: dw [N, K] = dy^T x, db [N] = column sums of dy (dy [M, N], x [M, K]).
+ * Small problems (the flow conditioner layers) get db from the GEMM kernel itself; db may be NULL. */
+int pgv_linear_wgrad_f32(pgv_handle* h, const float* dy, const float* x, float* dw, float* db, int M, int N, int K, pgv_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PGV_CHECK_ARG(h && dy && x && dw && M > 0 && N > 0 && K > 0, "pgv_linear_wgrad_f32: bad argument");
+    if (static_cast<long long>(N) * K <= 1024LL * 1024 && M <= 4096) {
+        dim3 g(ceil_div(K, 32), ceil_div(N, 32));
+        gemm_f32_small_kernel<1, 0><<<g, 256, 0, stream>>>(dy, N, x, K, dw, K, N, K, M, nullptr, 0, nullptr, 0, db);
+        PGV_LAUNCH_CHECK();
+        return 0;
+    }
+    if (int rc = pgv_gemm_f32(h, 1, 0, dy, N, x, K, dw, K, N, K, M, nullptr, 0, nullptr, 0, stream_)) return rc;
+    return db != nullptr ? pgv_colsum(dy, db, M, N, stream_) : 0;
 }
 
 int pgv_gemm_nt_f32(pgv_handle* h, const float* a, int lda, const float* b, int ldb, float* c, int ldc, int m, int n, int k,

@@ -128,7 +128,21 @@ class FlowVAE(nn.Module):
         else:
             z_0_sampled = reparametrize(z_0_mu_logvar, None)
         z_K_sampled, log_abs_det_jac = self.flow_transform(z_0_sampled)
-        x_out = self.decoder(z_K_sampled, None if noise is None else noise.get('dec_fc_mask'))
+        dec_mask = None if noise is None else noise.get('dec_fc_mask')
+        side = getattr(self, 'decoder_stream', None)
+        if side is None:
+            x_out = self.decoder(z_K_sampled, dec_mask)
+        else:
+            # The decoder and whatever the caller does next with z_K (the regression flow, train.py:218) are independent:
+            # enqueue the decoder on a side stream so both run concurrently.  The caller must make its stream wait for
+            # `decoder_stream` before it reads x_out.  (autograd runs each backward node on its forward stream, so the two
+            # backward branches overlap as well.)
+            main = torch.cuda.current_stream(x.device)
+            side.wait_stream(main)
+            z_K_sampled.record_stream(side)
+            with torch.cuda.stream(side):
+                x_out = self.decoder(z_K_sampled, dec_mask)
+            x_out.record_stream(main)
         return z_0_mu_logvar, z_0_sampled, z_K_sampled, log_abs_det_jac, x_out
 
     def latent_loss(self, z_0_mu_logvar, z_0_sampled, z_K_sampled, log_abs_det_jac):

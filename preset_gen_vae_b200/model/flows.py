@@ -49,6 +49,30 @@ class ResidualBlock(nn.Module):
             p += [lin.weight, lin.bias]
         return p
 
+    def fwd_fused(self, x, t0, m0, r0, mask, next_bn):
+        """Training forward with the BatchNorms fused into the Linear layers (column-slice kernels).  (t0, m0, r0) =
+        relu(bn0(x)) and its statistics come from the kernel that produced x; if `next_bn` is given, the second Linear also
+        applies the following block's first BatchNorm and hands (t0', m0', r0') on."""
+        bn0, bn1 = self.batch_norm_layers
+        l0, l1 = self.linear_layers
+        u, t1, m1, r1 = ops.linear_bn_fwd(t0, l0.weight, l0.bias, bn1, mask=mask)
+        self._nbt_pending += 1
+        ctx = (x, m0, r0, t0, u, m1, r1, t1, mask)
+        if next_bn is None:
+            return ops.linear_fwd(t1, l1.weight, l1.bias, residual=x), None, ctx
+        y, nt0, nm0, nr0 = ops.linear_bn_fwd(t1, l1.weight, l1.bias, next_bn, residual=x)
+        return y, (nt0, nm0, nr0), ctx
+
+    def bwd_fused(self, dy, ctx, grads):
+        x, m0, r0, t0, u, m1, r1, t1, mask = ctx
+        bn0, bn1 = self.batch_norm_layers
+        l0, l1 = self.linear_layers
+        grads[id(l1.weight)], grads[id(l1.bias)] = ops.linear_wgrad(dy, t1)
+        du, grads[id(bn1.weight)], grads[id(bn1.bias)] = ops.linear_dgrad_bn_bwd(dy, l1.weight, u, bn1, m1, r1, mask=mask)
+        grads[id(l0.weight)], grads[id(l0.bias)] = ops.linear_wgrad(du, t0)
+        dx, grads[id(bn0.weight)], grads[id(bn0.bias)] = ops.linear_dgrad_bn_bwd(du, l0.weight, x, bn0, m0, r0, add_post=dy)   # + residual path
+        return dx
+
     def fwd(self, x, training, mask):
         bn0, bn1 = self.batch_norm_layers
         l0, l1 = self.linear_layers
@@ -103,6 +127,17 @@ class ResidualNet(nn.Module):
         return p + [self.final_layer.weight, self.final_layer.bias]
 
     def fwd(self, x, training, masks):
+        blocks = list(self.blocks)
+        if training and blocks and ops.colslice_ok(x.shape[0]):
+            # every Linear that feeds a BatchNorm1d computes that BatchNorm (+ReLU, +Dropout mask) in its epilogue
+            h, t0, m0, r0 = ops.linear_bn_fwd(x, self.initial_layer.weight, self.initial_layer.bias, blocks[0].batch_norm_layers[0])
+            ctxs, handoff = [], (t0, m0, r0)
+            for j, blk in enumerate(blocks):
+                nxt = blocks[j + 1].batch_norm_layers[0] if j + 1 < len(blocks) else None
+                h, handoff, c = blk.fwd_fused(h, *handoff, None if masks is None else masks[j], nxt)
+                ctxs.append(c)
+            out = ops.linear_fwd(h, self.final_layer.weight, self.final_layer.bias)
+            return out, (x, ctxs, h, True)
         h = ops.linear_fwd(x, self.initial_layer.weight, self.initial_layer.bias)
         ctxs = []
         for j, blk in enumerate(self.blocks):
@@ -110,14 +145,14 @@ class ResidualNet(nn.Module):
             h, c = blk.fwd(h_in, training, None if masks is None else masks[j])
             ctxs.append(c)
         out = ops.linear_fwd(h, self.final_layer.weight, self.final_layer.bias)
-        return out, (x, ctxs, h)
+        return out, (x, ctxs, h, False)
 
     def bwd(self, dout, ctx, grads):
-        x, ctxs, h_last = ctx
+        x, ctxs, h_last, fused = ctx
         grads[id(self.final_layer.weight)], grads[id(self.final_layer.bias)] = ops.linear_wgrad(dout, h_last)
         d = ops.linear_dgrad(dout, self.final_layer.weight)
         for blk, c in zip(reversed(list(self.blocks)), reversed(ctxs)):
-            d = blk.bwd(d, c, grads)
+            d = blk.bwd_fused(d, c, grads) if fused else blk.bwd(d, c, grads)
         grads[id(self.initial_layer.weight)], grads[id(self.initial_layer.bias)] = ops.linear_wgrad(d, x)
         return ops.linear_dgrad(d, self.initial_layer.weight)
 

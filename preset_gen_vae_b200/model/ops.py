@@ -398,12 +398,45 @@ def _use_tc(M, N, K):
     return _precision == 'tf32' and M * N * K >= SMALL_GEMM_MACS
 
 
+use_colslice = True    # small Linear layers (flow conditioners): column-slice GEMM, BatchNorm1d fused where one follows
+CS_MAX_ROWS = 256
+
+
+def colslice_ok(M):
+    return use_colslice and M <= CS_MAX_ROWS
+
+
+def linear_bn_fwd(x, w, bias, bn, residual=None, mask=None, keep_pre=True):
+    """(y_pre, t, mean, rstd): y_pre = x @ w.T + bias + residual; t = mask * relu(BatchNorm1d(y_pre)) in training mode."""
+    M, K = x.shape
+    N = w.shape[0]
+    y_pre = _empty(x, M, N) if keep_pre else None
+    t, mean, rstd = _empty(x, M, N), _empty(x, N), _empty(x, N)
+    _call('pgv_linear_bn_fwd', _f(x), _f(w), _f(bias), _f(residual), _f(y_pre), _f(t), _f(bn.weight), _f(bn.bias), _f(mask), _f(mean),
+          _f(rstd), _f(bn.running_mean), _f(bn.running_var), bn.momentum, bn.eps, M, N, K, _s(x),
+          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + 2 * M * N))
+    return y_pre, t, mean, rstd
+
+
+def linear_dgrad_bn_bwd(dy, w, bn_x, bn, mean, rstd, mask=None, add_post=None):
+    """dt = dy @ w, pushed back through mask * relu(BatchNorm1d(bn_x)); returns (dx [+ add_post], dgamma, dbeta)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    dx, dg, db = _empty(dy, M, K), _empty(dy, K), _empty(dy, K)
+    _call('pgv_linear_dgrad_bn_bwd', _f(dy), _f(w), _f(bn_x), _f(bn.weight), _f(bn.bias), _f(mean), _f(rstd), _f(mask), _f(add_post), _f(dx),
+          _f(dg), _f(db), M, N, K, _s(dy), flops=2 * M * N * K, nbytes=4 * (M * N + N * K + 3 * M * K))
+    return dx, dg, db
+
+
 def linear_fwd(x, w, bias, relu=False, residual=None):
     """y = act(x @ w.T + bias + residual); x [M,K], w [N,K] (nn.Linear layout)."""
     M, K = x.shape
     N = w.shape[0]
     y = _empty(x, M, N)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    if not _use_tc(M, N, K) and colslice_ok(M):
+        _call('pgv_linear_cs_fwd', _f(x), _f(w), _f(bias), _f(residual), _f(y), M, N, K, int(relu), _s(x), **acct)
+        return y
     if _use_tc(M, N, K):
         _call('pgv_linear_fwd_tf32', _h(x), _f(x), _f(w), _f(bias), _f(residual), _f(y), M, N, K, int(relu), _s(x), **acct)
     else:
@@ -417,6 +450,9 @@ def linear_dgrad(dy, w):
     K = w.shape[1]
     dx = _empty(dy, M, K)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    if not _use_tc(M, N, K) and colslice_ok(M):
+        _call('pgv_linear_cs_dgrad', _f(dy), _f(w), _f(dx), M, N, K, _s(dy), **acct)
+        return dx
     if _use_tc(M, N, K):
         _call('pgv_linear_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(dx), M, N, K, _s(dy), **acct)
     else:
@@ -430,10 +466,11 @@ def linear_wgrad(dy, x, want_bias=True):
     K = x.shape[1]
     dw = _empty(dy, N, K)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    if _use_tc(M, N, K):
-        _call('pgv_linear_wgrad_tf32', _h(dy), _f(dy), _f(x), _f(dw), M, N, K, _s(dy), **acct)
-    else:
-        _call('pgv_gemm_f32', _h(dy), 1, 0, _f(dy), N, _f(x), K, _f(dw), K, N, K, M, None, 0, None, 0, _s(dy), **acct)
+    if not _use_tc(M, N, K):
+        db = _empty(dy, N) if want_bias else None
+        _call('pgv_linear_wgrad_f32', _h(dy), _f(dy), _f(x), _f(dw), _f(db), M, N, K, _s(dy), **acct)
+        return dw, db
+    _call('pgv_linear_wgrad_tf32', _h(dy), _f(dy), _f(x), _f(dw), M, N, K, _s(dy), **acct)
     db = None
     if want_bias:
         db = _empty(dy, N)

@@ -20,7 +20,7 @@ from .utils import audio as paudio
 
 class TrainStep:
     def __init__(self, model_config, train_config, idx_helper, device=None, process_group=None, use_cuda_graph=True,
-                 spec_stats=None, beta=None, seed=0):
+                 spec_stats=None, beta=None, seed=0, overlap_branches=True):
         self.mc, self.tc, self.idx_helper = model_config, train_config, idx_helper
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         if self.device.index is None:
@@ -34,6 +34,8 @@ class TrainStep:
         with torch.cuda.device(self.device):
             self.model = build.build_extended_ae_model(model_config, train_config, idx_helper)[3].to(self.device)
         self.model.train()
+        # decoder branch on a side stream, concurrent with the regression-flow branch (both only depend on z_K)
+        self._side = torch.cuda.Stream(device=self.device) if overlap_branches else None
         self.frontend = paudio.build_spectrogram(model_config, device=self.device)
         self.recons_criterion = ploss.MSELoss() if train_config.normalize_losses else ploss.L2Loss()
         self.controls_criterion = ploss.SynthParamsLoss(
@@ -81,11 +83,17 @@ class TrainStep:
         x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
         ops.launches += _lib.lib().pgv_frontend_launch_count(self.mc.mel_bins)
         x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
-        z0_ml, z0, zk, logdet, x_out = self.model(x_in, sample_info)
+        self.model.ae_model.decoder_stream = self._side
+        try:
+            z0_ml, z0, zk, logdet, x_out = self.model(x_in, sample_info)
+        finally:
+            self.model.ae_model.decoder_stream = None
         v_out = self.model.reg_model(zk)
-        recons = self.recons_criterion(x_out, x_in)
-        lat = self.model.latent_loss(z0_ml, z0, zk, logdet)
         cont = self.controls_criterion(v_out, v_in)
+        lat = self.model.latent_loss(z0_ml, z0, zk, logdet)
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+        recons = self.recons_criterion(x_out, x_in)
         total = ploss.total_loss(recons, lat, cont, self._hyper_dev[4:5])
         for p in self.params:
             p.grad = None

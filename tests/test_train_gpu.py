@@ -40,18 +40,25 @@ def test_eager_step_matches_manual_forward_backward_and_torch_adam(idx_helper):
     lat = ref_model.latent_loss(z0_ml, z0, zk, ld)
     con = ploss.SynthParamsLoss(idx_helper, True, cat_bce=False, cat_softmax=True, cat_softmax_t=0.2)(v_out, v_in)
     (rec + tr.beta * lat + con).backward()
-    ref_opt.step()
     got = losses.tolist()
     for a, b in zip(got, (rec.item(), lat.item(), con.item())):
         assert abs(a - b) <= 2e-5 * abs(b) + 1e-6       # atomics in wgrad / split-K make runs non bit-identical
-    # Gradients landed in the flat buffer.  Two runs of the same kernels are not bit-identical: split-K / weight-gradient
-    # kernels accumulate with fp32 atomics, so activations differ by ~1e-6 relative between runs, which flips the (Leaky)ReLU
-    # branch of a ~1e-6 fraction of elements; each flip is an O(1) change of that element's gradient, i.e. ~sqrt(1e-6) = 1e-3 ..
-    # 1e-2 in L2 per tensor (tools/gpu_determinism.py measures 4.5e-3 globally at B=16).  Hence a consistency bound, not a
-    # precision test; precision is tested against the fp64 oracle in test_model_gpu.py.
+    # Gradients landed in the flat buffer.  Two runs of the same kernels are not bit-identical (fp32 atomics in the split-K /
+    # weight-gradient kernels: ~1e-6 relative noise on activations) and this network amplifies such noise strongly: the fp64
+    # CPU oracle itself changes its decoder weight gradients by 1e-2 relative-L2 when the input is perturbed by 1e-6
+    # (branch flips of LeakyReLU / Hardtanh elements near their kinks).  tools/gpu_determinism.py measures
+    # 4e-2 (decoder) / 4e-3 (encoder) run to run at B=16.  Hence a consistency bound here, not a precision test; precision is
+    # tested against the fp64 oracle in test_model_gpu.py.
+    num = den = dot = 0.0
+    for p, q in zip(tr.params, ref_model.parameters()):
+        num += float(((p.grad - q.grad) ** 2).sum()); den += float((q.grad ** 2).sum()); dot += float((p.grad * q.grad).sum())
+    assert num ** 0.5 <= 2e-2 * den ** 0.5
     for p, q in list(zip(tr.params, ref_model.parameters()))[::17]:
-        gn = float(q.grad.norm())
-        assert float((p.grad - q.grad).norm()) <= 5e-2 * gn + 1e-7
+        assert float((p.grad - q.grad).norm()) <= 1.5e-1 * float(q.grad.norm()) + 1e-7
+    # the fused Adam on the flat buffers against torch.optim.Adam fed with the SAME gradients
+    for p, q in zip(tr.params, ref_model.parameters()):
+        q.grad = p.grad.clone()
+    ref_opt.step()
     worst = max(float((p.data - q.data).abs().max()) for p, q in zip(tr.params, ref_model.parameters()))
     assert worst < 5e-6                                   # one Adam step moves weights by <= lr = 2e-4
 

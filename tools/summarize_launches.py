@@ -45,6 +45,13 @@ def main(path):
     print('|---|---|---|---|---|---|')
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print('| %s | %d | %.1f | %.1f%% | %.1f | %.1f |' % (k, a[0], a[1], 100 * a[1] / tot, a[2] / 1e6, a[3] / 1e6))
+    if len(sys.argv) > 2:        # per-kernel-family DRAM traffic of one step, for bench.py's roofline.traffic
+        import json
+        fam = {}
+        for k, a in agg.items():
+            f = fam.setdefault(re.sub(r'<.*', '', k), dict(launches=0, us=0.0, dram_bytes=0.0))
+            f['launches'] += a[0]; f['us'] += a[1]; f['dram_bytes'] += a[2] + a[3]
+        json.dump(fam, open(sys.argv[2], 'w'), indent=1, sort_keys=True)
 
 
 if __name__ == '__main__':
