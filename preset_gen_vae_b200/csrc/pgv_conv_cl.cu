@@ -13,7 +13,7 @@
 //       pixel, so both tiles are MN-major (atoms of 4 pixels x 128 bytes, SWIZZLE_128B_BASE32B).  The reduction runs over
 //       (oh, ow, b) with b fastest, so that the 32 pixels of a k-block share their tap geometry.
 //
-// Nothing goes through registers: 8 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
+// Nothing goes through registers: 16 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
 // the swizzled tile and hand completion to the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so up to CL_STAGES
 // k-blocks (192 KB) are in flight per SM.  The operands are therefore NOT rounded on the way in: activations are
 // rounded to TF32 (round-to-nearest) by the kernels that write them (BatchNorm apply, thin-layer kernels, layout
@@ -36,7 +36,9 @@ enum { CL_EPI_ROWS = 0, CL_EPI_QUAD = 1 };
 
 constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_STAGES = 6;
 constexpr int CL_A_BYTES = CL_BLOCK_M * 128, CL_B_BYTES = CL_MAX_N * 128, CL_STAGE_BYTES = CL_A_BYTES + CL_B_BYTES;
-constexpr int CL_PRODUCER_WARPS = 8, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
+constexpr int CL_PRODUCER_WARPS = 16, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
+constexpr int CL_SLOTS = (CL_BLOCK_M * 8) / CL_PRODUCERS;          // 16-byte chunks of one operand tile per producer thread (2)
+constexpr int CL_ROWS_PER_PASS = CL_PRODUCERS / 8;               // GEMM mode: rows covered by one pass of the producers (64)
 constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
 constexpr int CL_SMEM = 1024 + CL_STAGES * CL_STAGE_BYTES + 256;
 
@@ -119,17 +121,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         const int t = threadIdx.x;
         int stage = 0; uint32_t phase = 0;
         if (MODE == CL_GEMM) {
-            // thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows r0 + 32 i
+            // thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows r0 + CL_ROWS_PER_PASS * i
             const int j = t & 7, r0 = t >> 3;
-            const uint32_t dst0 = cl_sw128(r0, j);                    // rows r0 + 32 i: + i * 4096 (same row & 7)
+            const uint32_t dst0 = cl_sw128(r0, j);                    // rows r0 + 64 i: + i * 8192 (same row & 7)
+            constexpr uint32_t PASS_BYTES = CL_ROWS_PER_PASS * 128;
             const long long row_pitch = static_cast<long long>(p.W) * p.C;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
-                long long a_base[4]; uint32_t a_msk[4];             // mask: bits 0-7 valid kh, bits 8-15 valid kw
-                const float* b_ptr[4];
+                long long a_base[CL_SLOTS]; uint32_t a_msk[CL_SLOTS];             // mask: bits 0-7 valid kh, bits 8-15 valid kw
+                const float* b_ptr[CL_SLOTS];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + r0 + 32 * i;
+                for (int i = 0; i < CL_SLOTS; ++i) {
+                    const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + r0 + CL_ROWS_PER_PASS * i;
                     uint32_t b, rem, oh, ow;
                     p.fd_HgWg.divmod(m, b, rem);
                     p.fd_Wg.divmod(rem, oh, ow);
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     for (int e = 0; e < p.KH; ++e) if (ih0 + e >= 0 && ih0 + e < p.H) hm |= 1u << e;
                     for (int e = 0; e < p.KW; ++e) if (iw0 + e >= 0 && iw0 + e < p.W) wm |= 1u << e;
                     a_msk[i] = (m < static_cast<uint32_t>(p.gemm_m)) ? (hm | (wm << 8)) : 0u;
-                    const int row = r0 + 32 * i, n = wi.tn * p.n_tile + row;
+                    const int row = r0 + CL_ROWS_PER_PASS * i, n = wi.tn * p.n_tile + row;
                     b_ptr[i] = (row < p.n_tile && n < p.gemm_n) ? p.b + static_cast<size_t>(n) * p.gemm_k + 4 * j : nullptr;
                 }
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
@@ -152,15 +155,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     const uint32_t sA = smem_base + stage * CL_STAGE_BYTES + dst0, sB = sA + CL_A_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < CL_SLOTS; ++i) {
                         const bool ok = (a_msk[i] & sel) == sel;
-                        cp_async16_ca(sA + i * 4096, ok ? p.a + a_base[i] + koff : p.a, ok ? 16u : 0u);
+                        cp_async16_ca(sA + i * PASS_BYTES, ok ? p.a + a_base[i] + koff : p.a, ok ? 16u : 0u);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (r0 + 32 * i < p.n_tile) {
+                    for (int i = 0; i < CL_SLOTS; ++i) {
+                        if (r0 + CL_ROWS_PER_PASS * i < p.n_tile) {
                             const bool ok = b_ptr[i] != nullptr;
-                            cp_async16_cg(sB + i * 4096, ok ? b_ptr[i] + static_cast<size_t>(kb) * CL_BLOCK_K : p.b, ok ? 16u : 0u);
+                            cp_async16_cg(sB + i * PASS_BYTES, ok ? b_ptr[i] + static_cast<size_t>(kb) * CL_BLOCK_K : p.b, ok ? 16u : 0u);
                         }
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
@@ -170,8 +173,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         } else {
             // WGRAD.  A tile: pixel kk = (t / 32) + 8 i (i = k-group), 16-byte chunk cc = t % 32 along the 128 m of the tile:
             // a warp copies 512 contiguous bytes of one pixel.  B tile: n_tile / 4 chunks per pixel, same idea.
-            const int cc = t & 31, kq = t >> 5;                      // kq = kk & 7 for all four slots
-            const uint32_t a_dst0 = static_cast<uint32_t>((cc >> 3) * 1024 + kq * 128) + cl_sw32(cc & 7, kq);   // + i * 4096
+            // pixel kk = (t / 32) + CL_PRODUCER_WARPS * i: with 16 producer warps kk & 7 = (t / 32) & 7 and the 8-pixel group is (t / 32) / 8 + 2 i
+            const int cc = t & 31, kk0 = t >> 5, kq = kk0 & 7;
+            const uint32_t a_dst0 = static_cast<uint32_t>((kk0 >> 3) * 4096 + (cc >> 3) * 1024 + kq * 128) + cl_sw32(cc & 7, kq);
+            constexpr uint32_t A_SLOT_BYTES = (CL_PRODUCER_WARPS / 8) * 4096;
             const int cpp = p.n_tile >> 2;                            // B chunks per pixel: 8, 16 or 32
             const int cpp_shift = (cpp == 8) ? 3 : ((cpp == 16) ? 4 : 5);
             const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;    // one 8-pixel group of the B tile
@@ -186,9 +191,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 const bool m_ok = m < static_cast<uint32_t>(p.gemm_m);
                 const long long m_off = static_cast<long long>(kh) * p.W * p.C + rem;
                 // B slots: id = t + 256 s -> (pixel, chunk)
-                int b_kk[4], b_nc[4]; uint32_t b_dst[4]; bool b_on[4], b_ok[4];
+                int b_kk[CL_SLOTS], b_nc[CL_SLOTS]; uint32_t b_dst[CL_SLOTS]; bool b_on[CL_SLOTS], b_ok[CL_SLOTS];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < CL_SLOTS; ++s) {
                     const int id = t + CL_PRODUCERS * s;
                     b_on[s] = id < 32 * cpp;
                     b_kk[s] = id >> cpp_shift;
@@ -211,13 +216,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     const uint32_t sA = smem_base + stage * CL_STAGE_BYTES, sB = sA + CL_A_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int img = img0 + kq + 8 * i;
+                    for (int i = 0; i < CL_SLOTS; ++i) {
+                        const int img = img0 + kk0 + CL_PRODUCER_WARPS * i;
                         const bool ok = tap_ok && img < p.B;
-                        cp_async16_ca(sA + a_dst0 + i * 4096, ok ? p.a + img * img_a + a_off : p.a, ok ? 16u : 0u);
+                        cp_async16_ca(sA + a_dst0 + i * A_SLOT_BYTES, ok ? p.a + img * img_a + a_off : p.a, ok ? 16u : 0u);
                     }
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
+                    for (int s = 0; s < CL_SLOTS; ++s) {
                         if (b_on[s]) {
                             const int img = img0 + b_kk[s];
                             const bool ok = b_ok[s] && img < p.B;

@@ -148,8 +148,11 @@ class SpectrogramDecoder(nn.Module):
         if drop_mask is not None:
             dflat = ops.mul(dflat, drop_mask)
         lin = self.mlp[0]
-        dw, db = ops.linear_wgrad(dflat, z)
-        grads[id(lin.weight)], grads[id(lin.bias)] = dw, db
+        # fc_weight_grad_out (set by TrainStep): the 30 M-element weight gradient is written straight into the flat gradient
+        # buffer instead of a temporary that would be copied there; autograd then gets no tensor for it
+        direct = getattr(self, 'fc_weight_grad_out', None)
+        dw, db = ops.linear_wgrad(dflat, z, out=direct)
+        grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
         dz = ops.linear_dgrad(dflat, lin.weight) if needs[0] else None
         return (dz, None)[:len(needs)] if len(needs) > 1 else dz
 

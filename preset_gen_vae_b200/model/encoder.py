@@ -195,8 +195,11 @@ class SpectrogramEncoder(nn.Module):
             dy, dg, db = ops.bn1d_train_bwd(dy, y_pre, self.out_bn, mean, rstd)
             grads[id(self.out_bn.weight)], grads[id(self.out_bn.bias)] = dg, db
         lin = self.mlp[1]
-        dw, db = ops.linear_wgrad(dy, fc_in)
-        grads[id(lin.weight)], grads[id(lin.bias)] = dw, db
+        # fc_weight_grad_out (set by TrainStep): the 30 M-element weight gradient is written straight into the flat gradient
+        # buffer instead of a temporary that would be copied there; autograd then gets no tensor for it
+        direct = getattr(self, 'fc_weight_grad_out', None)
+        dw, db = ops.linear_wgrad(dy, fc_in, out=direct)
+        grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
         dflat = ops.linear_dgrad(dy, lin.weight)
         if drop_mask is not None:
             dflat = ops.mul(dflat, drop_mask)

@@ -460,11 +460,12 @@ def linear_dgrad(dy, w):
     return dx
 
 
-def linear_wgrad(dy, x, want_bias=True):
-    """dw = dy.T @ x [N,K]; db = column sums of dy."""
+def linear_wgrad(dy, x, want_bias=True, out=None):
+    """dw = dy.T @ x [N,K]; db = column sums of dy.  `out`: preallocated [N, K] destination (e.g. a slice of the flat gradient buffer)."""
     M, N = dy.shape
     K = x.shape[1]
-    dw = _empty(dy, N, K)
+    dw = out if out is not None else _empty(dy, N, K)
+    assert dw.shape == (N, K) and dw.is_contiguous()
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     if not _use_tc(M, N, K):
         db = _empty(dy, N) if want_bias else None

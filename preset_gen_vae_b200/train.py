@@ -65,15 +65,28 @@ class TrainStep:
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.n_param_elems = sum(sizes)
-        self._table_host = torch.zeros(len(params) * 3, dtype=torch.int64).pin_memory()
-        self._table_dev = torch.zeros(len(params) * 3, dtype=torch.int64, device=self.device)
-        self._table_host[1::3] = torch.from_numpy(np.asarray(self._offs, dtype=np.int64))
-        self._table_host[2::3] = torch.tensor(sizes, dtype=torch.int64)
+        # The two fully-connected weights are three quarters of all gradient bytes: their weight-gradient kernels write directly into the
+        # flat buffer (single-GPU runs; with several ranks the pack kernel also applies the 1/world factor to every tensor).
+        self._direct = {}
+        if self.world == 1:
+            views = self.layout.views(self.flat_grads, [p.shape for p in params])
+            for owner, lin in ((self.model.ae_model.encoder, self.model.ae_model.encoder.mlp[1]),
+                               (self.model.ae_model.decoder, self.model.ae_model.decoder.mlp[0])):
+                idx = next(i for i, p in enumerate(params) if p is lin.weight)
+                owner.fc_weight_grad_out = views[idx]
+                self._direct[idx] = views[idx]
+        self._packed = [i for i in range(len(params)) if i not in self._direct]
+        self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
+        self._table_dev = torch.zeros(len(self._packed) * 3, dtype=torch.int64, device=self.device)
+        self._table_host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in self._packed], dtype=np.int64))
+        self._table_host[2::3] = torch.tensor([sizes[i] for i in self._packed], dtype=torch.int64)
 
     def _pack_grads(self, scale=1.0):
-        self._table_host[0::3] = torch.tensor([p.grad.data_ptr() for p in self.params], dtype=torch.int64)
+        for i, view in self._direct.items():           # already in place; expose them like every other gradient
+            self.params[i].grad = view
+        self._table_host[0::3] = torch.tensor([self.params[i].grad.data_ptr() for i in self._packed], dtype=torch.int64)
         self._table_dev.copy_(self._table_host, non_blocking=True)
-        _lib.check(_lib.lib().pgv_multi_pack(_lib.ptr(self._table_dev), len(self.params), max(self._sizes),
+        _lib.check(_lib.lib().pgv_multi_pack(_lib.ptr(self._table_dev), len(self._packed), max(self._sizes[i] for i in self._packed),
                                              _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
         ops.launches += 1
 

@@ -26,6 +26,8 @@ def test_eager_step_matches_manual_forward_backward_and_torch_adam(idx_helper):
     tr, audio, v_in, info = make(B, False, idx_helper)
     assert tr.flat_params.numel() >= 60372037 and all(p.data_ptr() >= tr.flat_params.data_ptr() for p in tr.params)
     ref_model = copy.deepcopy(tr.model)
+    ref_model.ae_model.encoder.fc_weight_grad_out = ref_model.ae_model.decoder.fc_weight_grad_out = None   # plain autograd path
+    assert len(tr._direct) == 2 and sum(v.numel() for v in tr._direct.values()) == 1220 * 24576 + 24576 * 610
     ref_opt = torch.optim.Adam(ref_model.parameters(), lr=tr.tc.initial_learning_rate, weight_decay=tr.tc.weight_decay,
                                betas=tr.tc.adam_betas)
     torch.manual_seed(11)
