@@ -13,7 +13,7 @@
 //       pixel, so both tiles are MN-major (atoms of 4 pixels x 128 bytes, SWIZZLE_128B_BASE32B).  The reduction runs over
 //       (oh, ow, b) with b fastest, so that the 32 pixels of a k-block share their tap geometry.
 //
-// Nothing goes through registers: 16 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
+// Nothing goes through registers: 4 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
 // the swizzled tile and hand completion to the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so up to CL_STAGES
 // k-blocks (192 KB) are in flight per SM.  The operands are therefore NOT rounded on the way in: activations are
 // rounded to TF32 (round-to-nearest) by the kernels that write them (BatchNorm apply, thin-layer kernels, layout
@@ -36,9 +36,9 @@ enum { CL_EPI_ROWS = 0, CL_EPI_QUAD = 1 };
 
 constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_STAGES = 6;
 constexpr int CL_A_BYTES = CL_BLOCK_M * 128, CL_B_BYTES = CL_MAX_N * 128, CL_STAGE_BYTES = CL_A_BYTES + CL_B_BYTES;
-constexpr int CL_PRODUCER_WARPS = 16, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
-constexpr int CL_SLOTS = (CL_BLOCK_M * 8) / CL_PRODUCERS;          // 16-byte chunks of one operand tile per producer thread (2)
-constexpr int CL_ROWS_PER_PASS = CL_PRODUCERS / 8;               // GEMM mode: rows covered by one pass of the producers (64)
+constexpr int CL_PRODUCER_WARPS = 8, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
+constexpr int CL_SLOTS = (CL_BLOCK_M * 8) / CL_PRODUCERS;          // 16-byte chunks of one operand tile per producer thread (4)
+constexpr int CL_ROWS_PER_PASS = CL_PRODUCERS / 8;               // GEMM mode: rows covered by one pass of the producers (32)
 constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
 constexpr int CL_SMEM = 1024 + CL_STAGES * CL_STAGE_BYTES + 256;
 
@@ -54,9 +54,9 @@ struct ConvClParams {
     int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
     int bblocks;         // WGRAD: ceil(B / 32) k-blocks per output position
     int round_out, atomic_out;
-    int variant;         // debug (PGV_WGRAD_VARIANT): 1 swaps LBO / SBO of the MN-major descriptors
     float slope;
     FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC;
+    alignas(64) CUtensorMap tmap_b;      // GEMM mode: prepared weights [gemm_n][gemm_k], box 32 x n_tile, 128-byte swizzle
 };
 
 __device__ __forceinline__ uint32_t cl_sw128(int row, int chunk) {
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&bar_full[s], CL_PRODUCERS); mbar_init(&bar_empty[s], 1); }
+            for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&bar_full[s], CL_PRODUCERS + (MODE == CL_GEMM ? 1 : 0)); mbar_init(&bar_empty[s], 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
             fence_mbar_init();
         }
@@ -121,15 +121,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         const int t = threadIdx.x;
         int stage = 0; uint32_t phase = 0;
         if (MODE == CL_GEMM) {
-            // thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows r0 + CL_ROWS_PER_PASS * i
+            // A operand: thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows
+            // r0 + CL_ROWS_PER_PASS * i.  B operand (prepared weights, a plain K-major matrix): ONE TMA box per k-block, issued by
+            // thread 0, which also posts the expected byte count on the stage's barrier.
             const int j = t & 7, r0 = t >> 3;
-            const uint32_t dst0 = cl_sw128(r0, j);                    // rows r0 + 64 i: + i * 8192 (same row & 7)
+            const uint32_t dst0 = cl_sw128(r0, j);                    // rows r0 + 32 i: + i * 4096 (same row & 7)
             constexpr uint32_t PASS_BYTES = CL_ROWS_PER_PASS * 128;
+            const uint32_t span = static_cast<uint32_t>(p.KW) * p.C;  // a multiple of 32: a k-block never straddles two kernel rows
             const long long row_pitch = static_cast<long long>(p.W) * p.C;
+            const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
+            if (t == 0) tma_prefetch_desc(&p.tmap_b);
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
-                long long a_base[CL_SLOTS]; uint32_t a_msk[CL_SLOTS];             // mask: bits 0-7 valid kh, bits 8-15 valid kw
-                const float* b_ptr[CL_SLOTS];
+                const float* a_ptr[CL_SLOTS]; uint32_t a_msk[CL_SLOTS];          // mask: bits 0-7 valid kh, bits 8-15 valid kw
 #pragma unroll
                 for (int i = 0; i < CL_SLOTS; ++i) {
                     const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + r0 + CL_ROWS_PER_PASS * i;
@@ -137,46 +141,44 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     p.fd_HgWg.divmod(m, b, rem);
                     p.fd_Wg.divmod(rem, oh, ow);
                     const int ih0 = static_cast<int>(oh) * p.stride - p.pad, iw0 = static_cast<int>(ow) * p.stride - p.pad;
-                    a_base[i] = ((static_cast<long long>(b) * p.H + ih0) * p.W + iw0) * p.C;
-                    uint32_t hm = 0, wm = 0;
-                    for (int e = 0; e < p.KH; ++e) if (ih0 + e >= 0 && ih0 + e < p.H) hm |= 1u << e;
-                    for (int e = 0; e < p.KW; ++e) if (iw0 + e >= 0 && iw0 + e < p.W) wm |= 1u << e;
+                    a_ptr[i] = p.a + ((static_cast<long long>(b) * p.H + ih0) * p.W + iw0) * p.C;     // only dereferenced where the masks allow
+                    const int h_lo = max(0, -ih0), h_hi = min(p.KH, p.H - ih0), w_lo = max(0, -iw0), w_hi = min(p.KW, p.W - iw0);
+                    const uint32_t hm = h_hi > h_lo ? ((1u << h_hi) - (1u << h_lo)) : 0u, wm = w_hi > w_lo ? ((1u << w_hi) - (1u << w_lo)) : 0u;
                     a_msk[i] = (m < static_cast<uint32_t>(p.gemm_m)) ? (hm | (wm << 8)) : 0u;
-                    const int row = r0 + CL_ROWS_PER_PASS * i, n = wi.tn * p.n_tile + row;
-                    b_ptr[i] = (row < p.n_tile && n < p.gemm_n) ? p.b + static_cast<size_t>(n) * p.gemm_k + 4 * j : nullptr;
                 }
+                uint32_t kh, rem;                                   // this thread's chunk: k = 32 kb + 4 j = (kh, rem = kw * C + c)
+                p.fd_span.divmod(static_cast<uint32_t>(wi.kb0) * CL_BLOCK_K + 4 * j, kh, rem);
+                long long koff = static_cast<long long>(kh) * row_pitch + rem;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-                    const uint32_t k = static_cast<uint32_t>(kb) * CL_BLOCK_K + 4 * j;
-                    uint32_t kh, rem;
-                    p.fd_span.divmod(k, kh, rem);
-                    const uint32_t kw = p.fd_C.div(rem);
-                    const long long koff = static_cast<long long>(kh) * row_pitch + rem;
-                    const uint32_t sel = (1u << kh) | (1u << (8 + kw));
+                    const uint32_t sel = (1u << kh) | (256u << p.fd_C.div(rem));
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    const uint32_t sA = smem_base + stage * CL_STAGE_BYTES + dst0, sB = sA + CL_A_BYTES;
+                    if (t == 0) {
+                        mbar_arrive_expect_tx(&bar_full[stage], b_bytes);
+                        tma_load_2d(smem + stage * CL_STAGE_BYTES + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                    }
+                    const uint32_t sA = smem_base + stage * CL_STAGE_BYTES + dst0;
 #pragma unroll
                     for (int i = 0; i < CL_SLOTS; ++i) {
                         const bool ok = (a_msk[i] & sel) == sel;
-                        cp_async16_ca(sA + i * PASS_BYTES, ok ? p.a + a_base[i] + koff : p.a, ok ? 16u : 0u);
-                    }
-#pragma unroll
-                    for (int i = 0; i < CL_SLOTS; ++i) {
-                        if (r0 + CL_ROWS_PER_PASS * i < p.n_tile) {
-                            const bool ok = b_ptr[i] != nullptr;
-                            cp_async16_cg(sB + i * PASS_BYTES, ok ? b_ptr[i] + static_cast<size_t>(kb) * CL_BLOCK_K : p.b, ok ? 16u : 0u);
-                        }
+                        cp_async16_ca(sA + i * PASS_BYTES, ok ? a_ptr[i] + koff : p.a, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                    rem += CL_BLOCK_K; koff += CL_BLOCK_K;
+                    if (rem >= span) { rem -= span; ++kh; koff += row_pitch - span; }
                 }
             }
         } else {
             // WGRAD.  A tile: pixel kk = (t / 32) + 8 i (i = k-group), 16-byte chunk cc = t % 32 along the 128 m of the tile:
             // a warp copies 512 contiguous bytes of one pixel.  B tile: n_tile / 4 chunks per pixel, same idea.
-            // pixel kk = (t / 32) + CL_PRODUCER_WARPS * i: with 16 producer warps kk & 7 = (t / 32) & 7 and the 8-pixel group is (t / 32) / 8 + 2 i
-            const int cc = t & 31, kk0 = t >> 5, kq = kk0 & 7;
-            const uint32_t a_dst0 = static_cast<uint32_t>((kk0 >> 3) * 4096 + (cc >> 3) * 1024 + kq * 128) + cl_sw32(cc & 7, kq);
-            constexpr uint32_t A_SLOT_BYTES = (CL_PRODUCER_WARPS / 8) * 4096;
+            // slot i of this thread: pixel kk = (t / 32) + CL_PRODUCER_WARPS * i of the k-block
+            const int cc = t & 31, kk0 = t >> 5;
+            uint32_t a_dst[CL_SLOTS];
+#pragma unroll
+            for (int i = 0; i < CL_SLOTS; ++i) {
+                const int kk = kk0 + CL_PRODUCER_WARPS * i;
+                a_dst[i] = static_cast<uint32_t>((kk >> 3) * 4096 + (cc >> 3) * 1024 + (kk & 7) * 128) + cl_sw32(cc & 7, kk & 7);
+            }
             const int cpp = p.n_tile >> 2;                            // B chunks per pixel: 8, 16 or 32
             const int cpp_shift = (cpp == 8) ? 3 : ((cpp == 16) ? 4 : 5);
             const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;    // one 8-pixel group of the B tile
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     for (int i = 0; i < CL_SLOTS; ++i) {
                         const int img = img0 + kk0 + CL_PRODUCER_WARPS * i;
                         const bool ok = tap_ok && img < p.B;
-                        cp_async16_ca(sA + a_dst0 + i * A_SLOT_BYTES, ok ? p.a + img * img_a + a_off : p.a, ok ? 16u : 0u);
+                        cp_async16_ca(sA + a_dst[i], ok ? p.a + img * img_a + a_off : p.a, ok ? 16u : 0u);
                     }
 #pragma unroll
                     for (int s = 0; s < CL_SLOTS; ++s) {
@@ -247,7 +249,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 const uint32_t tmem_d = tmem_base + acc * CL_MAX_N;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&bar_full[stage], phase);
-                    fence_proxy_async_smem();          // cp.async wrote through the generic proxy; tcgen05.mma reads through the async proxy
+                    // The phase completes through the producers' cp.async.mbarrier.arrive, i.e. only once their copies have landed;
+                    // like CUTLASS's sm100 cp.async mainloop (sm100_mma_cpasync_warpspecialized.hpp) no proxy fence is issued here.
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_base + stage * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
                     if (MODE == CL_GEMM) {
@@ -258,9 +261,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
 #pragma unroll
                         for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
                             // one MMA = 8 pixels = two 4-row atoms 512 bytes apart (SBO); 32-element groups along M / N are 1024 bytes apart (LBO)
-                            const uint32_t lbo = p.variant == 1 ? 512u : 1024u, sbo = p.variant == 1 ? 1024u : 512u;
-                            const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, lbo, sbo);
-                            const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, lbo, sbo);
+                            const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, 1024, 512);
+                            const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, 1024, 512);
                             umma_tf32(tmem_d, da, db, idesc, (kb > wi.kb0 || g > 0) ? 1u : 0u);
                         }
                     }
@@ -452,6 +454,9 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
             PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems, stream));
         }
     }
+    const uint64_t bd[2] = {static_cast<uint64_t>(p.gemm_k), static_cast<uint64_t>(N)}, bs[1] = {static_cast<uint64_t>(p.gemm_k) * 4};
+    const uint32_t bbox[2] = {CL_BLOCK_K, static_cast<uint32_t>(p.n_tile)};
+    if (int rc = make_tmap_f32(h, &p.tmap_b, bw, 2, bd, bs, bbox)) return rc;
     return launch_conv_cl<CL_GEMM>(h, p, stream);
 }
 
@@ -533,7 +538,6 @@ int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwc
     p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
     p.slope = -1.0f;
     p.fd_HgWg.init(Ho * Wo); p.fd_Wg.init(Wo); p.fd_span.init(KW * Cin); p.fd_C.init(Cin); p.fd_bblocks.init(p.bblocks); p.fd_qC.init(1);
-    if (const char* v = getenv("PGV_WGRAD_VARIANT")) p.variant = atoi(v);
     PGV_CUDA(cudaMemsetAsync(dwcl, 0, sizeof(float) * static_cast<size_t>(Cout) * p.gemm_m, stream));
     return launch_conv_cl<CL_WGRAD>(h, p, stream);
 }

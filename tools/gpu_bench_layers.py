@@ -1,4 +1,4 @@
-"""Per-layer timing of the tensor-core conv / linear kernels at the training batch (CUDA events, 5 reps after warm-up)."""
+"""Per-layer device time of the tensor-core conv / linear kernels at the training batch (each op replayed from a CUDA graph)."""
 import sys
 
 import torch
@@ -18,17 +18,28 @@ DEC = [('dec2', 256, 512, 4, 5, 7), ('dec3', 128, 256, 4, 9, 12), ('dec4', 64, 1
        ('dec6', 16, 32, 4, 65, 88), ('dec7', 8, 16, 4, 129, 174), ('dec8', 1, 8, 5, 257, 347)]
 
 
-def timeit(fn, reps=5):
-    for _ in range(2):
-        fn()
+def timeit(fn, reps=10):
+    """Device time per call: the op is captured `reps` times into a CUDA graph (no Python / launch overhead in the timed region)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    return e0.elapsed_time(e1) / (3 * reps)
 
 
 tot = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
