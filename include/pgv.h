@@ -196,6 +196,16 @@ PGV_API int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, c
  * pgv_conv_cl_unpack_dw converts it to the PyTorch layout [Cout, Cin, KH, KW]. */
 PGV_API int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH,
                               int KW, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+/* nn.Linear on the same kernel, for layers large enough for the tensor cores (encoder / decoder FC, encoder.py:84, decoder.py:70).
+ * Operands as stored: x / dy TF32-rounded with 16-byte-aligned rows, wr = rounded weights [N, K], wt = rounded transposed weights
+ * [K, N]; K may carry zero padding (pgv_round_copy).  dw is written with row pitch lddw, columns < k_valid. */
+PGV_API int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const float* bias, float* y, int M, int N, int K,
+                              pgv_stream_t stream);
+PGV_API int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, pgv_stream_t stream);
+PGV_API int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid,
+                                pgv_stream_t stream);
+/* dst [rows, ldd] = TF32-rounded src [rows, lds] (first `cols` columns), zero in columns cols..ldd-1. */
+PGV_API int pgv_round_copy(const float* src, int lds, float* dst, int ldd, int rows, int cols, pgv_stream_t stream);
 PGV_API int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Cin, int KH, int KW, pgv_stream_t stream);
 /* BatchNorm2d on channels-last tensors viewed as [P = B*H*W, C] (same semantics as pgv_bn2d_*; C % 4 == 0).
  * workspace: 16*C bytes. */

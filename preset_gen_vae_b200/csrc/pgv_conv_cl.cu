@@ -50,7 +50,8 @@ struct ConvClParams {
     int B, H, W, C, KH, KW, stride, pad, Hg, Wg;     // gather geometry: window KH x KW over [H, W, C], output grid Hg x Wg
     int gemm_m, gemm_n, gemm_k;
     int n_tile, n_tiles, m_tiles, kb_total, kb_per_split, k_splits;
-    int epi, ldo;        // CL_EPI_ROWS: out[m * ldo + n]
+    int epi, ldo;        // CL_EPI_ROWS: out[m * ldo + n]          WGRAD: out[n * ldo + m] for m < m_valid
+    int m_valid;
     int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
     int bblocks;         // WGRAD: ceil(B / 32) k-blocks per output position
     int round_out, atomic_out;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ClItem wi = cl_decode(p, item);
             const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + row;
-            const bool row_ok = m < static_cast<uint32_t>(p.gemm_m);
+            const bool row_ok = m < static_cast<uint32_t>(MODE == CL_WGRAD ? p.m_valid : p.gemm_m);
             float* dst = p.out;
             int qi = 0, qj = 0;
             if (MODE == CL_WGRAD) {
@@ -309,7 +310,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 if (MODE == CL_WGRAD) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (nbase + e < p.gemm_n) atomicAdd(dst + static_cast<size_t>(nbase + e) * p.gemm_m, __uint_as_float(v[e]));
+                        if (nbase + e < p.gemm_n) {
+                            float* o = dst + static_cast<size_t>(nbase + e) * p.ldo;
+                            if (p.atomic_out) atomicAdd(o, __uint_as_float(v[e]));
+                            else *o = __uint_as_float(v[e]);
+                        }
                     continue;
                 }
 #pragma unroll
@@ -335,7 +340,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                         r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
                     }
                     if (p.atomic_out) {
-                        atomicAdd(o, r.x); atomicAdd(o + 1, r.y); atomicAdd(o + 2, r.z); atomicAdd(o + 3, r.w);
+                        atomicAdd(o, r.x);
+                        if (n + 1 < p.gemm_n) atomicAdd(o + 1, r.y);
+                        if (n + 2 < p.gemm_n) atomicAdd(o + 2, r.z);
+                        if (n + 3 < p.gemm_n) atomicAdd(o + 3, r.w);
                     } else {
                         r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
                         r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
@@ -396,6 +404,16 @@ __global__ void __launch_bounds__(256) cl_unpack_dw_kernel(const float* __restri
     }
 }
 
+// dst[r][c] = TF32-rounded src[r][c] for c < cols, 0 for cols <= c < ldd (re-pitches rows to a 16-byte-aligned length)
+__global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int cols) {
+    const long long total = static_cast<long long>(rows) * ldd;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int c = static_cast<int>(i % ldd);
+        const long long r = i / ldd;
+        dst[i] = c < cols ? to_tf32_rna(__ldg(src + r * lds + c)) : 0.0f;
+    }
+}
+
 template <int MODE>
 static int launch_conv_cl(const pgv_handle* h, const ConvClParams& p, cudaStream_t stream) {
     static bool configured = false;
@@ -425,8 +443,9 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
                         int round_out, size_t out_elems, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || N <= 0 || Hg <= 0 || Wg <= 0 || KH <= 0 || KH > 8 || KW <= 0 || KW > 8 || stride <= 0 || pad < 0)
         return set_error(-1, "%s: bad geometry", who);
-    if (C % 4 != 0 || (KH * KW * C) % CL_BLOCK_K != 0 || N % 4 != 0)
-        return set_error(-1, "%s: channels-last kernels need C %% 4 == 0, K %% 32 == 0 and N %% 4 == 0 (C=%d, K=%d, N=%d)", who, C, KH * KW * C, N);
+    const bool unaligned_n = N % 4 != 0;           // only the atomic (scalar) epilogue can write rows whose pitch is not 16-byte aligned
+    if (C % 4 != 0 || (unaligned_n && (slope >= 0.0f || round_out || bias != nullptr || epi != CL_EPI_ROWS)))
+        return set_error(-1, "%s: channels-last kernels need C %% 4 == 0 and (N %% 4 == 0 or a linear, bias-free epilogue) (C=%d, N=%d)", who, C, N);
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(bw) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15)
         return set_error(-1, "%s: pointers must be 16-byte aligned", who);
     const long long m = static_cast<long long>(B) * Hg * Wg;
@@ -438,7 +457,7 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     p.gemm_m = static_cast<int>(m); p.gemm_n = N; p.gemm_k = KH * KW * C;
     p.n_tile = cl_pick_n_tile(N, 16); p.n_tiles = ceil_div(N, p.n_tile);
     p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
-    p.kb_total = p.gemm_k / CL_BLOCK_K; p.kb_per_split = p.kb_total; p.k_splits = 1;
+    p.kb_total = ceil_div(p.gemm_k, CL_BLOCK_K); p.kb_per_split = p.kb_total; p.k_splits = 1;      // a K tail is zero-filled by the gather masks / TMA
     p.epi = epi; p.ldo = N; p.qH = qH; p.qW = qW; p.qC = qC;
     p.slope = slope; p.round_out = round_out;
     p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1);
@@ -451,9 +470,10 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
             p.kb_per_split = ceil_div(p.kb_total, splits);
             p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
             p.atomic_out = 1;
-            PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems, stream));
         }
     }
+    if (unaligned_n) p.atomic_out = 1;
+    if (p.atomic_out) PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems, stream));
     const uint64_t bd[2] = {static_cast<uint64_t>(p.gemm_k), static_cast<uint64_t>(N)}, bs[1] = {static_cast<uint64_t>(p.gemm_k) * 4};
     const uint32_t bbox[2] = {CL_BLOCK_K, static_cast<uint32_t>(p.n_tile)};
     if (int rc = make_tmap_f32(h, &p.tmap_b, bw, 2, bd, bs, bbox)) return rc;
@@ -512,19 +532,17 @@ int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const flo
                         round_out, out_elems, s);
 }
 
-int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH, int KW,
-                      int stride, int pad, int Ho, int Wo, pgv_stream_t stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PGV_CHECK_ARG(h && x && dy && dwcl, "pgv_conv_cl_wgrad: NULL argument");
-    PGV_CHECK_ARG(B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "pgv_conv_cl_wgrad: bad geometry");
-    PGV_CHECK_ARG(Cin % 4 == 0 && Cout % 4 == 0 && (KW * Cin) % 32 == 0, "pgv_conv_cl_wgrad: needs Cin %% 4 == 0, Cout %% 4 == 0, KW*Cin %% 32 == 0");
-    PGV_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dwcl)) & 15) == 0,
-                  "pgv_conv_cl_wgrad: pointers must be 16-byte aligned");
+static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, const float* dy, float* out, int ldo, int m_valid, int B, int H,
+                              int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, cudaStream_t stream) {
+    if (!(h && x && dy && out)) return set_error(-1, "%s: NULL argument", who);
+    if (!(B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0)) return set_error(-1, "%s: bad geometry", who);
+    if (Cin % 4 != 0 || Cout % 4 != 0) return set_error(-1, "%s: needs Cin %% 4 == 0 and Cout %% 4 == 0 (Cin=%d, Cout=%d)", who, Cin, Cout);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return set_error(-1, "%s: operand pointers must be 16-byte aligned", who);
     ConvClParams p;
     memset(&p, 0, sizeof(p));
-    p.a = x; p.b = dy; p.out = dwcl;
+    p.a = x; p.b = dy; p.out = out;
     p.B = B; p.H = H; p.W = W; p.C = Cin; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.Hg = Ho; p.Wg = Wo;
-    p.gemm_m = KH * KW * Cin; p.gemm_n = Cout;
+    p.gemm_m = KH * KW * Cin; p.gemm_n = Cout; p.ldo = ldo; p.m_valid = m_valid;
     p.n_tile = cl_pick_n_tile(Cout, 32); p.n_tiles = ceil_div(Cout, p.n_tile);
     if (p.n_tile != 32 && p.n_tile != 64 && p.n_tile != 128) { p.n_tile = p.n_tile <= 64 ? 64 : 128; p.n_tiles = ceil_div(Cout, p.n_tile); }
     p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
@@ -536,10 +554,45 @@ int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwc
     if (splits < 1) splits = 1;
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+    p.atomic_out = p.k_splits > 1 ? 1 : 0;
     p.slope = -1.0f;
     p.fd_HgWg.init(Ho * Wo); p.fd_Wg.init(Wo); p.fd_span.init(KW * Cin); p.fd_C.init(Cin); p.fd_bblocks.init(p.bblocks); p.fd_qC.init(1);
-    PGV_CUDA(cudaMemsetAsync(dwcl, 0, sizeof(float) * static_cast<size_t>(Cout) * p.gemm_m, stream));
+    if (p.atomic_out) PGV_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * m_valid, Cout, stream));
     return launch_conv_cl<CL_WGRAD>(h, p, stream);
+}
+
+int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH, int KW,
+                      int stride, int pad, int Ho, int Wo, pgv_stream_t stream) {
+    return conv_cl_wgrad_impl(h, "pgv_conv_cl_wgrad", x, dy, dwcl, KH * KW * Cin, KH * KW * Cin, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo,
+                              static_cast<cudaStream_t>(stream));
+}
+
+/* ---- nn.Linear on the same kernel (operands TF32-rounded by the caller, see pgv_round_copy / pgv_transpose_inner) ---- */
+int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const float* bias, float* y, int M, int N, int K, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && x && wr && y && M > 0 && N > 0 && K > 0, "pgv_linear_cl_fwd: bad argument");
+    return conv_cl_gemm(h, "pgv_linear_cl_fwd", x, wr, bias, y, M, 1, 1, K, 1, 1, 1, 0, 1, 1, N, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
+                        static_cast<size_t>(M) * N, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, pgv_stream_t stream) {
+    PGV_CHECK_ARG(h && dy && wt && dx && M > 0 && N > 0 && K > 0, "pgv_linear_cl_dgrad: bad argument");
+    return conv_cl_gemm(h, "pgv_linear_cl_dgrad", dy, wt, nullptr, dx, M, 1, 1, N, 1, 1, 1, 0, 1, 1, K, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
+                        static_cast<size_t>(M) * K, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid,
+                        pgv_stream_t stream) {
+    PGV_CHECK_ARG(k_valid > 0 && k_valid <= K && lddw >= k_valid, "pgv_linear_cl_wgrad: bad leading dimension");
+    return conv_cl_wgrad_impl(h, "pgv_linear_cl_wgrad", x, dy, dw, lddw, k_valid, M, 1, 1, K, N, 1, 1, 1, 0, 1, 1, static_cast<cudaStream_t>(stream));
+}
+
+int pgv_round_copy(const float* src, int lds, float* dst, int ldd, int rows, int cols, pgv_stream_t stream) {
+    PGV_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols, "pgv_round_copy: bad argument");
+    const long long total = static_cast<long long>(rows) * ldd;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+    round_copy_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, dst, ldd, rows, cols);
+    PGV_LAUNCH_CHECK();
+    return 0;
 }
 
 int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Cin, int KH, int KW, pgv_stream_t stream) {

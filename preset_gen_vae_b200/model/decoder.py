@@ -117,7 +117,7 @@ class SpectrogramDecoder(nn.Module):
         z = inputs[0].contiguous()
         drop_mask = inputs[1] if len(inputs) > 1 else None
         lin = self.mlp[0]
-        h = ops.linear_fwd(z, lin.weight, lin.bias)
+        h, fc_ctx = ops.fc_fwd(z, lin.weight, lin.bias, training)
         if training and drop_mask is not None:
             h = ops.mul(h, drop_mask)
         h = h.view(-1, *self.cnn_input_shape)
@@ -130,10 +130,10 @@ class SpectrogramDecoder(nn.Module):
             outs.append(y)
             ctxs.append(c)
         x_out = outs[0] if C == 1 else torch.cat(outs, dim=1)
-        return x_out, (z, drop_mask, un_ctx, ctxs)
+        return x_out, (fc_ctx, drop_mask, un_ctx, ctxs)
 
     def prog_bwd(self, dout, ctx, grads, needs):
-        z, drop_mask, un_ctx, ctxs = ctx
+        fc_ctx, drop_mask, un_ctx, ctxs = ctx
         C = self.spectrogram_channels
         dparts = []
         for ch in range(C):
@@ -151,9 +151,8 @@ class SpectrogramDecoder(nn.Module):
         # fc_weight_grad_out (set by TrainStep): the 30 M-element weight gradient is written straight into the flat gradient
         # buffer instead of a temporary that would be copied there; autograd then gets no tensor for it
         direct = getattr(self, 'fc_weight_grad_out', None)
-        dw, db = ops.linear_wgrad(dflat, z, out=direct)
+        dz, dw, db = ops.fc_bwd(dflat, fc_ctx, lin.weight, bool(needs[0]), out=direct)
         grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
-        dz = ops.linear_dgrad(dflat, lin.weight) if needs[0] else None
         return (dz, None)[:len(needs)] if len(needs) > 1 else dz
 
     def forward(self, z_sampled, dropout_mask=None):

@@ -174,7 +174,7 @@ class SpectrogramEncoder(nn.Module):
         flat = ops.to_nchw(h).reshape(B, -1)          # nn.Linear expects the (c, h, w) flattening order
         fc_in = ops.mul(flat, drop_mask) if (training and drop_mask is not None) else flat
         lin = self.mlp[1]
-        y = ops.linear_fwd(fc_in, lin.weight, lin.bias)
+        y, fc_ctx = ops.fc_fwd(fc_in, lin.weight, lin.bias, training)
         bn_ctx = None
         if self.out_bn is not None:
             if training:
@@ -184,10 +184,10 @@ class SpectrogramEncoder(nn.Module):
                 bn_ctx = (y_pre, mean, rstd)
             else:
                 y = ops.bn1d_eval_fwd(y, self.out_bn)
-        return y.view(B, 2, self.dim_z), (ch_ctx, mix_ctx, cnn_shape, fc_in, drop_mask, bn_ctx)
+        return y.view(B, 2, self.dim_z), (ch_ctx, mix_ctx, cnn_shape, fc_ctx, drop_mask, bn_ctx)
 
     def prog_bwd(self, dout, ctx, grads, needs):
-        ch_ctx, mix_ctx, cnn_shape, fc_in, drop_mask, bn_ctx = ctx
+        ch_ctx, mix_ctx, cnn_shape, fc_ctx, drop_mask, bn_ctx = ctx
         B, C = dout.shape[0], self.spectrogram_channels
         dy = dout.reshape(B, -1)
         if bn_ctx is not None:
@@ -198,9 +198,8 @@ class SpectrogramEncoder(nn.Module):
         # fc_weight_grad_out (set by TrainStep): the 30 M-element weight gradient is written straight into the flat gradient
         # buffer instead of a temporary that would be copied there; autograd then gets no tensor for it
         direct = getattr(self, 'fc_weight_grad_out', None)
-        dw, db = ops.linear_wgrad(dy, fc_in, out=direct)
+        dflat, dw, db = ops.fc_bwd(dy, fc_ctx, lin.weight, True, out=direct)
         grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
-        dflat = ops.linear_dgrad(dy, lin.weight)
         if drop_mask is not None:
             dflat = ops.mul(dflat, drop_mask)
         dh = dflat.view(cnn_shape)

@@ -479,6 +479,64 @@ def linear_wgrad(dy, x, want_bias=True, out=None):
     return dw, db
 
 
+# ---- the two big fully-connected layers (encoder.py:84, decoder.py:70) on the channels-last tensor-core kernel ----
+use_fc_cl = True
+
+
+def round_copy(x, ld=None):
+    """TF32-rounded copy of the 2-D tensor x with row pitch `ld` (>= columns, zero padded): [rows, ld]."""
+    rows, cols = x.shape
+    ld = cols if ld is None else ld
+    y = _empty(x, rows, ld)
+    _call('pgv_round_copy', _f(x), x.stride(0), _f(y), ld, rows, cols, _s(x), nbytes=4 * (x.numel() + y.numel()))
+    return y
+
+
+def fc_route(M, N, K):
+    """'cl': cp.async / TMA fed tcgen05 kernel on rounded, 16-byte-aligned copies of the operands; else the generic Linear path."""
+    return 'cl' if (cl_mode() and use_fc_cl and _use_tc(M, N, K) and N % 4 == 0) else 'generic'
+
+
+def fc_fwd(x, w, bias, training=True):
+    """y = x @ w.T + bias for a large Linear.  Returns (y, ctx); ctx carries the rounded operands the backward re-uses."""
+    M, K = x.shape
+    N = w.shape[0]
+    if fc_route(M, N, K) != 'cl':
+        return linear_fwd(x, w, bias), (x, None, None, K)
+    Kp = (K + 3) // 4 * 4
+    xr, wr = round_copy(x, Kp), round_copy(w, Kp)
+    wt = None
+    if training:                                   # rounded W^T [K, N] for the data gradient (tiled transpose, both sides coalesced)
+        wt = _empty(w, K, N)
+        _call('pgv_transpose_inner', _f(w), _f(wt), 1, N, K, 1, _s(w), nbytes=8 * w.numel())
+    y = _empty(x, M, N)
+    _call('pgv_linear_cl_fwd', _h(x), _f(xr), _f(wr), _f(bias), _f(y), M, N, Kp, _s(x), n=2,
+          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    return y, (xr, wt, Kp, K)
+
+
+def fc_bwd(dy, ctx, w, need_dx=True, out=None):
+    """(dx, dw, db) of fc_fwd; `out`: preallocated [N, K] destination for dw (e.g. a slice of the flat gradient buffer)."""
+    xr, wt, Kp, K = ctx
+    M, N = dy.shape
+    if wt is None:
+        dw, db = linear_wgrad(dy, xr, out=out)
+        return (linear_dgrad(dy, w) if need_dx else None), dw, db
+    db = _empty(dy, N)
+    _call('pgv_colsum', _f(dy), _f(db), M, N, _s(dy))
+    dyr = round_copy(dy)
+    dw = out if out is not None else _empty(dy, N, K)
+    assert dw.shape == (N, K) and dw.is_contiguous()
+    _call('pgv_linear_cl_wgrad', _h(dy), _f(dyr), _f(xr), _f(dw), K, M, N, Kp, K, _s(dy), n=2,
+          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    dx = None
+    if need_dx:
+        dx = _empty(dy, M, K)
+        _call('pgv_linear_cl_dgrad', _h(dy), _f(dyr), _f(wt), _f(dx), M, N, K, _s(dy), n=2,
+              flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    return dx, dw, db
+
+
 # ------------------------------------------------------------------------------------------------ latent space / flows
 def reparam_fwd(mu_logvar, eps):
     B, _, D = mu_logvar.shape

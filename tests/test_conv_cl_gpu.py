@@ -141,3 +141,23 @@ def test_block_forward_backward_on_the_channels_last_route(transposed):
     assert rel(blk.conv.weight.grad, ref_conv.weight.grad) < 3e-2
     assert rel(blk.bn.weight.grad, ref_bn.weight.grad) < 3e-2 and rel(blk.bn.bias.grad, ref_bn.bias.grad) < 3e-2
     assert rel(blk.conv.bias.grad, ref_conv.bias.grad) < 1e-1       # a sum with heavy cancellation over B*H*W pixels
+
+
+@pytest.mark.parametrize("m,n,k", [(160, 1220, 24576), (160, 24576, 610), (64, 1024, 1030), (5, 36, 26)])
+def test_big_linear_layers_on_the_channels_last_kernel(m, n, k):
+    """encoder / decoder FC (and a padded-K case) through fc_fwd / fc_bwd: rounded + re-pitched operand copies, weights by TMA,
+    K tail, unaligned-N atomic epilogue (dx of the decoder FC has 610 columns), direct weight-gradient destination."""
+    x, w, b = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=0.05), rnd(n, seed=3)
+    dy = rnd(m, n, seed=4)
+    route = ops.fc_route(m, n, k)
+    assert route == ('generic' if m == 5 else 'cl')
+    y, ctx = ops.fc_fwd(x, w, b, True)
+    out = torch.full((n, k), 7.0, device=DEV)
+    dx, dw, db = ops.fc_bwd(dy, ctx, w, True, out=out)
+    assert dw.data_ptr() == out.data_ptr()
+    errs = (rel(y, x.double() @ w.double().T + b.double()), rel(dx, dy.double() @ w.double()), rel(dw, dy.double().T @ x.double()),
+            rel(db, dy.double().sum(0)))
+    print("fc", route, (m, n, k), "rel-L2 fwd %.2e dgrad %.2e wgrad %.2e db %.2e" % errs)
+    assert max(errs) < 2e-3
+    y_eval, ctx_eval = ops.fc_fwd(x, w, b, False)
+    assert ctx_eval[1] is None and rel(y_eval, y) < 1e-6
