@@ -194,46 +194,67 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 const bool m_ok = m < static_cast<uint32_t>(p.gemm_m);
                 const long long m_off = static_cast<long long>(kh) * p.W * p.C + rem;
                 // B slots: id = t + 256 s -> (pixel, chunk)
-                int b_kk[CL_SLOTS], b_nc[CL_SLOTS]; uint32_t b_dst[CL_SLOTS]; bool b_on[CL_SLOTS], b_ok[CL_SLOTS];
+                int b_kk[CL_SLOTS]; uint32_t b_dst[CL_SLOTS]; bool b_on[CL_SLOTS], b_ok[CL_SLOTS];
+                const float* b_base[CL_SLOTS];                   // dy address of (image b_kk, position 0, this thread's 4 columns)
 #pragma unroll
                 for (int s = 0; s < CL_SLOTS; ++s) {
                     const int id = t + CL_PRODUCERS * s;
                     b_on[s] = id < 32 * cpp;
                     b_kk[s] = id >> cpp_shift;
-                    b_nc[s] = id & (cpp - 1);
-                    const int kk = b_kk[s], nc = b_nc[s];
+                    const int kk = b_kk[s], nc = id & (cpp - 1);
                     b_dst[s] = static_cast<uint32_t>((kk >> 3) * b_group_bytes + (nc >> 3) * 1024 + (kk & 7) * 128) + cl_sw32(nc & 7, kk & 7);
                     b_ok[s] = b_on[s] && (wi.tn * p.n_tile + 4 * nc) < p.gemm_n;
+                    b_base[s] = p.b + kk * img_b + wi.tn * p.n_tile + 4 * nc;
                 }
-                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-                    uint32_t pos, bb, oh, ow;
-                    p.fd_bblocks.divmod(static_cast<uint32_t>(kb), pos, bb);
-                    p.fd_Wg.divmod(pos, oh, ow);
+                const float* a_base[CL_SLOTS];                   // x address of (image kk0 + 8 i, row 0, column 0, this thread's tap / channels)
+#pragma unroll
+                for (int i = 0; i < CL_SLOTS; ++i) a_base[i] = p.a + (kk0 + CL_PRODUCER_WARPS * i) * img_a + m_off;
+                // k-block state: output position (oh, ow) and image block bb; pointers advance by 32 images per k-block and are
+                // recomputed when the position changes (every `bblocks` k-blocks)
+                uint32_t pos, bb, oh, ow;
+                p.fd_bblocks.divmod(static_cast<uint32_t>(wi.kb0), pos, bb);
+                p.fd_Wg.divmod(pos, oh, ow);
+                const float* a_ptr[CL_SLOTS]; const float* b_ptr[CL_SLOTS];
+                bool tap_ok = false;
+                int img0 = 0;
+                auto set_position = [&]() {
                     const int ih = static_cast<int>(oh) * p.stride - p.pad + static_cast<int>(kh);
                     const int iw = static_cast<int>(ow) * p.stride - p.pad + static_cast<int>(kw);
-                    const bool tap_ok = m_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-                    const long long a_off = (static_cast<long long>(oh) * p.stride - p.pad) * p.W * p.C +
-                                            (static_cast<long long>(ow) * p.stride - p.pad) * p.C + m_off;
-                    const long long b_off = static_cast<long long>(pos) * p.gemm_n + wi.tn * p.n_tile;
-                    const int img0 = static_cast<int>(bb) * 32;
+                    tap_ok = m_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                    img0 = static_cast<int>(bb) * 32;
+                    const long long a_off = ((static_cast<long long>(oh) * p.stride - p.pad) * p.W + (static_cast<long long>(ow) * p.stride - p.pad)) * p.C +
+                                            img0 * img_a;
+                    const long long b_off = static_cast<long long>(pos) * p.gemm_n + img0 * img_b;
+#pragma unroll
+                    for (int i = 0; i < CL_SLOTS; ++i) { a_ptr[i] = a_base[i] + a_off; b_ptr[i] = b_base[i] + b_off; }
+                };
+                set_position();
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     const uint32_t sA = smem_base + stage * CL_STAGE_BYTES, sB = sA + CL_A_BYTES;
 #pragma unroll
                     for (int i = 0; i < CL_SLOTS; ++i) {
-                        const int img = img0 + kk0 + CL_PRODUCER_WARPS * i;
-                        const bool ok = tap_ok && img < p.B;
-                        cp_async16_ca(sA + a_dst[i], ok ? p.a + img * img_a + a_off : p.a, ok ? 16u : 0u);
+                        const bool ok = tap_ok && img0 + kk0 + CL_PRODUCER_WARPS * i < p.B;
+                        cp_async16_ca(sA + a_dst[i], ok ? a_ptr[i] : p.a, ok ? 16u : 0u);
                     }
 #pragma unroll
                     for (int s = 0; s < CL_SLOTS; ++s) {
                         if (b_on[s]) {
-                            const int img = img0 + b_kk[s];
-                            const bool ok = b_ok[s] && img < p.B;
-                            cp_async16_cg(sB + b_dst[s], ok ? p.b + img * img_b + b_off + 4 * b_nc[s] : p.b, ok ? 16u : 0u);
+                            const bool ok = b_ok[s] && img0 + b_kk[s] < p.B;
+                            cp_async16_cg(sB + b_dst[s], ok ? b_ptr[s] : p.b, ok ? 16u : 0u);
                         }
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                    if (++bb < static_cast<uint32_t>(p.bblocks)) {
+                        img0 += 32;
+#pragma unroll
+                        for (int i = 0; i < CL_SLOTS; ++i) { a_ptr[i] += 32 * img_a; b_ptr[i] += 32 * img_b; }
+                    } else {
+                        bb = 0; ++pos;
+                        if (++ow == static_cast<uint32_t>(p.Wg)) { ow = 0; ++oh; }
+                        set_position();
+                    }
                 }
             }
         }

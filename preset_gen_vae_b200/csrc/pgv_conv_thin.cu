@@ -12,6 +12,12 @@ namespace pgv {
 
 constexpr int THIN_K = 5, THIN_TAPS = 25, THIN_MAXC = 8;
 
+// The 200 weights (+ biases) of a thin layer, copied device-to-device into constant memory right before the launch (a memcpy
+// node when captured): every thread uses the same weight at the same time, so the FMAs take it as a constant-bank operand
+// instead of one shared-memory load per FMA.  One bank per kernel so that a forward and a transposed launch never share it.
+__constant__ float c_thin_fwd_w[THIN_MAXC * THIN_TAPS + THIN_MAXC];
+__constant__ float c_thin_quad_w[THIN_MAXC * THIN_TAPS + 1];       // + the single output-channel bias
+
 __device__ __forceinline__ float thin_round(float v, int round_out) {
     if (!round_out) return v;
     uint32_t r;
@@ -66,6 +72,85 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const float* __restr
             for (int t = 0; t < THIN_TAPS; ++t) acc = fmaf(in[t], sw[c * THIN_TAPS + t], acc);
             yb[c * cs] = thin_round((slope >= 0.0f && acc < 0.0f) ? acc * slope : acc, round_out);
         }
+    }
+}
+
+// Channels-last, C == 8 forward: weights and biases as constant-bank operands (c_thin_fwd_w), two float4 stores per pixel.
+__global__ void __launch_bounds__(256) thin_conv_fwd_cl8_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int Ho,
+                                                                int Wo, float slope, int round_out) {
+    const int HWo = Ho * Wo;
+    const long long total = static_cast<long long>(B) * HWo;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int b = static_cast<int>(i / HWo), pix = static_cast<int>(i % HWo), oh = pix / Wo, ow = pix % Wo;
+        const float* xb = x + static_cast<size_t>(b) * H * W;
+        float in[THIN_TAPS];
+#pragma unroll
+        for (int r = 0; r < THIN_K; ++r) {
+            const int ih = 2 * oh - 2 + r;
+#pragma unroll
+            for (int s = 0; s < THIN_K; ++s) {
+                const int iw = 2 * ow - 2 + s;
+                in[r * THIN_K + s] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
+            }
+        }
+        float o[THIN_MAXC];
+#pragma unroll
+        for (int c = 0; c < THIN_MAXC; ++c) {
+            float acc = c_thin_fwd_w[THIN_MAXC * THIN_TAPS + c];
+#pragma unroll
+            for (int t = 0; t < THIN_TAPS; ++t) acc = fmaf(in[t], c_thin_fwd_w[c * THIN_TAPS + t], acc);
+            o[c] = thin_round((slope >= 0.0f && acc < 0.0f) ? acc * slope : acc, round_out);
+        }
+        float4* yo = reinterpret_cast<float4*>(y + static_cast<size_t>(i) * THIN_MAXC);
+        yo[0] = make_float4(o[0], o[1], o[2], o[3]);
+        yo[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// Channels-last, C == 8 transposed form: one thread per 2x2 output quad (ih = 2i + ph, iw = 2j + pw).  The four pixels read the
+// same 3x3 neighbourhood of y (rows i+1-a, columns j+1-d; kernel element (ph + 2a, pw + 2d)), loaded once as 18 float4;
+// weights are constant-bank operands (c_thin_quad_w).
+__global__ void __launch_bounds__(256) thin_conv_quad_cl8_kernel(const float* __restrict__ y, float* __restrict__ x, int B, int H, int W, int Ho,
+                                                                 int Wo, float lo, float hi) {
+    const float bias0 = c_thin_quad_w[THIN_MAXC * THIN_TAPS];
+    const int Hq = (H + 1) >> 1, Wq = (W + 1) >> 1;
+    const long long total = static_cast<long long>(B) * Hq * Wq;
+    for (long long q = blockIdx.x * 256LL + threadIdx.x; q < total; q += 256LL * gridDim.x) {
+        const int b = static_cast<int>(q / (Hq * Wq)), rq = static_cast<int>(q % (Hq * Wq)), i = rq / Wq, j = rq % Wq;
+        const float* yb = y + static_cast<size_t>(b) * Ho * Wo * THIN_MAXC;
+        float acc[2][2] = {{bias0, bias0}, {bias0, bias0}};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int oh = i + 1 - a;
+            if (oh < 0 || oh >= Ho) continue;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int ow = j + 1 - d;
+                if (ow < 0 || ow >= Wo) continue;
+                const float4* src = reinterpret_cast<const float4*>(yb + (static_cast<size_t>(oh) * Wo + ow) * THIN_MAXC);
+                const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                const float vs[THIN_MAXC] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph) {
+                    if (ph + 2 * a >= THIN_K) continue;
+#pragma unroll
+                    for (int pw = 0; pw < 2; ++pw) {
+                        if (pw + 2 * d >= THIN_K) continue;
+#pragma unroll
+                        for (int c = 0; c < THIN_MAXC; ++c)
+                            acc[ph][pw] = fmaf(vs[c], c_thin_quad_w[c * THIN_TAPS + (ph + 2 * a) * THIN_K + pw + 2 * d], acc[ph][pw]);
+                    }
+                }
+            }
+        }
+        float* xb = x + static_cast<size_t>(b) * H * W;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+            for (int pw = 0; pw < 2; ++pw) {
+                const int ih = 2 * i + ph, iw = 2 * j + pw;
+                if (ih < H && iw < W) xb[ih * W + iw] = fminf(fmaxf(acc[ph][pw], lo), hi);
+            }
     }
 }
 
@@ -217,6 +302,21 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_cl8_kernel(const float* _
     }
 }
 
+// Fills a constant bank: 200 weights from `w`, then `n_bias` biases from `bias` (zeros when NULL), all device-to-device on `st`.
+template <typename Sym>
+static int thin_load_constants(const Sym& symbol, const float* w, const float* bias, int n_bias, cudaStream_t st) {
+    constexpr size_t WB = sizeof(float) * THIN_MAXC * THIN_TAPS;
+    PGV_CUDA(cudaMemcpyToSymbolAsync(symbol, w, WB, 0, cudaMemcpyDeviceToDevice, st));
+    if (bias != nullptr) {
+        PGV_CUDA(cudaMemcpyToSymbolAsync(symbol, bias, sizeof(float) * n_bias, WB, cudaMemcpyDeviceToDevice, st));
+    } else {
+        void* base = nullptr;
+        PGV_CUDA(cudaGetSymbolAddress(&base, symbol));
+        PGV_CUDA(cudaMemsetAsync(static_cast<char*>(base) + WB, 0, sizeof(float) * n_bias, st));
+    }
+    return 0;
+}
+
 static bool thin_geometry(int C, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo) {
     return C >= 1 && C <= THIN_MAXC && kh == 5 && kw == 5 && stride == 2 && pad == 2 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1;
 }
@@ -237,7 +337,11 @@ int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, floa
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_fwd: unsupported geometry");
     const long long total = static_cast<long long>(B) * Ho * Wo;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-    if (channels_last)
+    if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (int rc = thin_load_constants(c_thin_fwd_w, w, bias, THIN_MAXC, st)) return rc;
+        thin_conv_fwd_cl8_kernel<<<grid, 256, 0, st>>>(x, y, B, H, W, Ho, Wo, lrelu_slope, round_out);
+    } else if (channels_last)
         thin_conv_fwd_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, B, C, H, W, Ho, Wo, lrelu_slope, round_out);
     else
         thin_conv_fwd_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, B, C, H, W, Ho, Wo, lrelu_slope, round_out);
@@ -251,7 +355,13 @@ int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, fl
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_dgrad: unsupported geometry");
     const long long total = static_cast<long long>(B) * H * W;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-    if (channels_last)
+    if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (int rc = thin_load_constants(c_thin_quad_w, w, bias, 1, st)) return rc;
+        const long long quads = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
+        const int qgrid = static_cast<int>(std::min<long long>((quads + 255) / 256, 148LL * 32));
+        thin_conv_quad_cl8_kernel<<<qgrid, 256, 0, st>>>(y, x, B, H, W, Ho, Wo, clamp_lo, clamp_hi);
+    } else if (channels_last)
         thin_conv_dgrad_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);
     else
         thin_conv_dgrad_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);

@@ -57,42 +57,48 @@ __global__ void scatter_add_cols_kernel(float* __restrict__ dst, const int* __re
 }
 
 // Affine coupling.  params[b, j] = shift, params[b, n_t + j] = unconstrained scale; s = sigmoid(u + 2) + 1e-3.
-// forward: y_t = x_t * s + t, logdet += sum log s ; inverse: y_t = (x_t - t) / s, logdet -= sum log s.  Warp per row.
-__global__ void __launch_bounds__(256) coupling_fwd_kernel(const float* __restrict__ x, const float* __restrict__ params,
+// forward: y_t = x_t * s + t, logdet += sum log s ; inverse: y_t = (x_t - t) / s, logdet -= sum log s.  One 128-thread block per row.
+constexpr int CPL_THREADS = 128;
+__global__ void __launch_bounds__(CPL_THREADS) coupling_fwd_kernel(const float* __restrict__ x, const float* __restrict__ params,
                                                            const int* __restrict__ id_idx, const int* __restrict__ tr_idx,
                                                            float* __restrict__ y, const float* __restrict__ ld_in, float* __restrict__ ld_out,
                                                            int B, int D, int n_id, int n_t, int inverse) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= B) return;
+    __shared__ float red[CPL_THREADS / 32];
+    const int row = blockIdx.x, tid = threadIdx.x;
     const float* xr = x + static_cast<size_t>(row) * D;
     float* yr = y + static_cast<size_t>(row) * D;
     const float* pr = params + static_cast<size_t>(row) * 2 * n_t;
-    for (int j = lane; j < n_id; j += 32) yr[id_idx[j]] = xr[id_idx[j]];
+    for (int j = tid; j < n_id; j += CPL_THREADS) yr[id_idx[j]] = xr[id_idx[j]];
     float ld = 0.0f;
-    for (int j = lane; j < n_t; j += 32) {
+    for (int j = tid; j < n_t; j += CPL_THREADS) {
         const float s = sigmoidf_(pr[n_t + j] + 2.0f) + 1e-3f, t = pr[j];
         const int c = tr_idx[j];
         yr[c] = inverse ? (xr[c] - t) / s : fmaf(xr[c], s, t);
         ld += logf(s);
     }
     ld = warp_sum_f(ld);
-    if (lane == 0) ld_out[row] = (ld_in != nullptr ? ld_in[row] : 0.0f) + (inverse ? -ld : ld);
+    if ((tid & 31) == 0) red[tid >> 5] = ld;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.0f;
+        for (int w = 0; w < CPL_THREADS / 32; ++w) tot += red[w];
+        ld_out[row] = (ld_in != nullptr ? ld_in[row] : 0.0f) + (inverse ? -tot : tot);
+    }
 }
 
 // Backward of the forward direction.  dx gets the direct paths (identity columns pass through, transformed columns
 // times s); dparams feeds the conditioner network, whose input gradient is scatter-added into dx afterwards.
-__global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dld,
+__global__ void __launch_bounds__(CPL_THREADS) coupling_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dld,
                                                            const float* __restrict__ x, const float* __restrict__ params,
                                                            const int* __restrict__ id_idx, const int* __restrict__ tr_idx,
                                                            float* __restrict__ dx, float* __restrict__ dparams, int B, int D, int n_id, int n_t) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= B) return;
+    const int row = blockIdx.x, tid = threadIdx.x;
     const size_t ro = static_cast<size_t>(row) * D;
     const float* pr = params + static_cast<size_t>(row) * 2 * n_t;
     float* dpr = dparams + static_cast<size_t>(row) * 2 * n_t;
     const float gl = dld != nullptr ? dld[row] : 0.0f;
-    for (int j = lane; j < n_id; j += 32) dx[ro + id_idx[j]] = dy[ro + id_idx[j]];
-    for (int j = lane; j < n_t; j += 32) {
+    for (int j = tid; j < n_id; j += CPL_THREADS) dx[ro + id_idx[j]] = dy[ro + id_idx[j]];
+    for (int j = tid; j < n_t; j += CPL_THREADS) {
         const int c = tr_idx[j];
         const float sg = sigmoidf_(pr[n_t + j] + 2.0f), s = sg + 1e-3f, g = dy[ro + c];
         dx[ro + c] = g * s;
@@ -227,7 +233,7 @@ int pgv_coupling_fwd(const float* x, const float* params, const int* identity_id
                      pgv_stream_t stream) {
     PGV_CHECK_ARG(x && params && identity_idx && transform_idx && y && logdet_out, "pgv_coupling_fwd: NULL argument");
     PGV_CHECK_ARG(n_identity + n_transform == D && B > 0, "pgv_coupling_fwd: index lists must partition the %d features", D);
-    coupling_fwd_kernel<<<ceil_div(B, 8), 256, 0, PGV_STREAM(stream)>>>(x, params, identity_idx, transform_idx, y, logdet_in, logdet_out, B, D,
+    coupling_fwd_kernel<<<B, CPL_THREADS, 0, PGV_STREAM(stream)>>>(x, params, identity_idx, transform_idx, y, logdet_in, logdet_out, B, D,
                                                                        n_identity, n_transform, inverse);
     PGV_LAUNCH_CHECK();
     return 0;
@@ -238,7 +244,7 @@ int pgv_coupling_bwd(const float* dy, const float* dlogdet, const float* x, cons
                      pgv_stream_t stream) {
     PGV_CHECK_ARG(dy && x && params && identity_idx && transform_idx && dx && dparams, "pgv_coupling_bwd: NULL argument");
     PGV_CHECK_ARG(n_identity + n_transform == D && B > 0, "pgv_coupling_bwd: index lists must partition the features");
-    coupling_bwd_kernel<<<ceil_div(B, 8), 256, 0, PGV_STREAM(stream)>>>(dy, dlogdet, x, params, identity_idx, transform_idx, dx, dparams, B, D,
+    coupling_bwd_kernel<<<B, CPL_THREADS, 0, PGV_STREAM(stream)>>>(dy, dlogdet, x, params, identity_idx, transform_idx, dx, dparams, B, D,
                                                                        n_identity, n_transform);
     PGV_LAUNCH_CHECK();
     return 0;
