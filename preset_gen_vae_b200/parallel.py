@@ -47,7 +47,8 @@ class FlatLayout:
 
 
 def allreduce_mean_(flat_grads_prescaled: torch.Tensor, group=None):
-    """Sum over ranks of a buffer every rank already scaled by 1/world  ==  mean gradient."""
+    """Sum over ranks of the flat gradient buffer.  The mean needs a 1/world factor, applied either beforehand by the caller
+    (pre-scaled buffer) or afterwards (TrainStep: the fused Adam kernel's grad_scale)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat_grads_prescaled, op=dist.ReduceOp.SUM, group=group)
     return flat_grads_prescaled

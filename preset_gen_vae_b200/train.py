@@ -66,15 +66,15 @@ class TrainStep:
         self.exp_avg_sq = torch.zeros_like(flat)
         self.n_param_elems = sum(sizes)
         # The two fully-connected weights are three quarters of all gradient bytes: their weight-gradient kernels write directly into the
-        # flat buffer (single-GPU runs; with several ranks the pack kernel also applies the 1/world factor to every tensor).
+        # flat buffer.  Gradients are stored unscaled; with several ranks the all-reduce sums them and the 1/world factor is the
+        # grad_scale the fused Adam kernel reads from device memory.
         self._direct = {}
-        if self.world == 1:
-            views = self.layout.views(self.flat_grads, [p.shape for p in params])
-            for owner, lin in ((self.model.ae_model.encoder, self.model.ae_model.encoder.mlp[1]),
-                               (self.model.ae_model.decoder, self.model.ae_model.decoder.mlp[0])):
-                idx = next(i for i, p in enumerate(params) if p is lin.weight)
-                owner.fc_weight_grad_out = views[idx]
-                self._direct[idx] = views[idx]
+        views = self.layout.views(self.flat_grads, [p.shape for p in params])
+        for owner, lin in ((self.model.ae_model.encoder, self.model.ae_model.encoder.mlp[1]),
+                           (self.model.ae_model.decoder, self.model.ae_model.decoder.mlp[0])):
+            idx = next(i for i, p in enumerate(params) if p is lin.weight)
+            owner.fc_weight_grad_out = views[idx]
+            self._direct[idx] = views[idx]
         self._packed = [i for i in range(len(params)) if i not in self._direct]
         self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
         self._table_dev = torch.zeros(len(self._packed) * 3, dtype=torch.int64, device=self.device)
@@ -111,7 +111,7 @@ class TrainStep:
         for p in self.params:
             p.grad = None
         total.backward()
-        self._pack_grads(1.0 / self.world)
+        self._pack_grads(1.0)
         if with_optimizer:
             self._adam()
         return torch.stack([recons.detach(), lat.detach(), cont.detach()])
@@ -130,12 +130,12 @@ class TrainStep:
         self._hyper_host[0] = self.lr
         self._hyper_host[1] = 1.0 - b1 ** self.step_count
         self._hyper_host[2] = float(np.sqrt(1.0 - b2 ** self.step_count))
-        self._hyper_host[3] = 1.0
+        self._hyper_host[3] = 1.0 / self.world          # grad_scale: the all-reduce SUMS the per-rank gradients
         self._hyper_host[4] = self.beta
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
     def _allreduce(self):
-        parallel.allreduce_mean_(self.flat_grads, self.pg)              # sum; the 1/world factor was applied while packing
+        parallel.allreduce_mean_(self.flat_grads, self.pg)              # sum over ranks; Adam applies the 1/world factor (grad_scale)
 
     def step(self, audio, v_in, sample_info):
         """audio [B, C, L] fp32, v_in [B, L_params] fp32, sample_info [B, 3] int32: CUDA tensors on this rank's device.
@@ -157,6 +157,40 @@ class TrainStep:
             self._adam()
         self.losses = losses
         return losses
+
+    # ------------------------------------------------------------------ host-fed steps with input prefetch
+    def prefetch(self, audio_host, v_in_host, sample_info_host):
+        """Starts the host -> device copy of the NEXT step's inputs (pinned CPU tensors) on a copy stream, so that it overlaps
+        the step currently running on the compute stream.  `step_prefetched()` consumes them."""
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staged, self._staged_ready, self._staged_free = None, None, None
+        if self._staged is None or self._staged[0].shape != audio_host.shape:
+            self._staged = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in (audio_host, v_in_host, sample_info_host))
+            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self._staged_free is not None:           # the staging buffers were last read by the copy into the step's static inputs
+            self._copy_stream.wait_event(self._staged_free)
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._staged, (audio_host, v_in_host, sample_info_host)):
+                dst.copy_(src, non_blocking=True)
+            self._staged_ready = torch.cuda.Event()
+            self._staged_ready.record(self._copy_stream)
+
+    def step_prefetched(self):
+        """One training step on the inputs handed to the last `prefetch()` call."""
+        assert getattr(self, '_staged_ready', None) is not None, "call prefetch() first"
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._staged_ready)
+        self._staged_ready = None
+        self._staged_free = torch.cuda.Event()
+        if self.use_graph and self._graph is not None:
+            for dst, src in zip(self._static[:3], self._staged):      # device to device, then the staging buffers are free again
+                dst.copy_(src, non_blocking=True)
+            self._staged_free.record(main)
+            return self.step(*self._static[:3])
+        out = self.step(*self._staged)
+        self._staged_free.record(main)
+        return out
 
     def _capture(self, audio, v_in, sample_info, with_optimizer):
         static_in = (audio.clone(), v_in.clone(), sample_info.clone())

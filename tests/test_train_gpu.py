@@ -82,6 +82,13 @@ def test_cuda_graph_steps_train(idx_helper):
     # batched inference tail: audio -> preset parameters in [0, 1]
     v = tr.infer(audio)
     assert v.shape == (B, 610) and float(v.min()) >= 0.0 and float(v.max()) <= 1.0 and tr.model.training
+    # host-fed API with input prefetch: same batch from pinned host memory gives the same kind of step
+    host = tuple(t.cpu().pin_memory() for t in (audio, v_in, info))
+    tr.prefetch(*host)
+    l_host = tr.step_prefetched()
+    tr.prefetch(*host)
+    torch.cuda.synchronize()
+    assert torch.isfinite(l_host).all() and float(l_host[0]) < float(hist[0, 0]) and tr.step_count == 7
     # schedules reach the captured graph through device memory: lr = 0 must freeze the weights
     tr.lr = 0.0
     snap = tr.flat_params.clone()
