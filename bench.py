@@ -36,6 +36,9 @@ DFT_FLOP_PER_CLIP, MEL_FLOP_PER_CLIP = 729.13e6, 91.50e6
 KERNEL_OF = {'pgv_conv_cl_fwd': 'conv_cl_kernel', 'pgv_conv_cl_dgrad': 'conv_cl_kernel', 'pgv_conv_cl_wgrad': 'conv_cl_kernel',
              'pgv_conv2d_fwd_tf32': 'conv_tc_kernel', 'pgv_conv2d_dgrad_tf32': 'conv_tc_kernel', 'pgv_conv2d_wgrad_tf32': 'conv_tc_kernel',
              'pgv_linear_fwd_tf32': 'conv_tc_kernel', 'pgv_linear_dgrad_tf32': 'conv_tc_kernel', 'pgv_linear_wgrad_tf32': 'conv_tc_kernel',
+             'pgv_linear_cl_fwd': 'conv_cl_kernel', 'pgv_linear_cl_dgrad': 'conv_cl_kernel', 'pgv_linear_cl_wgrad': 'conv_cl_kernel',
+             'pgv_linear_cs_fwd': 'colslice_gemm_kernel', 'pgv_linear_cs_dgrad': 'colslice_gemm_kernel', 'pgv_linear_bn_fwd': 'colslice_gemm_kernel',
+             'pgv_linear_dgrad_bn_bwd': 'colslice_gemm_kernel',
              'pgv_gemm_f32': 'gemm_f32_small_kernel', 'pgv_linear_wgrad_f32': 'gemm_f32_small_kernel'}
 
 

@@ -111,8 +111,9 @@ PGV_API int pgv_linear_wgrad_f32(pgv_handle* h, const float* dy, const float* x,
                                  pgv_stream_t stream);
 
 /* Column-slice GEMM family for the flow conditioners (nflows ResidualNet / ResidualBlock: VAE.py:118-125, flows.py:42-90,
- * regression.py:142-148): one block owns 16 output columns for all M <= pgv_colslice_max_rows() rows, so BatchNorm1d batch
- * statistics are block-local and the normalisation is fused into the GEMM.  Exact fp32.  x [M, K], w [N, K] (nn.Linear).
+ * regression.py:142-148): a thread-block cluster owns 16 output columns for all M <= pgv_colslice_max_rows() rows (32 rows per
+ * CTA), so BatchNorm1d batch statistics stay on chip and the normalisation is fused into the GEMM.  Exact fp32.  x [M, K],
+ * w [N, K] (nn.Linear).  The two plain entry points need no cluster and take any M.
  *   pgv_linear_cs_fwd       y = act(x w^T + bias + residual)
  *   pgv_linear_cs_dgrad     dx [M, K] = dy [M, N] w
  *   pgv_linear_bn_fwd       y_pre = x w^T + bias + residual (stored if non-NULL); out = mask * relu(BN(y_pre)) with batch

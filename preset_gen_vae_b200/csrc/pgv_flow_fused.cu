@@ -277,7 +277,7 @@ int pgv_colslice_max_rows(void) { return CS_MAXM; }
 
 int pgv_linear_cs_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N, int K, int relu,
                       pgv_stream_t stream) {
-    PGV_CHECK_ARG(x && w && y && M > 0 && M <= CS_MAXM && N > 0 && K > 0, "pgv_linear_cs_fwd: bad argument (M <= %d)", CS_MAXM);
+    PGV_CHECK_ARG(x && w && y && M > 0 && M <= 65535 * CS_ROWS && N > 0 && K > 0, "pgv_linear_cs_fwd: bad argument");
     CsParams p;
     memset(&p, 0, sizeof(p));
     p.a = x; p.lda = K; p.b = w; p.ldb = K; p.M = M; p.N = N; p.Kd = K; p.bias = bias; p.add_pre = residual; p.out = y; p.relu = relu;
@@ -285,7 +285,7 @@ int pgv_linear_cs_fwd(const float* x, const float* w, const float* bias, const f
 }
 
 int pgv_linear_cs_dgrad(const float* dy, const float* w, float* dx, int M, int N, int K, pgv_stream_t stream) {
-    PGV_CHECK_ARG(dy && w && dx && M > 0 && M <= CS_MAXM && N > 0 && K > 0, "pgv_linear_cs_dgrad: bad argument (M <= %d)", CS_MAXM);
+    PGV_CHECK_ARG(dy && w && dx && M > 0 && M <= 65535 * CS_ROWS && N > 0 && K > 0, "pgv_linear_cs_dgrad: bad argument");
     CsParams p;
     memset(&p, 0, sizeof(p));
     p.a = dy; p.lda = N; p.b = w; p.ldb = K; p.M = M; p.N = K; p.Kd = N; p.out = dx;

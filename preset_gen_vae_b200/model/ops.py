@@ -392,10 +392,11 @@ def flowbn_train_bwd(dy, x, t, mean, var, g_ld_sum):
 # persistent tensor-core kernel's fixed cost (TMEM allocation, barrier set-up, pipeline fill) exceeds the whole job, so
 # such layers run on the exact-fp32 CUDA-core GEMM instead.
 SMALL_GEMM_MACS = 48_000_000
+SMALL_WEIGHT_ELEMS = 1 << 20      # the flow conditioner layers (<= 610 x 300 weights) never go to the tensor cores, whatever the batch
 
 
 def _use_tc(M, N, K):
-    return _precision == 'tf32' and M * N * K >= SMALL_GEMM_MACS
+    return _precision == 'tf32' and M * N * K >= SMALL_GEMM_MACS and N * K >= SMALL_WEIGHT_ELEMS
 
 
 use_colslice = True    # small Linear layers (flow conditioners): column-slice GEMM, BatchNorm1d fused where one follows
@@ -434,7 +435,7 @@ def linear_fwd(x, w, bias, relu=False, residual=None):
     N = w.shape[0]
     y = _empty(x, M, N)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    if not _use_tc(M, N, K) and colslice_ok(M):
+    if not _use_tc(M, N, K) and use_colslice:
         _call('pgv_linear_cs_fwd', _f(x), _f(w), _f(bias), _f(residual), _f(y), M, N, K, int(relu), _s(x), **acct)
         return y
     if _use_tc(M, N, K):
@@ -450,7 +451,7 @@ def linear_dgrad(dy, w):
     K = w.shape[1]
     dx = _empty(dy, M, K)
     acct = dict(flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    if not _use_tc(M, N, K) and colslice_ok(M):
+    if not _use_tc(M, N, K) and use_colslice:
         _call('pgv_linear_cs_dgrad', _f(dy), _f(w), _f(dx), M, N, K, _s(dy), **acct)
         return dx
     if _use_tc(M, N, K):

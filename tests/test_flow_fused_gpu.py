@@ -20,11 +20,11 @@ def rnd(*shape, seed=0, scale=1.0):
     return torch.randn(*shape, device=DEV, generator=g) * scale
 
 
-@pytest.mark.parametrize("m,n,k", [(160, 300, 305), (160, 610, 300), (160, 300, 300), (7, 33, 19), (256, 300, 300), (1, 16, 4)])
+@pytest.mark.parametrize("m,n,k", [(160, 300, 305), (160, 610, 300), (160, 300, 300), (7, 33, 19), (256, 300, 300), (1, 16, 4), (1024, 300, 300)])
 def test_colslice_linear_forward_and_data_gradient(m, n, k):
     ops.set_precision('tf32')           # small layers run in exact fp32 whatever the precision mode
     x, w, b, res = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=0.1), rnd(n, seed=3), rnd(m, n, seed=4)
-    assert ops.colslice_ok(m) and not ops._use_tc(m, n, k)
+    assert not ops._use_tc(m, n, k)          # conditioner-sized weights stay off the tensor cores whatever the batch (inference: 1024 rows)
     y = ops.linear_fwd(x, w, b, relu=True, residual=res)
     assert rel(y, torch.relu(x.double() @ w.double().T + b.double() + res.double())) < 2e-6
     assert rel(ops.linear_fwd(x, w, None), x.double() @ w.double().T) < 2e-6

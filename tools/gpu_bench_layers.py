@@ -77,8 +77,14 @@ for name, cin, cout, H, W in [('enc8 1x1', 512, 2048, 3, 4), ('dec1 1x1', 512, 2
     t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, w.shape, 1, 0, want_bias=False))
     tot['fwd'] += t_f; tot['dgrad'] += t_d; tot['wgrad'] += t_w
     print("%-10s %8.2f   %7.3f (%6.1f)   %7.3f (%6.1f)   %7.3f (%6.1f)" % (name, fl, t_f, fl / t_f, t_d, fl / t_d, t_w, fl / t_w))
-for name, M, N, K in [('enc FC', B, 1220, 24576), ('dec FC', B, 24576, 610), ('flow 300x300', B, 300, 300), ('flow 305->300', B, 300, 305),
-                      ('flow 300->610', B, 610, 300)]:
+for name, M, N, K in [('enc FC', B, 1220, 24576), ('dec FC', B, 24576, 610)]:        # big Linear layers: ops.fc_fwd / fc_bwd (incl. operand copies)
+    a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; bias = torch.randn(N, device=dev); dy = torch.randn(M, N, device=dev)
+    fl = 2 * M * N * K / 1e9
+    y, ctx = ops.fc_fwd(a, w, bias, True)
+    t_f = timeit(lambda: ops.fc_fwd(a, w, bias, True)); t_b = timeit(lambda: ops.fc_bwd(dy, ctx, w, True))
+    print("%-14s %6.2f   fwd incl. rounded copies %7.3f ms (%6.1f TF/s)   dgrad + wgrad + db %7.3f ms (%6.1f TF/s)   [route %s]" %
+          (name, fl, t_f, fl / t_f, t_b, 2 * fl / t_b, ops.fc_route(M, N, K)))
+for name, M, N, K in [('flow 300x300', B, 300, 300), ('flow 305->300', B, 300, 305), ('flow 300->610', B, 610, 300)]:
     a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; bias = torch.randn(N, device=dev); dy = torch.randn(M, N, device=dev)
     fl = 2 * M * N * K / 1e9
     t_f = timeit(lambda: ops.linear_fwd(a, w, bias)); t_d = timeit(lambda: ops.linear_dgrad(dy, w)); t_w = timeit(lambda: ops.linear_wgrad(dy, a))
