@@ -34,13 +34,15 @@ namespace pgv {
 enum { CL_GEMM = 0, CL_WGRAD = 1 };
 enum { CL_EPI_ROWS = 0, CL_EPI_QUAD = 1 };
 
-constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_STAGES = 6;
+constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_STAGES = 5;
 constexpr int CL_A_BYTES = CL_BLOCK_M * 128, CL_B_BYTES = CL_MAX_N * 128, CL_STAGE_BYTES = CL_A_BYTES + CL_B_BYTES;
 constexpr int CL_PRODUCER_WARPS = 8, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
 constexpr int CL_SLOTS = (CL_BLOCK_M * 8) / CL_PRODUCERS;          // 16-byte chunks of one operand tile per producer thread (4)
 constexpr int CL_ROWS_PER_PASS = CL_PRODUCERS / 8;               // GEMM mode: rows covered by one pass of the producers (32)
-constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/;
-constexpr int CL_SMEM = 1024 + CL_STAGES * CL_STAGE_BYTES + 256;
+constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/ + 32 /*weights by TMA*/;
+// epilogue staging: per epilogue warp 32 rows x 32 columns (+4 pad) of fp32 and one 64-bit destination offset per row
+constexpr int CL_EPI_LD = 36, CL_EPI_WARP_BYTES = 32 * CL_EPI_LD * 4 + 32 * 8;
+constexpr int CL_SMEM = 1024 + CL_STAGES * CL_STAGE_BYTES + 256 + 4 * CL_EPI_WARP_BYTES;
 
 struct ConvClParams {
     const float* a;      // GEMM: gathered activations [B, H, W, C]      WGRAD: x [B, H, W, C]
@@ -55,6 +57,7 @@ struct ConvClParams {
     int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
     int bblocks;         // WGRAD: ceil(B / 32) k-blocks per output position
     int round_out, atomic_out;
+    long long* trace;    // debug (tools/gpu_trace_conv.py): clock64 timestamps of CTA 0, [role][64 events][8]; NULL in production
     float slope;
     FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC;
     alignas(64) CUtensorMap tmap_b;      // GEMM mode: prepared weights [gemm_n][gemm_k], box 32 x n_tile, 128-byte swizzle
@@ -69,6 +72,14 @@ __device__ __forceinline__ uint32_t cl_sw128(int row, int chunk) {
 // index (byte-address bits [5,7) ^= bits [7,9)).  Offset of 16-byte chunk `c16` (0..7) inside row `row` of a 128-byte-row block:
 __device__ __forceinline__ uint32_t cl_sw32(int c16, int row) {
     return static_cast<uint32_t>(((((c16 >> 1) ^ (row & 3)) << 1) | (c16 & 1)) << 4);
+}
+
+__device__ __forceinline__ void cl_trace(const ConvClParams& p, int role, int& n, long long a, long long b, long long c, int tag) {
+    if (p.trace != nullptr && blockIdx.x == 0 && n < 64) {
+        long long* e = p.trace + (role * 64 + n) * 8;
+        e[0] = a; e[1] = b; e[2] = c; e[6] = tag;
+        ++n;
+    }
 }
 
 struct ClItem { int tm, tn, kb0, kb1; };
@@ -98,7 +109,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     uint64_t* bar_tempty = bar_tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int MMA_WARP = CL_PRODUCER_WARPS, EPI_WARP0 = CL_PRODUCER_WARPS + 1;
+    constexpr int MMA_WARP = CL_PRODUCER_WARPS, TMA_WARP = CL_PRODUCER_WARPS + 5;      // warps MMA_WARP + 1 .. + 4 are the epilogue
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -121,6 +132,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         // ================================================================== producers
         const int t = threadIdx.x;
         int stage = 0; uint32_t phase = 0;
+        int trace_n = 0;
         if (MODE == CL_GEMM) {
             // A operand: thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows
             // r0 + CL_ROWS_PER_PASS * i.  B operand (prepared weights, a plain K-major matrix): ONE TMA box per k-block, issued by
@@ -130,8 +142,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             constexpr uint32_t PASS_BYTES = CL_ROWS_PER_PASS * 128;
             const uint32_t span = static_cast<uint32_t>(p.KW) * p.C;  // a multiple of 32: a k-block never straddles two kernel rows
             const long long row_pitch = static_cast<long long>(p.W) * p.C;
-            const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
-            if (t == 0) tma_prefetch_desc(&p.tmap_b);
+            // the ~170-cycle latency of testing the stage's "empty" barrier is taken off the critical path: the test for the NEXT
+            // stage is issued right after the copies of the current one
+            bool ready = mbar_test_wait(&bar_empty[0], 1);
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
                 const float* a_ptr[CL_SLOTS]; uint32_t a_msk[CL_SLOTS];          // mask: bits 0-7 valid kh, bits 8-15 valid kw
@@ -152,11 +165,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 long long koff = static_cast<long long>(kh) * row_pitch + rem;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     const uint32_t sel = (1u << kh) | (256u << p.fd_C.div(rem));
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
-                    if (t == 0) {
-                        mbar_arrive_expect_tx(&bar_full[stage], b_bytes);
-                        tma_load_2d(smem + stage * CL_STAGE_BYTES + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
-                    }
+                    const long long tr_a = (p.trace && t == 0) ? clock64() : 0;
+                    if (!ready) mbar_wait(&bar_empty[stage], phase ^ 1);
+                    const long long tr_b = (p.trace && t == 0) ? clock64() : 0;
+                    const int nstage = (stage + 1 == CL_STAGES) ? 0 : stage + 1;          // test the next stage before this stage's copies
+                    const bool next_ready = mbar_test_wait(&bar_empty[nstage], (nstage == 0 ? (phase ^ 1) : phase) ^ 1);
                     const uint32_t sA = smem_base + stage * CL_STAGE_BYTES + dst0;
 #pragma unroll
                     for (int i = 0; i < CL_SLOTS; ++i) {
@@ -164,7 +177,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                         cp_async16_ca(sA + i * PASS_BYTES, ok ? a_ptr[i] + koff : p.a, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
+                    if (p.trace && t == 0) cl_trace(p, 0, trace_n, tr_a, tr_b, clock64(), kb);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                    ready = next_ready;
                     rem += CL_BLOCK_K; koff += CL_BLOCK_K;
                     if (rem >= span) { rem -= span; ++kh; koff += row_pitch - span; }
                 }
@@ -184,6 +199,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             const int cpp_shift = (cpp == 8) ? 3 : ((cpp == 16) ? 4 : 5);
             const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;    // one 8-pixel group of the B tile
             const long long img_a = static_cast<long long>(p.H) * p.W * p.C, img_b = static_cast<long long>(p.Hg) * p.Wg * p.gemm_n;
+            bool wready = mbar_test_wait(&bar_empty[0], 1);
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
                 // this thread's 4 consecutive m (fixed for the tile): tap (kh, kw) and channel
@@ -230,7 +246,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 };
                 set_position();
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    if (!wready) mbar_wait(&bar_empty[stage], phase ^ 1);
+                    const int nstage = (stage + 1 == CL_STAGES) ? 0 : stage + 1;
+                    const bool next_ready = mbar_test_wait(&bar_empty[nstage], (nstage == 0 ? (phase ^ 1) : phase) ^ 1);
                     const uint32_t sA = smem_base + stage * CL_STAGE_BYTES, sB = sA + CL_A_BYTES;
 #pragma unroll
                     for (int i = 0; i < CL_SLOTS; ++i) {
@@ -246,6 +264,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                    wready = next_ready;
                     if (++bb < static_cast<uint32_t>(p.bblocks)) {
                         img0 += 32;
 #pragma unroll
@@ -264,16 +283,24 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             const uint32_t idesc = umma_idesc_tf32(CL_BLOCK_M, p.n_tile) | (MODE == CL_WGRAD ? (UMMA_IDESC_A_MN | UMMA_IDESC_B_MN) : 0u);
             const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            int trace_n = 0;
+            bool full_ready = false;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * CL_MAX_N;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-                    mbar_wait(&bar_full[stage], phase);
+                    const long long tr_a = p.trace ? clock64() : 0;
+                    if (!full_ready) mbar_wait(&bar_full[stage], phase);
+                    const long long tr_b = p.trace ? clock64() : 0;
                     // The phase completes through the producers' cp.async.mbarrier.arrive, i.e. only once their copies have landed;
                     // like CUTLASS's sm100 cp.async mainloop (sm100_mma_cpasync_warpspecialized.hpp) no proxy fence is issued here.
                     tc_fence_after_sync();
+                    // the NEXT stage's barrier test is issued before this stage's MMAs, so that its ~170-cycle latency is hidden behind
+                    // their issue instead of being added to every k-block
+                    const int nstage = (stage + 1 == CL_STAGES) ? 0 : stage + 1;
+                    const bool next_ready = mbar_test_wait(&bar_full[nstage], nstage == 0 ? (phase ^ 1) : phase);
                     const uint32_t a_addr = smem_base + stage * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
                     if (MODE == CL_GEMM) {
                         const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
@@ -289,92 +316,182 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                         }
                     }
                     umma_commit(&bar_empty[stage]);
+                    if (p.trace) cl_trace(p, 1, trace_n, tr_a, tr_b, clock64(), kb);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                    full_ready = next_ready;
                 }
                 umma_commit(&bar_tfull[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
+    } else if (warp == TMA_WARP) {
+        // ================================================================== weights (GEMM mode): one TMA box per k-block
+        if (MODE == CL_GEMM && lane == 0) {
+            const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
+            tma_prefetch_desc(&p.tmap_b);
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ClItem wi = cl_decode(p, item);
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[stage], b_bytes);
+                    tma_load_2d(smem + stage * CL_STAGE_BYTES + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                    if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
     } else {
-        // ================================================================== epilogue: TMEM -> registers -> global
+        // ================================================================== epilogue: TMEM -> registers -> (shared) -> global
+        // A TMEM lane is an output row, so after tcgen05.ld a thread holds consecutive CHANNELS of one pixel while a coalesced
+        // store wants consecutive lanes on consecutive channels.  GEMM mode therefore passes every 32-column chunk through a
+        // per-warp shared-memory tile: thread = row on the way in, 8 lanes x float4 = 128 contiguous bytes of a row on the way out
+        // (measured before: 16 k cycles to drain one 128 x 128 tile with row-strided float4 stores).
         const int quad = warp & 3, row = quad * 32 + lane;
+        float* stg = reinterpret_cast<float*>(smem + CL_STAGES * CL_STAGE_BYTES + 256 + quad * CL_EPI_WARP_BYTES);
+        long long* stg_dst = reinterpret_cast<long long*>(stg + 32 * CL_EPI_LD);     // per row: element offset of its destination, -1 = no row
         int acc = 0; uint32_t acc_phase = 0;
+        int etrace_n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ClItem wi = cl_decode(p, item);
             const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + row;
             const bool row_ok = m < static_cast<uint32_t>(MODE == CL_WGRAD ? p.m_valid : p.gemm_m);
-            float* dst = p.out;
-            int qi = 0, qj = 0;
+            long long dst_off = -1;
+            int qflags = 0;                                                  // quad epilogue: bit 0 = row 2i+1 exists, bit 1 = column 2j+1 exists
             if (MODE == CL_WGRAD) {
-                dst = p.out + m;                                             // dWcl[n][m]: lanes write consecutive m
-            } else if (p.epi == CL_EPI_ROWS) {
-                dst = p.out + static_cast<size_t>(m) * p.ldo;
-            } else {
-                uint32_t b, rem, i, j;
-                p.fd_HgWg.divmod(m, b, rem);
-                p.fd_Wg.divmod(rem, i, j);
-                qi = 2 * static_cast<int>(i); qj = 2 * static_cast<int>(j);
-                dst = p.out + ((static_cast<size_t>(b) * p.qH + qi) * p.qW + qj) * p.qC;
+                dst_off = m;                                                 // dWcl[n][m]: lanes write consecutive m
+            } else if (row_ok) {
+                if (p.epi == CL_EPI_ROWS) {
+                    dst_off = static_cast<long long>(m) * p.ldo;
+                } else {
+                    uint32_t b, rem, i, j;
+                    p.fd_HgWg.divmod(m, b, rem);
+                    p.fd_Wg.divmod(rem, i, j);
+                    const int qi = 2 * static_cast<int>(i), qj = 2 * static_cast<int>(j);
+                    dst_off = ((static_cast<long long>(b) * p.qH + qi) * p.qW + qj) * p.qC;
+                    qflags = (qi + 1 < p.qH ? 1 : 0) | (qj + 1 < p.qW ? 2 : 0);
+                }
             }
             const bool add_bias = p.bias != nullptr && (!p.atomic_out || wi.kb0 == 0);
+            if (MODE == CL_GEMM) {
+                __syncwarp();
+                stg_dst[lane] = row_ok ? (dst_off * 4 + qflags) : -1;        // destination element offset << 2 | quad flags
+                __syncwarp();
+            }
+            const long long tr_a = p.trace ? clock64() : 0;
             mbar_wait(&bar_tfull[acc], acc_phase);
+            const long long tr_b = p.trace ? clock64() : 0;
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * CL_MAX_N + (static_cast<uint32_t>(quad * 32) << 16);
+            if (MODE == CL_WGRAD) {
 #pragma unroll 1
-            for (int c = 0; c < p.n_tile; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c, v);
-                tmem_ld_wait();
-                if (!row_ok) continue;
-                const int nbase = wi.tn * p.n_tile + c;
-                if (MODE == CL_WGRAD) {
+                for (int c = 0; c < p.n_tile; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    const int nbase = wi.tn * p.n_tile + c;
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
                         if (nbase + e < p.gemm_n) {
-                            float* o = dst + static_cast<size_t>(nbase + e) * p.ldo;
+                            float* o = p.out + dst_off + static_cast<size_t>(nbase + e) * p.ldo;
                             if (p.atomic_out) atomicAdd(o, __uint_as_float(v[e]));
                             else *o = __uint_as_float(v[e]);
                         }
-                    continue;
                 }
+            } else if (p.n_tile <= 16) {
+                // 16-column tiles (the 8 / 16-channel layers): a row is only 64 bytes, the thread stores its own row directly
+                uint32_t v[16];
+                tmem_ld16(taddr, v);
+                tmem_ld_wait();
+                if (row_ok) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int n = nbase + 4 * g;
-                    if (n >= p.gemm_n) break;
-                    float* o;
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = wi.tn * p.n_tile + 4 * g;
+                        if (n >= p.gemm_n) break;
+                        int bidx = n;
+                        long long cls_off = n;
+                        if (p.epi == CL_EPI_QUAD) {
+                            uint32_t cls, ch;
+                            p.fd_qC.divmod(static_cast<uint32_t>(n), cls, ch);
+                            const int need = static_cast<int>(((cls >> 1) & 1u) | ((cls & 1u) << 1));
+                            if ((need & qflags) != need) continue;
+                            bidx = static_cast<int>(ch);
+                            cls_off = (static_cast<long long>(cls >> 1) * p.qW + (cls & 1u)) * p.qC + ch;
+                        }
+                        float4 r = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                               __uint_as_float(v[4 * g + 3]));
+                        if (add_bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + bidx));
+                            r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
+                        }
+                        float* o = p.out + dst_off + cls_off;
+                        if (p.atomic_out) {
+                            atomicAdd(o, r.x);
+                            if (n + 1 < p.gemm_n) atomicAdd(o + 1, r.y);
+                            if (n + 2 < p.gemm_n) atomicAdd(o + 2, r.z);
+                            if (n + 3 < p.gemm_n) atomicAdd(o + 3, r.w);
+                        } else {
+                            r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
+                            r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
+                            *reinterpret_cast<float4*>(o) = r;
+                        }
+                    }
+                }
+            } else {
+                const int col4 = lane & 7, rsub = lane >> 3;                 // read-back role: float4 column group, row within a group of 4
+#pragma unroll 1
+                for (int c = 0; c < p.n_tile; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(v));
+                    if (c + 16 < p.n_tile) tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        *reinterpret_cast<uint4*>(stg + lane * CL_EPI_LD + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                    __syncwarp();
+                    const int n = wi.tn * p.n_tile + c + 4 * col4;           // this lane's 4 columns
+                    const bool col_ok = c + 4 * col4 < p.n_tile && n < p.gemm_n;
                     int bidx = n;
-                    if (p.epi == CL_EPI_ROWS) {
-                        o = dst + n;
-                    } else {
+                    long long cls_off = n;                                   // column part of the destination offset
+                    int need = 0;                                            // quad: flag bits the destination pixel needs
+                    if (p.epi == CL_EPI_QUAD && col_ok) {
                         uint32_t cls, ch;
                         p.fd_qC.divmod(static_cast<uint32_t>(n), cls, ch);
-                        const int ih = qi + static_cast<int>(cls >> 1), iw = qj + static_cast<int>(cls & 1u);
-                        if (ih >= p.qH || iw >= p.qW) continue;              // odd H / W: the last row / column has no partner
-                        o = dst + (static_cast<size_t>(cls >> 1) * p.qW + (cls & 1u)) * p.qC + ch;
                         bidx = static_cast<int>(ch);
+                        cls_off = (static_cast<long long>(cls >> 1) * p.qW + (cls & 1u)) * p.qC + ch;
+                        need = static_cast<int>(((cls >> 1) & 1u) | ((cls & 1u) << 1));
                     }
-                    float4 r = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                                           __uint_as_float(v[4 * g + 3]));
-                    if (add_bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + bidx));
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (add_bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(p.bias + bidx));
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + rsub;
+                        const long long d = stg_dst[rl];
+                        if (!col_ok || d < 0) continue;
+                        const int flags = static_cast<int>(d & 3);
+                        if ((need & flags) != need) continue;                // odd H / W: the last row / column of a quad may not exist
+                        float4 r = *reinterpret_cast<const float4*>(stg + rl * CL_EPI_LD + 4 * col4);
                         r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
+                        float* o = p.out + (d >> 2) + cls_off;
+                        if (p.atomic_out) {
+                            atomicAdd(o, r.x);
+                            if (n + 1 < p.gemm_n) atomicAdd(o + 1, r.y);
+                            if (n + 2 < p.gemm_n) atomicAdd(o + 2, r.z);
+                            if (n + 3 < p.gemm_n) atomicAdd(o + 3, r.w);
+                        } else {
+                            r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
+                            r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
+                            *reinterpret_cast<float4*>(o) = r;
+                        }
                     }
-                    if (p.atomic_out) {
-                        atomicAdd(o, r.x);
-                        if (n + 1 < p.gemm_n) atomicAdd(o + 1, r.y);
-                        if (n + 2 < p.gemm_n) atomicAdd(o + 2, r.z);
-                        if (n + 3 < p.gemm_n) atomicAdd(o + 3, r.w);
-                    } else {
-                        r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
-                        r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
-                        *reinterpret_cast<float4*>(o) = r;
-                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            if (p.trace && quad == 1 && lane == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -435,8 +552,11 @@ __global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict
     }
 }
 
+extern long long* g_conv_trace_ptr;          // set by pgv_debug_set_conv_trace (pgv_conv_tc.cu)
+
 template <int MODE>
-static int launch_conv_cl(const pgv_handle* h, const ConvClParams& p, cudaStream_t stream) {
+static int launch_conv_cl(const pgv_handle* h, ConvClParams& p, cudaStream_t stream) {
+    p.trace = g_conv_trace_ptr;
     static bool configured = false;
     if (!configured) {
         PGV_CUDA(cudaFuncSetAttribute(conv_cl_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
