@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         }
     } else if (warp == MMA_WARP) {
         // ================================================================== MMA issuer
-        if (lane == 0) {
+        // The whole warp runs the loop (waits, address arithmetic) so that every operand of tcgen05.mma stays in uniform registers;
+        // one elected lane issues.  (Under `if (lane == 0)` the compiler wraps EVERY UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+        // loop to make its operands uniform.)
+        {
             const uint32_t idesc = umma_idesc_tf32(CL_BLOCK_M, p.n_tile) | (MODE == CL_WGRAD ? (UMMA_IDESC_A_MN | UMMA_IDESC_B_MN) : 0u);
             const uint32_t b_group_bytes = static_cast<uint32_t>(p.n_tile >> 5) * 1024;
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -302,41 +305,48 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     const int nstage = (stage + 1 == CL_STAGES) ? 0 : stage + 1;
                     const bool next_ready = mbar_test_wait(&bar_full[nstage], nstage == 0 ? (phase ^ 1) : phase);
                     const uint32_t a_addr = smem_base + stage * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
-                    if (MODE == CL_GEMM) {
-                        const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
+                    if (elect_one()) {
+                        if (MODE == CL_GEMM) {
+                            const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
 #pragma unroll
-                        for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
-                    } else {
+                            for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
+                        } else {
 #pragma unroll
-                        for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
-                            // one MMA = 8 pixels = two 4-row atoms 512 bytes apart (SBO); 32-element groups along M / N are 1024 bytes apart (LBO)
-                            const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, 1024, 512);
-                            const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, 1024, 512);
-                            umma_tf32(tmem_d, da, db, idesc, (kb > wi.kb0 || g > 0) ? 1u : 0u);
+                            for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
+                                // one MMA = 8 pixels = two 4-row atoms 512 bytes apart (SBO); 32-element groups along M / N are 1024 bytes apart (LBO)
+                                const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, 1024, 512);
+                                const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, 1024, 512);
+                                umma_tf32(tmem_d, da, db, idesc, (kb > wi.kb0 || g > 0) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&bar_empty[stage]);
                     }
-                    umma_commit(&bar_empty[stage]);
-                    if (p.trace) cl_trace(p, 1, trace_n, tr_a, tr_b, clock64(), kb);
+                    __syncwarp();
+                    if (p.trace && lane == 0) cl_trace(p, 1, trace_n, tr_a, tr_b, clock64(), kb);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
                     full_ready = next_ready;
                 }
-                umma_commit(&bar_tfull[acc]);
+                if (elect_one()) umma_commit(&bar_tfull[acc]);
+                __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
     } else if (warp == TMA_WARP) {
         // ================================================================== weights (GEMM mode): one TMA box per k-block
-        if (MODE == CL_GEMM && lane == 0) {
+        if (MODE == CL_GEMM) {
             const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
-            tma_prefetch_desc(&p.tmap_b);
+            if (lane == 0) tma_prefetch_desc(&p.tmap_b);
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[stage], b_bytes);
-                    tma_load_2d(smem + stage * CL_STAGE_BYTES + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&bar_full[stage], b_bytes);
+                        tma_load_2d(smem + stage * CL_STAGE_BYTES + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                    }
+                    __syncwarp();
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
