@@ -65,22 +65,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(const __grid
     const uint32_t tmem_base = *tmem_ptr;
     const int n_tiles = P::num_tiles(p), n_kb = P::num_k_blocks(p);
 
+    // Producer and MMA warps run their loops with all 32 lanes converged and let ONE elected lane issue: the operands of the TMA
+    // / tcgen05.mma instructions then live in uniform registers (under `if (lane == 0)` the compiler has to wrap every such
+    // instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop).
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 int tm, tn; P::tile_coords(p, tile, tm, tn);
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[stage], S::STAGE_BYTES);
-                    uint8_t* sA = smem + stage * S::STAGE_BYTES;
-                    P::load(p, tm, tn, kb, sA, sA + GEMM_A_BYTES, &bar_full[stage]);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&bar_full[stage], S::STAGE_BYTES);
+                        uint8_t* sA = smem + stage * S::STAGE_BYTES;
+                        P::load(p, tm, tn, kb, sA, sA + GEMM_A_BYTES, &bar_full[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = umma_idesc_tf32(GEMM_BLOCK_M, P::BLOCK_N);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -92,15 +98,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(const __grid
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
                     const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(a_addr + GEMM_A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-                        // advance 32 B (= 2 x 16 B units) inside the 128 B swizzle row per UMMA_K step
-                        umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+                            // advance 32 B (= 2 x 16 B units) inside the 128 B swizzle row per UMMA_K step
+                            umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit(&bar_empty[stage]);
                     }
-                    umma_commit(&bar_empty[stage]);
+                    __syncwarp();
                     if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&bar_tfull[acc]);
+                if (elect_one()) umma_commit(&bar_tfull[acc]);
+                __syncwarp();
                 if (++acc == P::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
