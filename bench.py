@@ -308,8 +308,10 @@ def main_ours(args):
                                 'peak = TF32 dense = half of the %s bf16 burst figure' % pk['src']}
     else:
         # EVERY rank runs the instrumented eager steps (they contain the gradient all-reduce); rank 0 reports.
-        trainer_graph = trainer.use_graph
-        trainer.use_graph = False
+        # The instrumented pass is eager and single-stream (no decoder side stream), so that the events around each entry point
+        # measure that kernel alone and not the time it shared the GPU with a concurrent branch.
+        trainer_graph, trainer_side = trainer.use_graph, trainer._side
+        trainer.use_graph, trainer._side = False, None
         dev_step()
         torch.cuda.synchronize(dev)
         # keep the GPU busy while the CPU enqueues the instrumented steps, so that the CUDA events around each entry
@@ -322,7 +324,7 @@ def main_ours(args):
             dev_step()
         prof = ops.stop_profile()
         del blocker
-        trainer.use_graph = trainer_graph
+        trainer.use_graph, trainer._side = trainer_graph, trainer_side
         if rank == 0:
             tot = sum(v['ms'] for v in prof.values())
             breakdown = {k: round(v['ms'] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:10]}
