@@ -74,10 +74,11 @@ __device__ __forceinline__ uint32_t cl_sw32(int c16, int row) {
     return static_cast<uint32_t>(((((c16 >> 1) ^ (row & 3)) << 1) | (c16 & 1)) << 4);
 }
 
-__device__ __forceinline__ void cl_trace(const ConvClParams& p, int role, int& n, long long a, long long b, long long c, int tag) {
+__device__ __forceinline__ void cl_trace(const ConvClParams& p, int role, int& n, long long a, long long b, long long c, int tag,
+                                         long long d = 0, long long e2 = 0, long long f = 0) {
     if (p.trace != nullptr && blockIdx.x == 0 && n < 64) {
         long long* e = p.trace + (role * 64 + n) * 8;
-        e[0] = a; e[1] = b; e[2] = c; e[6] = tag;
+        e[0] = a; e[1] = b; e[2] = c; e[3] = d; e[4] = e2; e[5] = f; e[6] = tag;
         ++n;
     }
 }
@@ -293,38 +294,53 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * CL_MAX_N;
-                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-                    const long long tr_a = p.trace ? clock64() : 0;
-                    if (!full_ready) mbar_wait(&bar_full[stage], phase);
-                    const long long tr_b = p.trace ? clock64() : 0;
-                    // The phase completes through the producers' cp.async.mbarrier.arrive, i.e. only once their copies have landed;
-                    // like CUTLASS's sm100 cp.async mainloop (sm100_mma_cpasync_warpspecialized.hpp) no proxy fence is issued here.
-                    tc_fence_after_sync();
-                    // the NEXT stage's barrier test is issued before this stage's MMAs, so that its ~170-cycle latency is hidden behind
-                    // their issue instead of being added to every k-block
-                    const int nstage = (stage + 1 == CL_STAGES) ? 0 : stage + 1;
-                    const bool next_ready = mbar_test_wait(&bar_full[nstage], nstage == 0 ? (phase ^ 1) : phase);
-                    const uint32_t a_addr = smem_base + stage * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
-                    if (elect_one()) {
-                        if (MODE == CL_GEMM) {
-                            const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
+                // Two k-blocks per round trip where the tile has them: both stages are waited for (the second test overlaps the first
+                // wait), then ONE elected issue of 8 MMAs + 2 commits.  The fixed cost of an iteration (barrier tests, fence, elect,
+                // re-convergence, loop) is of the order of the MMA issue time itself, so halving it per k-block matters.
+                auto issue_stage = [&](int stg, bool accumulate) {
+                    const uint32_t a_addr = smem_base + stg * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
+                    if (MODE == CL_GEMM) {
+                        const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
 #pragma unroll
-                            for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
-                        } else {
+                        for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+                    } else {
 #pragma unroll
-                            for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
-                                // one MMA = 8 pixels = two 4-row atoms 512 bytes apart (SBO); 32-element groups along M / N are 1024 bytes apart (LBO)
-                                const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, 1024, 512);
-                                const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, 1024, 512);
-                                umma_tf32(tmem_d, da, db, idesc, (kb > wi.kb0 || g > 0) ? 1u : 0u);
-                            }
+                        for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
+                            // one MMA = 8 pixels = two 4-row atoms 512 bytes apart (SBO); 32-element groups along M / N are 1024 bytes apart (LBO)
+                            const uint64_t da = umma_smem_desc_mn_sw128_32b(a_addr + g * 4096, 1024, 512);
+                            const uint64_t db = umma_smem_desc_mn_sw128_32b(b_addr + g * b_group_bytes, 1024, 512);
+                            umma_tf32(tmem_d, da, db, idesc, (accumulate || g > 0) ? 1u : 0u);
                         }
-                        umma_commit(&bar_empty[stage]);
                     }
+                    umma_commit(&bar_empty[stg]);
+                };
+                for (int kb = wi.kb0; kb < wi.kb1;) {
+                    const bool pair = kb + 1 < wi.kb1;
+                    const int s0 = stage, s1 = (s0 + 1 == CL_STAGES) ? 0 : s0 + 1;
+                    const uint32_t ph0 = phase, ph1 = (s1 == 0) ? ph0 ^ 1 : ph0;
+                    const long long tr_a = p.trace ? clock64() : 0;
+                    if (!full_ready) mbar_wait(&bar_full[s0], ph0);
+                    // The phases complete through the producers' cp.async.mbarrier.arrive, i.e. only once their copies have landed;
+                    // like CUTLASS's sm100 cp.async mainloop (sm100_mma_cpasync_warpspecialized.hpp) no proxy fence is issued here.
+                    bool r1 = mbar_test_wait(&bar_full[s1], ph1);
+                    if (pair && !r1) { mbar_wait(&bar_full[s1], ph1); r1 = true; }
+                    int s2 = s1; uint32_t ph2 = ph1; bool r2 = r1;          // the stage after this round trip and whether it is already full
+                    if (pair) {
+                        s2 = (s1 + 1 == CL_STAGES) ? 0 : s1 + 1;
+                        ph2 = (s2 == 0) ? ph1 ^ 1 : ph1;
+                        r2 = mbar_test_wait(&bar_full[s2], ph2);
+                    }
+                    const long long tr_b = p.trace ? clock64() : 0;
+                    tc_fence_after_sync();
+                    if (elect_one()) {
+                        issue_stage(s0, kb > wi.kb0);
+                        if (pair) issue_stage(s1, true);
+                    }
+                    const long long tr_e = p.trace ? clock64() : 0;
                     __syncwarp();
-                    if (p.trace && lane == 0) cl_trace(p, 1, trace_n, tr_a, tr_b, clock64(), kb);
-                    if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
-                    full_ready = next_ready;
+                    if (p.trace && lane == 0) cl_trace(p, 1, trace_n, tr_a, tr_b, clock64(), kb, tr_b, tr_e);
+                    stage = s2; phase = ph2; full_ready = r2;
+                    kb += pair ? 2 : 1;
                 }
                 if (elect_one()) umma_commit(&bar_tfull[acc]);
                 __syncwarp();

@@ -34,5 +34,9 @@ for name, fn in cases.items():
             a, b, c = (int(v) for v in t[role, i, :3]); tag = int(t[role, i, 6])
             if a == 0:
                 break
-            print("   #%2d tag %4d  wait %6d  work %5d | start %8d  period %s" % (i, tag, b - a, c - b, a - t0, '' if prev is None else a - prev))
+            extra = ''
+            if role == 1:
+                d, e = int(t[role, i, 3]), int(t[role, i, 4])
+                extra = '  [fence+test %d  mma+commit %d  syncwarp %d]' % (d - b, e - d, c - e)
+            print("   #%2d tag %4d  wait %6d  work %5d | start %8d  period %s%s" % (i, tag, b - a, c - b, a - t0, '' if prev is None else a - prev, extra))
             prev = a
