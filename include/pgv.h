@@ -209,15 +209,15 @@ PGV_API int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, 
 PGV_API int pgv_round_copy(const float* src, int lds, float* dst, int ldd, int rows, int cols, pgv_stream_t stream);
 PGV_API int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Cin, int KH, int KW, pgv_stream_t stream);
 /* BatchNorm2d on channels-last tensors viewed as [P = B*H*W, C] (same semantics as pgv_bn2d_*; C % 4 == 0).
- * workspace: 16*C bytes. */
+ * workspace: 24*C bytes.  dx_colsum (optional, [C]): per-channel sums of dx = bias gradient of the convolution feeding the block. */
 PGV_API int pgv_bn_cl_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_rstd,
                                 float* running_mean, float* running_var, float momentum, float eps, size_t P, int C, int round_out,
                                 void* workspace, pgv_stream_t stream);
 PGV_API int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                                float* y, float eps, size_t P, int C, int round_out, pgv_stream_t stream);
 PGV_API int pgv_bn_cl_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd,
-                                float* dx, float* dgamma, float* dbeta, float lrelu_slope, size_t P, int C, int round_out, void* workspace,
-                                pgv_stream_t stream);
+                                float* dx, float* dgamma, float* dbeta, float* dx_colsum, float lrelu_slope, size_t P, int C, int round_out,
+                                void* workspace, pgv_stream_t stream);
 /* out[c] = sum over rows of x [P, C] (bias gradient).  workspace: 16*C bytes. */
 PGV_API int pgv_colsum_cl(const float* x, float* out, size_t P, int C, void* workspace, pgv_stream_t stream);
 /* dx = dy * (a > 0 ? 1 : slope), flat arrays of n elements (n % 4 == 0), optionally rounded to TF32. */

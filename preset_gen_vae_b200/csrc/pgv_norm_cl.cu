@@ -147,11 +147,17 @@ __global__ void __launch_bounds__(256) cl_bn_bwd_apply_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                                               const float* __restrict__ save_rstd, const double* __restrict__ ws,
                                                               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              float slope, size_t P, int C, int tcb, int round_out) {
+                                                              float slope, size_t P, int C, int tcb, int round_out, double* __restrict__ colsum) {
+    // colsum (optional, double[C], zero on entry): per-channel sums of the dx written here = the bias gradient of the convolution
+    // that feeds this block, for free instead of another pass over dx
+    extern __shared__ double red[];                                    // [256][4], only used with colsum
     const int cg = blockIdx.y * tcb + (threadIdx.x % tcb), rl = threadIdx.x / tcb, RL = 256 / tcb;
-    if (cg * 4 >= C) return;
+    const bool col_ok = cg * 4 < C;
+    if (!col_ok && colsum == nullptr) return;
     const double n = static_cast<double>(P);
     float m[4], r_[4], gr[4], mdy[4], mdyx[4];
+    double cs[4] = {0, 0, 0, 0};
+    if (col_ok) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int c = 4 * cg + e;
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(256) cl_bn_bwd_apply_kernel(const float* __res
             dgamma[c] = static_cast<float>(ws[2 * c + 1]);
         }
     }
+    float ps[4] = {0, 0, 0, 0};
+    int np = 0;
 #pragma unroll 4
     for (size_t r = static_cast<size_t>(blockIdx.x) * RL + rl; r < P; r += static_cast<size_t>(gridDim.x) * RL) {
         const float4 xv = ld4(x + r * C + 4 * cg), dv = ld4(dy + r * C + 4 * cg);
@@ -174,14 +182,34 @@ __global__ void __launch_bounds__(256) cl_bn_bwd_apply_kernel(const float* __res
             float d = gr[e] * (ds[e] - mdy[e] - (xs[e] - m[e]) * r_[e] * mdyx[e]);
             if (slope >= 0.0f && !(xs[e] > 0.0f)) d *= slope;
             o[e] = rnd(d, round_out);
+            ps[e] += o[e];
         }
         *reinterpret_cast<float4*>(dx + r * C + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+        if (++np == 64) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { cs[e] += ps[e]; ps[e] = 0.0f; }
+            np = 0;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cs[e] += ps[e];
+    }
+    if (colsum == nullptr) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[threadIdx.x * 4 + e] = cs[e];
+    __syncthreads();
+    if (rl == 0 && col_ok) {
+        for (int o = 1; o < RL; ++o)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cs[e] += red[(o * tcb + threadIdx.x) * 4 + e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(colsum + 4 * cg + e, cs[e]);
     }
 }
 
-__global__ void __launch_bounds__(256) cl_sum_finish_kernel(const double* __restrict__ ws, float* __restrict__ out, int C) {
+__global__ void __launch_bounds__(256) cl_sum_finish_kernel(const double* __restrict__ ws, float* __restrict__ out, int C, int stride) {
     const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c < C) out[c] = static_cast<float>(ws[2 * c]);
+    if (c < C) out[c] = static_cast<float>(ws[stride * c]);
 }
 
 // dx = dy * (a > 0 ? 1 : slope) on flat arrays (layout-agnostic), optional TF32 rounding of the result
@@ -247,18 +275,25 @@ int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, co
 }
 
 int pgv_bn_cl_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,
-                        float* dgamma, float* dbeta, float lrelu_slope, size_t P, int C, int round_out, void* workspace, pgv_stream_t stream) {
+                        float* dgamma, float* dbeta, float* dx_colsum, float lrelu_slope, size_t P, int C, int round_out, void* workspace,
+                        pgv_stream_t stream) {
     PGV_CHECK_ARG(dy && x && gamma && save_mean && save_rstd && dx && dgamma && dbeta && workspace, "pgv_bn_cl_train_bwd: NULL argument");
     PGV_CHECK_ARG(P > 0 && C > 0 && C % 4 == 0, "pgv_bn_cl_train_bwd: needs C %% 4 == 0 (C=%d)", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     double* ws = static_cast<double*>(workspace);
-    PGV_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, s));
+    PGV_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, s));
     const ClMap mp = cl_map(C);
     const dim3 grid(cl_grid_rows(P, mp.rl_count), ceil_div(C / 4, mp.tcb));
     cl_reduce_kernel<1><<<grid, 256, 256 * 8 * sizeof(double), s>>>(x, dy, save_mean, save_rstd, ws, P, C, mp.tcb);
     PGV_LAUNCH_CHECK();
-    cl_bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(dy, x, gamma, save_mean, save_rstd, ws, dx, dgamma, dbeta, lrelu_slope, P, C, mp.tcb, round_out);
+    cl_bn_bwd_apply_kernel<<<grid, 256, dx_colsum ? 256 * 4 * sizeof(double) : 0, s>>>(dy, x, gamma, save_mean, save_rstd, ws, dx, dgamma, dbeta,
+                                                                                       lrelu_slope, P, C, mp.tcb, round_out,
+                                                                                       dx_colsum ? ws + 2 * C : nullptr);
     PGV_LAUNCH_CHECK();
+    if (dx_colsum != nullptr) {
+        cl_sum_finish_kernel<<<ceil_div(C, 256), 256, 0, s>>>(ws + 2 * C, dx_colsum, C, 1);
+        PGV_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -272,7 +307,7 @@ int pgv_colsum_cl(const float* x, float* out, size_t P, int C, void* workspace, 
     const dim3 grid(cl_grid_rows(P, mp.rl_count), ceil_div(C / 4, mp.tcb));
     cl_reduce_kernel<2><<<grid, 256, 256 * 8 * sizeof(double), s>>>(x, nullptr, nullptr, nullptr, ws, P, C, mp.tcb);
     PGV_LAUNCH_CHECK();
-    cl_sum_finish_kernel<<<ceil_div(C, 256), 256, 0, s>>>(ws, out, C);
+    cl_sum_finish_kernel<<<ceil_div(C, 256), 256, 0, s>>>(ws, out, C, 2);
     PGV_LAUNCH_CHECK();
     return 0;
 }

@@ -67,12 +67,13 @@ class _BlockBase(nn.Sequential):
         return ops.bn2d_eval_fwd(a, self.bn), None, None
 
     def _pre_bwd(self, dy, a, mean, rstd, grads):
+        """Returns (dz, bias gradient of the convolution or None if it still has to be computed from dz)."""
         if self.bn is None:
-            return ops.lrelu_bwd(dy, a, self.slope)
-        dz, dg, db = ops.bn2d_train_bwd(dy, a, self.bn.weight, mean, rstd, self.slope)
+            return ops.lrelu_bwd(dy, a, self.slope), None
+        dz, dg, db, dbias = ops.bn2d_train_bwd(dy, a, self.bn.weight, mean, rstd, self.slope, want_colsum=True)
         grads[id(self.bn.weight)] = dg
         grads[id(self.bn.bias)] = db
-        return dz
+        return dz, dbias
 
     def forward(self, x):
         from .program import run_program
@@ -127,8 +128,8 @@ class Conv2D(_BlockBase):
     def bwd(self, dy, ctx, grads, need_dx=True):
         x, a, mean, rstd, wq = ctx
         c = self.conv
-        dz = self._pre_bwd(dy, a, mean, rstd, grads)
-        dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True)
+        dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads)
+        dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True, db=dbias)
         grads[id(c.weight)], grads[id(c.bias)] = dw, db
         if not need_dx:
             return None
@@ -163,8 +164,8 @@ class TConv2D(_BlockBase):
 
     def bwd(self, dy, ctx, grads, need_dx=True):
         x, a, mean, rstd, wf = ctx
-        dz = self._pre_bwd(dy, a, mean, rstd, grads)
-        return tconv_bwd(dz, x, self.conv, grads, need_dx, wf=wf)
+        dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads)
+        return tconv_bwd(dz, x, self.conv, grads, need_dx, wf=wf, dbias=dbias)
 
 
 def tconv_out_hw(conv, h, w):
@@ -192,11 +193,11 @@ def tconv_clamp_fusable(x, conv):
     return ops.use_thin and ops._thin(cout_t, cin_t, kh, kw, conv.stride[0], conv.padding[0], H, W, x.shape[2], x.shape[3])
 
 
-def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None):
-    """dz: gradient w.r.t. the transposed convolution's (pre-activation) output."""
+def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None, dbias=None):
+    """dz: gradient w.r.t. the transposed convolution's (pre-activation) output; dbias: its per-channel sums if already known."""
     dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False)
     grads[id(conv.weight)] = dw
-    grads[id(conv.bias)] = ops.channel_sum(dz)
+    grads[id(conv.bias)] = dbias if dbias is not None else ops.channel_sum(dz)
     if not need_dx:
         return None
     return ops.conv2d_fwd(dz, conv.weight, None, conv.stride[0], conv.padding[0], -1.0, out_hw=x.shape[2:], wf=wf)

@@ -250,7 +250,8 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, w
     return dx
 
 
-def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
+def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias, db=None):
+    """db: bias gradient if the caller already has it (BatchNorm backward by-product); else computed here when want_bias."""
     B, Cin, H, W = x.shape
     _, Cout, Ho, Wo = dy.shape
     _, _, kh, kw = w_shape
@@ -260,19 +261,19 @@ def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias):
     if route == 'thin':
         _call('pgv_conv5x5s2_c1_wgrad', _f(to_nchw(x)), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, int(is_cl(dy)), _s(x), n=2,
               flops=flops, nbytes=4 * (x.numel() + dy.numel()))
-        return dw, (channel_sum(dy) if want_bias else None)
+        return dw, (db if db is not None else (channel_sum(dy) if want_bias else None))
     if route == 'cl':
         x, dy = to_cl(x, round_out=True), to_cl(dy, round_out=True)
         dwcl = _empty(x, Cout, kh * kw * Cin)
         _call('pgv_conv_cl_wgrad', _h(x), _f(x), _f(dy), _f(dwcl), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
               flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
         _call('pgv_conv_cl_unpack_dw', _f(dwcl), _f(dw), Cout, Cin, kh, kw, _s(x), nbytes=8 * dw.numel())
-        return dw, (channel_sum(dy) if want_bias else None)
+        return dw, (db if db is not None else (channel_sum(dy) if want_bias else None))
     x, dy = to_nchw(x), to_nchw(dy)
     if route == 'tc':
         _call('pgv_conv2d_wgrad_tf32', _h(x), _f(x), _f(dy), _f(dw), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
               flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
-        return dw, (channel_sum(dy) if want_bias else None)
+        return dw, (db if db is not None else (channel_sum(dy) if want_bias else None))
     db = _empty(x, Cout) if want_bias else None
     _call('pgv_conv2d_wgrad_f32', _f(x), _f(dy), _f(dw), _f(db), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, _s(x),
           n=4 if want_bias else 2, flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
@@ -315,17 +316,20 @@ def bn2d_eval_fwd(x, bn):
     return y
 
 
-def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope):
+def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope, want_colsum=False):
+    """(dx, dgamma, dbeta[, colsum(dx)]): colsum(dx) is the bias gradient of the convolution in front of the block; the
+    channels-last kernel produces it while writing dx."""
     B, C = x.shape[:2]
     dy = same_layout(dy, x)
     dx, dg, db = torch.empty_like(x), _empty(x, C), _empty(x, C)
     if is_cl(x):
-        _call('pgv_bn_cl_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B * x[0, 0].numel(), C, 1,
-              _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 5 * x.numel())
-        return dx, dg, db
+        cs = _empty(x, C) if want_colsum else None
+        _call('pgv_bn_cl_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), _f(cs), slope, B * x[0, 0].numel(), C,
+              1, _f(_ws(x, 24 * C)), _s(x), n=4 if want_colsum else 3, nbytes=4 * 5 * x.numel())
+        return (dx, dg, db, cs) if want_colsum else (dx, dg, db)
     _call('pgv_bn2d_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B, C, x[0, 0].numel(),
           _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 5 * x.numel())
-    return dx, dg, db
+    return (dx, dg, db, channel_sum(dx)) if want_colsum else (dx, dg, db)
 
 
 def lrelu_bwd(dy, a, slope=LRELU_SLOPE):

@@ -81,6 +81,9 @@ def test_batchnorm2d_channels_last(B, C, H, W):
     gz, gg, gb = torch.autograd.grad(out, (z, ref_bn.weight, ref_bn.bias), dy.double())
     dz, dg, db = ops.bn2d_train_bwd(dy, a, bn.weight, mean, rstd, 0.1)
     assert ops.is_cl(dz) and rel(dz, gz) < 4e-4 and rel(dg, gg) < 5e-6 and rel(db, gb) < 5e-6
+    dz2, _, _, colsum = ops.bn2d_train_bwd(dy, a, bn.weight, mean, rstd, 0.1, want_colsum=True)      # + bias gradient of the conv in front
+    assert torch.equal(dz2, dz)
+    assert float((colsum.double() - dz.double().sum((0, 2, 3))).abs().max()) <= 1e-5 * float(dz.double().abs().sum((0, 2, 3)).max())
     bn.eval()
     ref_bn.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
     ref_bn.eval()
