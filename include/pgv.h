@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PGV_VERSION 101
+#define PGV_VERSION 102
 #if defined(__GNUC__)
 #define PGV_API __attribute__((visibility("default")))
 #else
@@ -193,6 +193,15 @@ PGV_API int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, cons
 PGV_API int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin,
                               int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
                               pgv_stream_t stream);
+/* The same two calls for a convolution followed by (Leaky)ReLU and BatchNorm2d (model/layer.py:10-46 of the reference): the epilogue
+ * also accumulates the batch statistics of what it stores, bn_sums[2c] = sum and bn_sums[2c + 1] = sum of squares of channel c
+ * (zero-filled by the call; only for launches with one N tile: Cout <= 128, or 4 * Cin <= 128 for the 4x4 data gradient), which pgv_bn_cl_train_apply then turns into the normalisation. */
+PGV_API int pgv_conv_cl_fwd_bn(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin,
+                               int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
+                               double* bn_sums, pgv_stream_t stream);
+PGV_API int pgv_conv_cl_dgrad_bn(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin,
+                                 int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
+                                 double* bn_sums, pgv_stream_t stream);
 /* dwcl [Cout][(kh, kw, ci)] = sum over pixels of dy x patch(x) (split over CTAs, fp32 atomics; zero-filled by the call);
  * pgv_conv_cl_unpack_dw converts it to the PyTorch layout [Cout, Cin, KH, KW]. */
 PGV_API int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH,
@@ -213,6 +222,9 @@ PGV_API int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Ci
 PGV_API int pgv_bn_cl_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_rstd,
                                 float* running_mean, float* running_var, float momentum, float eps, size_t P, int C, int round_out,
                                 void* workspace, pgv_stream_t stream);
+PGV_API int pgv_bn_cl_train_apply(const float* x, const double* sums, const float* gamma, const float* beta, float* y, float* save_mean,
+                                  float* save_rstd, float* running_mean, float* running_var, float momentum, float eps, size_t P, int C,
+                                  int round_out, pgv_stream_t stream);
 PGV_API int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                                float* y, float eps, size_t P, int C, int round_out, pgv_stream_t stream);
 PGV_API int pgv_bn_cl_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd,

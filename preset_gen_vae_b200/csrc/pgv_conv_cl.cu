@@ -57,6 +57,8 @@ struct ConvClParams {
     int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
     int bblocks;         // WGRAD: ceil(B / 32) k-blocks per output position
     int round_out, atomic_out;
+    double* stats;       // GEMM: if not NULL, stats[2c] += sum, stats[2c + 1] += sum of squares of the stored values of channel c
+    int stat_c;          // number of channels (gemm_n, or qC with the quad epilogue)
     long long* trace;    // debug (tools/gpu_trace_conv.py): clock64 timestamps of CTA 0, [role][64 events][8]; NULL in production
     float slope;
     FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int MMA_WARP = CL_PRODUCER_WARPS, TMA_WARP = CL_PRODUCER_WARPS + 5;      // warps MMA_WARP + 1 .. + 4 are the epilogue
+    const bool with_stats = MODE == CL_GEMM && p.stats != nullptr;
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -378,6 +381,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         long long* stg_dst = reinterpret_cast<long long*>(stg + 32 * CL_EPI_LD);     // per row: element offset of its destination, -1 = no row
         int acc = 0; uint32_t acc_phase = 0;
         int etrace_n = 0;
+        // BatchNorm statistics of the stored values (launches with one N tile only, so that a thread sees the same columns in
+        // every tile): fp32 sums in registers over all tiles of the CTA, folded once at the end.  Direct epilogue: st_*[e] =
+        // column e of the thread's rows; staged epilogue: st_*[4 * chunk + e] = column 32 * chunk + 4 * col4 + e of its 8 rows per tile.
+        float st_s[16], st_q[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) st_s[e] = st_q[e] = 0.0f;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ClItem wi = cl_decode(p, item);
             const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + row;
@@ -461,13 +470,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                             r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
                             r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
                             *reinterpret_cast<float4*>(o) = r;
+                            st_s[4 * g] += r.x; st_s[4 * g + 1] += r.y; st_s[4 * g + 2] += r.z; st_s[4 * g + 3] += r.w;
+                            st_q[4 * g] = fmaf(r.x, r.x, st_q[4 * g]); st_q[4 * g + 1] = fmaf(r.y, r.y, st_q[4 * g + 1]);
+                            st_q[4 * g + 2] = fmaf(r.z, r.z, st_q[4 * g + 2]); st_q[4 * g + 3] = fmaf(r.w, r.w, st_q[4 * g + 3]);
                         }
                     }
                 }
             } else {
                 const int col4 = lane & 7, rsub = lane >> 3;                 // read-back role: float4 column group, row within a group of 4
-#pragma unroll 1
-                for (int c = 0; c < p.n_tile; c += 32) {
+#pragma unroll
+                for (int ci = 0; ci < CL_MAX_N / 32; ++ci) {
+                    const int c = ci * 32;
+                    if (c >= p.n_tile) break;
                     uint32_t v[32];
                     tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(v));
                     if (c + 16 < p.n_tile) tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
@@ -509,6 +523,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                             r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
                             r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
                             *reinterpret_cast<float4*>(o) = r;
+                            st_s[4 * ci] += r.x; st_s[4 * ci + 1] += r.y; st_s[4 * ci + 2] += r.z; st_s[4 * ci + 3] += r.w;
+                            st_q[4 * ci] = fmaf(r.x, r.x, st_q[4 * ci]); st_q[4 * ci + 1] = fmaf(r.y, r.y, st_q[4 * ci + 1]);
+                            st_q[4 * ci + 2] = fmaf(r.z, r.z, st_q[4 * ci + 2]); st_q[4 * ci + 3] = fmaf(r.w, r.w, st_q[4 * ci + 3]);
                         }
                     }
                     __syncwarp();
@@ -521,10 +538,41 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (with_stats) {
+            const bool direct = p.n_tile <= 16;
+            // direct: fold all 32 lanes (rows), lane e then owns column e; staged: fold the 4 lanes (xor 8, 16) that share columns
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    if (o >= 8 || direct) {
+                        st_s[e] += __shfl_xor_sync(0xffffffffu, st_s[e], o);
+                        st_q[e] += __shfl_xor_sync(0xffffffffu, st_q[e], o);
+                    }
+            }
+            // per-warp partial sums of column n -> this warp's (now idle) staging tile: stg[2n] = sum, stg[2n + 1] = sum of squares
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = direct ? e : 32 * (e >> 2) + 4 * (lane & 7) + (e & 3);       // column of entry e (the launch has one N tile)
+                const bool mine = direct ? lane == e : lane < 8;
+                if (mine && n < p.n_tile) { stg[2 * n] = st_s[e]; stg[2 * n + 1] = st_q[e]; }
+            }
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * CL_MAX_N);
+    if (with_stats) {
+        // fold the 4 epilogue warps (and, quad epilogue, the columns (class, c) of the 4 pixel classes) and add to the global sums
+        const float* part = reinterpret_cast<const float*>(smem + CL_STAGES * CL_STAGE_BYTES + 256);
+        for (int i = threadIdx.x; i < 2 * p.stat_c; i += CL_THREADS) {
+            double v = 0.0;
+            for (int n = i >> 1; n < p.gemm_n; n += p.stat_c)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v += static_cast<double>(part[q * (CL_EPI_WARP_BYTES / 4) + 2 * n + (i & 1)]);
+            atomicAdd(p.stats + i, v);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ weight re-packing
@@ -607,7 +655,7 @@ static int cl_pick_n_tile(int n, int granule) {
 // Shared by forward and data gradient: out = act(bias + gather(in) * Bw^T).
 static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, const float* bw, const float* bias, float* out, int B, int H,
                         int W, int C, int KH, int KW, int stride, int pad, int Hg, int Wg, int N, int epi, int qH, int qW, int qC, float slope,
-                        int round_out, size_t out_elems, cudaStream_t stream) {
+                        int round_out, size_t out_elems, double* stats, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || N <= 0 || Hg <= 0 || Wg <= 0 || KH <= 0 || KH > 8 || KW <= 0 || KW > 8 || stride <= 0 || pad < 0)
         return set_error(-1, "%s: bad geometry", who);
     const bool unaligned_n = N % 4 != 0;           // only the atomic (scalar) epilogue can write rows whose pitch is not 16-byte aligned
@@ -640,6 +688,13 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
         }
     }
     if (unaligned_n) p.atomic_out = 1;
+    if (stats != nullptr) {
+        p.stats = stats;
+        p.stat_c = epi == CL_EPI_QUAD ? qC : N;
+        if (p.atomic_out || p.n_tiles != 1 || p.stat_c % 4 != 0)
+            return set_error(-1, "%s: output statistics need a non-split launch with one N tile (N=%d <= %d)", who, N, CL_MAX_N);
+        PGV_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * p.stat_c, stream));
+    }
     if (p.atomic_out) PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems, stream));
     const uint64_t bd[2] = {static_cast<uint64_t>(p.gemm_k), static_cast<uint64_t>(N)}, bs[1] = {static_cast<uint64_t>(p.gemm_k) * 4};
     const uint32_t bbox[2] = {CL_BLOCK_K, static_cast<uint32_t>(p.n_tile)};
@@ -672,31 +727,42 @@ int pgv_conv_cl_supported(int Cin, int Cout, int KH, int KW, int stride, int pad
     return 0;
 }
 
-int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
-                    int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
+int pgv_conv_cl_fwd_bn(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
+                       int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, pgv_stream_t stream) {
     PGV_CHECK_ARG(h && x && wf && y, "pgv_conv_cl_fwd: NULL argument");
     PGV_CHECK_ARG((Ho - 1) * stride - 2 * pad + KH <= H + stride && (Wo - 1) * stride - 2 * pad + KW <= W + stride,
                   "pgv_conv_cl_fwd: output %dx%d does not fit input %dx%d", Ho, Wo, H, W);
     return conv_cl_gemm(h, "pgv_conv_cl_fwd", x, wf, bias, y, B, H, W, Cin, KH, KW, stride, pad, Ho, Wo, Cout, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
-                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, static_cast<cudaStream_t>(stream));
+                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, bn_sums, static_cast<cudaStream_t>(stream));
 }
 
-int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
-                      int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
+int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
+                    int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
+    return pgv_conv_cl_fwd_bn(h, x, wf, bias, y, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, stream);
+}
+
+int pgv_conv_cl_dgrad_bn(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
+                         int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums,
+                         pgv_stream_t stream) {
     PGV_CHECK_ARG(h && dy && wq && dx, "pgv_conv_cl_dgrad: NULL argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t out_elems = static_cast<size_t>(B) * H * W * Cin;
     if (KH == 1 && KW == 1 && stride == 1 && pad == 0) {
         PGV_CHECK_ARG(H == Ho && W == Wo, "pgv_conv_cl_dgrad: 1x1 geometry mismatch");
         return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 1, 1, 1, 0, Ho, Wo, Cin, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
-                            round_out, out_elems, s);
+                            round_out, out_elems, bn_sums, s);
     }
     PGV_CHECK_ARG(KH == 4 && KW == 4 && stride == 2, "pgv_conv_cl_dgrad: only 4x4/stride 2/pad 2 and 1x1/stride 1");
     // pad = 2: the four pixels (2i + ph, 2j + pw) of a quad all read the 2x2 patch of dy whose corner is (i, j)
     PGV_CHECK_ARG(pad == 2, "pgv_conv_cl_dgrad: pad %d not implemented", pad);
     const int Hq = (H + 1) / 2, Wq = (W + 1) / 2;
     return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 2, 2, 1, 0, Hq, Wq, 4 * Cin, CL_EPI_QUAD, H, W, Cin, lrelu_slope,
-                        round_out, out_elems, s);
+                        round_out, out_elems, bn_sums, s);
+}
+
+int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
+                      int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
+    return pgv_conv_cl_dgrad_bn(h, dy, wq, bias, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, stream);
 }
 
 static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, const float* dy, float* out, int ldo, int m_valid, int B, int H,
@@ -738,13 +804,13 @@ int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwc
 int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const float* bias, float* y, int M, int N, int K, pgv_stream_t stream) {
     PGV_CHECK_ARG(h && x && wr && y && M > 0 && N > 0 && K > 0, "pgv_linear_cl_fwd: bad argument");
     return conv_cl_gemm(h, "pgv_linear_cl_fwd", x, wr, bias, y, M, 1, 1, K, 1, 1, 1, 0, 1, 1, N, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
-                        static_cast<size_t>(M) * N, static_cast<cudaStream_t>(stream));
+                        static_cast<size_t>(M) * N, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, pgv_stream_t stream) {
     PGV_CHECK_ARG(h && dy && wt && dx && M > 0 && N > 0 && K > 0, "pgv_linear_cl_dgrad: bad argument");
     return conv_cl_gemm(h, "pgv_linear_cl_dgrad", dy, wt, nullptr, dx, M, 1, 1, N, 1, 1, 1, 0, 1, 1, K, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
-                        static_cast<size_t>(M) * K, static_cast<cudaStream_t>(stream));
+                        static_cast<size_t>(M) * K, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid,

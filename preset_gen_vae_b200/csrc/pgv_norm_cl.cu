@@ -263,6 +263,21 @@ int pgv_bn_cl_train_fwd(const float* x, const float* gamma, const float* beta, f
     return 0;
 }
 
+/* Second half of pgv_bn_cl_train_fwd for statistics that a convolution epilogue already accumulated (pgv_conv_cl_fwd_bn / _dgrad_bn):
+   sums[2c] = sum, sums[2c + 1] = sum of squares of channel c over the P rows of x. */
+int pgv_bn_cl_train_apply(const float* x, const double* sums, const float* gamma, const float* beta, float* y, float* save_mean, float* save_rstd,
+                          float* running_mean, float* running_var, float momentum, float eps, size_t P, int C, int round_out,
+                          pgv_stream_t stream) {
+    PGV_CHECK_ARG(x && sums && gamma && beta && y && save_mean && save_rstd, "pgv_bn_cl_train_apply: NULL argument");
+    PGV_CHECK_ARG(P > 0 && C > 0 && C % 4 == 0, "pgv_bn_cl_train_apply: needs C %% 4 == 0 (C=%d)", C);
+    const ClMap mp = cl_map(C);
+    const dim3 grid(cl_grid_rows(P, mp.rl_count), ceil_div(C / 4, mp.tcb));
+    cl_bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, sums, gamma, beta, y, save_mean, save_rstd, running_mean, running_var,
+                                                                            momentum, eps, P, C, mp.tcb, round_out);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
 int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float* y,
                        float eps, size_t P, int C, int round_out, pgv_stream_t stream) {
     PGV_CHECK_ARG(x && gamma && beta && running_mean && running_var && y, "pgv_bn_cl_eval_fwd: NULL argument");

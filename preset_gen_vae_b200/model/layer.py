@@ -57,11 +57,11 @@ class _BlockBase(nn.Sequential):
             self.bn.num_batches_tracked += self._nbt_pending
         self._nbt_pending = 0
 
-    def _post(self, a, training):
+    def _post(self, a, training, sums=None):
         if self.bn is None:
             return a, None, None
         if training:
-            y, mean, rstd = ops.bn2d_train_fwd(a, self.bn)
+            y, mean, rstd = ops.bn2d_train_fwd(a, self.bn, sums)
             self._nbt_pending += 1
             return y, mean, rstd
         return ops.bn2d_eval_fwd(a, self.bn), None, None
@@ -121,8 +121,10 @@ class Conv2D(_BlockBase):
             x = ops.to_cl(x, round_out=True)
             wf, wq = ops.prep_conv_weights(c.weight, c.stride[0], c.padding[0], dgrad=training)
         # without a BatchNorm behind it, the activation itself is the next tensor-core operand
-        a = ops.conv2d_fwd(x, c.weight, c.bias, c.stride[0], c.padding[0], self.slope, wf=wf, round_out=self.bn is None)
-        y, mean, rstd = self._post(a, training)
+        want_sums = training and self.bn is not None       # the conv epilogue also accumulates the BatchNorm statistics
+        a = ops.conv2d_fwd(x, c.weight, c.bias, c.stride[0], c.padding[0], self.slope, wf=wf, round_out=self.bn is None, bn_sums=want_sums)
+        a, sums = a if want_sums else (a, None)
+        y, mean, rstd = self._post(a, training, sums)
         return y, (x, a, mean, rstd, wq)
 
     def bwd(self, dy, ctx, grads, need_dx=True):
@@ -158,8 +160,10 @@ class TConv2D(_BlockBase):
         if tconv_route(x, c) == 'cl':
             x = ops.to_cl(x, round_out=True)
             wf, wq = ops.prep_conv_weights(c.weight, c.stride[0], c.padding[0], fwd=training)
-        a = tconv_fwd(x, c, self.slope, wq=wq, round_out=self.bn is None)
-        y, mean, rstd = self._post(a, training)
+        want_sums = training and self.bn is not None
+        a = tconv_fwd(x, c, self.slope, wq=wq, round_out=self.bn is None, bn_sums=want_sums)
+        a, sums = a if want_sums else (a, None)
+        y, mean, rstd = self._post(a, training, sums)
         return y, (x, a, mean, rstd, wf)
 
     def bwd(self, dy, ctx, grads, need_dx=True):
@@ -180,10 +184,10 @@ def tconv_route(x, conv):
     return ops.conv_route(cout_t, cin_t, kh, kw, conv.stride[0], conv.padding[0], H, W, x.shape[2], x.shape[3])
 
 
-def tconv_fwd(x, conv, slope=-1.0, clamp=None, wq=None, round_out=False):
+def tconv_fwd(x, conv, slope=-1.0, clamp=None, wq=None, round_out=False, bn_sums=False):
     """ConvTranspose2d forward (+bias, optional fused LeakyReLU or Hardtanh clamp) = conv data-gradient."""
     return ops.conv2d_dgrad(x, conv.weight, tconv_out_hw(conv, x.shape[2], x.shape[3]), conv.stride[0], conv.padding[0],
-                            bias=conv.bias, slope=slope, clamp=clamp, wq=wq, round_out=round_out)
+                            bias=conv.bias, slope=slope, clamp=clamp, wq=wq, round_out=round_out, bn_sums=bn_sums)
 
 
 def tconv_clamp_fusable(x, conv):

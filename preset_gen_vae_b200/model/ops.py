@@ -184,8 +184,20 @@ def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True):
     return wf, wq
 
 
-def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_out=False):
-    """round_out: round the result to TF32 (set when it feeds a channels-last tensor-core kernel directly)."""
+BN_SUMS_MAX_N = 128     # the conv epilogue accumulates statistics in registers, which needs a single N tile (CL_MAX_N)
+use_bn_sums = True
+
+
+def _bn_sums(ref, C, gemm_n, route):
+    """fp64 [C][2] buffer for the (sum, sum of squares) by-product of a channels-last convolution, or None if the launch has none."""
+    if route == 'cl' and use_bn_sums and gemm_n <= BN_SUMS_MAX_N:
+        return torch.empty(2 * C, dtype=torch.float64, device=ref.device)
+    return None
+
+
+def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_out=False, bn_sums=False):
+    """round_out: round the result to TF32 (set when it feeds a channels-last tensor-core kernel directly).
+    bn_sums: return (y, sums) where sums holds the batch statistics of y for ops.bn2d_train_fwd (None if the route has no such by-product)."""
     B, Cin, H, W = x.shape
     Cout, _, kh, kw = w.shape
     Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
@@ -196,29 +208,31 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_
         y = _empty_cl(x, B, Cout, Ho, Wo) if cl else _empty(x, B, Cout, Ho, Wo)
         _call('pgv_conv5x5s2_c1_fwd', _f(to_nchw(x)), _f(w), _f(bias), _f(y), B, Cout, H, W, Ho, Wo, slope, int(cl), int(cl and round_out),
               _s(x), flops=flops, nbytes=4 * (x.numel() + y.numel()))
-        return y
+        return (y, None) if bn_sums else y
     if route == 'cl':
         x = to_cl(x, round_out=True)
         if wf is None:
             wf, _ = prep_conv_weights(w, stride, pad, dgrad=False)
         y = _empty_cl(x, B, Cout, Ho, Wo)
-        _call('pgv_conv_cl_fwd', _h(x), _f(x), _f(wf), _f(bias), _f(y), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope, int(round_out),
-              _s(x), flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
-        return y
+        sums = _bn_sums(x, Cout, Cout, route) if bn_sums else None
+        _call('pgv_conv_cl_fwd_bn', _h(x), _f(x), _f(wf), _f(bias), _f(y), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope, int(round_out),
+              _f(sums), _s(x), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
+        return (y, sums) if bn_sums else y
     x = to_nchw(x)
     y = _empty(x, B, Cout, Ho, Wo)
     _call('pgv_conv2d_fwd_tf32' if route == 'tc' else 'pgv_conv2d_fwd_f32', *((_h(x),) if route == 'tc' else ()), _f(x), _f(w), _f(bias), _f(y),
           B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(x), flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
-    return y
+    return (y, None) if bn_sums else y
 
 
 def _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
     return bool(_lib.lib().pgv_conv5x5s2_c1_supported(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo))
 
 
-def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, wq=None, round_out=False):
+def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, wq=None, round_out=False, bn_sums=False):
     """dx of the convolution with weight w [Cout, Cin, kh, kw]; also the forward of ConvTranspose2d(weight=w).
-    clamp=(lo, hi) fuses a Hardtanh (only available on the thin-layer kernel; callers check `tconv_clamp_fusable`)."""
+    clamp=(lo, hi) fuses a Hardtanh (only available on the thin-layer kernel; callers check `tconv_clamp_fusable`).
+    bn_sums: as in conv2d_fwd, returns (dx, sums)."""
     B, Cout, Ho, Wo = dy.shape
     _, Cin, kh, kw = w.shape
     H, W = in_hw
@@ -229,25 +243,26 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, w
         dx = _empty(dy, B, Cin, H, W)
         _call('pgv_conv5x5s2_c1_dgrad', _f(dy), _f(w), _f(bias), _f(dx), B, Cout, H, W, Ho, Wo, lo, hi, int(is_cl(dy)), _s(dy),
               flops=flops, nbytes=4 * (dx.numel() + dy.numel()))
-        return dx
+        return (dx, None) if bn_sums else dx
     assert clamp is None, "fused clamp needs the thin-layer kernel"
     if route == 'cl':
         dy = to_cl(dy, round_out=True)
         if wq is None:
             _, wq = prep_conv_weights(w, stride, pad, fwd=False)
         dx = _empty_cl(dy, B, Cin, H, W)
-        _call('pgv_conv_cl_dgrad', _h(dy), _f(dy), _f(wq), _f(bias), _f(dx), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope,
-              int(round_out), _s(dy), flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
-        return dx
+        sums = _bn_sums(dy, Cin, (4 if kh == 4 else 1) * Cin, route) if bn_sums else None
+        _call('pgv_conv_cl_dgrad_bn', _h(dy), _f(dy), _f(wq), _f(bias), _f(dx), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope,
+              int(round_out), _f(sums), _s(dy), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
+        return (dx, sums) if bn_sums else dx
     dy = to_nchw(dy)
     dx = _empty(dy, B, Cin, H, W)
     if _precision == 'tf32' and stride <= 2:
         _call('pgv_conv2d_dgrad_tf32', _h(dy), _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope,
               _s(dy), flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
-        return dx
+        return (dx, None) if bn_sums else dx
     _call('pgv_conv2d_dgrad_f32', _f(dy), _f(w), _f(bias), _f(dx), B, Cin, H, W, Cout, kh, kw, stride, pad, Ho, Wo, slope, _s(dy),
           flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
-    return dx
+    return (dx, None) if bn_sums else dx
 
 
 def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias, db=None):
@@ -291,10 +306,16 @@ def channel_sum(x):
 
 
 # ------------------------------------------------------------------------------------------------ normalisation
-def bn2d_train_fwd(x, bn):
+def bn2d_train_fwd(x, bn, sums=None):
+    """sums: batch statistics of x already accumulated by the convolution that produced it (conv2d_fwd / conv2d_dgrad, bn_sums=True)."""
     B, C = x.shape[:2]
     HW = x[0, 0].numel()
     y, mean, rstd = torch.empty_like(x), _empty(x, C), _empty(x, C)
+    if sums is not None:
+        assert is_cl(x) and sums.numel() == 2 * C
+        _call('pgv_bn_cl_train_apply', _f(x), _f(sums), _f(bn.weight), _f(bn.bias), _f(y), _f(mean), _f(rstd), _f(bn.running_mean),
+              _f(bn.running_var), bn.momentum, bn.eps, B * HW, C, 1, _s(x), nbytes=4 * 2 * x.numel())
+        return y, mean, rstd
     if is_cl(x):        # result rounded to TF32: its consumers are the cp.async-fed tensor-core kernels
         _call('pgv_bn_cl_train_fwd', _f(x), _f(bn.weight), _f(bn.bias), _f(y), _f(mean), _f(rstd), _f(bn.running_mean), _f(bn.running_var),
               bn.momentum, bn.eps, B * HW, C, 1, _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 3 * x.numel())

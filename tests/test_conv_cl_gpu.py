@@ -146,6 +146,40 @@ def test_block_forward_backward_on_the_channels_last_route(transposed):
     assert rel(blk.conv.bias.grad, ref_conv.bias.grad) < 1e-1       # a sum with heavy cancellation over B*H*W pixels
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 129, 174), (16, 32, 65, 88), (32, 64, 33, 45), (64, 128, 17, 23), (128, 256, 9, 12)])
+def test_conv_epilogue_accumulates_the_batchnorm_statistics(cin, cout, H, W):
+    """pgv_conv_cl_fwd_bn / pgv_conv_cl_dgrad_bn: sums[c] = (sum, sum of squares) of exactly the values the kernel stored, for the
+    16-column direct epilogue, the staged epilogue (1 to 4 column chunks) and the quad epilogue with odd output sizes; BatchNorm
+    from these sums equals BatchNorm from its own reduction pass.  Launches with several N tiles have no such by-product."""
+    B = 3
+    x, w, b = rnd(B, cin, H, W, seed=70), rnd(cout, cin, 4, 4, seed=71, scale=0.1), rnd(cout, seed=72)
+    y, sums = ops.conv2d_fwd(x, w, b, 2, 2, slope=0.1, bn_sums=True)
+    assert torch.equal(y, ops.conv2d_fwd(x, w, b, 2, 2, slope=0.1))
+    if cout > 128:
+        assert sums is None
+        return
+    yd = y.double()
+    want = torch.stack([yd.sum((0, 2, 3)), (yd * yd).sum((0, 2, 3))], 1).reshape(-1)
+    scale = torch.stack([yd.abs().sum((0, 2, 3)), (yd * yd).sum((0, 2, 3))], 1).reshape(-1)
+    assert float(((sums - want).abs() / scale).max()) < 2e-6
+    bn = torch.nn.BatchNorm2d(cout).to(DEV)
+    bn2 = torch.nn.BatchNorm2d(cout).to(DEV)
+    o1, m1, r1 = ops.bn2d_train_fwd(y, bn)
+    o2, m2, r2 = ops.bn2d_train_fwd(y, bn2, sums)
+    assert rel(o2, o1) < 1e-5 and rel(m2, m1) < 1e-5 and rel(r2, r1) < 1e-5 and rel(bn2.running_var, bn.running_var) < 1e-5
+    # transposed convolution = data gradient of the same weights: input [B, cout, Ho, Wo] -> [B, cin, H, W] (H, W odd: partial quads)
+    dy, bt = rnd(B, cout, y.shape[2], y.shape[3], seed=73), rnd(cin, seed=74)
+    t, tsums = ops.conv2d_dgrad(dy, w, (H, W), 2, 2, bias=bt, slope=0.1, bn_sums=True)
+    assert torch.equal(t, ops.conv2d_dgrad(dy, w, (H, W), 2, 2, bias=bt, slope=0.1))
+    if 4 * cin > 128:
+        assert tsums is None
+        return
+    td = t.double()
+    want = torch.stack([td.sum((0, 2, 3)), (td * td).sum((0, 2, 3))], 1).reshape(-1)
+    scale = torch.stack([td.abs().sum((0, 2, 3)), (td * td).sum((0, 2, 3))], 1).reshape(-1)
+    assert float(((tsums - want).abs() / scale).max()) < 2e-6
+
+
 @pytest.mark.parametrize("m,n,k", [(160, 1220, 24576), (160, 24576, 610), (64, 1024, 1030), (5, 36, 26)])
 def test_big_linear_layers_on_the_channels_last_kernel(m, n, k):
     """encoder / decoder FC (and a padded-K case) through fc_fwd / fc_bwd: rounded + re-pitched operand copies, weights by TMA,

@@ -74,7 +74,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in protos:
         assert hasattr(cdll, name), name
     L = _lib.lib()
-    assert L.pgv_version() == 101
+    assert L.pgv_version() == 102
     assert L.pgv_frontend_num_frames(88576, 256) == 347 and L.pgv_frontend_num_frames(88200, 256) == 345
     assert L.pgv_frontend_mel_ld(1024) == 544
     assert L.pgv_frontend_workspace_bytes(1, 88576, 1000, 256, 257) == 0      # unsupported n_fft
