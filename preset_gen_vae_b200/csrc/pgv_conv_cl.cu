@@ -387,6 +387,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         float st_s[16], st_q[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) st_s[e] = st_q[e] = 0.0f;
+        // bias of this thread's columns (4 per column group / chunk), re-loaded only when the N tile changes and always BEFORE the
+        // wait for the accumulator: a global load issued inside the drain costs 300-600 cycles of exposed latency per chunk
+        float4 bvs[4];
+        int bias_tn = -1;
+        const int col4 = lane & 7, rsub = lane >> 3;                         // staged read-back role: float4 column group, row within a group of 4
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ClItem wi = cl_decode(p, item);
             const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + row;
@@ -408,6 +413,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 }
             }
             const bool add_bias = p.bias != nullptr && (!p.atomic_out || wi.kb0 == 0);
+            if (MODE == CL_GEMM && p.bias != nullptr && wi.tn != bias_tn) {
+                bias_tn = wi.tn;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cn = p.n_tile <= 16 ? 4 * k : 32 * k + 4 * col4;          // column inside the tile: direct / staged epilogue
+                    const int n = wi.tn * p.n_tile + cn;
+                    bvs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cn < p.n_tile && n < p.gemm_n) {
+                        uint32_t cls = 0, ch = static_cast<uint32_t>(n);
+                        if (p.epi == CL_EPI_QUAD) p.fd_qC.divmod(static_cast<uint32_t>(n), cls, ch);
+                        bvs[k] = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                    }
+                }
+            }
             if (MODE == CL_GEMM) {
                 __syncwarp();
                 stg_dst[lane] = row_ok ? (dst_off * 4 + qflags) : -1;        // destination element offset << 2 | quad flags
@@ -416,6 +435,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             const long long tr_a = p.trace ? clock64() : 0;
             mbar_wait(&bar_tfull[acc], acc_phase);
             const long long tr_b = p.trace ? clock64() : 0;
+            long long tr_ld = 0;                                             // trace: arrival of the first tcgen05.ld
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * CL_MAX_N + (static_cast<uint32_t>(quad * 32) << 16);
             if (MODE == CL_WGRAD) {
@@ -439,27 +459,23 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 uint32_t v[16];
                 tmem_ld16(taddr, v);
                 tmem_ld_wait();
+                if (p.trace) tr_ld = clock64();
                 if (row_ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int n = wi.tn * p.n_tile + 4 * g;
                         if (n >= p.gemm_n) break;
-                        int bidx = n;
                         long long cls_off = n;
                         if (p.epi == CL_EPI_QUAD) {
                             uint32_t cls, ch;
                             p.fd_qC.divmod(static_cast<uint32_t>(n), cls, ch);
                             const int need = static_cast<int>(((cls >> 1) & 1u) | ((cls & 1u) << 1));
                             if ((need & qflags) != need) continue;
-                            bidx = static_cast<int>(ch);
                             cls_off = (static_cast<long long>(cls >> 1) * p.qW + (cls & 1u)) * p.qC + ch;
                         }
                         float4 r = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                                                __uint_as_float(v[4 * g + 3]));
-                        if (add_bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + bidx));
-                            r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
-                        }
+                        if (add_bias) { r.x += bvs[g].x; r.y += bvs[g].y; r.z += bvs[g].z; r.w += bvs[g].w; }
                         float* o = p.out + dst_off + cls_off;
                         if (p.atomic_out) {
                             atomicAdd(o, r.x);
@@ -477,7 +493,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     }
                 }
             } else {
-                const int col4 = lane & 7, rsub = lane >> 3;                 // read-back role: float4 column group, row within a group of 4
 #pragma unroll
                 for (int ci = 0; ci < CL_MAX_N / 32; ++ci) {
                     const int c = ci * 32;
@@ -486,46 +501,54 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(v));
                     if (c + 16 < p.n_tile) tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
                     tmem_ld_wait();
+                    if (p.trace && ci == 0) tr_ld = clock64();
 #pragma unroll
                     for (int g = 0; g < 8; ++g)
                         *reinterpret_cast<uint4*>(stg + lane * CL_EPI_LD + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                     __syncwarp();
                     const int n = wi.tn * p.n_tile + c + 4 * col4;           // this lane's 4 columns
                     const bool col_ok = c + 4 * col4 < p.n_tile && n < p.gemm_n;
-                    int bidx = n;
                     long long cls_off = n;                                   // column part of the destination offset
                     int need = 0;                                            // quad: flag bits the destination pixel needs
                     if (p.epi == CL_EPI_QUAD && col_ok) {
                         uint32_t cls, ch;
                         p.fd_qC.divmod(static_cast<uint32_t>(n), cls, ch);
-                        bidx = static_cast<int>(ch);
                         cls_off = (static_cast<long long>(cls >> 1) * p.qW + (cls & 1u)) * p.qC + ch;
                         need = static_cast<int>(((cls >> 1) & 1u) | ((cls & 1u) << 1));
                     }
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (add_bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(p.bias + bidx));
+                    const float4 bv = add_bias ? bvs[ci] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // the shared-memory reads of four row groups are issued back to back, ahead of the stores that use them
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + rsub;
-                        const long long d = stg_dst[rl];
-                        if (!col_ok || d < 0) continue;
-                        const int flags = static_cast<int>(d & 3);
-                        if ((need & flags) != need) continue;                // odd H / W: the last row / column of a quad may not exist
-                        float4 r = *reinterpret_cast<const float4*>(stg + rl * CL_EPI_LD + 4 * col4);
-                        r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
-                        float* o = p.out + (d >> 2) + cls_off;
-                        if (p.atomic_out) {
-                            atomicAdd(o, r.x);
-                            if (n + 1 < p.gemm_n) atomicAdd(o + 1, r.y);
-                            if (n + 2 < p.gemm_n) atomicAdd(o + 2, r.z);
-                            if (n + 3 < p.gemm_n) atomicAdd(o + 3, r.w);
-                        } else {
-                            r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
-                            r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
-                            *reinterpret_cast<float4*>(o) = r;
-                            st_s[4 * ci] += r.x; st_s[4 * ci + 1] += r.y; st_s[4 * ci + 2] += r.z; st_s[4 * ci + 3] += r.w;
-                            st_q[4 * ci] = fmaf(r.x, r.x, st_q[4 * ci]); st_q[4 * ci + 1] = fmaf(r.y, r.y, st_q[4 * ci + 1]);
-                            st_q[4 * ci + 2] = fmaf(r.z, r.z, st_q[4 * ci + 2]); st_q[4 * ci + 3] = fmaf(r.w, r.w, st_q[4 * ci + 3]);
+                    for (int half = 0; half < 2; ++half) {
+                        long long dd[4];
+                        float4 rr[4];
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) dd[it] = stg_dst[(half * 4 + it) * 4 + rsub];
+#pragma unroll
+                        for (int it = 0; it < 4; ++it)
+                            rr[it] = *reinterpret_cast<const float4*>(stg + ((half * 4 + it) * 4 + rsub) * CL_EPI_LD + 4 * col4);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const long long d = dd[it];
+                            if (!col_ok || d < 0) continue;
+                            const int flags = static_cast<int>(d & 3);
+                            if ((need & flags) != need) continue;                // odd H / W: the last row / column of a quad may not exist
+                            float4 r = rr[it];
+                            r.x += bv.x; r.y += bv.y; r.z += bv.z; r.w += bv.w;
+                            float* o = p.out + (d >> 2) + cls_off;
+                            if (p.atomic_out) {
+                                atomicAdd(o, r.x);
+                                if (n + 1 < p.gemm_n) atomicAdd(o + 1, r.y);
+                                if (n + 2 < p.gemm_n) atomicAdd(o + 2, r.z);
+                                if (n + 3 < p.gemm_n) atomicAdd(o + 3, r.w);
+                            } else {
+                                r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
+                                r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
+                                *reinterpret_cast<float4*>(o) = r;
+                                st_s[4 * ci] += r.x; st_s[4 * ci + 1] += r.y; st_s[4 * ci + 2] += r.z; st_s[4 * ci + 3] += r.w;
+                                st_q[4 * ci] = fmaf(r.x, r.x, st_q[4 * ci]); st_q[4 * ci + 1] = fmaf(r.y, r.y, st_q[4 * ci + 1]);
+                                st_q[4 * ci + 2] = fmaf(r.z, r.z, st_q[4 * ci + 2]); st_q[4 * ci + 3] = fmaf(r.w, r.w, st_q[4 * ci + 3]);
+                            }
                         }
                     }
                     __syncwarp();
@@ -534,7 +557,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-            if (p.trace && quad == 1 && lane == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item);
+            if (p.trace && quad == 1 && lane == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item, tr_ld);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
