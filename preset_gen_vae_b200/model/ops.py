@@ -528,24 +528,27 @@ def fc_fwd(x, w, bias, training=True):
     M, K = x.shape
     N = w.shape[0]
     if fc_route(M, N, K) != 'cl':
-        return linear_fwd(x, w, bias), (x, None, None, K)
+        return linear_fwd(x, w, bias), (x, None, None, K, None)
     Kp = (K + 3) // 4 * 4
     xr, wr = round_copy(x, Kp), round_copy(w, Kp)
+    # Data gradient dx = dy @ W.  With M % 4 == 0 it runs on the weight-gradient form of the kernel, whose operands are both
+    # "reduction index x contiguous output index": W [N, Kp] as stored (the rounded copy the forward already made) and dy^T [N, M].
+    # Otherwise it needs the rounded transpose W^T [K, N], a second pass over the whole weight matrix.
     wt = None
-    if training:                                   # rounded W^T [K, N] for the data gradient (tiled transpose, both sides coalesced)
+    if training and M % 4 != 0:
         wt = _empty(w, K, N)
         _call('pgv_transpose_inner', _f(w), _f(wt), 1, N, K, 1, _s(w), nbytes=8 * w.numel())
     y = _empty(x, M, N)
     _call('pgv_linear_cl_fwd', _h(x), _f(xr), _f(wr), _f(bias), _f(y), M, N, Kp, _s(x), n=2,
           flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    return y, (xr, wt, Kp, K)
+    return y, (xr, wt, Kp, K, wr if training and wt is None else None)
 
 
 def fc_bwd(dy, ctx, w, need_dx=True, out=None):
     """(dx, dw, db) of fc_fwd; `out`: preallocated [N, K] destination for dw (e.g. a slice of the flat gradient buffer)."""
-    xr, wt, Kp, K = ctx
+    xr, wt, Kp, K, wr = ctx
     M, N = dy.shape
-    if wt is None:
+    if wt is None and wr is None:
         dw, db = linear_wgrad(dy, xr, out=out)
         return (linear_dgrad(dy, w) if need_dx else None), dw, db
     db = _empty(dy, N)
@@ -555,11 +558,19 @@ def fc_bwd(dy, ctx, w, need_dx=True, out=None):
     assert dw.shape == (N, K) and dw.is_contiguous()
     _call('pgv_linear_cl_wgrad', _h(dy), _f(dyr), _f(xr), _f(dw), K, M, N, Kp, K, _s(dy), n=2,
           flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
-    dx = None
-    if need_dx:
-        dx = _empty(dy, M, K)
-        _call('pgv_linear_cl_dgrad', _h(dy), _f(dyr), _f(wt), _f(dx), M, N, K, _s(dy), n=2,
+    if not need_dx:
+        return None, dw, db
+    if wr is not None:
+        # dx^T [Kp, M] = W[N, Kp]^T dy^T[N, M] (reduction over N), then a small transpose back
+        dyt, dxt, dxp = _empty(dy, N, M), _empty(dy, Kp, M), _empty(dy, M, Kp)
+        _call('pgv_transpose_inner', _f(dy), _f(dyt), 1, M, N, 1, _s(dy), nbytes=8 * dy.numel())
+        _call('pgv_linear_cl_wgrad', _h(dy), _f(wr), _f(dyt), _f(dxt), M, N, Kp, M, M, _s(dy), n=2,
               flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+        _call('pgv_transpose_inner', _f(dxt), _f(dxp), 1, Kp, M, 0, _s(dy), nbytes=8 * dxp.numel())
+        return (dxp if Kp == K else dxp[:, :K].contiguous()), dw, db
+    dx = _empty(dy, M, K)
+    _call('pgv_linear_cl_dgrad', _h(dy), _f(dyr), _f(wt), _f(dx), M, N, K, _s(dy), n=2,
+          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     return dx, dw, db
 
 

@@ -180,21 +180,24 @@ def test_conv_epilogue_accumulates_the_batchnorm_statistics(cin, cout, H, W):
     assert float(((tsums - want).abs() / scale).max()) < 2e-6
 
 
-@pytest.mark.parametrize("m,n,k", [(160, 1220, 24576), (160, 24576, 610), (64, 1024, 1030), (5, 36, 26)])
+@pytest.mark.parametrize("m,n,k", [(160, 1220, 24576), (160, 24576, 610), (64, 1024, 1030), (62, 1024, 1030), (5, 36, 26)])
 def test_big_linear_layers_on_the_channels_last_kernel(m, n, k):
     """encoder / decoder FC (and a padded-K case) through fc_fwd / fc_bwd: rounded + re-pitched operand copies, weights by TMA,
-    K tail, unaligned-N atomic epilogue (dx of the decoder FC has 610 columns), direct weight-gradient destination."""
+    K tail, direct weight-gradient destination; the data gradient on the weight-gradient form of the kernel (M % 4 == 0: W as stored
+    and dy^T, padded K of the decoder FC sliced away) and on the transposed-weight form (M = 62, unaligned-N atomic epilogue)."""
     x, w, b = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=0.05), rnd(n, seed=3)
     dy = rnd(m, n, seed=4)
     route = ops.fc_route(m, n, k)
     assert route == ('generic' if m == 5 else 'cl')
     y, ctx = ops.fc_fwd(x, w, b, True)
+    if route == 'cl':
+        assert (ctx[1] is None) == (m % 4 == 0) and (ctx[4] is None) == (m % 4 != 0)
     out = torch.full((n, k), 7.0, device=DEV)
     dx, dw, db = ops.fc_bwd(dy, ctx, w, True, out=out)
     assert dw.data_ptr() == out.data_ptr()
     errs = (rel(y, x.double() @ w.double().T + b.double()), rel(dx, dy.double() @ w.double()), rel(dw, dy.double().T @ x.double()),
             rel(db, dy.double().sum(0)))
     print("fc", route, (m, n, k), "rel-L2 fwd %.2e dgrad %.2e wgrad %.2e db %.2e" % errs)
-    assert max(errs) < 2e-3
+    assert max(errs) < 2e-3 and dx.is_contiguous() and dx.shape == (m, k)
     y_eval, ctx_eval = ops.fc_fwd(x, w, b, False)
     assert ctx_eval[1] is None and rel(y_eval, y) < 1e-6
