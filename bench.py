@@ -34,6 +34,7 @@ DFT_FLOP_PER_CLIP, MEL_FLOP_PER_CLIP = 729.13e6, 91.50e6
 
 # C entry point -> CUDA kernel it launches (one kernel serves several entry points)
 KERNEL_OF = {'pgv_conv_cl_fwd': 'conv_cl_kernel', 'pgv_conv_cl_dgrad': 'conv_cl_kernel', 'pgv_conv_cl_wgrad': 'conv_cl_kernel',
+             'pgv_conv_cl_fwd_bn': 'conv_cl_kernel', 'pgv_conv_cl_dgrad_bn': 'conv_cl_kernel',
              'pgv_conv2d_fwd_tf32': 'conv_tc_kernel', 'pgv_conv2d_dgrad_tf32': 'conv_tc_kernel', 'pgv_conv2d_wgrad_tf32': 'conv_tc_kernel',
              'pgv_linear_fwd_tf32': 'conv_tc_kernel', 'pgv_linear_dgrad_tf32': 'conv_tc_kernel', 'pgv_linear_wgrad_tf32': 'conv_tc_kernel',
              'pgv_linear_cl_fwd': 'conv_cl_kernel', 'pgv_linear_cl_dgrad': 'conv_cl_kernel', 'pgv_linear_cl_wgrad': 'conv_cl_kernel',
