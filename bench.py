@@ -189,7 +189,7 @@ def main_reference(args):
             'config': {'workload': workload_name(args.workload, cpu_batch), 'note': 'reference algorithm on the host CPU (no GPU)'},
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(workload, batch):
@@ -380,12 +380,32 @@ def main_ours(args):
                 'roofline': roofline, 'cpu_baseline': cpu_baseline}
         if breakdown is not None:
             line['ms_by_entry_point_eager'] = breakdown
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+_json_out = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to fd 1 when
+    NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private
+    duplicate of the original stdout."""
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
