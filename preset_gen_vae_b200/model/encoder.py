@@ -199,6 +199,9 @@ class SpectrogramEncoder(nn.Module):
         # buffer instead of a temporary that would be copied there; autograd then gets no tensor for it
         direct = getattr(self, 'fc_weight_grad_out', None)
         dflat, dw, db = ops.fc_bwd(dy, fc_ctx, lin.weight, True, out=direct)
+        ready = getattr(self, 'fc_grads_ready_event', None)
+        if ready is not None:       # train.py: both FC weight gradients (the decoder's backward has already joined) are final here
+            ready.record()
         grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
         if drop_mask is not None:
             dflat = ops.mul(dflat, drop_mask)

@@ -20,7 +20,7 @@ from .utils import audio as paudio
 
 class TrainStep:
     def __init__(self, model_config, train_config, idx_helper, device=None, process_group=None, use_cuda_graph=True,
-                 spec_stats=None, beta=None, seed=0, overlap_branches=True):
+                 spec_stats=None, beta=None, seed=0, overlap_branches=True, overlap_allreduce=True):
         self.mc, self.tc, self.idx_helper = model_config, train_config, idx_helper
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         if self.device.index is None:
@@ -43,6 +43,13 @@ class TrainStep:
             cat_softmax=(not model_config.params_reg_softmax and not train_config.params_cat_bceloss),
             cat_softmax_t=train_config.params_cat_softmax_temperature)
         self._flatten_parameters()
+        # Several ranks: the two FC weight gradients (three quarters of the gradient bytes) are final as soon as the encoder's
+        # backward has passed its FC layer, long before the captured step ends.  An EXTERNAL event recorded at that point inside
+        # the graph lets a communication stream start their all-reduce under the encoder's convolution backward.
+        self._fc_ready = None
+        if self.world > 1 and use_cuda_graph and overlap_allreduce:
+            self._fc_ready = torch.cuda.Event(external=True)
+            self._comm_stream = torch.cuda.Stream(device=self.device)
         self.step_count = 0
         self.lr = train_config.initial_learning_rate
         self._hyper_host = torch.zeros(5, dtype=torch.float32).pin_memory()         # lr, bias corrections, grad scale, beta
@@ -76,6 +83,15 @@ class TrainStep:
             owner.fc_weight_grad_out = views[idx]
             self._direct[idx] = views[idx]
         self._packed = [i for i in range(len(params)) if i not in self._direct]
+        # flat-buffer segments around the directly written gradients (all-reduced after the step; see _allreduce)
+        self._rest_segments, pos = [], 0
+        for idx in sorted(self._direct, key=lambda i: self._offs[i]):
+            lo = int(self._offs[idx])
+            if lo > pos:
+                self._rest_segments.append(self.flat_grads[pos:lo])
+            pos = lo + sizes[idx]
+        if pos < self.layout.total:
+            self._rest_segments.append(self.flat_grads[pos:])
         self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
         self._table_dev = torch.zeros(len(self._packed) * 3, dtype=torch.int64, device=self.device)
         self._table_host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in self._packed], dtype=np.int64))
@@ -134,8 +150,23 @@ class TrainStep:
         self._hyper_host[4] = self.beta
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
-    def _allreduce(self):
-        parallel.allreduce_mean_(self.flat_grads, self.pg)              # sum over ranks; Adam applies the 1/world factor (grad_scale)
+    def _allreduce(self, overlapped=False):
+        """Sum of the flat gradient buffer over the ranks (Adam applies the 1/world factor through grad_scale).  `overlapped`: the
+        step that was just launched is the captured graph containing the `_fc_ready` record, so the FC slices are reduced from the
+        communication stream as soon as that event fires and only the remaining segments wait for the end of the step."""
+        if not overlapped:
+            parallel.allreduce_mean_(self.flat_grads, self.pg)
+            return
+        dist = torch.distributed
+        self._comm_stream.wait_event(self._fc_ready)
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for idx in sorted(self._direct, key=lambda i: self._offs[i]):
+                works.append(dist.all_reduce(self._direct[idx], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for seg in self._rest_segments:
+            works.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for w in works:
+            w.wait()                                   # the compute stream waits for the collectives
 
     def step(self, audio, v_in, sample_info):
         """audio [B, C, L] fp32, v_in [B, L_params] fp32, sample_info [B, 3] int32: CUDA tensors on this rank's device.
@@ -153,7 +184,7 @@ class TrainStep:
             self._graph.replay()
             losses = self._static[3]
         if not fused_opt:
-            self._allreduce()
+            self._allreduce(overlapped=self.use_graph and self._fc_ready is not None)
             self._adam()
         self.losses = losses
         return losses
@@ -208,8 +239,12 @@ class TrainStep:
         self.model.load_state_dict(bn_state, strict=False)
         graph = torch.cuda.CUDAGraph()
         before = ops.launches
-        with torch.cuda.graph(graph):
-            losses = self._device_step(*static_in, with_optimizer=with_optimizer)
+        self.model.ae_model.encoder.fc_grads_ready_event = self._fc_ready        # recorded (as an external node) by Encoder's backward
+        try:
+            with torch.cuda.graph(graph):
+                losses = self._device_step(*static_in, with_optimizer=with_optimizer)
+        finally:
+            self.model.ae_model.encoder.fc_grads_ready_event = None
         self.launches_per_step = ops.launches - before
         self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
         self.model.load_state_dict(bn_state, strict=False)

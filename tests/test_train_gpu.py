@@ -107,3 +107,27 @@ def test_total_loss_reads_beta_from_device():
     assert abs(r.grad.item() - 1.0) < 1e-7 and abs(l.grad.item() - 0.2) < 1e-7 and abs(c.grad.item() - 1.0) < 1e-7
     beta.fill_(0.5)
     assert abs(ploss.total_loss(r, l, c, beta).item() - 2.75) < 1e-6
+
+
+def test_external_event_recorded_inside_a_graph_orders_later_stream_work():
+    """TrainStep's all-reduce overlap (several ranks) relies on this: an event created with external=True and recorded by a node
+    INSIDE a captured graph orders work that another stream enqueues after each replay - on every replay, not only the first
+    (a stale completion from the previous replay would let the copy below run before this replay's increment)."""
+    a = torch.zeros(1 << 20, device='cuda')
+    b = torch.zeros_like(a)
+    ev = torch.cuda.Event(external=True)
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        torch.cuda._sleep(20_000_000)           # ~10 ms of device time in front of the increment
+        a.add_(1)
+        ev.record()
+        torch.cuda._sleep(2_000_000)
+    torch.cuda.synchronize()
+    for k in range(1, 5):
+        g.replay()
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            b.copy_(a, non_blocking=True)
+        torch.cuda.synchronize()
+        assert float(b[0]) == k and float(b[-1]) == k

@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytestR.log 2>&1; echo pytest=$?; grep -E "passed|failed|^FAILED" gpurun_out/pytestR.log | tail
-timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_R.json 2> gpurun_out/bench_R.err; echo bench=$?
+timeout 120 python -m pytest tests/test_train_gpu.py -m gpu -q -x -k external 2>&1 | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/check_overlap_allreduce.py 2>&1 | grep -v "^\*\|OMP_NUM" | tail -8
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_train_2gpu_r01.json 2> gpurun_out/bench2.err; echo rc=$?
 python -c "
-import json; d=json.load(open('gpurun_out/bench_R.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'])"
+import json; d=json.loads([l for l in open('gpurun_out/bench_train_2gpu_r01.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'])"; tail -3 gpurun_out/bench2.err
