@@ -366,7 +366,7 @@ def main_ours(args):
                 roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
                             'traffic': traffic, 'share_of_step': top['ms'] / tot, 'note': 'peak = %s copy bandwidth' % pk['src']}
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:       # reported at N=1 only
         cpu_baseline, _ = run_cpu(args.workload, min(B, args.cpu_batch), budget_s=args.cpu_budget)
     if rank == 0:
         line = {'metric': METRIC[args.workload], 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
