@@ -46,6 +46,44 @@ class FlatLayout:
         return flat
 
 
+def complement_segments(total: int, excluded: Sequence[Sequence[int]]):
+    """[lo, hi) ranges of a flat buffer of `total` elements that are NOT covered by the `excluded` (offset, size) slots.
+    TrainStep all-reduces the excluded slots (the FC weight gradients) early and these ranges after the step."""
+    out, pos = [], 0
+    for lo, n in sorted((int(o), int(n)) for o, n in excluded):
+        if lo < pos or lo + n > total:
+            raise ValueError("excluded slots overlap or leave the buffer")
+        if lo > pos:
+            out.append((pos, lo))
+        pos = lo + n
+    if pos < total:
+        out.append((pos, total))
+    return out
+
+
+def allreduce_segments_(flat: torch.Tensor, slots: Sequence[Sequence[int]], group=None, early_stream=None, early_event=None):
+    """Sum over ranks of `flat`, issued as one collective per excluded slot followed by one per complement range (same order on
+    every rank).  With `early_stream` / `early_event` (CUDA) the slot collectives are enqueued from that stream once the event
+    has fired, i.e. possibly while the rest of the buffer is still being produced.  Returns when the caller's stream may read
+    the reduced buffer."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return flat
+    works = []
+    if early_stream is not None:
+        early_stream.wait_event(early_event)
+        with torch.cuda.stream(early_stream):
+            for lo, n in sorted((int(o), int(n)) for o, n in slots):
+                works.append(dist.all_reduce(flat[lo:lo + n], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    else:
+        for lo, n in sorted((int(o), int(n)) for o, n in slots):
+            works.append(dist.all_reduce(flat[lo:lo + n], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for lo, hi in complement_segments(flat.numel(), slots):
+        works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return flat
+
+
 def allreduce_mean_(flat_grads_prescaled: torch.Tensor, group=None):
     """Sum over ranks of the flat gradient buffer.  The mean needs a 1/world factor, applied either beforehand by the caller
     (pre-scaled buffer) or afterwards (TrainStep: the fused Adam kernel's grad_scale)."""

@@ -83,15 +83,7 @@ class TrainStep:
             owner.fc_weight_grad_out = views[idx]
             self._direct[idx] = views[idx]
         self._packed = [i for i in range(len(params)) if i not in self._direct]
-        # flat-buffer segments around the directly written gradients (all-reduced after the step; see _allreduce)
-        self._rest_segments, pos = [], 0
-        for idx in sorted(self._direct, key=lambda i: self._offs[i]):
-            lo = int(self._offs[idx])
-            if lo > pos:
-                self._rest_segments.append(self.flat_grads[pos:lo])
-            pos = lo + sizes[idx]
-        if pos < self.layout.total:
-            self._rest_segments.append(self.flat_grads[pos:])
+        self._direct_slots = [(int(self._offs[i]), sizes[i]) for i in sorted(self._direct)]     # (offset, size) in the flat buffers
         self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
         self._table_dev = torch.zeros(len(self._packed) * 3, dtype=torch.int64, device=self.device)
         self._table_host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in self._packed], dtype=np.int64))
@@ -157,16 +149,7 @@ class TrainStep:
         if not overlapped:
             parallel.allreduce_mean_(self.flat_grads, self.pg)
             return
-        dist = torch.distributed
-        self._comm_stream.wait_event(self._fc_ready)
-        works = []
-        with torch.cuda.stream(self._comm_stream):
-            for idx in sorted(self._direct, key=lambda i: self._offs[i]):
-                works.append(dist.all_reduce(self._direct[idx], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-        for seg in self._rest_segments:
-            works.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-        for w in works:
-            w.wait()                                   # the compute stream waits for the collectives
+        parallel.allreduce_segments_(self.flat_grads, self._direct_slots, self.pg, early_stream=self._comm_stream, early_event=self._fc_ready)
 
     def step(self, audio, v_in, sample_info):
         """audio [B, C, L] fp32, v_in [B, L_params] fp32, sample_info [B, 3] int32: CUDA tensors on this rank's device.

@@ -39,9 +39,13 @@ def _worker(rank, world, port, ret):
         ref.load_state_dict(model.state_dict())
         torch.nn.functional.mse_loss(ref(x), y).backward()
         err = max(float((v - p.grad).abs().max()) for v, p in zip(layout.views(flat, [p.shape for p in params]), ref.parameters()))
+        # the segmented all-reduce (two "early" slots + the ranges around them) gives the same buffer as one all-reduce
+        seg = torch.arange(40.0) * (rank + 1)
+        parallel.allreduce_segments_(seg, [(24, 8), (4, 12)])
+        seg_err = float((seg - torch.arange(40.0) * 3).abs().max())
         counts = parallel.global_useful_counts(torch.tensor([3.0 + rank, 4.0]))
         slow = parallel.max_over_ranks(1.0 + rank, 'cpu')
-        ret[rank] = (err, counts.tolist(), slow, layout.offsets.tolist())
+        ret[rank] = (err, counts.tolist(), slow, layout.offsets.tolist(), seg_err)
     finally:
         dist.destroy_process_group()
 
@@ -53,10 +57,21 @@ def test_two_rank_gradient_allreduce_equals_full_batch():
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert len(ret) == 2
         for rank in range(world):
-            err, counts, slow, offsets = ret[rank]
+            err, counts, slow, offsets, seg_err = ret[rank]
+            assert seg_err == 0.0
             assert err < 1e-6                                    # equal shards: mean of shard means == full-batch mean
             assert counts == [7.0, 8.0] and slow == 2.0
             assert all(o % 4 == 0 for o in offsets)              # 16-byte aligned slots
+
+
+def test_complement_segments():
+    assert parallel.complement_segments(40, [(24, 8), (4, 12)]) == [(0, 4), (16, 24), (32, 40)]
+    assert parallel.complement_segments(10, [(0, 10)]) == [] and parallel.complement_segments(10, []) == [(0, 10)]
+    assert parallel.complement_segments(10, [(0, 3), (3, 7)]) == []
+    with pytest.raises(ValueError):
+        parallel.complement_segments(10, [(0, 6), (4, 2)])
+    with pytest.raises(ValueError):
+        parallel.complement_segments(10, [(8, 4)])
 
 
 def test_shard_range_and_layout():

@@ -1,3 +1,5 @@
+# Round-end verification on one B200 (run through gpurun): GPU tests, smoke, ncu launch list + traffic, the four bench lines,
+# one ncu --set full capture of conv_cl_kernel, per-layer / small-kernel / pipeline-trace logs.  Outputs land in gpurun_out/.
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytestZ.log 2>&1; echo pytest=$?; tail -2 gpurun_out/pytestZ.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smokeZ.log 2>&1; echo smoke=$?; tail -1 gpurun_out/smokeZ.log
