@@ -18,6 +18,17 @@ from .model import build, loss as ploss, ops
 from .utils import audio as paudio
 
 
+class _HostLosses:
+    """Pending device -> host copy of (recons, latent, controls); see TrainStep.losses_to_host_async."""
+
+    def __init__(self, buf, event):
+        self._buf, self._event = buf, event
+
+    def get(self):
+        self._event.synchronize()
+        return self._buf.clone()
+
+
 class TrainStep:
     def __init__(self, model_config, train_config, idx_helper, device=None, process_group=None, use_cuda_graph=True,
                  spec_stats=None, beta=None, seed=0, overlap_branches=True, overlap_allreduce=True):
@@ -52,7 +63,10 @@ class TrainStep:
             self._comm_stream = torch.cuda.Stream(device=self.device)
         self.step_count = 0
         self.lr = train_config.initial_learning_rate
-        self._hyper_host = torch.zeros(5, dtype=torch.float32).pin_memory()         # lr, bias corrections, grad scale, beta
+        # lr, bias corrections, grad scale, beta: staged through a ring of pinned buffers because the host runs ahead of the device
+        # (an asynchronous copy reads its pinned source when it EXECUTES, so a buffer is only rewritten after its last copy is done)
+        self._hyper_ring = [torch.zeros(5, dtype=torch.float32).pin_memory() for _ in range(8)]
+        self._hyper_events = [None] * len(self._hyper_ring)
         self._hyper_dev = torch.zeros(5, dtype=torch.float32, device=self.device)
         self._graph = None
         self._static = None
@@ -135,12 +149,18 @@ class TrainStep:
     def _refresh_hyper(self):
         self.step_count += 1
         b1, b2 = self.tc.adam_betas
-        self._hyper_host[0] = self.lr
-        self._hyper_host[1] = 1.0 - b1 ** self.step_count
-        self._hyper_host[2] = float(np.sqrt(1.0 - b2 ** self.step_count))
-        self._hyper_host[3] = 1.0 / self.world          # grad_scale: the all-reduce SUMS the per-rank gradients
-        self._hyper_host[4] = self.beta
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        slot = self.step_count % len(self._hyper_ring)
+        host = self._hyper_ring[slot]
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()
+        host[0] = self.lr
+        host[1] = 1.0 - b1 ** self.step_count
+        host[2] = float(np.sqrt(1.0 - b2 ** self.step_count))
+        host[3] = 1.0 / self.world                      # grad_scale: the all-reduce SUMS the per-rank gradients
+        host[4] = self.beta
+        self._hyper_dev.copy_(host, non_blocking=True)
+        self._hyper_events[slot] = torch.cuda.Event()
+        self._hyper_events[slot].record(torch.cuda.current_stream(self.device))
 
     def _allreduce(self, overlapped=False):
         """Sum of the flat gradient buffer over the ranks (Adam applies the 1/world factor through grad_scale).  `overlapped`: the
@@ -205,6 +225,21 @@ class TrainStep:
         out = self.step(*self._staged)
         self._staged_free.record(main)
         return out
+
+    def losses_to_host_async(self, losses=None):
+        """Starts the device -> host copy of a step's loss triple (default: the last step's) into pinned memory on the compute
+        stream and returns a handle; `handle.get()` blocks only until THAT copy has finished, so a training loop can log the
+        losses of step i while step i+1 is already running instead of draining the GPU every step."""
+        losses = self.losses if losses is None else losses
+        if getattr(self, '_loss_ring', None) is None:
+            self._loss_ring = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_ring_pos = 0
+        buf = self._loss_ring[self._loss_ring_pos % len(self._loss_ring)]
+        self._loss_ring_pos += 1
+        buf.copy_(losses, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return _HostLosses(buf, ev)
 
     def _capture(self, audio, v_in, sample_info, with_optimizer):
         static_in = (audio.clone(), v_in.clone(), sample_info.clone())

@@ -86,9 +86,13 @@ def test_cuda_graph_steps_train(idx_helper):
     host = tuple(t.cpu().pin_memory() for t in (audio, v_in, info))
     tr.prefetch(*host)
     l_host = tr.step_prefetched()
+    handle = tr.losses_to_host_async()                      # non-blocking read-back of this step's losses ...
     tr.prefetch(*host)
+    l_next = tr.step_prefetched().clone()                   # ... while the next step (which overwrites the static loss tensor) runs
+    got = handle.get()
     torch.cuda.synchronize()
-    assert torch.isfinite(l_host).all() and float(l_host[0]) < float(hist[0, 0]) and tr.step_count == 7
+    assert not got.is_cuda and torch.isfinite(got).all() and float(got[0]) < float(hist[0, 0]) and tr.step_count == 8
+    assert not torch.equal(got, l_next.cpu())                # the handle kept step 7's values, not step 8's
     # schedules reach the captured graph through device memory: lr = 0 must freeze the weights
     tr.lr = 0.0
     snap = tr.flat_params.clone()
