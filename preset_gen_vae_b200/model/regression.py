@@ -130,11 +130,15 @@ class MLPRegression(nn.Module):
                 self.reg_model.add_module('drp{}'.format(l + 1), nn.Dropout(dropout_p))
             self.reg_model.add_module('act{}'.format(l + 1), nn.ReLU())
             self._layers.append((fc, bn))
-        self._last = nn.Linear(num_hidden_neurons, self.idx_helper.learnable_preset_size)
-        self.reg_model.add_module('fc{}'.format(num_hidden_layers + 1), self._last)
+        self._last_name = 'fc{}'.format(num_hidden_layers + 1)
+        self.reg_model.add_module(self._last_name, nn.Linear(num_hidden_neurons, self.idx_helper.learnable_preset_size))
         self.reg_model.add_module('act', PresetActivation(self.idx_helper, cat_softmax_activation=cat_softmax_activation))
         self._nbt_pending = [0] * num_hidden_layers
         self._prog = _MLP(self)
+
+    @property
+    def _last(self):            # not registered a second time: the state_dict must have the reference's keys only
+        return getattr(self.reg_model, self._last_name)
 
     def state_dict(self, *args, **kwargs):
         for l, (fc, bn) in enumerate(self._layers):

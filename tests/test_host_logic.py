@@ -97,3 +97,20 @@ def test_synthetic_inputs_are_deterministic(idx_helper):
     torch.manual_seed(1)   # same stream as the global generator the reference draws from
     assert torch.equal(n1['enc_fc_mask'], torch.empty(3, 24576).bernoulli_(0.7) / 0.7)
     assert torch.equal(n1['eps'], torch.randn(3, 610))
+
+
+@pytest.mark.parametrize("arch", ["flow_realnvp_6l300", "mlp_3l1024"])
+def test_state_dict_layout_matches_the_oracle_for_both_regression_heads(idx_helper, arch):
+    """Checkpoint compatibility (row b of the scope table): same keys, same shapes, loadable with strict=True, for the flow
+    head of the default config and for the MLP head (regression.py:61-102) - modules are only constructed here, no kernels run."""
+    from oracle import model as omodel
+    from preset_gen_vae_b200 import config as pcfg
+    from preset_gen_vae_b200.model import build
+    m_cfg, t_cfg = pcfg.make_default(minibatch_size=4, params_regression_architecture=arch)
+    pcfg.apply_dataset_dims(m_cfg, idx_helper)
+    ref = omodel.build_extended_ae_model(m_cfg, t_cfg, idx_helper)[3].state_dict()
+    mine = build.build_extended_ae_model(m_cfg, t_cfg, idx_helper)[3]
+    sd = mine.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape and sd[k].dtype == ref[k].dtype for k in ref)
+    mine.load_state_dict(ref, strict=True)

@@ -34,8 +34,11 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def make_pair(idx_helper, B, notes=None, stack=False, **model_over):
+def make_pair(idx_helper, B, notes=None, stack=False, train_over=None, **model_over):
     m_cfg, t_cfg = pcfg.make_default(minibatch_size=B, midi_notes=notes, stack_spectrograms=stack, **model_over)
+    for k, v in (train_over or {}).items():
+        assert hasattr(t_cfg, k), k
+        setattr(t_cfg, k, v)
     pcfg.apply_dataset_dims(m_cfg, idx_helper)
     torch.manual_seed(0)
     orc = omodel.build_extended_ae_model(m_cfg, t_cfg, idx_helper)[3]
@@ -70,7 +73,8 @@ def run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, precision, orc32=None):
     mine.train()
     dn = to_dev(noise)
     z0_ml, z0, zk, logdet, x_out = mine(x.cuda(), info.cuda(), dn)
-    v_out = mine.reg_model(zk, dropout_masks=dn['reg_masks'])
+    flow_head = m_cfg.params_regression_architecture.startswith('flow_')
+    v_out = mine.reg_model(zk, dropout_masks=dn['reg_masks'] if flow_head else None)
     recons = ploss.MSELoss()(x_out, x.cuda())
     lat = mine.latent_loss(z0_ml, z0, zk, logdet)
     crit = ploss.SynthParamsLoss(idx_helper, True, cat_bce=False, cat_softmax=not m_cfg.params_reg_softmax, cat_softmax_t=0.2)
@@ -192,6 +196,20 @@ def test_midi_concat_and_softmax_head_config(idx_helper):
     B = 3
     orc, mine, m_cfg, t_cfg = make_pair(idx_helper, B, SIX_NOTES, False, params_reg_softmax=True)
     assert m_cfg.concat_midi_to_z and m_cfg.input_tensor_size[1] == 1
+    mine.load_state_dict(orc.state_dict())
+    mine.cuda()
+    orc32, orc = orc, copy.deepcopy(orc).double()
+    res = run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, 'fp32', orc32)
+    ops.set_precision('tf32')
+    check(orc, mine, *res, out_tol=2e-4, loss_tol=2e-5, grad_tol=2e-3, min_cos=0.99999, orc32=orc32)
+
+
+def test_mlp_regression_head_config(idx_helper):
+    """params_regression_architecture = 'mlp_3l1024' (regression.py:61-102: Linear -> BatchNorm1d -> Dropout -> ReLU stack and the
+    PresetActivation) in the full training step; reg_fc_dropout = 0 because the reference draws this head's masks from nn.Dropout."""
+    B = 4
+    orc, mine, m_cfg, t_cfg = make_pair(idx_helper, B, train_over={'reg_fc_dropout': 0.0}, params_regression_architecture='mlp_3l1024')
+    assert type(mine.reg_model).__name__ == 'MLPRegression' and type(orc.reg_model).__name__ == 'MLPRegression'
     mine.load_state_dict(orc.state_dict())
     mine.cuda()
     orc32, orc = orc, copy.deepcopy(orc).double()
