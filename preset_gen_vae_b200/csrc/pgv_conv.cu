@@ -139,14 +139,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     }
 }
 
-// db[c] += sum over (b, h, w) of dy[b, c, h, w]
+// db[c] += sum over (b, h, w) of dy[b, c, h, w].  grid = (C, images, chunks of H*W): with one channel (the decoder's last layer:
+// 57 MB per step) the images alone are too few blocks to pull the HBM bandwidth.
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int C, int HW) {
     const int c = blockIdx.x;
+    const int len = (HW + gridDim.z - 1) / gridDim.z, lo = blockIdx.z * len, hi = min(HW, lo + len);
     double acc = 0.0;
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const float* p = dy + (static_cast<size_t>(b) * C + c) * HW;
         float part = 0.0f;
-        for (int i = threadIdx.x; i < HW; i += 256) part += p[i];
+        for (int i = lo + threadIdx.x; i < hi; i += 256) part += __ldg(p + i);
         acc += part;
     }
     __shared__ double red[8];
@@ -158,6 +160,16 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
         for (int i = 0; i < 8; ++i) v += red[i];
         atomicAdd(db + c, static_cast<float>(v));
     }
+}
+
+// grid for channel_sum_kernel: at least ~4 blocks per SM when the tensor is large enough to give each block >= 1024 elements
+static dim3 channel_sum_grid(int B, int C, int HW) {
+    const int nb = B < 64 ? B : 64;
+    long long chunks = (148LL * 4 + static_cast<long long>(C) * nb - 1) / (static_cast<long long>(C) * nb);
+    const long long max_chunks = (HW + 1023) / 1024;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    return dim3(C, nb, static_cast<unsigned>(chunks));
 }
 
 static int check_geom(const ConvGeom& g, const char* who) {
@@ -231,8 +243,7 @@ int pgv_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* db, 
     PGV_LAUNCH_CHECK();
     if (db != nullptr) {
         PGV_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
-        dim3 g2(Cout, B < 64 ? B : 64);
-        channel_sum_kernel<<<g2, 256, 0, s>>>(dy, db, B, Cout, Ho * Wo);
+        channel_sum_kernel<<<channel_sum_grid(B, Cout, Ho * Wo), 256, 0, s>>>(dy, db, B, Cout, Ho * Wo);
         PGV_LAUNCH_CHECK();
     }
     return 0;
@@ -243,8 +254,7 @@ int pgv_channel_sum(const float* x, float* out, int B, int C, int HW, pgv_stream
     PGV_CHECK_ARG(x && out && B > 0 && C > 0 && HW > 0, "pgv_channel_sum: bad argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, s));
-    dim3 g2(C, B < 64 ? B : 64);
-    channel_sum_kernel<<<g2, 256, 0, s>>>(x, out, B, C, HW);
+    channel_sum_kernel<<<channel_sum_grid(B, C, HW), 256, 0, s>>>(x, out, B, C, HW);
     PGV_LAUNCH_CHECK();
     return 0;
 }
