@@ -42,4 +42,27 @@ dist.broadcast(other.copy_(a), src=0)
 same = bool(torch.equal(other, a))
 print("rank %d: overlap vs plain all-reduce: rel-L2 %.3e (FC slices %s); identical on both ranks: %s" % (rank, rel, fc, same), flush=True)
 assert rel < 5e-2 and max(fc) < 5e-2 and same
+# a step with lr > 0: the segmented optimizer (FC slices first, then the ranges around them) must move every parameter the way the
+# single Adam launch of the plain path does
+upd = []
+for t in trainers:
+    before = t.flat_params.clone()
+    t.lr = 1e-4
+    audio = synthetic.make_audio(B, 1, seed=31 + rank).cuda()
+    v_in = synthetic.make_preset_targets(idx, B, seed=31 + rank).cuda()
+    info = synthetic.make_sample_info(B).cuda()
+    torch.manual_seed(7)
+    t.step(audio, v_in, info)
+    torch.cuda.synchronize()
+    upd.append((t.flat_params - before).double())
+ua, ub = upd
+cos = float((ua * ub).sum() / (ua.norm() * ub.norm()))
+tr = trainers[0]
+ranges = [(lo, lo + n) for lo, n in tr._direct_slots] + [(lo, hi) for lo, hi in
+          __import__('preset_gen_vae_b200.parallel', fromlist=['x']).complement_segments(tr.flat_grads.numel(), tr._direct_slots)]
+moved = [float((ua[lo:hi] != 0).double().mean()) for lo, hi in ranges]
+moved_ref = [float((ub[lo:hi] != 0).double().mean()) for lo, hi in ranges]
+print("rank %d: parameter update overlap vs plain: cosine %.4f; fraction of elements moved per range %s (plain %s)" %
+      (rank, cos, ['%.3f' % m for m in moved], ['%.3f' % m for m in moved_ref]), flush=True)
+assert cos > 0.9 and all(abs(a - b) < 0.02 for a, b in zip(moved, moved_ref))
 dist.destroy_process_group()
