@@ -13,14 +13,18 @@
 //       pixel, so both tiles are MN-major (atoms of 4 pixels x 128 bytes, SWIZZLE_128B_BASE32B).  The reduction runs over
 //       (oh, ow, b) with b fastest, so that the 32 pixels of a k-block share their tap geometry.
 //
-// Nothing goes through registers: 4 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
+// Nothing goes through registers: 8 producer warps issue cp.async (LDGSTS, zero-fill for padding / tails) straight into
 // the swizzled tile and hand completion to the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so up to CL_STAGES
-// k-blocks (192 KB) are in flight per SM.  The operands are therefore NOT rounded on the way in: activations are
-// rounded to TF32 (round-to-nearest) by the kernels that write them (BatchNorm apply, thin-layer kernels, layout
-// converters: `round_out` flags) and weights by pgv_conv_cl_prep_weights, which is numerically identical to rounding
-// in the gather and keeps the tensor core's own truncation out of the picture.
-// One thread issues tcgen05.mma (M = 128, N = tile width, K = 8); accumulators are double-buffered in TMEM; 4 epilogue
-// warps drain them (bias, LeakyReLU, optional TF32 rounding, float4 stores along the channel dimension).
+// k-blocks (160 KB) are in flight per SM; in GEMM mode the weight tile of a k-block is one TMA box issued by a dedicated
+// warp.  The operands are therefore NOT rounded on the way in: activations are rounded to TF32 (round-to-nearest) by the
+// kernels that write them (BatchNorm apply, thin-layer kernels, layout converters: `round_out` flags) and weights by
+// pgv_conv_cl_prep_weights, which is numerically identical to rounding in the gather and keeps the tensor core's own
+// truncation out of the picture.
+// One elected lane of a converged warp issues tcgen05.mma (M = 128, N = tile width, K = 8), two k-blocks per barrier round
+// trip when both are ready; accumulators are double-buffered in TMEM; 4 epilogue warps drain them through a per-warp
+// shared-memory tile (bias, LeakyReLU, optional TF32 rounding, float4 stores along the channel dimension) and, for
+// launches with a single N tile, also accumulate the per-channel sum / sum of squares of what they store (the batch
+// statistics of the BatchNorm2d that follows).
 #include <stdlib.h>
 #include <string.h>
 
