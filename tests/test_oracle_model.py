@@ -90,3 +90,31 @@ def test_latent_loss_identity_flow():
     got = vae.latent_loss(torch.stack([mu, logvar], dim=1), z0, z0, torch.zeros(B))
     want = (0.5 * (z0 ** 2 - logvar - eps ** 2).sum(dim=1)).mean() / D
     assert torch.allclose(got, want, atol=1e-5)
+
+
+@pytest.mark.parametrize("between_bn", [False, True])
+def test_flow_logdet_equals_the_log_abs_determinant_of_the_autograd_jacobian(between_bn):
+    """An anchor for the nflows restatement that does not depend on nflows (which is absent here, DESIGN.md §3 "parity unpinned"):
+    for a small RealNVP (affine couplings with ResidualNet conditioners, optional flow BatchNorm in eval mode) the logabsdet the
+    transform returns must be log|det J| of the map itself, J from torch.autograd, and inverse(forward(z)) == z."""
+    from oracle import nflows_port as nf
+    torch.manual_seed(3)
+    D = 6
+    flow = nf.SimpleRealNVP(D, 8, num_layers=4, num_blocks_per_layer=2, batch_norm_within_layers=True,
+                            batch_norm_between_layers=between_bn).double()
+    t = flow._transform
+    with torch.no_grad():                                  # non-trivial parameters everywhere (final conditioner layers start near zero)
+        for p in t.parameters():
+            p.add_(torch.randn_like(p) * 0.3)
+        for m in t.modules():
+            if hasattr(m, 'running_var'):
+                m.running_var.uniform_(0.5, 2.0)
+                m.running_mean.normal_()
+    t.eval()
+    z = torch.randn(3, D, dtype=torch.float64)
+    y, ld = t.forward(z)
+    for i in range(z.shape[0]):
+        J = torch.autograd.functional.jacobian(lambda v: t.forward(v[None])[0][0], z[i])
+        assert torch.allclose(torch.linalg.slogdet(J)[1], ld[i], atol=1e-9)
+    zi, ldi = t.inverse(y)
+    assert torch.allclose(zi, z, atol=1e-9) and torch.allclose(ldi, -ld, atol=1e-9)
