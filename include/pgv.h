@@ -195,25 +195,38 @@ PGV_API int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, c
                               pgv_stream_t stream);
 /* The same two calls for a convolution followed by (Leaky)ReLU and BatchNorm2d (model/layer.py:10-46 of the reference): the epilogue
  * also accumulates the batch statistics of what it stores, bn_sums[2c] = sum and bn_sums[2c + 1] = sum of squares of channel c
- * (zero-filled by the call; only for launches with one N tile: Cout <= 128, or 4 * Cin <= 128 for the 4x4 data gradient), which pgv_bn_cl_train_apply then turns into the normalisation. */
+ * (zero-filled by the call; only for launches with one N tile: Cout <= 128, or 4 * Cin <= 128 for the 4x4 data gradient), which
+ * pgv_bn_cl_train_apply then turns into the normalisation; bn_sums may be NULL.
+ * ws / ws_bytes (optional, 16-byte aligned, ws_bytes >= pgv_conv_cl_workspace_bytes() of ZERO-FILLED header + room for partial tiles;
+ * the header is left zero by every call): with it, launches whose tiles do not fill the GPU split the reduction over several CTAs and
+ * combine the partial accumulators in a fixed order (deterministic; no atomics).  One workspace per stream.
+ * The activation operand is fetched by TMA: tiled boxes for 1x1 / stride 1, im2col-mode loads (cuTensorMapEncodeIm2col) for 4x4 /
+ * stride 2 and for the 2x2 window of the data gradient when the channel count is 8, 16 or a multiple of 32; cp.async gathers otherwise. */
 PGV_API int pgv_conv_cl_fwd_bn(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin,
                                int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
-                               double* bn_sums, pgv_stream_t stream);
+                               double* bn_sums, void* ws, size_t ws_bytes, pgv_stream_t stream);
 PGV_API int pgv_conv_cl_dgrad_bn(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin,
                                  int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
-                                 double* bn_sums, pgv_stream_t stream);
-/* dwcl [Cout][(kh, kw, ci)] = sum over pixels of dy x patch(x) (split over CTAs, fp32 atomics; zero-filled by the call);
- * pgv_conv_cl_unpack_dw converts it to the PyTorch layout [Cout, Cin, KH, KW]. */
-PGV_API int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH,
-                              int KW, int stride, int pad, int Ho, int Wo, pgv_stream_t stream);
+                                 double* bn_sums, void* ws, size_t ws_bytes, pgv_stream_t stream);
+/* Weight gradient of the convolution: sum over pixels of dy x patch(x), split over CTAs.  oihw_layout != 0: dw is the PyTorch tensor
+ * [Cout, Cin, KH, KW] (e.g. a slice of a flat gradient buffer); else the forward-operand matrix [Cout][(kh, kw, ci)].
+ * With a workspace the partial sums are combined in a fixed order by a finish kernel (deterministic); without one, fp32 atomics into
+ * the zero-filled destination. */
+PGV_API int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dw, int oihw_layout, int B, int H, int W, int Cin,
+                              int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, void* ws, size_t ws_bytes, pgv_stream_t stream);
 /* nn.Linear on the same kernel, for layers large enough for the tensor cores (encoder / decoder FC, encoder.py:84, decoder.py:70).
  * Operands as stored: x / dy TF32-rounded with 16-byte-aligned rows, wr = rounded weights [N, K], wt = rounded transposed weights
- * [K, N]; K may carry zero padding (pgv_round_copy).  dw is written with row pitch lddw, columns < k_valid. */
+ * [K, N]; K may carry zero padding (pgv_round_copy).  dw is written with row pitch lddw, columns < k_valid.  ws as above. */
 PGV_API int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const float* bias, float* y, int M, int N, int K,
-                              pgv_stream_t stream);
-PGV_API int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, pgv_stream_t stream);
-PGV_API int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid,
+                              void* ws, size_t ws_bytes, pgv_stream_t stream);
+PGV_API int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, void* ws, size_t ws_bytes,
                                 pgv_stream_t stream);
+PGV_API int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid,
+                                void* ws, size_t ws_bytes, pgv_stream_t stream);
+/* Bytes of the zero-filled header at the start of a channels-last workspace. */
+PGV_API int pgv_conv_cl_workspace_bytes(void);
+/* Debug / A-B switch: 0 forces the cp.async gather of the activation operand, -1 (default) lets the library choose TMA where it can. */
+PGV_API int pgv_debug_set_conv_a_mode(int mode);
 /* dst [rows, ldd] = TF32-rounded src [rows, lds] (first `cols` columns), zero in columns cols..ldd-1. */
 PGV_API int pgv_round_copy(const float* src, int lds, float* dst, int ldd, int rows, int cols, pgv_stream_t stream);
 PGV_API int pgv_conv_cl_unpack_dw(const float* dwcl, float* dw, int Cout, int Cin, int KH, int KW, pgv_stream_t stream);

@@ -23,8 +23,8 @@ def useless_masks(idx_helper, u_in):
     (data/preset.py:247-283, loss.py:120-126)."""
     t = idx_helper.device_tables() if hasattr(idx_helper, 'device_tables') else _tables_from_reference(idx_helper)
     def mask(vol_cols):
-        vol = torch.as_tensor(vol_cols, dtype=torch.long)
-        m = torch.zeros(u_in.shape[0], len(vol_cols), dtype=torch.bool)
+        vol = torch.as_tensor(vol_cols, dtype=torch.long, device=u_in.device)
+        m = torch.zeros(u_in.shape[0], len(vol_cols), dtype=torch.bool, device=u_in.device)
         has = vol >= 0
         m[:, has] = u_in[:, vol[has]] < 1e-3
         return m
@@ -64,7 +64,7 @@ def synth_params_loss(idx_helper, u_out, u_in, normalize_losses=True, categorica
         useless_num[:] = False
         useless_grp[:] = False
     B = u_in.shape[0]
-    num_cols = torch.as_tensor(t['num_cols'], dtype=torch.long)
+    num_cols = torch.as_tensor(t['num_cols'], dtype=torch.long, device=u_in.device)
     num_loss = 0.0
     if len(num_cols) > 0:
         keep = (~useless_num).to(u_out.dtype)

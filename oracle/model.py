@@ -189,7 +189,7 @@ class FlowVAE(nn.Module):                                      # VAE.py:69-193
         mu0 = z0_mu_logvar[:, 0, :]
         sigma0 = torch.exp(z0_mu_logvar[:, 1, :] / 2.0)
         if self.training:
-            eps = torch.normal(torch.zeros(B, self.dim_z), torch.ones(B, self.dim_z)).to(mu0.dtype) if noise is None \
+            eps = torch.normal(torch.zeros(B, self.dim_z, device=mu0.device), torch.ones(B, self.dim_z, device=mu0.device)).to(mu0.dtype) if noise is None \
                 else noise['eps'].to(mu0.dtype)
             z0 = mu0 + sigma0 * eps
         else:

@@ -70,6 +70,11 @@ int pgv_init(pgv_handle** out, int device) {
         return pgv::set_error(-4, "pgv_init: cannot resolve cuTensorMapEncodeTiled (%s)", cudaGetErrorString(e));
     }
     h->encode_tiled = reinterpret_cast<decltype(h->encode_tiled)>(fn);
+    fn = nullptr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q);
+    h->encode_im2col = (e == cudaSuccess && q == cudaDriverEntryPointSuccess) ? reinterpret_cast<decltype(h->encode_im2col)>(fn) : nullptr;
+    h->driver_version = 0;
+    cudaDriverGetVersion(&h->driver_version);
     *out = h;
     return 0;
 }

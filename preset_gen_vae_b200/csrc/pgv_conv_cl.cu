@@ -65,8 +65,19 @@ struct ConvClParams {
     int stat_c;          // number of channels (gemm_n, or qC with the quad epilogue)
     long long* trace;    // debug (tools/gpu_trace_conv.py): clock64 timestamps of CTA 0, [role][64 events][8]; NULL in production
     float slope;
+    // A operand of GEMM mode: 0 = cp.async gather by the producer warps, 1 = one tiled TMA box per k-block (1x1 convolutions / Linear:
+    // A is a plain [gemm_m][C] matrix), 2 = TMA im2col loads (one per tap and k-block: `a_sub` loads of 128 pixels x min(C, 32) channels)
+    int a_mode, a_sub, a_sbo;      // a_sbo: byte distance of 8-row groups inside one load's tile (1024 / 512 / 256 for 128 / 64 / 32-byte rows)
+    unsigned a_layout;             // UMMA layout type of the A tile: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+    // deterministic split-K: partial accumulator tiles go to `ws` ([tile][split][column][128 rows], fp32) instead of fp32 atomics.
+    // GEMM mode: the CTA that finishes a tile last (ws_cnt[tile], self-resetting) sums the partials in split order and runs the
+    // normal epilogue; WGRAD mode: a finish kernel sums them and writes the weight gradient in its final layout.
+    float* ws;
+    unsigned* ws_cnt;
+    int wg_cin, wg_taps;           // WGRAD: if wg_taps > 0, out is the PyTorch weight layout [Cout][Cin][taps] (row m = tap * Cin + ci)
     FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC;
     alignas(64) CUtensorMap tmap_b;      // GEMM mode: prepared weights [gemm_n][gemm_k], box 32 x n_tile, 128-byte swizzle
+    alignas(64) CUtensorMap tmap_a;      // GEMM mode, a_mode 1: [gemm_m][C] tiled, box 32 x 128; a_mode 2: im2col map of the [B, H, W, C] activation
 };
 
 __device__ __forceinline__ uint32_t cl_sw128(int row, int chunk) {
@@ -115,13 +126,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     uint64_t* bar_tfull = bar_empty + CL_STAGES;
     uint64_t* bar_tempty = bar_tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    volatile uint32_t* ws_flag = tmem_ptr + 1;                              // split-K: "this CTA finishes the tile" (epilogue warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int MMA_WARP = CL_PRODUCER_WARPS, TMA_WARP = CL_PRODUCER_WARPS + 5;      // warps MMA_WARP + 1 .. + 4 are the epilogue
     const bool with_stats = MODE == CL_GEMM && p.stats != nullptr;
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&bar_full[s], CL_PRODUCERS + (MODE == CL_GEMM ? 1 : 0)); mbar_init(&bar_empty[s], 1); }
+            // arrivals per stage: the producer threads' cp.async completions (+ the TMA warp's expect_tx arrive in GEMM mode); with a
+            // TMA-fed A operand the TMA warp is the only producer
+            const uint32_t full_count = MODE == CL_WGRAD ? CL_PRODUCERS : (p.a_mode != 0 ? 1 : CL_PRODUCERS + 1);
+            for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&bar_full[s], full_count); mbar_init(&bar_empty[s], 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
             fence_mbar_init();
         }
@@ -141,7 +156,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         const int t = threadIdx.x;
         int stage = 0; uint32_t phase = 0;
         int trace_n = 0;
-        if (MODE == CL_GEMM) {
+        if (MODE == CL_GEMM && p.a_mode != 0) {
+            // A operand through TMA (issued by the TMA warp): nothing to gather
+        } else if (MODE == CL_GEMM) {
             // A operand: thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows
             // r0 + CL_ROWS_PER_PASS * i.  B operand (prepared weights, a plain K-major matrix): ONE TMA box per k-block, issued by
             // thread 0, which also posts the expected byte count on the stage's barrier.
@@ -307,9 +324,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 auto issue_stage = [&](int stg, bool accumulate) {
                     const uint32_t a_addr = smem_base + stg * CL_STAGE_BYTES, b_addr = a_addr + CL_A_BYTES;
                     if (MODE == CL_GEMM) {
-                        const uint64_t da = umma_smem_desc_sw128(a_addr), db = umma_smem_desc_sw128(b_addr);
+                        const uint64_t db = umma_smem_desc_sw128(b_addr);
+                        if (p.a_sub == 1) {
+                            const uint64_t da = umma_smem_desc_sw128(a_addr);
 #pragma unroll
-                        for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < CL_BLOCK_K / 8; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+                        } else {
+                            // im2col loads of C = 8 / 16 channels: the k-block holds 4 / 2 single-tap tiles of 128 rows x 32 / 64 bytes
+                            // (SWIZZLE_32B / 64B), one K = 8 MMA per 32 bytes of a row; the weight tile keeps its 128-byte rows
+                            const uint32_t sub_bytes = CL_A_BYTES / p.a_sub, per_sub = (CL_BLOCK_K / 8) / p.a_sub;
+#pragma unroll
+                            for (int k = 0; k < CL_BLOCK_K / 8; ++k) {
+                                const uint32_t sub = static_cast<uint32_t>(k) / per_sub, within = static_cast<uint32_t>(k) % per_sub;
+                                const uint64_t da = umma_smem_desc_kmajor(a_addr + sub * sub_bytes + within * 32, p.a_sbo, p.a_layout);
+                                umma_tf32(tmem_d, da, db + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+                            }
+                        }
                     } else {
 #pragma unroll
                         for (int g = 0; g < CL_BLOCK_K / 8; ++g) {
@@ -358,19 +388,42 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     } else if (warp == TMA_WARP) {
         // ================================================================== weights (GEMM mode): one TMA box per k-block
         if (MODE == CL_GEMM) {
-            const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
-            if (lane == 0) tma_prefetch_desc(&p.tmap_b);
+            const uint32_t tx_bytes = static_cast<uint32_t>(p.n_tile) * 128u + (p.a_mode != 0 ? static_cast<uint32_t>(CL_A_BYTES) : 0u);
+            if (lane == 0) { tma_prefetch_desc(&p.tmap_b); if (p.a_mode != 0) tma_prefetch_desc(&p.tmap_a); }
+            const uint32_t span = static_cast<uint32_t>(p.KW) * p.C;
+            const uint32_t sub_bytes = CL_A_BYTES / (p.a_sub > 0 ? p.a_sub : 1);
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
+                // im2col: base pixel of the tile's first row = its output position scaled by the stride, minus the padding
+                int w0 = 0, h0 = 0, b0 = 0;
+                uint32_t kh = 0, rem = 0;
+                if (p.a_mode == 2) {
+                    uint32_t b, r, oh, ow;
+                    p.fd_HgWg.divmod(static_cast<uint32_t>(wi.tm) * CL_BLOCK_M, b, r);
+                    p.fd_Wg.divmod(r, oh, ow);
+                    b0 = static_cast<int>(b); h0 = static_cast<int>(oh) * p.stride - p.pad; w0 = static_cast<int>(ow) * p.stride - p.pad;
+                    p.fd_span.divmod(static_cast<uint32_t>(wi.kb0) * CL_BLOCK_K, kh, rem);           // k = (kh, rem = kw * C + c)
+                }
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&bar_full[stage], b_bytes);
-                        tma_load_2d(smem + stage * CL_STAGE_BYTES + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                        uint8_t* st = smem + stage * CL_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
+                        tma_load_2d(st + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                        if (p.a_mode == 1) {
+                            tma_load_2d(st, &p.tmap_a, &bar_full[stage], kb * CL_BLOCK_K, wi.tm * CL_BLOCK_M);
+                        } else if (p.a_mode == 2) {
+                            const uint32_t kw = p.fd_C.div(rem), c0 = rem - kw * static_cast<uint32_t>(p.C);
+                            for (int sidx = 0; sidx < p.a_sub; ++sidx)
+                                tma_load_im2col_4d(smem_u32(st) + sidx * sub_bytes, &p.tmap_a, &bar_full[stage], static_cast<int>(c0), w0, h0, b0,
+                                                   static_cast<uint16_t>(kw + sidx), static_cast<uint16_t>(kh));
+                        }
                     }
                     __syncwarp();
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                    rem += CL_BLOCK_K;
+                    if (rem >= span) { rem -= span; ++kh; }
                 }
             }
         }
@@ -404,6 +457,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             int qflags = 0;                                                  // quad epilogue: bit 0 = row 2i+1 exists, bit 1 = column 2j+1 exists
             if (MODE == CL_WGRAD) {
                 dst_off = m;                                                 // dWcl[n][m]: lanes write consecutive m
+                if (p.wg_taps > 0) {                                         // PyTorch layout [n][ci][tap], m = tap * Cin + ci
+                    uint32_t tap, ci;
+                    p.fd_C.divmod(m, tap, ci);
+                    dst_off = static_cast<long long>(ci) * p.wg_taps + tap;
+                }
             } else if (row_ok) {
                 if (p.epi == CL_EPI_ROWS) {
                     dst_off = static_cast<long long>(m) * p.ldo;
@@ -416,7 +474,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     qflags = (qi + 1 < p.qH ? 1 : 0) | (qj + 1 < p.qW ? 2 : 0);
                 }
             }
-            const bool add_bias = p.bias != nullptr && (!p.atomic_out || wi.kb0 == 0);
+            const bool add_bias = p.bias != nullptr && (!p.atomic_out || wi.kb0 == 0);     // workspace split-K: atomic_out = 0, the finishing CTA adds it
             if (MODE == CL_GEMM && p.bias != nullptr && wi.tn != bias_tn) {
                 bias_tn = wi.tn;
 #pragma unroll
@@ -442,11 +500,60 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             long long tr_ld = 0;                                             // trace: arrival of the first tcgen05.ld
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * CL_MAX_N + (static_cast<uint32_t>(quad * 32) << 16);
-            if (MODE == CL_WGRAD) {
+            // ---- deterministic split-K: park the partial tile in the workspace, column-major (lane = row: coalesced)
+            const float* ws_tile = nullptr;                                  // != NULL: this CTA finishes the tile from the workspace
+            if (p.ws != nullptr && p.k_splits > 1) {
+                const int tile = item / p.k_splits, split = item - tile * p.k_splits;
+                float* wsp = p.ws + (static_cast<size_t>(tile) * p.k_splits + split) * (static_cast<size_t>(p.n_tile) * CL_BLOCK_M) + row;
 #pragma unroll 1
                 for (int c = 0; c < p.n_tile; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) __stcg(wsp + (c + e) * CL_BLOCK_M, __uint_as_float(v[e]));
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[acc]);                // the accumulator is free again
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                if (MODE == CL_WGRAD) continue;                              // summed and laid out by wgrad_finish_kernel
+                __threadfence();
+                named_bar_sync(1, 128);
+                if (quad == 0 && lane == 0) {
+                    const unsigned old = atomicAdd(p.ws_cnt + tile, 1u);
+                    const bool last = old == static_cast<unsigned>(p.k_splits - 1);
+                    if (last) p.ws_cnt[tile] = 0u;                           // every contributor has arrived: ready for the next launch
+                    *ws_flag = last ? 1u : 0u;
+                }
+                named_bar_sync(1, 128);
+                if (*ws_flag == 0u) continue;
+                __threadfence();
+                ws_tile = p.ws + static_cast<size_t>(tile) * p.k_splits * (static_cast<size_t>(p.n_tile) * CL_BLOCK_M) + row;
+            }
+            // 16 accumulator columns of this thread's row: from TMEM, or summed over the splits in split order
+            auto load16 = [&](int c, uint32_t (&v)[16]) {
+                if (ws_tile == nullptr) {
+                    tmem_ld16(taddr + c, v);
+                } else {
+                    float a[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) a[e] = 0.0f;
+                    for (int sp = 0; sp < p.k_splits; ++sp) {
+                        const float* src = ws_tile + static_cast<size_t>(sp) * (static_cast<size_t>(p.n_tile) * CL_BLOCK_M) + c * CL_BLOCK_M;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) a[e] += __ldcg(src + e * CL_BLOCK_M);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(a[e]);
+                }
+            };
+            if (MODE == CL_WGRAD) {
+#pragma unroll 1
+                for (int c = 0; c < p.n_tile; c += 16) {
+                    uint32_t v[16];
+                    load16(c, v);
                     tmem_ld_wait();
                     if (!row_ok) continue;
                     const int nbase = wi.tn * p.n_tile + c;
@@ -461,7 +568,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             } else if (p.n_tile <= 16) {
                 // 16-column tiles (the 8 / 16-channel layers): a row is only 64 bytes, the thread stores its own row directly
                 uint32_t v[16];
-                tmem_ld16(taddr, v);
+                load16(0, v);
                 tmem_ld_wait();
                 if (p.trace) tr_ld = clock64();
                 if (row_ok) {
@@ -502,8 +609,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     const int c = ci * 32;
                     if (c >= p.n_tile) break;
                     uint32_t v[32];
-                    tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(v));
-                    if (c + 16 < p.n_tile) tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
+                    load16(c, *reinterpret_cast<uint32_t(*)[16]>(v));
+                    if (c + 16 < p.n_tile) load16(c + 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
                     tmem_ld_wait();
                     if (p.trace && ci == 0) tr_ld = clock64();
 #pragma unroll
@@ -558,10 +665,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     __syncwarp();
                 }
             }
+            if (p.trace && quad == 1 && lane == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item, tr_ld);
+            if (ws_tile != nullptr) continue;                                // the accumulator was released when the partial was parked
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-            if (p.trace && quad == 1 && lane == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item, tr_ld);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -679,16 +787,57 @@ static int cl_pick_n_tile(int n, int granule) {
     return t;
 }
 
+// Workspace of the deterministic split-K paths: [CL_WS_COUNTERS x u32 tile counters (zero on entry, self-resetting)][fp32 partial tiles].
+constexpr size_t CL_WS_COUNTERS = 4096, CL_WS_HEADER = CL_WS_COUNTERS * sizeof(unsigned);
+
+int g_conv_a_mode = -1;       // debug / A-B switch (pgv_debug_set_conv_a_mode): -1 = choose, 0 = force the cp.async gather
+
+// im2col tensor map over a channels-last activation [B, H, W, C] (dims in (C, W, H, N) order, as the TMA unit wants them): base pixels
+// run over the Hg x Wg output grid with the convolution stride, starting at -pad; a load fetches `cpp` channels of 128 consecutive
+// base pixels shifted by the filter offset.  Parameters as CUTLASS derives them (cute/atom/copy_traits_sm90_im2col.hpp,
+// cutlass/conv/collective/detail.hpp), with the upper corner chosen so that the box holds exactly Wg x Hg base pixels.
+static int make_tmap_im2col(const pgv_handle* h, CUtensorMap* out, const float* base, int B, int H, int W, int C, int stride, int pad, int Hg,
+                            int Wg, int cpp, CUtensorMapSwizzle swz) {
+    if (!h->encode_im2col) return set_error(-2, "pgv handle has no cuTensorMapEncodeIm2col");
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
+    const int lower[2] = {-pad, -pad};
+    const int upper[2] = {(Wg - 1) * stride - pad + 1 - W, (Hg - 1) * stride - pad + 1 - H};
+    if (upper[0] < -128 || upper[0] > 127 || upper[1] < -128 || upper[1] > 127 || pad > 128) return set_error(-1, "im2col corners out of range");
+    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+    CUresult r = h->encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
+                                  static_cast<cuuint32_t>(cpp), CL_BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeIm2col failed with CUresult %d", static_cast<int>(r));
+    // drivers up to CUDA 13.1 set a descriptor bit that breaks im2col loads from tensors smaller than 128 KB (same fix-up as CUTLASS)
+    if (h->driver_version <= 13010 && static_cast<size_t>(B) * H * W * C * 4 < 131072) reinterpret_cast<uint64_t*>(out)[1] &= ~(1ull << 21);
+    return 0;
+}
+
+// Split count of a GEMM-mode launch with the workspace: minimises (waves of CTAs) x (k-blocks per item + fixed cost per item).
+static int cl_pick_splits(int tiles, int kb_total, int sm_count, int max_splits) {
+    const int overhead = 8;                              // epilogue + pipeline fill of one item, in k-block units
+    int best = 1;
+    long long best_cost = static_cast<long long>(ceil_div(tiles, sm_count)) * (kb_total + overhead);
+    for (int sp = 2; sp <= max_splits && sp * 4 <= kb_total; ++sp) {
+        const int kbs = ceil_div(kb_total, sp), eff = ceil_div(kb_total, kbs);
+        const long long cost = static_cast<long long>(ceil_div(tiles * eff, sm_count)) * (kbs + overhead + eff / 2);
+        if (cost * 10 < best_cost * 9) { best_cost = cost; best = eff; }
+    }
+    return best;
+}
+
 // Shared by forward and data gradient: out = act(bias + gather(in) * Bw^T).
 static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, const float* bw, const float* bias, float* out, int B, int H,
                         int W, int C, int KH, int KW, int stride, int pad, int Hg, int Wg, int N, int epi, int qH, int qW, int qC, float slope,
-                        int round_out, size_t out_elems, double* stats, cudaStream_t stream) {
+                        int round_out, size_t out_elems, double* stats, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || N <= 0 || Hg <= 0 || Wg <= 0 || KH <= 0 || KH > 8 || KW <= 0 || KW > 8 || stride <= 0 || pad < 0)
         return set_error(-1, "%s: bad geometry", who);
     const bool unaligned_n = N % 4 != 0;           // only the atomic (scalar) epilogue can write rows whose pitch is not 16-byte aligned
     if (C % 4 != 0 || (unaligned_n && (slope >= 0.0f || round_out || bias != nullptr || epi != CL_EPI_ROWS)))
         return set_error(-1, "%s: channels-last kernels need C %% 4 == 0 and (N %% 4 == 0 or a linear, bias-free epilogue) (C=%d, N=%d)", who, C, N);
-    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(bw) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15)
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(bw) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+         reinterpret_cast<uintptr_t>(ws)) & 15)
         return set_error(-1, "%s: pointers must be 16-byte aligned", who);
     const long long m = static_cast<long long>(B) * Hg * Wg;
     if (m >= (1LL << 31) - CL_BLOCK_M) return set_error(-1, "%s: too many output pixels", who);
@@ -703,9 +852,42 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     p.epi = epi; p.ldo = N; p.qH = qH; p.qW = qW; p.qC = qC;
     p.slope = slope; p.round_out = round_out;
     p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1);
-    // long-K problems with few tiles and a linear epilogue: split K across CTAs, fp32 atomics into a zero-filled output
+    p.a_sub = 1; p.a_sbo = 1024; p.a_layout = 2;
+    // ---- A operand: TMA where the geometry allows it
+    const bool one_by_one = KH == 1 && KW == 1 && stride == 1 && pad == 0 && H == Hg && W == Wg;
+    if (g_conv_a_mode != 0) {
+        if (one_by_one) {
+            const uint64_t ad[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(m)}, as[1] = {static_cast<uint64_t>(C) * 4};
+            const uint32_t abox[2] = {CL_BLOCK_K, CL_BLOCK_M};
+            if (int rc = make_tmap_f32(h, &p.tmap_a, in, 2, ad, as, abox)) return rc;
+            p.a_mode = 1;
+        } else if ((C % CL_BLOCK_K == 0 || C == 8 || C == 16) && (KW * C) % CL_BLOCK_K == 0 && h->encode_im2col != nullptr) {
+            const int cpp = C < CL_BLOCK_K ? C : CL_BLOCK_K;
+            const CUtensorMapSwizzle swz = cpp == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : (cpp == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+            if (int rc = make_tmap_im2col(h, &p.tmap_a, in, B, H, W, C, stride, pad, Hg, Wg, cpp, swz)) return rc;
+            p.a_mode = 2;
+            p.a_sub = CL_BLOCK_K / cpp;
+            p.a_sbo = 8 * cpp * 4;
+            p.a_layout = cpp == 8 ? 6u : (cpp == 16 ? 4u : 2u);
+        }
+    }
+    // ---- split K across CTAs when the tiles alone do not fill the GPU
     const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
-    if (slope < 0.0f && !round_out && tiles < h->sm_count && p.kb_total >= 16) {
+    const bool linear_epi = slope < 0.0f && !round_out;
+    if (ws != nullptr && !unaligned_n && tiles <= static_cast<long long>(CL_WS_COUNTERS) && ws_bytes > CL_WS_HEADER) {
+        // deterministic: partial tiles through the workspace, the last CTA of a tile sums them in split order
+        const size_t tile_bytes = static_cast<size_t>(p.n_tile) * CL_BLOCK_M * sizeof(float);
+        const long long fit = static_cast<long long>((ws_bytes - CL_WS_HEADER) / (tile_bytes * tiles));
+        const int max_splits = static_cast<int>(std::min<long long>(fit, 16));
+        const int splits = stats != nullptr && p.n_tiles != 1 ? 1 : cl_pick_splits(static_cast<int>(tiles), p.kb_total, h->sm_count, max_splits);
+        if (splits > 1) {
+            p.kb_per_split = ceil_div(p.kb_total, splits);
+            p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
+            p.ws_cnt = static_cast<unsigned*>(ws);
+            p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + CL_WS_HEADER);
+        }
+    } else if (linear_epi && tiles < h->sm_count && p.kb_total >= 16) {
+        // no workspace: long-K problems with few tiles and a linear epilogue use fp32 atomics into a zero-filled output
         int splits = static_cast<int>((h->sm_count * 2) / tiles);
         if (splits > p.kb_total / 8) splits = p.kb_total / 8;
         if (splits > 1) {
@@ -719,7 +901,7 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
         p.stats = stats;
         p.stat_c = epi == CL_EPI_QUAD ? qC : N;
         if (p.atomic_out || p.n_tiles != 1 || p.stat_c % 4 != 0)
-            return set_error(-1, "%s: output statistics need a non-split launch with one N tile (N=%d <= %d)", who, N, CL_MAX_N);
+            return set_error(-1, "%s: output statistics need a non-atomic launch with one N tile (N=%d <= %d)", who, N, CL_MAX_N);
         PGV_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * p.stat_c, stream));
     }
     if (p.atomic_out) PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_elems, stream));
@@ -727,6 +909,23 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     const uint32_t bbox[2] = {CL_BLOCK_K, static_cast<uint32_t>(p.n_tile)};
     if (int rc = make_tmap_f32(h, &p.tmap_b, bw, 2, bd, bs, bbox)) return rc;
     return launch_conv_cl<CL_GEMM>(h, p, stream);
+}
+
+// Sums the split-K partials of a weight gradient in split order and writes it in its final layout.
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ out, int m_pad, int m_valid, int N,
+                                                           int n_tile, int n_tiles, int splits, int ldo, int cin, int taps) {
+    const long long total = static_cast<long long>(m_pad) * N;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int m = static_cast<int>(i % m_pad), n = static_cast<int>(i / m_pad);
+        if (m >= m_valid) continue;
+        const int tm = m / CL_BLOCK_M, row = m % CL_BLOCK_M, tn = n / n_tile, col = n % n_tile;
+        const size_t tile_elems = static_cast<size_t>(n_tile) * CL_BLOCK_M;
+        const float* src = ws + (static_cast<size_t>(tm) * n_tiles + tn) * splits * tile_elems + static_cast<size_t>(col) * CL_BLOCK_M + row;
+        float acc = 0.0f;
+        for (int sp = 0; sp < splits; ++sp) acc += __ldcg(src + sp * tile_elems);
+        const long long dst = taps > 0 ? (static_cast<long long>(m % cin) * taps + m / cin) : m;
+        out[dst + static_cast<long long>(n) * ldo] = acc;
+    }
 }
 
 }  // namespace pgv
@@ -755,54 +954,60 @@ int pgv_conv_cl_supported(int Cin, int Cout, int KH, int KW, int stride, int pad
 }
 
 int pgv_conv_cl_fwd_bn(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
-                       int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, pgv_stream_t stream) {
+                       int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, void* ws, size_t ws_bytes,
+                       pgv_stream_t stream) {
     PGV_CHECK_ARG(h && x && wf && y, "pgv_conv_cl_fwd: NULL argument");
     PGV_CHECK_ARG((Ho - 1) * stride - 2 * pad + KH <= H + stride && (Wo - 1) * stride - 2 * pad + KW <= W + stride,
                   "pgv_conv_cl_fwd: output %dx%d does not fit input %dx%d", Ho, Wo, H, W);
     return conv_cl_gemm(h, "pgv_conv_cl_fwd", x, wf, bias, y, B, H, W, Cin, KH, KW, stride, pad, Ho, Wo, Cout, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
-                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, bn_sums, static_cast<cudaStream_t>(stream));
+                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, bn_sums, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
                     int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
-    return pgv_conv_cl_fwd_bn(h, x, wf, bias, y, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, stream);
+    return pgv_conv_cl_fwd_bn(h, x, wf, bias, y, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, nullptr, 0, stream);
 }
 
 int pgv_conv_cl_dgrad_bn(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
-                         int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums,
-                         pgv_stream_t stream) {
+                         int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, void* ws,
+                         size_t ws_bytes, pgv_stream_t stream) {
     PGV_CHECK_ARG(h && dy && wq && dx, "pgv_conv_cl_dgrad: NULL argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t out_elems = static_cast<size_t>(B) * H * W * Cin;
     if (KH == 1 && KW == 1 && stride == 1 && pad == 0) {
         PGV_CHECK_ARG(H == Ho && W == Wo, "pgv_conv_cl_dgrad: 1x1 geometry mismatch");
         return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 1, 1, 1, 0, Ho, Wo, Cin, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
-                            round_out, out_elems, bn_sums, s);
+                            round_out, out_elems, bn_sums, ws, ws_bytes, s);
     }
     PGV_CHECK_ARG(KH == 4 && KW == 4 && stride == 2, "pgv_conv_cl_dgrad: only 4x4/stride 2/pad 2 and 1x1/stride 1");
     // pad = 2: the four pixels (2i + ph, 2j + pw) of a quad all read the 2x2 patch of dy whose corner is (i, j)
     PGV_CHECK_ARG(pad == 2, "pgv_conv_cl_dgrad: pad %d not implemented", pad);
     const int Hq = (H + 1) / 2, Wq = (W + 1) / 2;
     return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 2, 2, 1, 0, Hq, Wq, 4 * Cin, CL_EPI_QUAD, H, W, Cin, lrelu_slope,
-                        round_out, out_elems, bn_sums, s);
+                        round_out, out_elems, bn_sums, ws, ws_bytes, s);
 }
 
 int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
                       int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
-    return pgv_conv_cl_dgrad_bn(h, dy, wq, bias, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, stream);
+    return pgv_conv_cl_dgrad_bn(h, dy, wq, bias, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, nullptr, 0,
+                                stream);
 }
 
-static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, const float* dy, float* out, int ldo, int m_valid, int B, int H,
-                              int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, cudaStream_t stream) {
+// taps > 0: `out` is the PyTorch weight layout [Cout][Cin][taps]; else out[n * ldo + m] for m < m_valid.
+static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, const float* dy, float* out, int ldo, int m_valid, int taps, int B,
+                              int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, void* ws, size_t ws_bytes,
+                              cudaStream_t stream) {
     if (!(h && x && dy && out)) return set_error(-1, "%s: NULL argument", who);
     if (!(B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0)) return set_error(-1, "%s: bad geometry", who);
     if (Cin % 4 != 0 || Cout % 4 != 0) return set_error(-1, "%s: needs Cin %% 4 == 0 and Cout %% 4 == 0 (Cin=%d, Cout=%d)", who, Cin, Cout);
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return set_error(-1, "%s: operand pointers must be 16-byte aligned", who);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(ws)) & 15)
+        return set_error(-1, "%s: operand pointers must be 16-byte aligned", who);
     ConvClParams p;
     memset(&p, 0, sizeof(p));
     p.a = x; p.b = dy; p.out = out;
     p.B = B; p.H = H; p.W = W; p.C = Cin; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.Hg = Ho; p.Wg = Wo;
     p.gemm_m = KH * KW * Cin; p.gemm_n = Cout; p.ldo = ldo; p.m_valid = m_valid;
+    p.wg_cin = Cin; p.wg_taps = taps;
     p.n_tile = cl_pick_n_tile(Cout, 32); p.n_tiles = ceil_div(Cout, p.n_tile);
     if (p.n_tile != 32 && p.n_tile != 64 && p.n_tile != 128) { p.n_tile = p.n_tile <= 64 ? 64 : 128; p.n_tiles = ceil_div(Cout, p.n_tile); }
     p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
@@ -811,40 +1016,67 @@ static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, co
     const int tiles = p.m_tiles * p.n_tiles;
     int splits = ceil_div(h->sm_count * 2, tiles);
     if (splits > p.kb_total / 4) splits = p.kb_total / 4;
+    const size_t tile_bytes = static_cast<size_t>(p.n_tile) * CL_BLOCK_M * sizeof(float);
+    const bool use_ws = ws != nullptr && ws_bytes > CL_WS_HEADER + tile_bytes * tiles;
+    if (use_ws) {                                       // deterministic: partials through the workspace, summed by wgrad_finish_kernel
+        const long long fit = static_cast<long long>((ws_bytes - CL_WS_HEADER) / (tile_bytes * tiles));
+        if (splits > fit) splits = static_cast<int>(fit);
+    }
     if (splits < 1) splits = 1;
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
-    p.atomic_out = p.k_splits > 1 ? 1 : 0;
     p.slope = -1.0f;
     p.fd_HgWg.init(Ho * Wo); p.fd_Wg.init(Wo); p.fd_span.init(KW * Cin); p.fd_C.init(Cin); p.fd_bblocks.init(p.bblocks); p.fd_qC.init(1);
-    if (p.atomic_out) PGV_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * m_valid, Cout, stream));
+    if (p.k_splits > 1 && use_ws) {
+        p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + CL_WS_HEADER);
+        if (int rc = launch_conv_cl<CL_WGRAD>(h, p, stream)) return rc;
+        const long long total = static_cast<long long>(p.m_tiles) * CL_BLOCK_M * Cout;
+        const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+        wgrad_finish_kernel<<<grid, 256, 0, stream>>>(p.ws, out, p.m_tiles * CL_BLOCK_M, m_valid, Cout, p.n_tile, p.n_tiles, p.k_splits, ldo,
+                                                      Cin, taps);
+        PGV_LAUNCH_CHECK();
+        return 0;
+    }
+    p.atomic_out = p.k_splits > 1 ? 1 : 0;
+    if (p.atomic_out) {
+        if (taps > 0) PGV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(ldo) * Cout, stream));
+        else PGV_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * m_valid, Cout, stream));
+    }
     return launch_conv_cl<CL_WGRAD>(h, p, stream);
 }
 
-int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dwcl, int B, int H, int W, int Cin, int Cout, int KH, int KW,
-                      int stride, int pad, int Ho, int Wo, pgv_stream_t stream) {
-    return conv_cl_wgrad_impl(h, "pgv_conv_cl_wgrad", x, dy, dwcl, KH * KW * Cin, KH * KW * Cin, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo,
-                              static_cast<cudaStream_t>(stream));
+/* dw in the PyTorch layout [Cout][Cin][KH][KW] (oihw_layout = 1) or as the forward matrix [Cout][(kh, kw, ci)] (oihw_layout = 0) */
+int pgv_conv_cl_wgrad(pgv_handle* h, const float* x, const float* dy, float* dw, int oihw_layout, int B, int H, int W, int Cin, int Cout, int KH,
+                      int KW, int stride, int pad, int Ho, int Wo, void* ws, size_t ws_bytes, pgv_stream_t stream) {
+    return conv_cl_wgrad_impl(h, "pgv_conv_cl_wgrad", x, dy, dw, KH * KW * Cin, KH * KW * Cin, oihw_layout ? KH * KW : 0, B, H, W, Cin, Cout, KH, KW,
+                              stride, pad, Ho, Wo, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 /* ---- nn.Linear on the same kernel (operands TF32-rounded by the caller, see pgv_round_copy / pgv_transpose_inner) ---- */
-int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const float* bias, float* y, int M, int N, int K, pgv_stream_t stream) {
+int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const float* bias, float* y, int M, int N, int K, void* ws, size_t ws_bytes,
+                      pgv_stream_t stream) {
     PGV_CHECK_ARG(h && x && wr && y && M > 0 && N > 0 && K > 0, "pgv_linear_cl_fwd: bad argument");
     return conv_cl_gemm(h, "pgv_linear_cl_fwd", x, wr, bias, y, M, 1, 1, K, 1, 1, 1, 0, 1, 1, N, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
-                        static_cast<size_t>(M) * N, nullptr, static_cast<cudaStream_t>(stream));
+                        static_cast<size_t>(M) * N, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
-int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, pgv_stream_t stream) {
+int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, void* ws, size_t ws_bytes,
+                        pgv_stream_t stream) {
     PGV_CHECK_ARG(h && dy && wt && dx && M > 0 && N > 0 && K > 0, "pgv_linear_cl_dgrad: bad argument");
     return conv_cl_gemm(h, "pgv_linear_cl_dgrad", dy, wt, nullptr, dx, M, 1, 1, N, 1, 1, 1, 0, 1, 1, K, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
-                        static_cast<size_t>(M) * K, nullptr, static_cast<cudaStream_t>(stream));
+                        static_cast<size_t>(M) * K, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
-int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid,
-                        pgv_stream_t stream) {
+int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid, void* ws,
+                        size_t ws_bytes, pgv_stream_t stream) {
     PGV_CHECK_ARG(k_valid > 0 && k_valid <= K && lddw >= k_valid, "pgv_linear_cl_wgrad: bad leading dimension");
-    return conv_cl_wgrad_impl(h, "pgv_linear_cl_wgrad", x, dy, dw, lddw, k_valid, M, 1, 1, K, N, 1, 1, 1, 0, 1, 1, static_cast<cudaStream_t>(stream));
+    return conv_cl_wgrad_impl(h, "pgv_linear_cl_wgrad", x, dy, dw, lddw, k_valid, 0, M, 1, 1, K, N, 1, 1, 1, 0, 1, 1, ws, ws_bytes,
+                              static_cast<cudaStream_t>(stream));
 }
+
+int pgv_conv_cl_workspace_bytes(void) { return static_cast<int>(CL_WS_HEADER); }
+
+int pgv_debug_set_conv_a_mode(int mode) { g_conv_a_mode = mode; return 0; }
 
 int pgv_round_copy(const float* src, int lds, float* dst, int ldd, int rows, int cols, pgv_stream_t stream) {
     PGV_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols, "pgv_round_copy: bad argument");

@@ -82,6 +82,29 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
                  : "memory");
 }
 
+// im2col-mode load of a rank-4 [N, H, W, C] tensor (cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive base pixels starting at
+// (n, h, w) - traversing W, then H, then N with the map's traversal strides inside its bounding box - each shifted by the filter
+// offset (off_w, off_h), `channelsPerPixel` channels from c; out-of-bounds pixels are zero-filled.  SASS: UTMALDG.4D.IM2COL.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+                 : "memory");
+}
+// Tiled store shared -> global (SASS: UTMASTG); completion is tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until the issuing thread's bulk groups (all but the newest `N`) have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// named barrier among `count` threads of the CTA (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // ---------------------------------------------------------------- TMEM
 // Column count must be a power of two >= 32.  One warp allocates and the same warp frees.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -114,6 +137,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr_byte
     d |= static_cast<uint64_t>(1024 >> 4) << 32;  // stride byte offset  (16 B units)
     d |= static_cast<uint64_t>(1) << 46;          // version
     d |= static_cast<uint64_t>(2) << 61;          // SWIZZLE_128B
+    return d;
+}
+// K-major operand tile with rows of 32 / 64 / 128 bytes and the matching swizzle (what a TMA load with SWIZZLE_32B / 64B / 128B writes):
+// `layout` = 6 / 4 / 2 (UMMA LayoutType), `sbo_bytes` = distance between 8-row groups = 8 x row bytes.
+__device__ __forceinline__ uint64_t umma_smem_desc_kmajor(uint32_t smem_addr_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout & 7u) << 61;
     return d;
 }
 // Instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major, M x N tile.

@@ -131,8 +131,9 @@ class Conv2D(_BlockBase):
         x, a, mean, rstd, wq = ctx
         c = self.conv
         dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads)
-        dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True, db=dbias)
-        grads[id(c.weight)], grads[id(c.bias)] = dw, db
+        direct = ops.grad_out_of(c.weight)          # written in place into the flat gradient buffer: autograd gets no tensor for it
+        dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True, db=dbias, out=direct)
+        grads[id(c.weight)], grads[id(c.bias)] = (None if direct is not None else dw), db
         if not need_dx:
             return None
         return ops.conv2d_dgrad(dz, c.weight, x.shape[2:], c.stride[0], c.padding[0], wq=wq)
@@ -199,8 +200,9 @@ def tconv_clamp_fusable(x, conv):
 
 def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None, dbias=None):
     """dz: gradient w.r.t. the transposed convolution's (pre-activation) output; dbias: its per-channel sums if already known."""
-    dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False)
-    grads[id(conv.weight)] = dw
+    direct = ops.grad_out_of(conv.weight)
+    dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False, out=direct)
+    grads[id(conv.weight)] = None if direct is not None else dw
     grads[id(conv.bias)] = dbias if dbias is not None else ops.channel_sum(dz)
     if not need_dx:
         return None

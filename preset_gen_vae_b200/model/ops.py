@@ -160,6 +160,31 @@ def _ws(ref, nbytes):
 
 
 # ------------------------------------------------------------------------------------------------ convolutions
+# Deterministic split-K (pgv.h, pgv_conv_cl_*): one zero-headed workspace per (device, stream).  `deterministic = False` passes no
+# workspace, which selects the fp32-atomic accumulation of round 1 (kept for A/B measurements).
+deterministic = True
+CL_WS_BYTES = 48 << 20
+_cl_ws = {}
+
+
+def _clws(ref):
+    """(pointer, size) of this stream's channels-last workspace, or (NULL, 0)."""
+    if not deterministic:
+        return ctypes.c_void_p(0), 0
+    key = (ref.device.index, torch.cuda.current_stream(ref.device).cuda_stream)
+    buf = _cl_ws.get(key)
+    if buf is None:
+        buf = torch.zeros(CL_WS_BYTES, dtype=torch.uint8, device=ref.device)
+        _cl_ws[key] = buf
+    return ctypes.c_void_p(buf.data_ptr()), buf.numel()
+
+
+def grad_out_of(param):
+    """View into a flat gradient buffer registered on the parameter (TrainStep: `param._pgv_grad_out`): weight-gradient kernels that can
+    write their result in the parameter's own layout store it there directly and the gradient needs no packing pass."""
+    return getattr(param, '_pgv_grad_out', None)
+
+
 def conv_out_size(h, k, stride, pad):
     return (h + 2 * pad - k) // stride + 1
 
@@ -216,7 +241,7 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_
         y = _empty_cl(x, B, Cout, Ho, Wo)
         sums = _bn_sums(x, Cout, Cout, route) if bn_sums else None
         _call('pgv_conv_cl_fwd_bn', _h(x), _f(x), _f(wf), _f(bias), _f(y), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope, int(round_out),
-              _f(sums), _s(x), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
+              _f(sums), *_clws(x), _s(x), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
         return (y, sums) if bn_sums else y
     x = to_nchw(x)
     y = _empty(x, B, Cout, Ho, Wo)
@@ -252,7 +277,8 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, w
         dx = _empty_cl(dy, B, Cin, H, W)
         sums = _bn_sums(dy, Cin, (4 if kh == 4 else 1) * Cin, route) if bn_sums else None
         _call('pgv_conv_cl_dgrad_bn', _h(dy), _f(dy), _f(wq), _f(bias), _f(dx), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope,
-              int(round_out), _f(sums), _s(dy), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
+              int(round_out), _f(sums), *_clws(dy), _s(dy), n=2 if sums is not None else 1, flops=flops,
+              nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
         return (dx, sums) if bn_sums else dx
     dy = to_nchw(dy)
     dx = _empty(dy, B, Cin, H, W)
@@ -265,24 +291,25 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, w
     return (dx, None) if bn_sums else dx
 
 
-def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias, db=None):
-    """db: bias gradient if the caller already has it (BatchNorm backward by-product); else computed here when want_bias."""
+def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias, db=None, out=None):
+    """db: bias gradient if the caller already has it (BatchNorm backward by-product); else computed here when want_bias.
+    out: preallocated destination of dw in the weight's own layout (e.g. a view into the flat gradient buffer)."""
     B, Cin, H, W = x.shape
     _, Cout, Ho, Wo = dy.shape
     _, _, kh, kw = w_shape
     route = conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo)
     flops = 2 * B * Ho * Wo * Cout * Cin * kh * kw
-    dw = _empty(x, *w_shape)
+    dw = out if out is not None else _empty(x, *w_shape)
+    assert tuple(dw.shape) == tuple(w_shape) and dw.is_contiguous()
     if route == 'thin':
         _call('pgv_conv5x5s2_c1_wgrad', _f(to_nchw(x)), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, int(is_cl(dy)), _s(x), n=2,
               flops=flops, nbytes=4 * (x.numel() + dy.numel()))
         return dw, (db if db is not None else (channel_sum(dy) if want_bias else None))
     if route == 'cl':
         x, dy = to_cl(x, round_out=True), to_cl(dy, round_out=True)
-        dwcl = _empty(x, Cout, kh * kw * Cin)
-        _call('pgv_conv_cl_wgrad', _h(x), _f(x), _f(dy), _f(dwcl), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, _s(x), n=2,
+        # the kernel (or its split-K finish pass) writes the PyTorch layout [Cout, Cin, kh, kw] directly
+        _call('pgv_conv_cl_wgrad', _h(x), _f(x), _f(dy), _f(dw), 1, B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, *_clws(x), _s(x), n=2,
               flops=flops, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
-        _call('pgv_conv_cl_unpack_dw', _f(dwcl), _f(dw), Cout, Cin, kh, kw, _s(x), nbytes=8 * dw.numel())
         return dw, (db if db is not None else (channel_sum(dy) if want_bias else None))
     x, dy = to_nchw(x), to_nchw(dy)
     if route == 'tc':
@@ -539,7 +566,7 @@ def fc_fwd(x, w, bias, training=True):
         wt = _empty(w, K, N)
         _call('pgv_transpose_inner', _f(w), _f(wt), 1, N, K, 1, _s(w), nbytes=8 * w.numel())
     y = _empty(x, M, N)
-    _call('pgv_linear_cl_fwd', _h(x), _f(xr), _f(wr), _f(bias), _f(y), M, N, Kp, _s(x), n=2,
+    _call('pgv_linear_cl_fwd', _h(x), _f(xr), _f(wr), _f(bias), _f(y), M, N, Kp, *_clws(x), _s(x), n=2,
           flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     return y, (xr, wt, Kp, K, wr if training and wt is None else None)
 
@@ -556,7 +583,7 @@ def fc_bwd(dy, ctx, w, need_dx=True, out=None):
     dyr = round_copy(dy)
     dw = out if out is not None else _empty(dy, N, K)
     assert dw.shape == (N, K) and dw.is_contiguous()
-    _call('pgv_linear_cl_wgrad', _h(dy), _f(dyr), _f(xr), _f(dw), K, M, N, Kp, K, _s(dy), n=2,
+    _call('pgv_linear_cl_wgrad', _h(dy), _f(dyr), _f(xr), _f(dw), K, M, N, Kp, K, *_clws(dy), _s(dy), n=2,
           flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     if not need_dx:
         return None, dw, db
@@ -564,12 +591,12 @@ def fc_bwd(dy, ctx, w, need_dx=True, out=None):
         # dx^T [Kp, M] = W[N, Kp]^T dy^T[N, M] (reduction over N), then a small transpose back
         dyt, dxt, dxp = _empty(dy, N, M), _empty(dy, Kp, M), _empty(dy, M, Kp)
         _call('pgv_transpose_inner', _f(dy), _f(dyt), 1, M, N, 1, _s(dy), nbytes=8 * dy.numel())
-        _call('pgv_linear_cl_wgrad', _h(dy), _f(wr), _f(dyt), _f(dxt), M, N, Kp, M, M, _s(dy), n=2,
+        _call('pgv_linear_cl_wgrad', _h(dy), _f(wr), _f(dyt), _f(dxt), M, N, Kp, M, M, *_clws(dy), _s(dy), n=2,
               flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
         _call('pgv_transpose_inner', _f(dxt), _f(dxp), 1, Kp, M, 0, _s(dy), nbytes=8 * dxp.numel())
         return (dxp if Kp == K else dxp[:, :K].contiguous()), dw, db
     dx = _empty(dy, M, K)
-    _call('pgv_linear_cl_dgrad', _h(dy), _f(dyr), _f(wt), _f(dx), M, N, K, _s(dy), n=2,
+    _call('pgv_linear_cl_dgrad', _h(dy), _f(dyr), _f(wt), _f(dx), M, N, K, *_clws(dy), _s(dy), n=2,
           flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     return dx, dw, db
 

@@ -86,18 +86,30 @@ class TrainStep:
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.n_param_elems = sum(sizes)
-        # The two fully-connected weights are three quarters of all gradient bytes: their weight-gradient kernels write directly into the
-        # flat buffer.  Gradients are stored unscaled; with several ranks the all-reduce sums them and the 1/world factor is the
-        # grad_scale the fused Adam kernel reads from device memory.
+        # Weight-gradient kernels write straight into the flat buffer wherever they can produce the parameter's own layout: the two
+        # fully-connected weights (three quarters of all gradient bytes) and every convolution weight (the split-K finish pass of the
+        # channels-last kernel emits the PyTorch layout).  Gradients are stored unscaled; with several ranks the all-reduce sums them and
+        # the 1/world factor is the grad_scale the fused Adam kernel reads from device memory.
         self._direct = {}
         views = self.layout.views(self.flat_grads, [p.shape for p in params])
-        for owner, lin in ((self.model.ae_model.encoder, self.model.ae_model.encoder.mlp[1]),
-                           (self.model.ae_model.decoder, self.model.ae_model.decoder.mlp[0])):
-            idx = next(i for i, p in enumerate(params) if p is lin.weight)
+        index_of = {id(p): i for i, p in enumerate(params)}
+        enc, dec = self.model.ae_model.encoder, self.model.ae_model.decoder
+        for owner, lin in ((enc, enc.mlp[1]), (dec, dec.mlp[0])):
+            idx = index_of[id(lin.weight)]
             owner.fc_weight_grad_out = views[idx]
             self._direct[idx] = views[idx]
+        self._fc_slots = [(int(self._offs[i]), sizes[i]) for i in sorted(self._direct)]
+        conv_weights = [enc.features_mixer_cnn, dec.features_unmixer_cnn]
+        if enc.spectrogram_channels == 1:              # the per-channel CNNs are shared over the channels: their gradients are summed
+            conv_weights += [enc.single_ch_cnn, dec.single_ch_cnn]
+        for owner in conv_weights:
+            for m in owner.modules():
+                if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                    idx = index_of[id(m.weight)]
+                    m.weight._pgv_grad_out = views[idx]
+                    self._direct[idx] = views[idx]
         self._packed = [i for i in range(len(params)) if i not in self._direct]
-        self._direct_slots = [(int(self._offs[i]), sizes[i]) for i in sorted(self._direct)]     # (offset, size) in the flat buffers
+        self._direct_slots = self._fc_slots                                             # (offset, size) of the early all-reduce slices
         self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
         self._table_dev = torch.zeros(len(self._packed) * 3, dtype=torch.int64, device=self.device)
         self._table_host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in self._packed], dtype=np.int64))

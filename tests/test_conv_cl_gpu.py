@@ -201,3 +201,71 @@ def test_big_linear_layers_on_the_channels_last_kernel(m, n, k):
     assert max(errs) < 2e-3 and dx.is_contiguous() and dx.shape == (m, k)
     y_eval, ctx_eval = ops.fc_fwd(x, w, b, False)
     assert ctx_eval[1] is None and rel(y_eval, y) < 1e-6
+
+
+# every channels-last layer geometry of the two CNNs as (Cin, Cout, k, stride, pad, H, W) of the underlying convolution
+# (encoder.py:233-259; the decoder's transposed convolutions are the data gradients of the same shapes, decoder.py:199-220)
+CL_GEOMS = [(8, 16, 4, 2, 2, 129, 174), (16, 32, 4, 2, 2, 65, 88), (32, 64, 4, 2, 2, 33, 45), (64, 128, 4, 2, 2, 17, 23),
+            (128, 256, 4, 2, 2, 9, 12), (256, 512, 4, 2, 2, 5, 7), (512, 2048, 1, 1, 0, 3, 4), (1536, 768, 4, 2, 2, 5, 7)]
+
+
+def _set_a_mode(mode):
+    from preset_gen_vae_b200 import _lib
+    _lib.check(_lib.lib().pgv_debug_set_conv_a_mode(mode))
+
+
+@pytest.mark.parametrize("B", [3, 40])
+@pytest.mark.parametrize("cin,cout,k,s,p,H,W", CL_GEOMS)
+def test_tma_fed_activation_operand_equals_the_cpasync_gather(cin, cout, k, s, p, H, W, B):
+    """The TMA-fed activation operand (tiled boxes for 1x1, im2col-mode loads for the 4x4 / stride-2 window and the 2x2 window of the
+    data gradient; 8 / 16-channel tiles with 32 / 64-byte swizzles) must reproduce the cp.async gather BIT FOR BIT: both fill the
+    same shared-memory tiles for the same sequence of MMAs.  Covers padding, odd sizes (partial quads), row and image wrap-around
+    inside a 128-pixel tile, M tails, small tensors (< 128 KB) and split-K through the workspace."""
+    if B == 40 and cin * H * W > 400000:
+        B = 12
+    Ho, Wo = ops.conv_out_size(H, k, s, p), ops.conv_out_size(W, k, s, p)
+    x, w, b = rnd(B, cin, H, W, seed=21), rnd(cout, cin, k, k, seed=22, scale=0.1), rnd(cout, seed=23)
+    dy, b_in = rnd(B, cout, Ho, Wo, seed=24), rnd(cin, seed=25)
+    assert ops.conv_route(cin, cout, k, k, s, p, H, W, Ho, Wo) == 'cl'
+    got = {}
+    try:
+        for mode in (0, -1):
+            _set_a_mode(mode)
+            got[mode] = (ops.conv2d_fwd(x, w, b, s, p, slope=0.1), ops.conv2d_dgrad(dy, w, (H, W), s, p, bias=b_in, slope=0.1))
+    finally:
+        _set_a_mode(-1)
+    torch.cuda.synchronize()
+    assert torch.equal(got[0][0], got[-1][0]), "forward: TMA-fed A differs from the cp.async gather (max %g)" % float((got[0][0] - got[-1][0]).abs().max())
+    assert torch.equal(got[0][1], got[-1][1]), "dgrad: TMA-fed A differs from the cp.async gather (max %g)" % float((got[0][1] - got[-1][1]).abs().max())
+    pre = F.conv2d(x.double(), w.double(), b.double(), s, p)
+    assert rel(got[-1][0], F.leaky_relu(pre, 0.1)) < 2e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,H,W", CL_GEOMS)
+def test_split_k_through_the_workspace_is_deterministic(cin, cout, k, s, p, H, W):
+    """Deterministic mode (default): forward, data gradient and weight gradient are bit-identical run to run (fixed-order split-K,
+    no atomics), write the weight gradient directly in the PyTorch layout, and agree with the atomic path of round 1."""
+    B = 16
+    Ho, Wo = ops.conv_out_size(H, k, s, p), ops.conv_out_size(W, k, s, p)
+    x, w, b = rnd(B, cin, H, W, seed=31), rnd(cout, cin, k, k, seed=32, scale=0.1), rnd(cout, seed=33)
+    dy = rnd(B, cout, Ho, Wo, seed=34)
+
+    def run():
+        out = torch.full(w.shape, 7.0, device=DEV)
+        dw, _ = ops.conv2d_wgrad(x, dy, w.shape, s, p, want_bias=False, out=out)
+        assert dw.data_ptr() == out.data_ptr()
+        return ops.conv2d_fwd(x, w, b, s, p, slope=0.1), ops.conv2d_dgrad(dy, w, (H, W), s, p), dw
+    assert ops.deterministic
+    a, b2 = run(), run()
+    for u, v in zip(a, b2):
+        assert torch.equal(u, v)
+    ops.deterministic = False
+    try:
+        c = run()
+    finally:
+        ops.deterministic = True
+    for u, v in zip(a, c):
+        assert rel(u, v) < 1e-5
+    wd = w.double().requires_grad_()
+    gw, = torch.autograd.grad(F.conv2d(x.double(), wd, None, s, p), wd, dy.double())
+    assert rel(a[2], gw) < 2e-3

@@ -130,7 +130,9 @@ def test_train_step_parity_default_config(idx_helper, precision):
     if precision == 'fp32':
         check(orc, mine, *res, out_tol=1e-4, loss_tol=1e-5, grad_tol=2e-3, min_cos=0.999999, orc32=orc32)
     else:
-        check(orc, mine, *res, out_tol=2e-2, loss_tol=5e-3, grad_tol=None, min_cos=0.98)
+        # measured on B200 (profiles/parity_study_r02.log): 0.99766 here, 0.99824 for cuDNN's own TF32 step on the same inputs;
+        # tests/test_parity_default_gpu.py gates this precision against the live cuDNN-TF32 deviation at B = 8 and B = 160
+        check(orc, mine, *res, out_tol=1e-2, loss_tol=1e-3, grad_tol=None, min_cos=0.996)
     ops.set_precision('tf32')
     # running statistics after one training forward
     sd_o, sd_m = orc.state_dict(), mine.state_dict()

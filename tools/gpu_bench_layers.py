@@ -10,7 +10,13 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 dev = 'cuda'
 ops.set_precision('tf32')
 ops.use_cl = not (len(sys.argv) > 2 and sys.argv[2] == 'nchw')
-print('route:', 'channels-last + cp.async' if ops.use_cl else 'NCHW register-staged')
+if 'a0' in sys.argv:               # A operand by cp.async gathers instead of TMA (A/B)
+    from preset_gen_vae_b200 import _lib
+    _lib.check(_lib.lib().pgv_debug_set_conv_a_mode(0))
+if 'atomic' in sys.argv:           # round-1 split-K: fp32 atomics instead of the workspace
+    ops.deterministic = False
+print('route:', 'channels-last' if ops.use_cl else 'NCHW register-staged', '| A operand:', 'cp.async' if 'a0' in sys.argv else 'TMA where possible',
+      '| split-K:', 'atomics' if 'atomic' in sys.argv else 'workspace (deterministic)')
 # conv geometry (Cin, Cout, k, s, p, H, W, Ho, Wo) of the convolution whose fwd/dgrad/wgrad each layer uses
 ENC = [('enc1', 1, 8, 5, 257, 347), ('enc2', 8, 16, 4, 129, 174), ('enc3', 16, 32, 4, 65, 88), ('enc4', 32, 64, 4, 33, 45),
        ('enc5', 64, 128, 4, 17, 23), ('enc6', 128, 256, 4, 9, 12), ('enc7', 256, 512, 4, 5, 7)]
