@@ -337,6 +337,35 @@ PGV_API int pgv_latent_loss_bwd(const float* grad_out, const float* mu_logvar, c
 /* GaussianDkl (model/loss.py:46-66).  workspace >= 8 B. */
 PGV_API int pgv_dkl_fwd(const float* mu_logvar, int B, int D, int normalize, float* loss_out, void* workspace, pgv_stream_t stream);
 PGV_API int pgv_dkl_bwd(const float* grad_out, const float* mu_logvar, int B, int D, int normalize, float* d_mu_logvar, pgv_stream_t stream);
+/* ------------------------------------------------------------------ monitoring metrics, inference tail, inverse-flow loss
+ * Per-VST-parameter tables (one entry per monitored parameter): kind = 0 numerical learned as numerical, 1 numerical learned as
+ * one-hot, 2 categorical learned as numerical, 3 categorical learned as one-hot, 4 not learnable; col / len = learnable column range;
+ * card = cardinality (<= 0: continuous).
+ * pgv_preset_metrics = QuantizedNumericalParamsLoss (model/loss.py:187-261; l1 != 0: L1 instead of MSE) and CategoricalParamsAccuracy
+ * (model/loss.py:265-315) in one pass, as train.py:232-233 calls them every step: out4 = (numerical loss, mean accuracy * acc_scale,
+ * number of numerical, number of categorical parameters); acc (optional, [P]) = per-parameter accuracies (reduce=False), -1 elsewhere;
+ * partial = [P] floats of workspace. */
+PGV_API int pgv_preset_metrics(const float* v_out, const float* v_in, int B, int L, const int* kind, const int* col, const int* len,
+                               const int* card, int P, int l1, float acc_scale, float* partial, float* out4, float* acc, pgv_stream_t stream);
+/* PresetsParams.get_full from learnable presets (data/preset.py:350-369): full [B, P]; fill[p] = default value of a non-learnable
+ * parameter (-0.1 when it has none). */
+PGV_API int pgv_learnable_to_full(const float* v, int B, int L, const int* kind, const int* col, const int* len, const int* card,
+                                  const float* fill, int P, float* full, pgv_stream_t stream);
+/* FlowParamsLoss (model/loss.py:318-346): -mean_b(log N(z0; mu, exp(logvar)) + logdet_t + logdet_u) / divisor (1000 in the reference).
+ * rows_ws: [B] floats. */
+PGV_API int pgv_flow_params_loss_fwd(const float* mu_logvar, const float* z0, const float* logdet_t, const float* logdet_u, int B, int D,
+                                     float divisor, float* loss_out, float* rows_ws, pgv_stream_t stream);
+PGV_API int pgv_flow_params_loss_bwd(const float* grad_out, const float* mu_logvar, const float* z0, int B, int D, float divisor,
+                                     float* d_mu_logvar, float* dz0, float* dlogdet, pgv_stream_t stream);
+/* utils/exception.py:13-22 (train.py:245) without a host round trip: flags[0] |= 1 << i if scalar i (device pointer, may be NULL) is NaN. */
+PGV_API int pgv_nan_flags(const float* s0, const float* s1, const float* s2, const float* s3, const float* s4, int* flags, pgv_stream_t stream);
+/* data/abstractbasedataset.py:348-391: per_item4[i] = (min, max, mean, unbiased variance) of spectrogram i (x [N, elems]); dataset4
+ * (optional) = (min of mins, max of maxes, mean of means, sqrt(mean of variances)). */
+PGV_API int pgv_spectrogram_stats(const float* x, int N, size_t elems, float* per_item4, float* dataset4, pgv_stream_t stream);
+/* Backward of the inverse direction of the affine coupling (pgv_coupling_fwd with inverse != 0), given its result x_out: needed by
+ * FlowParamsLoss, which back-propagates through the inverse latent flow (model/VAE.py:128-131, regression.py:179-184). */
+PGV_API int pgv_coupling_inv_bwd(const float* dx_out, const float* dlogdet, const float* x_out, const float* params, const int* id_idx,
+                                 const int* tr_idx, float* dy, float* dparams, int B, int D, int n_id, int n_t, pgv_stream_t stream);
 /* SynthParamsLoss (model/loss.py:73-183) with the useless-parameter rule of data/preset.py:247-283 evaluated on the
  * device from v_in: tables as returned by PresetIndexesHelper.device_tables().  cat_softmax != 0 applies
  * softmax(q / temperature) inside the loss.  The same workspace must be passed to fwd and bwd. */

@@ -102,3 +102,69 @@ def train_step_losses(ext_model, x_in, v_in, sample_info, noise, beta, normalize
     total = recons + beta * lat + cont
     outs = dict(z0_mu_logvar=z0_mu_logvar, z0=z0, zK=zK, logdet=logdet, x_out=x_out, v_out=v_out)
     return outs, dict(recons=recons, latent=lat, controls=cont), total
+
+
+# ------------------------------------------------------------------------------------------------ monitoring metrics (train.py:232-233)
+def quantized_numerical_params_loss(idx_helper, u_out, u_in, l1=False):
+    """model/loss.py:217-261 (QuantizedNumericalParamsLoss.__call__ with numerical_loss = nn.MSELoss() / nn.L1Loss(), all parameters)."""
+    cols_in, cols_out = [], []
+    for vst_idx, learn_idx in idx_helper.num_idx_learned_as_num.items():          # loss.py:231-243
+        o = u_out[:, learn_idx].detach().clone()
+        card = idx_helper.vst_param_cardinals[vst_idx]
+        if card > 0:
+            o = torch.round(o * (card - 1.0)) / (card - 1.0)
+        cols_in.append(u_in[:, learn_idx].detach())
+        cols_out.append(o)
+    for vst_idx, learn_indexes in idx_helper.num_idx_learned_as_cat.items():      # loss.py:245-255
+        card = len(learn_indexes)
+        cols_in.append(torch.argmax(u_in[:, learn_indexes], dim=-1).float() / (card - 1.0))
+        cols_out.append(torch.argmax(u_out[:, learn_indexes], dim=-1).float() / (card - 1.0))
+    a, b = torch.stack(cols_out, 1), torch.stack(cols_in, 1)
+    return F.l1_loss(a, b) if l1 else F.mse_loss(a, b)
+
+
+def categorical_params_accuracy(idx_helper, u_out, u_in, reduce=True, percentage_output=True):
+    """model/loss.py:283-315."""
+    acc = {}
+    for vst_idx, learn_idx in idx_helper.cat_idx_learned_as_num.items():          # loss.py:289-299
+        card = idx_helper.vst_param_cardinals[vst_idx]
+        t = torch.round(u_in[:, learn_idx] * (card - 1.0)).to(torch.int32)
+        o = torch.round(u_out[:, learn_idx] * (card - 1.0)).to(torch.int32)
+        acc[vst_idx] = (t == o).count_nonzero().item() / t.numel()
+    for vst_idx, learn_indexes in idx_helper.cat_idx_learned_as_cat.items():      # loss.py:301-307
+        t, o = torch.argmax(u_in[:, learn_indexes], dim=-1), torch.argmax(u_out[:, learn_indexes], dim=-1)
+        acc[vst_idx] = (t == o).count_nonzero().item() / t.numel()
+    if percentage_output:
+        acc = {k: v * 100.0 for k, v in acc.items()}
+    return float(sum(acc.values()) / len(acc)) if reduce else acc
+
+
+def flow_params_loss(latent_flow_inverse, reg_flow_inverse, z0_mu_logvar, v_target):
+    """model/loss.py:333-346 with utils/probability.py:21-29."""
+    import numpy as np
+    z_K, ld_u = reg_flow_inverse(v_target)
+    z_0, ld_t = latent_flow_inverse(z_K)
+    mu, lv = z0_mu_logvar[:, 0, :], z0_mu_logvar[:, 1, :]
+    log_q = -0.5 * (z_0.shape[1] * np.log(2 * np.pi) + torch.sum(lv + (z_0 - mu) ** 2 / torch.exp(lv), dim=1))
+    return -torch.mean(log_q + ld_t + ld_u) / 1000.0
+
+
+def learnable_to_full(idx_helper, learnable, default_values):
+    """data/preset.py:350-369 (PresetsParams.get_full from learnable presets)."""
+    full = -0.1 * torch.ones((learnable.shape[0], idx_helper.full_preset_size))
+    for vst_idx, learn in enumerate(idx_helper.full_to_learnable):
+        if idx_helper.vst_param_learnable_model[vst_idx] is None:
+            if vst_idx in default_values:
+                full[:, vst_idx] = default_values[vst_idx]
+        elif isinstance(learn, int):
+            full[:, vst_idx] = learnable[:, learn]
+        else:
+            full[:, vst_idx] = torch.argmax(learnable[:, learn], dim=-1) / (idx_helper.vst_param_cardinals[vst_idx] - 1.0)
+    return full
+
+
+def spectrogram_stats(specs):
+    """data/abstractbasedataset.py:357-386: per-item (min, max, mean, torch.var) and the data-set summary of :357-360."""
+    import numpy as np
+    per = np.asarray([[s.min().item(), s.max().item(), torch.mean(s, dim=(0, 1)).item(), torch.var(s).item()] for s in specs], dtype=np.float64)
+    return per, dict(min=per[:, 0].min(), max=per[:, 1].max(), mean=per[:, 2].mean(), std=float(np.sqrt(per[:, 3].mean())))

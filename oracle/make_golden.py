@@ -273,6 +273,65 @@ def golden_model(ref_config, ref_build, ref_loss, ref_helper, my_helper, tag, B,
           "| params", sum(p.numel() for p in ext_ref.parameters()), "state entries", len(sd_init))
 
 
+def golden_metrics(ref_loss, ref_preset, ref_build, ref_config, fake, ref_helper, my_helper):
+    """Monitoring metrics (loss.py:187-315), FlowParamsLoss (loss.py:318-346), GaussianDkl / L2Loss (loss.py:15-66): the reference
+    classes on seeded inputs; the oracle restatements must reproduce them; the reference's numbers become tests/golden/metrics.npz."""
+    B = 48
+    g = torch.Generator().manual_seed(11)
+    v_in = synthetic.make_preset_targets(my_helper, B, seed=3)
+    v_out = (v_in + 0.35 * torch.randn(B, 610, generator=g)).clamp_(0.0, 1.0)      # a plausible, partly wrong inference
+    v_out[:, 5] = 0.5                                                               # exact .5 products exercise round-half-even
+    qmse = ref_loss.QuantizedNumericalParamsLoss(ref_helper, numerical_loss=torch.nn.MSELoss(reduction='mean'))(v_out, v_in)
+    ql1 = ref_loss.QuantizedNumericalParamsLoss(ref_helper, numerical_loss=torch.nn.L1Loss())(v_out, v_in)
+    acc = ref_loss.CategoricalParamsAccuracy(ref_helper, reduce=True, percentage_output=True)(v_out, v_in)
+    acc_d = ref_loss.CategoricalParamsAccuracy(ref_helper, reduce=False, percentage_output=False)(v_out, v_in)
+    lim = [4, 5, 6, 30, 40, 52, 100]
+    q_lim = ref_loss.QuantizedNumericalParamsLoss(ref_helper, limited_vst_params_indexes=lim)(v_out, v_in)
+    acc_lim = ref_loss.CategoricalParamsAccuracy(ref_helper, limited_vst_params_indexes=lim)(v_out, v_in)
+    assert abs(oloss.quantized_numerical_params_loss(my_helper, v_out, v_in).item() - qmse.item()) < 1e-7
+    assert abs(oloss.quantized_numerical_params_loss(my_helper, v_out, v_in, l1=True).item() - ql1.item()) < 1e-7
+    assert abs(oloss.categorical_params_accuracy(my_helper, v_out, v_in) - float(acc)) < 1e-9
+    assert oloss.categorical_params_accuracy(my_helper, v_out, v_in, reduce=False, percentage_output=False) == acc_d
+    full_ref = ref_preset.DexedPresetsParams(fake, learnable_presets=v_out).get_full()
+    assert torch.equal(full_ref, oloss.learnable_to_full(my_helper, v_out, mine_defaults()))
+    # GaussianDkl / L2Loss
+    ml = 0.5 * torch.randn(B, 2, 610, generator=g)
+    dkl = ref_loss.GaussianDkl(normalize=True)(ml[:, 0], ml[:, 1])
+    dkl_raw = ref_loss.GaussianDkl(normalize=False)(ml[:, 0], ml[:, 1])
+    assert abs(omodel.gaussian_dkl(ml[:, 0], ml[:, 1], True).item() - dkl.item()) < 1e-6
+    a, b = torch.randn(3, 2, 9, 7, generator=g), torch.randn(3, 2, 9, 7, generator=g)
+    l2 = [ref_loss.L2Loss(c, ba)(a, b).item() for c in (False, True) for ba in (False, True)]
+    assert all(abs(oloss.l2_loss(a, b, c, ba).item() - l2[2 * i + j]) < 1e-5 for i, c in enumerate((False, True)) for j, ba in enumerate((False, True)))
+    # FlowParamsLoss through the reference class, with the reference-built model's inverse-flow functions (forward_controls_loss=False
+    # builds the regression flow 'backwards', regression.py:179-184)
+    cfg = ref_config
+    _configure(cfg, 6)
+    cfg.model.forward_controls_loss = False
+    torch.manual_seed(0)
+    _, _, _, ext = ref_build.build_extended_ae_model(cfg.model, cfg.train, ref_helper)
+    cfg.model.forward_controls_loss = True
+    ext.train()
+    for blk in [m for m in ext.modules() if type(m).__name__ == 'ResidualBlock']:
+        blk.dropout.p = 0.0                                                          # no RNG in the fixture
+    crit = ref_loss.FlowParamsLoss(ref_helper, ext.ae_model.flow_inverse_function, ext.reg_model.flow_inverse_function)
+    ml6, v6 = ml[:6].clone().requires_grad_(), synthetic.make_preset_targets(my_helper, 6, seed=5)
+    fpl = crit(ml6, v6)
+    fpl.backward()
+    assert abs(oloss.flow_params_loss(ext.ae_model.flow_inverse_function, ext.reg_model.flow_inverse_function, ml6, v6).item() - fpl.item()) < 1e-6
+    g_names = [n for n, p in ext.named_parameters() if p.grad is not None]
+    np.savez_compressed(os.path.join(GOLDEN, 'metrics.npz'), v_in=v_in.numpy(), v_out=v_out.numpy(), qloss_mse=np.float64(qmse.item()),
+                        qloss_l1=np.float64(ql1.item()), accuracy_pct=np.float64(acc), qloss_limited=np.float64(q_lim.item()),
+                        accuracy_limited=np.float64(acc_lim), limited=np.asarray(lim),
+                        acc_keys=np.asarray(list(acc_d.keys())), acc_vals=np.asarray(list(acc_d.values()), dtype=np.float64),
+                        full_presets=full_ref.numpy(), mu_logvar=ml.numpy(), dkl=np.float64(dkl.item()), dkl_raw=np.float64(dkl_raw.item()),
+                        l2_a=a.numpy(), l2_b=b.numpy(), l2=np.asarray(l2), flow_params_loss=np.float64(fpl.item()),
+                        flow_params_v=v6.numpy(), flow_params_dml=ml6.grad.numpy(),
+                        flow_params_grad_norms=np.asarray([float(dict(ext.named_parameters())[n].grad.double().norm()) for n in g_names]),
+                        flow_params_grad_names=np.asarray(g_names))
+    print("metrics: oracle == reference | QLoss %.6f / L1 %.6f, accuracy %.3f %%, FlowParamsLoss %.6f (%d parameter tensors with gradients)"
+          % (qmse.item(), ql1.item(), float(acc), fpl.item(), len(g_names)))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -282,6 +341,7 @@ def main():
     golden_model(ref_config, ref_build, ref_loss, ref_helper, my_helper, 'c1_b4', B=4)
     six = ((40, 85), (50, 85), (60, 42), (60, 85), (60, 127), (70, 85))
     golden_model(ref_config, ref_build, ref_loss, ref_helper, my_helper, 'c6_b2', B=2, midi_notes=six, stack=True)
+    golden_metrics(ref_loss, ref_preset, ref_build, ref_config, fake, ref_helper, my_helper)
     print("golden fixtures written to", GOLDEN)
 
 

@@ -262,7 +262,44 @@ class tables_from_foreign_helper:
                     grp_vol_col=i32([grp_vol[g[0]] for g in groups]))
 
 
+PM_NUM_AS_NUM, PM_NUM_AS_CAT, PM_CAT_AS_NUM, PM_CAT_AS_CAT, PM_NONE = range(5)
+
+
+def metric_tables(idx_helper, limited_vst_params_indexes=None, default_values=None):
+    """Per-VST-parameter tables of the device metric / conversion kernels (pgv.h, pgv_preset_metrics / pgv_learnable_to_full), built
+    from the read-only surface shared by this package's PresetIndexesHelper and the reference's (data/preset.py:23-283):
+    kind (0 numerical->numerical, 1 numerical->one-hot, 2 categorical->numerical, 3 categorical->one-hot, 4 not learnable or
+    excluded by `limited_vst_params_indexes`), col / len (learnable column range), card, fill (default value or -0.1)."""
+    n = idx_helper.full_preset_size
+    kind, col, ln, card, fill = (np.full(n, PM_NONE, np.int32), np.zeros(n, np.int32), np.ones(n, np.int32), np.zeros(n, np.int32),
+                                 np.full(n, -0.1, np.float32))
+    numerical = set(idx_helper.numerical_vst_params)
+    for vst_idx, learn in enumerate(idx_helper.full_to_learnable):
+        card[vst_idx] = int(idx_helper.vst_param_cardinals[vst_idx])
+        if default_values is not None and vst_idx in default_values:
+            fill[vst_idx] = default_values[vst_idx]
+        if learn is None or (limited_vst_params_indexes is not None and vst_idx not in limited_vst_params_indexes):
+            continue
+        as_cat = not isinstance(learn, int)
+        col[vst_idx] = learn[0] if as_cat else learn
+        ln[vst_idx] = len(learn) if as_cat else 1
+        if vst_idx in numerical:
+            kind[vst_idx] = PM_NUM_AS_CAT if as_cat else PM_NUM_AS_NUM
+        else:
+            kind[vst_idx] = PM_CAT_AS_CAT if as_cat else PM_CAT_AS_NUM
+    return dict(kind=kind, col=col, len=ln, card=card, fill=fill)
+
+
 def learnable_to_full_presets(idx_helper, learnable_presets: torch.Tensor, default_values: dict) -> torch.Tensor:
+    """Inference tail (data/preset.py:350-369).  CUDA tensors go through pgv_learnable_to_full (one launch; per-group argmax on the
+    device); CPU tensors through the vectorised torch code below (host-side tooling, e.g. writing presets to disk)."""
+    if learnable_presets.is_cuda:
+        from ..model import ops
+        return ops.learnable_to_full(learnable_presets, ops.MetricTables(idx_helper, default_values=default_values))
+    return _learnable_to_full_presets_host(idx_helper, learnable_presets, default_values)
+
+
+def _learnable_to_full_presets_host(idx_helper, learnable_presets: torch.Tensor, default_values: dict) -> torch.Tensor:
     """Inference tail (data/preset.py:350-369): per-group argmax / (n-1) for categorical groups, copy for
     numerical columns, defaults (else -0.1) for non-learnable VST parameters.  Vectorised, runs on the tensor's device."""
     B = learnable_presets.shape[0]

@@ -210,6 +210,20 @@ class AffineCouplingTransform(Transform):
         prm, _ = self.transform_net.fwd(ops.gather_cols(y, id_idx), False, None)
         return ops.coupling_fwd(y, prm, id_idx, tr_idx, logdet, inverse=True)
 
+    def inv_fwd(self, y, logdet, training, masks):
+        """Inverse direction with the conditioner in its current mode, keeping what `inv_bwd` needs."""
+        id_idx, tr_idx = self._idx(y.device)
+        prm, net_ctx = self.transform_net.fwd(ops.gather_cols(y, id_idx), training, masks)
+        x, ld = ops.coupling_fwd(y, prm, id_idx, tr_idx, logdet, inverse=True)
+        return x, ld, (x, prm, net_ctx)
+
+    def inv_bwd(self, dx, dld, ctx, grads):
+        x, prm, net_ctx = ctx
+        id_idx, tr_idx = self._idx(x.device)
+        dy, dprm = ops.coupling_inv_bwd(dx, dld, x, prm, id_idx, tr_idx)
+        dident = self.transform_net.bwd(dprm, net_ctx, grads)
+        return ops.scatter_add_cols_(dy, id_idx, dident), dld
+
 
 class BatchNorm(Transform):
     """Invertible batch-norm transform placed between regression-flow couplings (flows.py:87-88)."""
@@ -323,12 +337,21 @@ class CompositeTransform(Transform):
                 all_masks.append(ms)
         return all_masks if any_mask else None
 
-    @torch.no_grad()
-    def inverse(self, inputs, context=None):
-        """Inverse pass (evaluation only, like nflows' BatchNorm.inverse); no autograd."""
+    def inverse(self, inputs, context=None, dropout_masks=None):
+        """Inverse pass.  Under torch.no_grad() / in eval mode: kernels only, no autograd.  In training mode with autograd enabled it
+        is ONE differentiable autograd node (FlowParamsLoss back-propagates through the inverse latent flow, model/loss.py:318-346);
+        like nflows, a cascade that contains BatchNorm transforms has no training-mode inverse."""
         assert context is None
         if self.training and any(isinstance(t, BatchNorm) for t in self._transforms):
             raise RuntimeError("Batch norm inverse is only available in eval mode, not in training mode.")
+        if self.training and torch.is_grad_enabled():
+            if dropout_masks is None:
+                dropout_masks = self._draw_masks(inputs)
+            return run_program(_InverseProgram(self), (inputs,), self.program_params(), True, dropout_masks)
+        with torch.no_grad():
+            return self._inverse_eval(inputs)
+
+    def _inverse_eval(self, inputs):
         x = inputs.contiguous()
         B = x.shape[0]
         logdet = None
@@ -339,6 +362,35 @@ class CompositeTransform(Transform):
                 x, ld = ops.flowbn_eval(x, t, inverse=True)
                 logdet = _add_scalar_to_rows(logdet, ld, B)
         return x, logdet
+
+
+class _InverseProgram:
+    """Differentiable inverse of a CompositeTransform made of couplings only (training mode)."""
+
+    def __init__(self, composite):
+        self.c = composite
+
+    def prog_fwd(self, inputs, training, extra):
+        x = inputs[0].contiguous()
+        couplings = list(self.c._transforms)
+        logdet, ctxs = None, []
+        for i in range(len(couplings) - 1, -1, -1):
+            masks = None if extra is None else extra[i]
+            x, logdet, c = couplings[i].inv_fwd(x, logdet, training, masks)
+            ctxs.append(c)
+        return (x, logdet), ctxs
+
+    def prog_bwd(self, douts, ctxs, grads, needs):
+        dx, dld = douts
+        B = ctxs[0][0].shape[0]
+        if dx is None:
+            dx = torch.zeros_like(ctxs[0][0])
+        if dld is None:
+            dld = torch.zeros(B, device=dx.device)
+        couplings = list(self.c._transforms)
+        for t, c in zip(couplings, reversed(ctxs)):          # forward ran couplings K-1 .. 0: unwind 0 .. K-1
+            dx, dld = t.inv_bwd(dx, dld, c, grads)
+        return dx
 
 
 def _resnet_factory(hidden_features, num_blocks, dropout_probability, use_batch_norm):

@@ -142,6 +142,93 @@ class SynthParamsLoss:
         return run_program(_SYNTH, (u_out, u_in), [], True, cfg)
 
 
+class QuantizedNumericalParamsLoss:
+    """model/loss.py:187-261: numerical VST parameters only, inferred values quantised like the synthesizer does (round to the
+    parameter's cardinality; one-hot representations -> argmax / (cardinal - 1)); not differentiable.  One kernel pass shared with
+    CategoricalParamsAccuracy (`PresetMetrics`); the result stays on the device (0-dim tensor), train.py:232 only logs it."""
+
+    def __init__(self, idx_helper, numerical_loss=None, limited_vst_params_indexes=None):
+        self.idx_helper = idx_helper
+        name = type(numerical_loss).__name__ if numerical_loss is not None else 'MSELoss'
+        if name not in ('MSELoss', 'L1Loss') or getattr(numerical_loss, 'reduction', 'mean') != 'mean':
+            raise NotImplementedError("numerical_loss must be nn.MSELoss() or nn.L1Loss() with mean reduction (train.py:121-122, eval.py)")
+        self.l1 = name == 'L1Loss'
+        self.numerical_loss = numerical_loss
+        self.limited_vst_params_indexes = limited_vst_params_indexes
+        self.num_params_count = len(idx_helper.num_idx_learned_as_num) + len(idx_helper.num_idx_learned_as_cat)
+        self._tables = ops.MetricTables(idx_helper, limited_vst_params_indexes)
+
+    def __call__(self, u_out, u_in):
+        out4, _ = ops.preset_metrics(u_out, u_in, self._tables, l1=self.l1)
+        if self.limited_vst_params_indexes is None:
+            return out4[0]
+        # limited lists: the reference still averages over ALL pre-allocated numerical columns, the unused ones zero-filled (loss.py:222-226)
+        return out4[0] * out4[2] / float(self.num_params_count)
+
+
+class CategoricalParamsAccuracy:
+    """model/loss.py:265-315: accuracy of the categorical VST parameters (one-hot: argmax match; numerical representation: match after
+    rounding to the class index).  reduce=True returns a 0-dim DEVICE tensor (the reference returns a numpy scalar after one `.item()`
+    per parameter); reduce=False returns {vst_idx: accuracy} like the reference (one device -> host copy)."""
+
+    def __init__(self, idx_helper, reduce=True, percentage_output=True, limited_vst_params_indexes=None):
+        self.idx_helper = idx_helper
+        self.reduce = reduce
+        self.percentage_output = percentage_output
+        self.limited_vst_params_indexes = limited_vst_params_indexes
+        self._tables = ops.MetricTables(idx_helper, limited_vst_params_indexes)
+
+    def __call__(self, u_out, u_in):
+        out4, acc = ops.preset_metrics(u_out, u_in, self._tables, acc_scale=100.0 if self.percentage_output else 1.0,
+                                       per_param=not self.reduce)
+        if self.reduce:
+            return out4[1]
+        acc = acc.cpu().tolist()
+        # the reference fills its dict with the numerically-learned parameters first, then the one-hot ones (loss.py:289-307)
+        keys = list(self.idx_helper.cat_idx_learned_as_num.keys()) + list(self.idx_helper.cat_idx_learned_as_cat.keys())
+        return {k: acc[k] for k in keys if acc[k] >= 0.0}
+
+
+class PresetMetrics:
+    """Both monitoring metrics of train.py:232-233 from ONE kernel pass: returns a device tensor
+    [QuantizedNumericalParamsLoss (MSE), CategoricalParamsAccuracy (%), #numerical, #categorical]."""
+
+    def __init__(self, idx_helper):
+        self._tables = ops.MetricTables(idx_helper)
+
+    def __call__(self, u_out, u_in):
+        return ops.preset_metrics(u_out, u_in, self._tables)[0]
+
+
+class _FlowParams:
+    def prog_fwd(self, inputs, training, divisor):
+        ml, z0, ld_t, ld_u = (t.contiguous() for t in inputs)
+        return ops.flow_params_loss_fwd(ml, z0, ld_t, ld_u, divisor).view(()), (ml, z0, divisor)
+
+    def prog_bwd(self, dout, ctx, grads, needs):
+        ml, z0, divisor = ctx
+        dml, dz0, dld = ops.flow_params_loss_bwd(dout.reshape(1), ml, z0, divisor)
+        return dml, dz0, dld, dld
+
+
+_FLOW_PARAMS = _FlowParams()
+
+
+class FlowParamsLoss:
+    """model/loss.py:318-346: -mean(log q_Z0(z0) + log|det J_invT| + log|det J_invU|) / 1000 with z0 = invT(invU(v_target)); the two
+    inverse-flow functions are the models' `flow_inverse_function`s (train.py:117-119) and are differentiated through."""
+
+    def __init__(self, idx_helper, latent_flow_inverse_function, reg_flow_inverse_function):
+        self.idx_helper = idx_helper
+        self.latent_flow_inverse_function = latent_flow_inverse_function
+        self.reg_flow_inverse_function = reg_flow_inverse_function
+
+    def __call__(self, z_0_mu_logvar, v_target):
+        z_K, ld_u = self.reg_flow_inverse_function(v_target)
+        z_0, ld_t = self.latent_flow_inverse_function(z_K)
+        return run_program(_FLOW_PARAMS, (z_0_mu_logvar, z_0, ld_t, ld_u), [], True, 1000.0)
+
+
 def _tables_for(idx_helper):
     """Device tables from this package's PresetIndexesHelper, or derived by probing a reference helper."""
     if hasattr(idx_helper, 'device_tables'):

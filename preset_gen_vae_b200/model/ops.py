@@ -773,3 +773,81 @@ def synth_loss_bwd(gout, v_out, v_in, tables, normalize, factor, cat_softmax, te
           _f(t['grp_start']), _f(t['grp_len']), _f(t['grp_vol_col']), tables.n_grp, int(normalize), float(factor), int(cat_softmax),
           float(temperature), _f(ws), _f(d), _s(v_out))
     return d
+
+
+# ------------------------------------------------------------------------------------------------ monitoring metrics / inference tail
+class MetricTables:
+    """Device copies of data.preset.metric_tables() (cached per device)."""
+
+    def __init__(self, idx_helper, limited_vst_params_indexes=None, default_values=None):
+        from ..data.preset import metric_tables
+        self.host = metric_tables(idx_helper, limited_vst_params_indexes, default_values)
+        self.P = len(self.host['kind'])
+        self._dev = {}
+
+    def on(self, device):
+        key = (device.type, device.index)
+        if key not in self._dev:
+            self._dev[key] = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in self.host.items()}
+        return self._dev[key]
+
+
+def preset_metrics(v_out, v_in, tables, l1=False, acc_scale=100.0, per_param=False):
+    """(out4, acc): out4 = [quantised numerical loss, mean accuracy * acc_scale, #numerical, #categorical] (device tensor);
+    acc = per-VST-parameter accuracies (-1 for non-categorical parameters) when per_param."""
+    t = tables.on(v_out.device)
+    v_out, v_in = v_out.detach().contiguous(), v_in.detach().contiguous()
+    B, L = v_out.shape
+    out4, partial = _empty(v_out, 4), _empty(v_out, tables.P)
+    acc = _empty(v_out, tables.P) if per_param else None
+    _call('pgv_preset_metrics', _f(v_out), _f(v_in), B, L, _f(t['kind']), _f(t['col']), _f(t['len']), _f(t['card']), tables.P, int(l1),
+          float(acc_scale), _f(partial), _f(out4), _f(acc), _s(v_out), n=2)
+    return out4, acc
+
+
+def learnable_to_full(v, tables):
+    t = tables.on(v.device)
+    v = v.detach().contiguous()
+    B, L = v.shape
+    full = _empty(v, B, tables.P)
+    _call('pgv_learnable_to_full', _f(v), B, L, _f(t['kind']), _f(t['col']), _f(t['len']), _f(t['card']), _f(t['fill']), tables.P, _f(full), _s(v))
+    return full
+
+
+def flow_params_loss_fwd(ml, z0, ld_t, ld_u, divisor):
+    B, _, D = ml.shape
+    out = _empty(ml, 1)
+    _call('pgv_flow_params_loss_fwd', _f(ml), _f(z0), _f(ld_t), _f(ld_u), B, D, float(divisor), _f(out), _f(_empty(ml, B)), _s(ml), n=2)
+    return out
+
+
+def flow_params_loss_bwd(gout, ml, z0, divisor):
+    B, _, D = ml.shape
+    dml, dz0, dld = torch.empty_like(ml), torch.empty_like(z0), _empty(ml, B)
+    _call('pgv_flow_params_loss_bwd', _f(gout), _f(ml), _f(z0), B, D, float(divisor), _f(dml), _f(dz0), _f(dld), _s(ml))
+    return dml, dz0, dld
+
+
+def nan_flags_(flags, *scalars):
+    """flags (int32 [1], device) |= bit i for every NaN scalar i (up to 5 one-element device tensors; train.py:245)."""
+    assert len(scalars) <= 5 and flags.dtype == torch.int32
+    ptrs = [_f(s.detach()) for s in scalars] + [ctypes.c_void_p(0)] * (5 - len(scalars))
+    _call('pgv_nan_flags', *ptrs, _f(flags), _s(flags))
+    return flags
+
+
+def spectrogram_stats(x):
+    """x [N, ...]: (per_item [N, 4] = min / max / mean / unbiased variance, dataset [4] = min, max, mean of means, sqrt(mean variance))."""
+    x = x.contiguous()
+    N = x.shape[0]
+    per, ds = _empty(x, N, 4), _empty(x, 4)
+    _call('pgv_spectrogram_stats', _f(x), N, x[0].numel(), _f(per), _f(ds), _s(x), n=2)
+    return per, ds
+
+
+def coupling_inv_bwd(dx_out, dlogdet, x_out, params, id_idx, tr_idx):
+    B, D = x_out.shape
+    dy, dp = torch.empty_like(x_out), torch.empty_like(params)
+    _call('pgv_coupling_inv_bwd', _f(dx_out), _f(dlogdet), _f(x_out), _f(params), _f(id_idx), _f(tr_idx), _f(dy), _f(dp), B, D, id_idx.numel(),
+          tr_idx.numel(), _s(x_out))
+    return dy, dp

@@ -1,0 +1,7 @@
+set -x
+timeout 600 python -m pytest tests/test_conv_cl_gpu.py tests/test_kernels_gpu.py -x -q -m gpu > gpurun_out/pytest_conv.log 2>&1; echo pytest_conv=$?; tail -15 gpurun_out/pytest_conv.log
+timeout 300 python tools/gpu_bench_layers.py 160 > gpurun_out/layers_r02a.log 2>&1; tail -28 gpurun_out/layers_r02a.log
+timeout 300 python tools/gpu_bench_layers.py 160 cl a0 > gpurun_out/layers_r02a_a0.log 2>&1; tail -3 gpurun_out/layers_r02a_a0.log
+timeout 300 python tools/gpu_bench_layers.py 160 cl atomic > gpurun_out/layers_r02a_atomic.log 2>&1; tail -3 gpurun_out/layers_r02a_atomic.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_all.log 2>&1; echo pytest_all=$?; tail -15 gpurun_out/pytest_all.log
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02a.json 2> gpurun_out/bench_r02a.err; echo bench=$?; cut -c1-600 gpurun_out/bench_r02a.json
