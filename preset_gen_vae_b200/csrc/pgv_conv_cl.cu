@@ -38,15 +38,19 @@ namespace pgv {
 enum { CL_GEMM = 0, CL_WGRAD = 1 };
 enum { CL_EPI_ROWS = 0, CL_EPI_QUAD = 1 };
 
-constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_STAGES = 5;
-constexpr int CL_A_BYTES = CL_BLOCK_M * 128, CL_B_BYTES = CL_MAX_N * 128, CL_STAGE_BYTES = CL_A_BYTES + CL_B_BYTES;
+// The ring of k-block stages takes all the shared memory the epilogue does not need: a stage is the 16 KB activation tile plus a weight
+// tile of n_tile x 128 bytes, so the 8 / 16 / 32-channel layers (whose per-SM throughput is bounded by the BYTES IN FLIGHT: four
+// k-blocks per tile, ~2 us of memory latency) run 10-11 stages deep and the 128-column layers 6.
+constexpr int CL_BLOCK_M = 128, CL_BLOCK_K = 32, CL_MAX_N = 128, CL_MAX_STAGES = 12;
+constexpr int CL_A_BYTES = CL_BLOCK_M * 128;
 constexpr int CL_PRODUCER_WARPS = 8, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
 constexpr int CL_SLOTS = (CL_BLOCK_M * 8) / CL_PRODUCERS;          // 16-byte chunks of one operand tile per producer thread (4)
 constexpr int CL_ROWS_PER_PASS = CL_PRODUCERS / 8;               // GEMM mode: rows covered by one pass of the producers (32)
 constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/ + 32 /*weights by TMA*/;
 // epilogue staging: per epilogue warp 32 rows x 32 columns (+4 pad) of fp32 and one 64-bit destination offset per row
 constexpr int CL_EPI_LD = 36, CL_EPI_WARP_BYTES = 32 * CL_EPI_LD * 4 + 32 * 8;
-constexpr int CL_SMEM = 1024 + CL_STAGES * CL_STAGE_BYTES + 256 + 4 * CL_EPI_WARP_BYTES;
+constexpr int CL_SMEM = 232448;                                     // 227 KB: the per-block maximum of sm_100
+constexpr int CL_RING_BYTES = (CL_SMEM - 1024 - 256 - 4 * CL_EPI_WARP_BYTES) / 1024 * 1024;
 
 struct ConvClParams {
     const float* a;      // GEMM: gathered activations [B, H, W, C]      WGRAD: x [B, H, W, C]
@@ -56,6 +60,7 @@ struct ConvClParams {
     int B, H, W, C, KH, KW, stride, pad, Hg, Wg;     // gather geometry: window KH x KW over [H, W, C], output grid Hg x Wg
     int gemm_m, gemm_n, gemm_k;
     int n_tile, n_tiles, m_tiles, kb_total, kb_per_split, k_splits;
+    int stages, stage_bytes;       // ring geometry (cl_set_ring)
     int epi, ldo;        // CL_EPI_ROWS: out[m * ldo + n]          WGRAD: out[n * ldo + m] for m < m_valid
     int m_valid;
     int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
@@ -121,9 +126,11 @@ template <int MODE>
 __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_constant__ ConvClParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + CL_STAGES * CL_STAGE_BYTES);
-    uint64_t* bar_empty = bar_full + CL_STAGES;
-    uint64_t* bar_tfull = bar_empty + CL_STAGES;
+    const int CL_STAGES = p.stages, CL_STAGE_BYTES = p.stage_bytes;
+    uint8_t* smem_ctl = smem + CL_RING_BYTES;                                // barriers, then the epilogue staging tiles
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_ctl);
+    uint64_t* bar_empty = bar_full + CL_MAX_STAGES;
+    uint64_t* bar_tfull = bar_empty + CL_MAX_STAGES;
     uint64_t* bar_tempty = bar_tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
     volatile uint32_t* ws_flag = tmem_ptr + 1;                              // split-K: "this CTA finishes the tile" (epilogue warps)
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         // per-warp shared-memory tile: thread = row on the way in, 8 lanes x float4 = 128 contiguous bytes of a row on the way out
         // (measured before: 16 k cycles to drain one 128 x 128 tile with row-strided float4 stores).
         const int quad = warp & 3, row = quad * 32 + lane;
-        float* stg = reinterpret_cast<float*>(smem + CL_STAGES * CL_STAGE_BYTES + 256 + quad * CL_EPI_WARP_BYTES);
+        float* stg = reinterpret_cast<float*>(smem_ctl + 256 + quad * CL_EPI_WARP_BYTES);
         long long* stg_dst = reinterpret_cast<long long*>(stg + 32 * CL_EPI_LD);     // per row: element offset of its destination, -1 = no row
         int acc = 0; uint32_t acc_phase = 0;
         int etrace_n = 0;
@@ -699,7 +706,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * CL_MAX_N);
     if (with_stats) {
         // fold the 4 epilogue warps (and, quad epilogue, the columns (class, c) of the 4 pixel classes) and add to the global sums
-        const float* part = reinterpret_cast<const float*>(smem + CL_STAGES * CL_STAGE_BYTES + 256);
+        const float* part = reinterpret_cast<const float*>(smem_ctl + 256);
         for (int i = threadIdx.x; i < 2 * p.stat_c; i += CL_THREADS) {
             double v = 0.0;
             for (int n = i >> 1; n < p.gemm_n; n += p.stat_c)
@@ -787,6 +794,11 @@ static int cl_pick_n_tile(int n, int granule) {
     return t;
 }
 
+static void cl_set_ring(ConvClParams& p) {
+    p.stage_bytes = static_cast<int>(align_up(static_cast<size_t>(CL_A_BYTES) + static_cast<size_t>(p.n_tile) * 128, 1024));
+    p.stages = std::min(CL_MAX_STAGES, CL_RING_BYTES / p.stage_bytes);
+}
+
 // Workspace of the deterministic split-K paths: [CL_WS_COUNTERS x u32 tile counters (zero on entry, self-resetting)][fp32 partial tiles].
 constexpr size_t CL_WS_COUNTERS = 4096, CL_WS_HEADER = CL_WS_COUNTERS * sizeof(unsigned);
 
@@ -814,14 +826,15 @@ static int make_tmap_im2col(const pgv_handle* h, CUtensorMap* out, const float* 
     return 0;
 }
 
-// Split count of a GEMM-mode launch with the workspace: minimises (waves of CTAs) x (k-blocks per item + fixed cost per item).
+// Split count of a GEMM-mode launch with the workspace: minimises (waves of CTAs) x (cost of one item), in k-block units (~0.3 us):
+// every item pays ~8 for pipeline fill + epilogue; a split item additionally ~6 for parking its partial tile, and the CTA that
+// finishes the tile ~4 per split for reading them back (measured: 60 tiles x 128 k-blocks gain 25 % from 2 splits, 88 x 64 lose).
 static int cl_pick_splits(int tiles, int kb_total, int sm_count, int max_splits) {
-    const int overhead = 8;                              // epilogue + pipeline fill of one item, in k-block units
     int best = 1;
-    long long best_cost = static_cast<long long>(ceil_div(tiles, sm_count)) * (kb_total + overhead);
-    for (int sp = 2; sp <= max_splits && sp * 4 <= kb_total; ++sp) {
+    long long best_cost = static_cast<long long>(ceil_div(tiles, sm_count)) * (kb_total + 8);
+    for (int sp = 2; sp <= max_splits && sp * 8 <= kb_total; ++sp) {
         const int kbs = ceil_div(kb_total, sp), eff = ceil_div(kb_total, kbs);
-        const long long cost = static_cast<long long>(ceil_div(tiles * eff, sm_count)) * (kbs + overhead + eff / 2);
+        const long long cost = static_cast<long long>(ceil_div(tiles * eff, sm_count)) * (kbs + 8 + 6 + 4 * eff);
         if (cost * 10 < best_cost * 9) { best_cost = cost; best = eff; }
     }
     return best;
@@ -853,6 +866,7 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     p.slope = slope; p.round_out = round_out;
     p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1);
     p.a_sub = 1; p.a_sbo = 1024; p.a_layout = 2;
+    cl_set_ring(p);
     // ---- A operand: TMA where the geometry allows it
     const bool one_by_one = KH == 1 && KW == 1 && stride == 1 && pad == 0 && H == Hg && W == Wg;
     if (g_conv_a_mode != 0) {
@@ -911,20 +925,33 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     return launch_conv_cl<CL_GEMM>(h, p, stream);
 }
 
-// Sums the split-K partials of a weight gradient in split order and writes it in its final layout.
+// Sums the split-K partials of a weight gradient and writes it in its final layout.  Block = 32 consecutive elements x 8 split lanes:
+// lane l adds the partials of splits l, l + 8, ... in order, then the 8 lane sums are added in lane order - the same order in every
+// run, so the result is reproducible bit for bit.
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ out, int m_pad, int m_valid, int N,
                                                            int n_tile, int n_tiles, int splits, int ldo, int cin, int taps) {
+    __shared__ float part[8][33];
+    const int ex = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const long long total = static_cast<long long>(m_pad) * N;
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+    const size_t tile_elems = static_cast<size_t>(n_tile) * CL_BLOCK_M;
+    for (long long base = blockIdx.x * 32LL; base < total; base += 32LL * gridDim.x) {
+        const long long i = base + ex;                       // m_pad is a multiple of 128: the 32 elements of a block share n and the tile
         const int m = static_cast<int>(i % m_pad), n = static_cast<int>(i / m_pad);
-        if (m >= m_valid) continue;
         const int tm = m / CL_BLOCK_M, row = m % CL_BLOCK_M, tn = n / n_tile, col = n % n_tile;
-        const size_t tile_elems = static_cast<size_t>(n_tile) * CL_BLOCK_M;
         const float* src = ws + (static_cast<size_t>(tm) * n_tiles + tn) * splits * tile_elems + static_cast<size_t>(col) * CL_BLOCK_M + row;
         float acc = 0.0f;
-        for (int sp = 0; sp < splits; ++sp) acc += __ldcg(src + sp * tile_elems);
-        const long long dst = taps > 0 ? (static_cast<long long>(m % cin) * taps + m / cin) : m;
-        out[dst + static_cast<long long>(n) * ldo] = acc;
+        if (i < total)
+            for (int sp = sl; sp < splits; sp += 8) acc += __ldcg(src + sp * tile_elems);
+        part[sl][ex] = acc;
+        __syncthreads();
+        if (sl == 0 && i < total && m < m_valid) {
+            float v = part[0][ex];
+#pragma unroll
+            for (int l = 1; l < 8; ++l) v += part[l][ex];
+            const long long dst = taps > 0 ? (static_cast<long long>(m % cin) * taps + m / cin) : m;
+            out[dst + static_cast<long long>(n) * ldo] = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -1011,6 +1038,7 @@ static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, co
     p.n_tile = cl_pick_n_tile(Cout, 32); p.n_tiles = ceil_div(Cout, p.n_tile);
     if (p.n_tile != 32 && p.n_tile != 64 && p.n_tile != 128) { p.n_tile = p.n_tile <= 64 ? 64 : 128; p.n_tiles = ceil_div(Cout, p.n_tile); }
     p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
+    cl_set_ring(p);
     p.bblocks = ceil_div(B, 32);
     p.kb_total = Ho * Wo * p.bblocks;
     const int tiles = p.m_tiles * p.n_tiles;
@@ -1031,7 +1059,7 @@ static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, co
         p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + CL_WS_HEADER);
         if (int rc = launch_conv_cl<CL_WGRAD>(h, p, stream)) return rc;
         const long long total = static_cast<long long>(p.m_tiles) * CL_BLOCK_M * Cout;
-        const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+        const int grid = static_cast<int>(std::min<long long>((total + 31) / 32, 148LL * 16));
         wgrad_finish_kernel<<<grid, 256, 0, stream>>>(p.ws, out, p.m_tiles * CL_BLOCK_M, m_valid, Cout, p.n_tile, p.n_tiles, p.k_splits, ldo,
                                                       Cin, taps);
         PGV_LAUNCH_CHECK();

@@ -265,7 +265,7 @@ def test_split_k_through_the_workspace_is_deterministic(cin, cout, k, s, p, H, W
     finally:
         ops.deterministic = True
     for u, v in zip(a, c):
-        assert rel(u, v) < 1e-5
+        assert rel(u, v) < 2e-4                    # different summation order of the K splits only
     wd = w.double().requires_grad_()
     gw, = torch.autograd.grad(F.conv2d(x.double(), wd, None, s, p), wd, dy.double())
     assert rel(a[2], gw) < 2e-3
