@@ -372,8 +372,12 @@ PGV_API int pgv_coupling_inv_bwd(const float* dx_out, const float* dlogdet, cons
 PGV_API size_t pgv_synth_loss_workspace_bytes(int n_groups);
 PGV_API int pgv_synth_loss_fwd(const float* v_out, const float* v_in, int B, int L, const int* num_cols, const int* num_vol_col, int n_num,
                                const int* grp_start, const int* grp_len, const int* grp_vol_col, int n_grp, int normalize,
-                               float cat_loss_factor, int cat_softmax, float softmax_temperature, float* loss_out, void* workspace,
-                               pgv_stream_t stream);
+                               float cat_loss_factor, int cat_softmax, float softmax_temperature, const double* group_counts,
+                               float* loss_out, void* workspace, pgv_stream_t stream);
+/* counts[g] = rows of v_in that are useful for categorical group g (its operator is not silent).  Data-parallel training all-reduces
+ * them and passes (sum / world) as `group_counts` above, so that the mean of the per-rank losses is the loss of the gathered batch
+ * (the reference's DataParallel computes the criterion on the gathered outputs, train.py:241 / loss.py:172); NULL = this batch's own. */
+PGV_API int pgv_synth_useful_counts(const float* v_in, int B, int L, const int* grp_vol_col, int n_grp, double* counts, pgv_stream_t stream);
 PGV_API int pgv_synth_loss_bwd(const float* grad_out, const float* v_out, const float* v_in, int B, int L, const int* num_cols,
                                const int* num_vol_col, int n_num, const int* grp_start, const int* grp_len, const int* grp_vol_col, int n_grp,
                                int normalize, float cat_loss_factor, int cat_softmax, float softmax_temperature, const void* workspace,

@@ -164,8 +164,14 @@ __global__ void __launch_bounds__(256) synth_loss_fwd_kernel(const float* __rest
         }
     }
 }
-__global__ void synth_loss_finish_kernel(const double* __restrict__ ws, float* __restrict__ out, double num_scale, double cat_scale, int n_grp) {
+// group_counts (optional): useful rows per group to normalise with instead of this batch's own counts - data-parallel training passes
+// (global count) / world so that the mean over ranks equals the loss of the gathered batch (loss.py:172); they replace the counts in
+// ws, which the backward kernel reads.
+__global__ void synth_loss_finish_kernel(double* __restrict__ ws, float* __restrict__ out, double num_scale, double cat_scale, int n_grp,
+                                         const double* __restrict__ group_counts) {
     double cat = 0.0;
+    if (group_counts != nullptr)
+        for (int g = 0; g < n_grp; ++g) ws[1 + n_grp + g] = group_counts[g];
     for (int g = 0; g < n_grp; ++g) cat += ws[1 + g] / ws[1 + n_grp + g];   // 0/0 -> NaN like the reference when a group has no useful row
     out[0] = static_cast<float>(ws[0] * num_scale + cat * cat_scale);
 }
@@ -204,6 +210,18 @@ __global__ void __launch_bounds__(256) synth_loss_bwd_kernel(const float* __rest
             for (int j = lane; j < n; j += 32) d[s + j] = in[s + j] != 0.0f ? -c / o[s + j] : 0.0f;
         }
     }
+}
+
+__global__ void __launch_bounds__(128) useful_counts_kernel(const float* __restrict__ vi, int B, int L, const int* __restrict__ grp_vol,
+                                                            double* __restrict__ counts) {
+    __shared__ int red[4];
+    const int vol = grp_vol[blockIdx.x];
+    int c = 0;
+    for (int b = threadIdx.x; b < B; b += 128) c += (vol >= 0 && vi[static_cast<size_t>(b) * L + vol] < 1e-3f) ? 0 : 1;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) counts[blockIdx.x] = static_cast<double>(red[0] + red[1] + red[2] + red[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ Adam
@@ -308,8 +326,8 @@ size_t pgv_synth_loss_workspace_bytes(int n_groups) { return sizeof(double) * (1
 
 int pgv_synth_loss_fwd(const float* v_out, const float* v_in, int B, int L, const int* num_cols, const int* num_vol_col, int n_num,
                        const int* grp_start, const int* grp_len, const int* grp_vol_col, int n_grp, int normalize,
-                       float cat_loss_factor, int cat_softmax, float softmax_temperature, float* loss_out, void* workspace,
-                       pgv_stream_t stream) {
+                       float cat_loss_factor, int cat_softmax, float softmax_temperature, const double* group_counts, float* loss_out,
+                       void* workspace, pgv_stream_t stream) {
     PGV_CHECK_ARG(v_out && v_in && loss_out && workspace && B > 0 && L > 0, "pgv_synth_loss_fwd: bad argument");
     PGV_CHECK_ARG(n_num == 0 || (num_cols && num_vol_col), "pgv_synth_loss_fwd: numerical tables missing");
     PGV_CHECK_ARG(n_grp == 0 || (grp_start && grp_len && grp_vol_col), "pgv_synth_loss_fwd: categorical tables missing");
@@ -322,7 +340,7 @@ int pgv_synth_loss_fwd(const float* v_out, const float* v_in, int B, int L, cons
     // numerical: MSELoss(mean) over [B, n_num] when normalised, else L2Loss (sum / B)          loss.py:105-108, 136
     const double num_scale = n_num > 0 ? (normalize ? 1.0 / (static_cast<double>(B) * n_num) : 1.0 / B) : 0.0;
     const double cat_scale = n_grp > 0 ? cat_loss_factor / (normalize ? n_grp : 1) : 0.0;    // loss.py:180-183
-    synth_loss_finish_kernel<<<1, 1, 0, s>>>(ws, loss_out, num_scale, cat_scale, n_grp);
+    synth_loss_finish_kernel<<<1, 1, 0, s>>>(ws, loss_out, num_scale, cat_scale, n_grp, group_counts);
     PGV_LAUNCH_CHECK();
     return 0;
 }
@@ -338,6 +356,14 @@ int pgv_synth_loss_bwd(const float* grad_out, const float* v_out, const float* v
     synth_loss_bwd_kernel<<<ceil_div(B, 8), 256, 0, PGV_STREAM(stream)>>>(grad_out, v_out, v_in, t, static_cast<const double*>(workspace), d_v_out,
                                                                          static_cast<float>(2.0 * num_scale), static_cast<float>(cat_scale),
                                                                          1.0f / softmax_temperature, cat_softmax, B, L);
+    PGV_LAUNCH_CHECK();
+    return 0;
+}
+
+/* counts[g] = rows of v_in whose operator-volume column does not silence categorical group g (data/preset.py:264-281) */
+int pgv_synth_useful_counts(const float* v_in, int B, int L, const int* grp_vol_col, int n_grp, double* counts, pgv_stream_t stream) {
+    PGV_CHECK_ARG(v_in && grp_vol_col && counts && B > 0 && L > 0 && n_grp > 0, "pgv_synth_useful_counts: bad argument");
+    useful_counts_kernel<<<n_grp, 128, 0, PGV_STREAM(stream)>>>(v_in, B, L, grp_vol_col, counts);
     PGV_LAUNCH_CHECK();
     return 0;
 }

@@ -99,12 +99,12 @@ def flow_latent_loss(z_0_mu_logvar, z_0_sampled, z_K_sampled, log_abs_det_jac, n
 class _Synth:
     def prog_fwd(self, inputs, training, cfg):
         v_out, v_in = inputs[0].contiguous(), inputs[1].contiguous()
-        tables, normalize, factor, cat_softmax, temp = cfg
-        out, ws = ops.synth_loss_fwd(v_out, v_in, tables, normalize, factor, cat_softmax, temp)
+        tables, normalize, factor, cat_softmax, temp, counts = cfg
+        out, ws = ops.synth_loss_fwd(v_out, v_in, tables, normalize, factor, cat_softmax, temp, counts)
         return out.view(()), (v_out, v_in, ws, cfg)
 
     def prog_bwd(self, dout, ctx, grads, needs):
-        v_out, v_in, ws, (tables, normalize, factor, cat_softmax, temp) = ctx
+        v_out, v_in, ws, (tables, normalize, factor, cat_softmax, temp, _) = ctx
         return ops.synth_loss_bwd(dout.reshape(1), v_out, v_in, tables, normalize, factor, cat_softmax, temp, ws), None
 
 
@@ -137,9 +137,14 @@ class SynthParamsLoss:
         self.cat_indexes = self.idx_helper.get_categorical_learnable_indexes()
         self._tables = _tables_for(idx_helper)
 
-    def __call__(self, u_out: torch.Tensor, u_in: torch.Tensor):
-        cfg = (self._tables, self.normalize_losses, self.cat_loss_factor, self.cat_softmax, self.cat_softmax_t)
+    def __call__(self, u_out: torch.Tensor, u_in: torch.Tensor, group_counts=None):
+        """group_counts (extension, fp64 [n_groups] device tensor): useful-row counts to normalise the categorical groups with instead
+        of this batch's own - see TrainStep (data-parallel shards) and pgv.h."""
+        cfg = (self._tables, self.normalize_losses, self.cat_loss_factor, self.cat_softmax, self.cat_softmax_t, group_counts)
         return run_program(_SYNTH, (u_out, u_in), [], True, cfg)
+
+    def useful_counts(self, u_in):
+        return ops.synth_useful_counts(u_in, self._tables)
 
 
 class QuantizedNumericalParamsLoss:
@@ -238,21 +243,34 @@ def _tables_for(idx_helper):
 
 
 class _Total:
-    """recons + beta * latent + controls (train.py:228) with beta read from DEVICE memory, so that the beta warm-up
-    schedule (train.py:122-124) reaches a captured CUDA graph."""
+    """recons + beta * latent + controls [+ 0.1 * beta * flow_input_dkl] (train.py:227, 236-246) with beta read from DEVICE memory, so
+    that the beta warm-up schedule (train.py:122-124) reaches a captured CUDA graph."""
 
-    def prog_fwd(self, inputs, training, extra):
-        recons, lat, cont, beta = (t.reshape(1) for t in inputs)
-        return ops.add(ops.add(recons, ops.mul(lat, beta)), cont).view(()), beta
+    def prog_fwd(self, inputs, training, factor):
+        recons, lat, cont, beta = (t.reshape(1) for t in inputs[:4])
+        total = ops.add(ops.add(recons, ops.mul(lat, beta)), cont)
+        f = None
+        if len(inputs) > 4:
+            f = torch.full((1,), factor, dtype=torch.float32, device=beta.device)
+            total = ops.add(total, ops.mul(ops.mul(inputs[4].reshape(1), f), beta))
+        return total.view(()), (beta, f)
 
     def prog_bwd(self, dout, ctx, grads, needs):
+        beta, f = ctx
         g = dout.reshape(1)
-        return g.view(()), ops.mul(g, ctx).view(()), g.view(()), None
+        gb = ops.mul(g, beta)
+        out = (g.view(()), gb.view(()), g.view(()), None)
+        if f is not None:
+            out = out + (ops.mul(gb, f).view(()),)
+        return out
 
 
 _TOTAL = _Total()
 
 
-def total_loss(recons, latent, controls, beta_dev):
-    """beta_dev: 1-element float32 device tensor."""
-    return run_program(_TOTAL, (recons, latent, controls, beta_dev), [], True)
+def total_loss(recons, latent, controls, beta_dev, flow_input=None, flow_input_factor=0.1):
+    """beta_dev: 1-element float32 device tensor.  flow_input: un-scaled GaussianDkl of the flow input (train.py:236-239), added as
+    flow_input_factor * beta * flow_input."""
+    if flow_input is None:
+        return run_program(_TOTAL, (recons, latent, controls, beta_dev), [], True, 1.0)
+    return run_program(_TOTAL, (recons, latent, controls, beta_dev, flow_input), [], True, float(flow_input_factor))

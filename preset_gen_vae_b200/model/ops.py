@@ -754,14 +754,22 @@ def dkl_bwd(gout, ml, normalize):
     return d
 
 
-def synth_loss_fwd(v_out, v_in, tables, normalize, factor, cat_softmax, temperature):
+def synth_useful_counts(v_in, tables):
+    """fp64 [n_groups]: rows of v_in that count for each categorical group (loss.py:172's normaliser)."""
+    t = tables.on(v_in.device)
+    counts = torch.empty(tables.n_grp, dtype=torch.float64, device=v_in.device)
+    _call('pgv_synth_useful_counts', _f(v_in.contiguous()), v_in.shape[0], v_in.shape[1], _f(t['grp_vol_col']), tables.n_grp, _f(counts), _s(v_in))
+    return counts
+
+
+def synth_loss_fwd(v_out, v_in, tables, normalize, factor, cat_softmax, temperature, group_counts=None):
     t = tables.on(v_out.device)
     B, L = v_out.shape
     out = _empty(v_out, 1)
     ws = torch.empty(_lib.lib().pgv_synth_loss_workspace_bytes(tables.n_grp), dtype=torch.uint8, device=v_out.device)
     _call('pgv_synth_loss_fwd', _f(v_out), _f(v_in), B, L, _f(t['num_cols']), _f(t['num_vol_col']), tables.n_num, _f(t['grp_start']),
           _f(t['grp_len']), _f(t['grp_vol_col']), tables.n_grp, int(normalize), float(factor), int(cat_softmax), float(temperature),
-          _f(out), _f(ws), _s(v_out), n=3)
+          _f(group_counts), _f(out), _f(ws), _s(v_out), n=3)
     return out, ws
 
 

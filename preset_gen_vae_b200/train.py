@@ -18,15 +18,40 @@ from .model import build, loss as ploss, ops
 from .utils import audio as paudio
 
 
+class ModelConvergenceError(ValueError):
+    """utils/exception.py:9-10 of the reference."""
+
+
+# layout of TrainStep.scalars (device, fp32): the step's un-weighted losses, the two monitoring metrics of train.py:232-233, the flow-input
+# regulariser of train.py:236-239 (0 unless latent_flow_input_regularization == 'dkl') and the NaN bit mask of train.py:245
+SCALAR_NAMES = ('recons', 'latent', 'controls', 'controls_qloss', 'controls_accuracy', 'flow_input', 'nan_mask')
+
+
+def check_nan_mask(mask, step=None):
+    """utils/exception.py:13-22: raises ModelConvergenceError naming the first NaN loss tensor."""
+    mask = int(mask)
+    if mask:
+        names = ('recons_loss', 'lat_loss', 'flow_input_loss', 'cont_loss')
+        bad = [names[i] for i in range(4) if mask >> i & 1]
+        raise ModelConvergenceError("Step {}: {} contain(s) a nan item".format(step, ', '.join(bad)))
+
+
 class _HostLosses:
-    """Pending device -> host copy of (recons, latent, controls); see TrainStep.losses_to_host_async."""
+    """Pending device -> host copy of a step's scalars; see TrainStep.losses_to_host_async."""
 
-    def __init__(self, buf, event):
-        self._buf, self._event = buf, event
+    def __init__(self, buf, event, step):
+        self._buf, self._event, self._step = buf, event, step
 
-    def get(self):
+    def get(self, check_nan=True):
+        """(recons, latent, controls) of that step; raises ModelConvergenceError if one of its loss terms was NaN (train.py:245)."""
         self._event.synchronize()
-        return self._buf.clone()
+        if check_nan:
+            check_nan_mask(self._buf[6].item(), self._step)
+        return self._buf[:3].clone()
+
+    def scalars(self):
+        self._event.synchronize()
+        return {k: float(v) for k, v in zip(SCALAR_NAMES, self._buf.tolist())}
 
 
 class TrainStep:
@@ -45,6 +70,20 @@ class TrainStep:
         with torch.cuda.device(self.device):
             self.model = build.build_extended_ae_model(model_config, train_config, idx_helper)[3].to(self.device)
         self.model.train()
+        # ... but independent noise (eps, dropout masks) per rank, like the per-device generators of the reference's DataParallel replicas
+        self.rank = 0 if process_group is None else torch.distributed.get_rank(process_group)
+        with torch.cuda.device(self.device):
+            torch.cuda.manual_seed(seed * 1000 + self.rank)
+        if not self.model.is_flow_based_latent_space:
+            raise NotImplementedError("TrainStep drives FlowVAE models (BasicVAE cannot be reached through ExtendedAE, SURVEY.md 9.10)")
+        reg = train_config.latent_flow_input_regularization.lower()
+        if reg not in ('bn', 'dkl', 'none'):
+            raise NotImplementedError("latent_flow_input_regularization = %r" % train_config.latent_flow_input_regularization)
+        self.flow_input_dkl = ploss.GaussianDkl(normalize=train_config.normalize_losses) if reg == 'dkl' else None     # train.py:128, 236-239
+        if not model_config.forward_controls_loss:
+            raise NotImplementedError("TrainStep implements the forward controls loss (config default); FlowParamsLoss (model/loss.py) is "
+                                      "available as a criterion for custom loops")
+        self.metrics_criterion = ploss.PresetMetrics(idx_helper)                                                   # train.py:121-124
         # decoder branch on a side stream, concurrent with the regression-flow branch (both only depend on z_K)
         self._side = torch.cuda.Stream(device=self.device) if overlap_branches else None
         self.frontend = paudio.build_spectrogram(model_config, device=self.device)
@@ -71,6 +110,15 @@ class TrainStep:
         self._graph = None
         self._static = None
         self.losses = None
+        self.scalars = None
+        self._nan_mask = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # Data parallel: SynthParamsLoss normalises every categorical group by its number of useful rows in the batch (loss.py:172) and the
+        # reference evaluates it on the GATHERED batch.  The counts only depend on the targets: each step all-reduces the 54 counts
+        # before the (captured) step and the criterion divides by (global count / world), so the mean of the per-rank losses - and of
+        # their gradients - is the gathered-batch value.
+        self._group_counts = None
+        if self.world > 1:
+            self._group_counts = torch.zeros(self.controls_criterion._tables.n_grp, dtype=torch.float64, device=self.device)
 
     # ------------------------------------------------------------------ flat parameter / gradient / Adam-state buffers
     def _flatten_parameters(self):
@@ -136,19 +184,26 @@ class TrainStep:
         finally:
             self.model.ae_model.decoder_stream = None
         v_out = self.model.reg_model(zk)
-        cont = self.controls_criterion(v_out, v_in)
+        with torch.no_grad():                        # monitoring metrics, before the criterion like train.py:232-233
+            metrics = self.metrics_criterion(v_out, v_in)
+        cont = self.controls_criterion(v_out, v_in, group_counts=self._group_counts)
         lat = self.model.latent_loss(z0_ml, z0, zk, logdet)
+        flow_in = self.flow_input_dkl(z0_ml[:, 0, :], z0_ml[:, 1, :], packed=z0_ml) if self.flow_input_dkl is not None else None
         if self._side is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._side)
         recons = self.recons_criterion(x_out, x_in)
-        total = ploss.total_loss(recons, lat, cont, self._hyper_dev[4:5])
+        total = ploss.total_loss(recons, lat, cont, self._hyper_dev[4:5], flow_in, 0.1)
+        self._nan_mask.zero_()
+        ops.nan_flags_(self._nan_mask, recons, lat, flow_in if flow_in is not None else recons, cont)               # train.py:245
         for p in self.params:
             p.grad = None
         total.backward()
         self._pack_grads(1.0)
         if with_optimizer:
             self._adam()
-        return torch.stack([recons.detach(), lat.detach(), cont.detach()])
+        zero = torch.zeros((), device=self.device)
+        return torch.stack([recons.detach(), lat.detach(), cont.detach(), metrics[0], metrics[1],
+                            flow_in.detach() if flow_in is not None else zero, self._nan_mask[0].float()])
 
     def _adam(self):
         tc = self.tc
@@ -188,8 +243,11 @@ class TrainStep:
         Returns a device tensor (recons, latent, controls) of this rank's un-weighted losses."""
         self._refresh_hyper()
         fused_opt = self.world == 1
+        if self._group_counts is not None:
+            counts = parallel.global_useful_counts(self.controls_criterion.useful_counts(v_in), self.pg)
+            self._group_counts.copy_(counts / self.world)
         if not self.use_graph:
-            losses = self._device_step(audio, v_in, sample_info, with_optimizer=fused_opt)
+            scalars = self._device_step(audio, v_in, sample_info, with_optimizer=fused_opt)
         else:
             if self._graph is None:
                 self._capture(audio, v_in, sample_info, fused_opt)
@@ -197,12 +255,13 @@ class TrainStep:
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
             self._graph.replay()
-            losses = self._static[3]
+            scalars = self._static[3].clone()          # the graph's output buffer is overwritten by the next replay
         if not fused_opt:
             self._allreduce(overlapped=self.use_graph and self._fc_ready is not None)
             self._adam()
-        self.losses = losses
-        return losses
+        self.scalars = scalars                         # SCALAR_NAMES
+        self.losses = scalars[:3]
+        return self.losses
 
     # ------------------------------------------------------------------ host-fed steps with input prefetch
     def prefetch(self, audio_host, v_in_host, sample_info_host):
@@ -242,16 +301,17 @@ class TrainStep:
         """Starts the device -> host copy of a step's loss triple (default: the last step's) into pinned memory on the compute
         stream and returns a handle; `handle.get()` blocks only until THAT copy has finished, so a training loop can log the
         losses of step i while step i+1 is already running instead of draining the GPU every step."""
-        losses = self.losses if losses is None else losses
+        scalars = self.scalars if losses is None else losses
         if getattr(self, '_loss_ring', None) is None:
-            self._loss_ring = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_ring = [torch.zeros(len(SCALAR_NAMES), dtype=torch.float32).pin_memory() for _ in range(4)]
             self._loss_ring_pos = 0
         buf = self._loss_ring[self._loss_ring_pos % len(self._loss_ring)]
         self._loss_ring_pos += 1
-        buf.copy_(losses, non_blocking=True)
+        buf.zero_()
+        buf[:scalars.numel()].copy_(scalars, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        return _HostLosses(buf, ev)
+        return _HostLosses(buf, ev, self.step_count)
 
     def _capture(self, audio, v_in, sample_info, with_optimizer):
         static_in = (audio.clone(), v_in.clone(), sample_info.clone())
@@ -281,17 +341,53 @@ class TrainStep:
         self._graph, self._static = graph, (*static_in, losses)
 
     @torch.no_grad()
-    def infer(self, audio):
-        """Batched inference audio -> latent -> preset parameters (eval.py:161-182, BASELINE config 5): encoder,
-        latent flow and regression flow in eval mode; the decoder is not needed for the parameters and is skipped."""
+    def infer(self, audio, sample_info=None, full_presets=False):
+        """Batched inference audio -> latent -> preset parameters (eval.py:161-182, BASELINE config 5): front end, encoder (+ MIDI
+        pitch / velocity concatenation when the model has it, VAE.py:155-165), latent flow and regression flow in eval mode; the decoder
+        is not needed for the parameters and is skipped.  full_presets: also run the learnable -> full VST preset conversion
+        (data/preset.py:350-369) on the device and return [B, 155]."""
         was_training = self.model.training
         self.model.eval()
-        B, C, L = audio.shape
-        x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
-        x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
-        from .model.VAE import reparametrize
-        z0_ml = self.model.ae_model.encoder(x_in)
-        zk, _ = self.model.ae_model.flow_transform(reparametrize(z0_ml, None))
-        v_out = self.model.reg_model(zk)
-        self.model.train(was_training)
-        return v_out
+        try:
+            B, C, L = audio.shape
+            x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
+            x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
+            ae = self.model.ae_model
+            decoder, ae.decoder = ae.decoder, _SkipDecoder()
+            try:
+                _, _, zk, _, _ = ae(x_in, sample_info)
+            finally:
+                ae.decoder = decoder
+            v_out = self.model.reg_model(zk)
+            if full_presets:
+                from .data.preset import learnable_to_full_presets
+                defaults = getattr(self.idx_helper, 'params_default_values', None) or {}
+                return learnable_to_full_presets(self.idx_helper, v_out, defaults)
+            return v_out
+        finally:
+            self.model.train(was_training)
+
+    # ------------------------------------------------------------------ checkpointing (logs/logger.py:199-202)
+    def state_dict(self):
+        """{'ae_model_state_dict', 'optimizer_state_dict'} in the spirit of the reference's checkpoint file: the optimizer part holds the
+        flat Adam moments (one fp32 vector each, in `model.parameters()` order with 16-byte aligned slots) and the step count."""
+        return {'ae_model_state_dict': self.model.state_dict(),
+                'optimizer_state_dict': {'step': self.step_count, 'lr': self.lr, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
+                                         'slot_offsets': [int(o) for o in self._offs], 'slot_sizes': list(self._sizes)}}
+
+    def load_state_dict(self, state):
+        self.model.load_state_dict(state['ae_model_state_dict'])
+        opt = state.get('optimizer_state_dict')
+        if opt is not None:
+            if list(opt['slot_sizes']) != list(self._sizes):
+                raise ValueError("optimizer state was saved for a different parameter layout")
+            self.exp_avg.copy_(opt['exp_avg'])
+            self.exp_avg_sq.copy_(opt['exp_avg_sq'])
+            self.step_count, self.lr = int(opt['step']), float(opt['lr'])
+
+
+class _SkipDecoder(torch.nn.Module):
+    """Stand-in for the decoder during parameter inference: FlowVAE.forward runs unchanged, without the decoder's work."""
+
+    def forward(self, z, dropout_mask=None):
+        return None

@@ -6,6 +6,7 @@ import torch
 
 from preset_gen_vae_b200 import config as pcfg, synthetic
 from preset_gen_vae_b200.model import loss as ploss, ops
+from preset_gen_vae_b200 import train as train_mod
 from preset_gen_vae_b200.train import TrainStep
 
 pytestmark = pytest.mark.gpu
@@ -27,7 +28,11 @@ def test_eager_step_matches_manual_forward_backward_and_torch_adam(idx_helper):
     assert tr.flat_params.numel() >= 60372037 and all(p.data_ptr() >= tr.flat_params.data_ptr() for p in tr.params)
     ref_model = copy.deepcopy(tr.model)
     ref_model.ae_model.encoder.fc_weight_grad_out = ref_model.ae_model.decoder.fc_weight_grad_out = None   # plain autograd path
-    assert len(tr._direct) == 2 and sum(v.numel() for v in tr._direct.values()) == 1220 * 24576 + 24576 * 610
+    for m in ref_model.modules():                                                                           # (deepcopy drops the python attribute anyway)
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+            assert not hasattr(m.weight, '_pgv_grad_out')
+    # the two FC weights and all 16 convolution weights are written straight into the flat gradient buffer
+    assert len(tr._direct) == 18 and sum(v.numel() for v in tr._direct.values()) == 1220 * 24576 + 24576 * 610 + 7688592
     ref_opt = torch.optim.Adam(ref_model.parameters(), lr=tr.tc.initial_learning_rate, weight_decay=tr.tc.weight_decay,
                                betas=tr.tc.adam_betas)
     torch.manual_seed(11)
@@ -43,6 +48,11 @@ def test_eager_step_matches_manual_forward_backward_and_torch_adam(idx_helper):
     con = ploss.SynthParamsLoss(idx_helper, True, cat_bce=False, cat_softmax=True, cat_softmax_t=0.2)(v_out, v_in)
     (rec + tr.beta * lat + con).backward()
     got = losses.tolist()
+    # monitoring metrics and NaN mask of the step (train.py:232-233, 245) ride along in tr.scalars
+    sc = dict(zip(train_mod.SCALAR_NAMES, tr.scalars.tolist()))
+    assert abs(sc['controls_qloss'] - ploss.QuantizedNumericalParamsLoss(idx_helper)(v_out, v_in).item()) < 1e-5
+    assert abs(sc['controls_accuracy'] - ploss.CategoricalParamsAccuracy(idx_helper)(v_out, v_in).item()) < 0.5
+    assert sc['nan_mask'] == 0.0 and sc['flow_input'] == 0.0
     for a, b in zip(got, (rec.item(), lat.item(), con.item())):
         assert abs(a - b) <= 2e-5 * abs(b) + 1e-6       # atomics in wgrad / split-K make runs non bit-identical
     # Gradients landed in the flat buffer.  Two runs of the same kernels are not bit-identical (fp32 atomics in the split-K /
@@ -135,3 +145,41 @@ def test_external_event_recorded_inside_a_graph_orders_later_stream_work():
             b.copy_(a, non_blocking=True)
         torch.cuda.synchronize()
         assert float(b[0]) == k and float(b[-1]) == k
+
+
+def test_dkl_regulariser_nan_guard_and_optimizer_state(idx_helper):
+    """latent_flow_input_regularization = 'dkl' (train.py:236-239): no BatchNorm on the encoder output (build.py:24) and
+    0.1 * beta * GaussianDkl(mu, logvar) in the loss; NaN guard (train.py:245) as a device flag surfaced by the loss read-back;
+    optimizer state save / restore."""
+    B = 4
+    m, t = pcfg.make_default(minibatch_size=B)
+    pcfg.apply_dataset_dims(m, idx_helper)
+    t.latent_flow_input_regularization = 'dkl'
+    tr = TrainStep(m, t, idx_helper, use_cuda_graph=False, seed=0)
+    assert not hasattr(tr.model.ae_model.encoder.mlp, 'lat_in_regularization') or tr.model.ae_model.encoder.out_bn is None
+    audio = synthetic.make_audio(B, 1, seed=3).cuda()
+    v_in = synthetic.make_preset_targets(idx_helper, B, seed=3).cuda()
+    info = synthetic.make_sample_info(B).cuda()
+    w0 = tr.flat_params.clone()
+    tr.step(audio, v_in, info)
+    sc = tr.losses_to_host_async().scalars()
+    assert sc['flow_input'] > 0.0 and sc['nan_mask'] == 0.0
+    # gradient of the extra term reaches the encoder: same step without it gives different encoder-FC gradients
+    g_with = tr.flat_grads.clone()
+    state = tr.state_dict()
+    assert state['optimizer_state_dict']['step'] == 1 and float(state['optimizer_state_dict']['exp_avg'].abs().sum()) > 0
+    tr2 = TrainStep(m, t, idx_helper, use_cuda_graph=False, seed=0)
+    tr2.load_state_dict(state)
+    assert tr2.step_count == 1 and torch.equal(tr2.exp_avg, tr.exp_avg) and torch.equal(tr2.flat_params, tr.flat_params)
+    assert not torch.equal(w0, tr.flat_params)
+    tr2.flow_input_dkl = None
+    torch.manual_seed(5)
+    tr2.step(audio, v_in, info)
+    tr.flat_params.copy_(tr2.flat_params)          # irrelevant for the gradient comparison below; keeps both models equal
+    assert float((g_with - tr2.flat_grads).abs().max()) > 0.0
+    # NaN guard
+    bad = audio.clone()
+    bad[0, 0, 100] = float('nan')
+    tr.step(bad, v_in, info)
+    with pytest.raises(train_mod.ModelConvergenceError):
+        tr.losses_to_host_async().get()
