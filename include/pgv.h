@@ -164,14 +164,15 @@ PGV_API int pgv_debug_set_conv_trace(void* trace_dev);
  * (encoder.py:241) and dec8 = ConvTranspose2d(8,1,5,2,2) (decoder.py:218), which are HBM-bound (8 flop/byte).  Conv-view
  * geometry: x [B,1,H,W], y [B,C<=8,Ho,Wo], w [C,1,5,5], stride 2, pad 2.  _dgrad is the transposed convolution and
  * clamps its result to [clamp_lo, clamp_hi] (the decoder's Hardtanh; pass -INF/+INF for none).  channels_last != 0: the
- * C-channel tensor (y / dy) is stored [B, Ho, Wo, C] instead of [B, C, Ho, Wo]; round_out rounds y to TF32 (nearest). */
+ * C-channel tensor (y / dy) is stored [B, Ho, Wo, C] instead of [B, C, Ho, Wo]; round_out rounds y to TF32 (nearest).
+ * _wgrad: with a workspace of >= 592 x 200 floats the per-block partial sums are combined in a fixed order; without, fp32 atomics. */
 PGV_API int pgv_conv5x5s2_c1_supported(int Cin, int Cout, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo);
 PGV_API int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int C, int H, int W, int Ho, int Wo,
                                  float lrelu_slope, int channels_last, int round_out, pgv_stream_t stream);
 PGV_API int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, float* x, int B, int C, int H, int W, int Ho, int Wo,
                                    float clamp_lo, float clamp_hi, int channels_last, pgv_stream_t stream);
 PGV_API int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo,
-                                   int channels_last, pgv_stream_t stream);
+                                   int channels_last, void* ws, size_t ws_bytes, pgv_stream_t stream);
 /* ---------------------------------------------------------------------------------------------------------------------
  * Channels-last (NHWC) convolution path: the default 'tf32' route of the Conv2D / TConv2D blocks (model/layer.py:10-46,
  * encoder.py:233-259, decoder.py:190-221).  Activations are [B, H, W, C]; the reduction index is (kh, kw, c), so every

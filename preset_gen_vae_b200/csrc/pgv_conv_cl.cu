@@ -395,7 +395,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     } else if (warp == TMA_WARP) {
         // ================================================================== weights (GEMM mode): one TMA box per k-block
         if (MODE == CL_GEMM) {
-            const uint32_t tx_bytes = static_cast<uint32_t>(p.n_tile) * 128u + (p.a_mode != 0 ? static_cast<uint32_t>(CL_A_BYTES) : 0u);
+            // (a_mode 4 is a measurement aid: no A loads at all, the MMAs multiply whatever the stage holds)
+            const uint32_t tx_bytes = static_cast<uint32_t>(p.n_tile) * 128u + ((p.a_mode == 1 || p.a_mode == 2) ? static_cast<uint32_t>(CL_A_BYTES) : 0u);
+            int trace_n = 0;
             if (lane == 0) { tma_prefetch_desc(&p.tmap_b); if (p.a_mode != 0) tma_prefetch_desc(&p.tmap_a); }
             const uint32_t span = static_cast<uint32_t>(p.KW) * p.C;
             const uint32_t sub_bytes = CL_A_BYTES / (p.a_sub > 0 ? p.a_sub : 1);
@@ -413,7 +415,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     p.fd_span.divmod(static_cast<uint32_t>(wi.kb0) * CL_BLOCK_K, kh, rem);           // k = (kh, rem = kw * C + c)
                 }
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+                    const long long tr_a = (p.trace && p.a_mode != 0) ? clock64() : 0;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
+                    const long long tr_b = (p.trace && p.a_mode != 0) ? clock64() : 0;
                     if (elect_one()) {
                         uint8_t* st = smem + stage * CL_STAGE_BYTES;
                         mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
@@ -428,6 +432,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                         }
                     }
                     __syncwarp();
+                    if (p.trace && p.a_mode != 0 && lane == 0) cl_trace(p, 0, trace_n, tr_a, tr_b, clock64(), kb);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
                     rem += CL_BLOCK_K;
                     if (rem >= span) { rem -= span; ++kh; }
@@ -869,7 +874,9 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     cl_set_ring(p);
     // ---- A operand: TMA where the geometry allows it
     const bool one_by_one = KH == 1 && KW == 1 && stride == 1 && pad == 0 && H == Hg && W == Wg;
-    if (g_conv_a_mode != 0) {
+    if (g_conv_a_mode == -2) {
+        p.a_mode = 4;
+    } else if (g_conv_a_mode != 0) {
         if (one_by_one) {
             const uint64_t ad[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(m)}, as[1] = {static_cast<uint64_t>(C) * 4};
             const uint32_t abox[2] = {CL_BLOCK_K, CL_BLOCK_M};
@@ -928,6 +935,25 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
 // Sums the split-K partials of a weight gradient and writes it in its final layout.  Block = 32 consecutive elements x 8 split lanes:
 // lane l adds the partials of splits l, l + 8, ... in order, then the 8 lane sums are added in lane order - the same order in every
 // run, so the result is reproducible bit for bit.
+// Few splits (the deep layers: 2-16 partial tiles of up to 2 M elements): one thread per element, splits added in order.
+__global__ void __launch_bounds__(256) wgrad_finish_few_kernel(const float* __restrict__ ws, float* __restrict__ out, int m_pad, int m_valid, int N,
+                                                               int n_tile, int n_tiles, int splits, int ldo, int cin, int taps) {
+    const long long total = static_cast<long long>(m_pad) * N;
+    const size_t tile_elems = static_cast<size_t>(n_tile) * CL_BLOCK_M;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+        const int m = static_cast<int>(i % m_pad), n = static_cast<int>(i / m_pad);
+        if (m >= m_valid) continue;
+        const int tm = m / CL_BLOCK_M, row = m % CL_BLOCK_M, tn = n / n_tile, col = n % n_tile;
+        const float* src = ws + (static_cast<size_t>(tm) * n_tiles + tn) * splits * tile_elems + static_cast<size_t>(col) * CL_BLOCK_M + row;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int sp = 0; sp < splits; ++sp) acc += __ldcg(src + sp * tile_elems);
+        const long long dst = taps > 0 ? (static_cast<long long>(m % cin) * taps + m / cin) : m;
+        out[dst + static_cast<long long>(n) * ldo] = acc;
+    }
+}
+
+// Many splits (the thin layers: one or two tiles, ~300 partials each):
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ out, int m_pad, int m_valid, int N,
                                                            int n_tile, int n_tiles, int splits, int ldo, int cin, int taps) {
     __shared__ float part[8][33];
@@ -939,9 +965,16 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
         const int m = static_cast<int>(i % m_pad), n = static_cast<int>(i / m_pad);
         const int tm = m / CL_BLOCK_M, row = m % CL_BLOCK_M, tn = n / n_tile, col = n % n_tile;
         const float* src = ws + (static_cast<size_t>(tm) * n_tiles + tn) * splits * tile_elems + static_cast<size_t>(col) * CL_BLOCK_M + row;
-        float acc = 0.0f;
-        if (i < total)
-            for (int sp = sl; sp < splits; sp += 8) acc += __ldcg(src + sp * tile_elems);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;      // four independent chains keep the loads in flight; combined in a fixed order
+        if (i < total) {
+            int sp = sl;
+            for (; sp + 24 < splits; sp += 32) {
+                a0 += __ldcg(src + sp * tile_elems); a1 += __ldcg(src + (sp + 8) * tile_elems);
+                a2 += __ldcg(src + (sp + 16) * tile_elems); a3 += __ldcg(src + (sp + 24) * tile_elems);
+            }
+            for (; sp < splits; sp += 8) a0 += __ldcg(src + sp * tile_elems);
+        }
+        const float acc = (a0 + a1) + (a2 + a3);
         part[sl][ex] = acc;
         __syncthreads();
         if (sl == 0 && i < total && m < m_valid) {
@@ -1059,9 +1092,15 @@ static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, co
         p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + CL_WS_HEADER);
         if (int rc = launch_conv_cl<CL_WGRAD>(h, p, stream)) return rc;
         const long long total = static_cast<long long>(p.m_tiles) * CL_BLOCK_M * Cout;
-        const int grid = static_cast<int>(std::min<long long>((total + 31) / 32, 148LL * 16));
-        wgrad_finish_kernel<<<grid, 256, 0, stream>>>(p.ws, out, p.m_tiles * CL_BLOCK_M, m_valid, Cout, p.n_tile, p.n_tiles, p.k_splits, ldo,
-                                                      Cin, taps);
+        if (p.k_splits <= 16) {
+            const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+            wgrad_finish_few_kernel<<<grid, 256, 0, stream>>>(p.ws, out, p.m_tiles * CL_BLOCK_M, m_valid, Cout, p.n_tile, p.n_tiles, p.k_splits,
+                                                              ldo, Cin, taps);
+        } else {
+            const int grid = static_cast<int>(std::min<long long>((total + 31) / 32, 148LL * 16));
+            wgrad_finish_kernel<<<grid, 256, 0, stream>>>(p.ws, out, p.m_tiles * CL_BLOCK_M, m_valid, Cout, p.n_tile, p.n_tiles, p.k_splits, ldo,
+                                                          Cin, taps);
+        }
         PGV_LAUNCH_CHECK();
         return 0;
     }

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float* __res
 constexpr int TW_TH = 8, TW_TW = 32, TW_PH = 2 * TW_TH + 3, TW_PW = 2 * TW_TW + 3;
 __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                               float* __restrict__ dw, int B, int C, int H, int W, int Ho, int Wo,
-                                                              int tiles_per_block, int channels_last) {
+                                                              int tiles_per_block, int channels_last, float* __restrict__ partial) {
     __shared__ float sdy[THIN_MAXC][TW_TH * TW_TW];
     __shared__ float sx[TW_PH * TW_PW];
     const int tiles_h = (Ho + TW_TH - 1) / TW_TH, tiles_w = (Wo + TW_TW - 1) / TW_TW, tiles_img = tiles_h * tiles_w;
@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __res
                 for (int qx = 0; qx < TW_TW; ++qx) acc = fmaf(sdy[c][py * TW_TW + qx], px[2 * py * TW_PW + 2 * qx], acc);
         }
     }
-    if (worker) atomicAdd(dw + c * THIN_TAPS + tap, acc);
+    if (worker) {
+        if (partial != nullptr) partial[static_cast<size_t>(blockIdx.x) * (THIN_MAXC * THIN_TAPS) + c * THIN_TAPS + tap] = acc;
+        else atomicAdd(dw + c * THIN_TAPS + tap, acc);
+    }
 }
 
 // Channels-last, C == 8 variant: lane = tap (25 of 32 lanes), 8 channel accumulators per lane, warp w walks row w of the 8 x 32
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __res
 // 0.4 shared-memory reads per FMA instead of 2, which is what bounds the generic kernel above.
 __global__ void __launch_bounds__(256) thin_conv_wgrad_cl8_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                   float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
-                                                                  int tiles_per_block) {
+                                                                  int tiles_per_block, float* __restrict__ partial) {
     __shared__ float4 sdy[TW_TH * TW_TW * 2];            // [pixel][2] : 8 channels
     __shared__ float sx[TW_PH * TW_PW];
     __shared__ float sred[8][THIN_TAPS][THIN_MAXC];
@@ -298,7 +301,25 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_cl8_kernel(const float* _
         float v = 0.0f;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) v += sred[w8][tap][c];
-        atomicAdd(dw + c * THIN_TAPS + tap, v);
+        if (partial != nullptr) partial[static_cast<size_t>(blockIdx.x) * (THIN_MAXC * THIN_TAPS) + c * THIN_TAPS + tap] = v;
+        else atomicAdd(dw + c * THIN_TAPS + tap, v);
+    }
+}
+
+// dw[i] = sum over blocks of partial[block][i], 8 lanes per output adding every 8th block in order, then combined in lane order
+__global__ void __launch_bounds__(256) thin_wgrad_finish_kernel(const float* __restrict__ partial, int blocks, int n_out, float* __restrict__ dw) {
+    __shared__ float part[8][33];
+    const int ex = threadIdx.x & 31, sl = threadIdx.x >> 5, i = blockIdx.x * 32 + ex;
+    float acc = 0.0f;
+    if (i < n_out)
+        for (int b = sl; b < blocks; b += 8) acc += __ldcg(partial + static_cast<size_t>(b) * (THIN_MAXC * THIN_TAPS) + i);
+    part[sl][ex] = acc;
+    __syncthreads();
+    if (sl == 0 && i < n_out) {
+        float v = part[0][ex];
+#pragma unroll
+        for (int l = 1; l < 8; ++l) v += part[l][ex];
+        dw[i] = v;
     }
 }
 
@@ -370,20 +391,26 @@ int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, fl
 }
 
 int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, int C, int H, int W, int Ho, int Wo, int channels_last,
-                           pgv_stream_t stream_) {
+                           void* ws, size_t ws_bytes, pgv_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PGV_CHECK_ARG(x && dy && dw, "pgv_conv5x5s2_c1_wgrad: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_wgrad: unsupported geometry");
-    PGV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C * THIN_TAPS, stream));
     const long long n_tiles = static_cast<long long>(B) * ((Ho + TW_TH - 1) / TW_TH) * ((Wo + TW_TW - 1) / TW_TW);
     int per_block = static_cast<int>((n_tiles + 148 * 4 - 1) / (148 * 4));
     if (per_block < 1) per_block = 1;
     const int grid = static_cast<int>((n_tiles + per_block - 1) / per_block);
+    // with a workspace (>= grid x 200 floats) the per-block sums are combined in a fixed order (deterministic); else fp32 atomics
+    float* partial = (ws != nullptr && ws_bytes >= static_cast<size_t>(grid) * THIN_MAXC * THIN_TAPS * sizeof(float)) ? static_cast<float*>(ws) : nullptr;
+    if (partial == nullptr) PGV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C * THIN_TAPS, stream));
     if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)
-        thin_conv_wgrad_cl8_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, H, W, Ho, Wo, per_block);
+        thin_conv_wgrad_cl8_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, H, W, Ho, Wo, per_block, partial);
     else
-        thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block, channels_last);
+        thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block, channels_last, partial);
     PGV_LAUNCH_CHECK();
+    if (partial != nullptr) {
+        thin_wgrad_finish_kernel<<<ceil_div(C * THIN_TAPS, 32), 256, 0, stream>>>(partial, grid, C * THIN_TAPS, dw);
+        PGV_LAUNCH_CHECK();
+    }
     return 0;
 }
 

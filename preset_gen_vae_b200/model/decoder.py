@@ -140,6 +140,8 @@ class SpectrogramDecoder(nn.Module):
             d = dout if C == 1 else dout[:, ch:ch + 1].contiguous()
             local = {}
             dparts.append(self.single_ch_cnn.bwd(d, ctxs[ch], local))
+            if C > 1:
+                ops.join_forks(dout)                       # the sums below read gradients produced on the child stream
             for k, v in local.items():
                 grads[k] = v if k not in grads else ops.add(grads[k], v)
         dh = dparts[0] if C == 1 else ops.cat_channels(dparts)
@@ -153,6 +155,7 @@ class SpectrogramDecoder(nn.Module):
         direct = getattr(self, 'fc_weight_grad_out', None)
         dz, dw, db = ops.fc_bwd(dflat, fc_ctx, lin.weight, bool(needs[0]), out=direct)
         grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
+        ops.join_forks(dout)                               # the weight gradients enqueued on the child stream (ops.forked)
         return (dz, None)[:len(needs)] if len(needs) > 1 else dz
 
     def forward(self, z_sampled, dropout_mask=None):

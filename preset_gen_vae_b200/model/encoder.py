@@ -217,12 +217,15 @@ class SpectrogramEncoder(nn.Module):
             local = {}
             for i in range(len(blocks) - 1, -1, -1):
                 d = blocks[i].bwd(d, ch_ctx[ch][i], local, need_dx or i > 0)
+            if C > 1:
+                ops.join_forks(dout)                       # the sums below read gradients produced on the child stream
             for k, v in local.items():                   # the CNN is shared: sum parameter gradients over channels
                 grads[k] = v if k not in grads else ops.add(grads[k], v)
             dxs.append(d)
         dx = None
         if need_dx:
             dx = dxs[0] if C == 1 else torch.cat(dxs, dim=1)
+        ops.join_forks(dout)                               # the weight gradients enqueued on the child stream (ops.forked)
         return (dx, None)[:len(needs)] if len(needs) > 1 else dx
 
     def _forward_cnns(self, x_spectrograms):

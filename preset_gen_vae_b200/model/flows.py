@@ -67,9 +67,11 @@ class ResidualBlock(nn.Module):
         x, m0, r0, t0, u, m1, r1, t1, mask = ctx
         bn0, bn1 = self.batch_norm_layers
         l0, l1 = self.linear_layers
-        grads[id(l1.weight)], grads[id(l1.bias)] = ops.linear_wgrad(dy, t1)
+        with ops.forked(dy, dy, t1):
+            grads[id(l1.weight)], grads[id(l1.bias)] = ops.linear_wgrad(dy, t1)
         du, grads[id(bn1.weight)], grads[id(bn1.bias)] = ops.linear_dgrad_bn_bwd(dy, l1.weight, u, bn1, m1, r1, mask=mask)
-        grads[id(l0.weight)], grads[id(l0.bias)] = ops.linear_wgrad(du, t0)
+        with ops.forked(du, du, t0):
+            grads[id(l0.weight)], grads[id(l0.bias)] = ops.linear_wgrad(du, t0)
         dx, grads[id(bn0.weight)], grads[id(bn0.bias)] = ops.linear_dgrad_bn_bwd(du, l0.weight, x, bn0, m0, r0, add_post=dy)   # + residual path
         return dx
 
@@ -92,10 +94,12 @@ class ResidualBlock(nn.Module):
         x, m0, r0, t0, u, m1, r1, t1, mask = ctx
         bn0, bn1 = self.batch_norm_layers
         l0, l1 = self.linear_layers
-        grads[id(l1.weight)], grads[id(l1.bias)] = ops.linear_wgrad(dy, t1)
+        with ops.forked(dy, dy, t1):
+            grads[id(l1.weight)], grads[id(l1.bias)] = ops.linear_wgrad(dy, t1)
         dt1 = ops.linear_dgrad(dy, l1.weight)
         du, grads[id(bn1.weight)], grads[id(bn1.bias)] = ops.bn1d_train_bwd(dt1, u, bn1, m1, r1, relu=True, mask=mask)
-        grads[id(l0.weight)], grads[id(l0.bias)] = ops.linear_wgrad(du, t0)
+        with ops.forked(du, du, t0):
+            grads[id(l0.weight)], grads[id(l0.bias)] = ops.linear_wgrad(du, t0)
         dt0 = ops.linear_dgrad(du, l0.weight)
         dx, grads[id(bn0.weight)], grads[id(bn0.bias)] = ops.bn1d_train_bwd(dt0, x, bn0, m0, r0, relu=True)
         return ops.add(dx, dy)                           # residual path
@@ -149,11 +153,13 @@ class ResidualNet(nn.Module):
 
     def bwd(self, dout, ctx, grads):
         x, ctxs, h_last, fused = ctx
-        grads[id(self.final_layer.weight)], grads[id(self.final_layer.bias)] = ops.linear_wgrad(dout, h_last)
+        with ops.forked(dout, dout, h_last):
+            grads[id(self.final_layer.weight)], grads[id(self.final_layer.bias)] = ops.linear_wgrad(dout, h_last)
         d = ops.linear_dgrad(dout, self.final_layer.weight)
         for blk, c in zip(reversed(list(self.blocks)), reversed(ctxs)):
             d = blk.bwd_fused(d, c, grads) if fused else blk.bwd(d, c, grads)
-        grads[id(self.initial_layer.weight)], grads[id(self.initial_layer.bias)] = ops.linear_wgrad(d, x)
+        with ops.forked(d, d, x):
+            grads[id(self.initial_layer.weight)], grads[id(self.initial_layer.bias)] = ops.linear_wgrad(d, x)
         return ops.linear_dgrad(d, self.initial_layer.weight)
 
 
@@ -311,6 +317,7 @@ class CompositeTransform(Transform):
                 g_sum = ops.colsum(dld.view(B, 1))
                 dy, du, db = ops.flowbn_train_bwd(dy, x_in, t, mean, var, g_sum)
                 grads[id(t.unconstrained_weight)], grads[id(t.bias)] = du, db
+        ops.join_forks(dy)                                 # the conditioners' weight gradients (ops.forked)
         return dy
 
     def forward(self, inputs, context=None, dropout_masks=None):
@@ -390,6 +397,7 @@ class _InverseProgram:
         couplings = list(self.c._transforms)
         for t, c in zip(couplings, reversed(ctxs)):          # forward ran couplings K-1 .. 0: unwind 0 .. K-1
             dx, dld = t.inv_bwd(dx, dld, c, grads)
+        ops.join_forks(dx)
         return dx
 
 

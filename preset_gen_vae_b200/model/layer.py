@@ -90,7 +90,9 @@ class _SingleBlock:
         return self.block.fwd(inputs[0].contiguous(), training)
 
     def prog_bwd(self, dout, ctx, grads, needs):
-        return self.block.bwd(dout, ctx, grads, needs[0])
+        dx = self.block.bwd(dout, ctx, grads, needs[0])
+        ops.join_forks(dout)
+        return dx
 
 
 class Conv2D(_BlockBase):
@@ -132,7 +134,8 @@ class Conv2D(_BlockBase):
         c = self.conv
         dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads)
         direct = ops.grad_out_of(c.weight)          # written in place into the flat gradient buffer: autograd gets no tensor for it
-        dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True, db=dbias, out=direct)
+        with ops.forked(x, x, dz):                   # joined by the owning module at the end of its backward
+            dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True, db=dbias, out=direct)
         grads[id(c.weight)], grads[id(c.bias)] = (None if direct is not None else dw), db
         if not need_dx:
             return None
@@ -201,9 +204,10 @@ def tconv_clamp_fusable(x, conv):
 def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None, dbias=None):
     """dz: gradient w.r.t. the transposed convolution's (pre-activation) output; dbias: its per-channel sums if already known."""
     direct = ops.grad_out_of(conv.weight)
-    dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False, out=direct)
+    with ops.forked(x, x, dz):
+        dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False, out=direct)
+        grads[id(conv.bias)] = dbias if dbias is not None else ops.channel_sum(dz)
     grads[id(conv.weight)] = None if direct is not None else dw
-    grads[id(conv.bias)] = dbias if dbias is not None else ops.channel_sum(dz)
     if not need_dx:
         return None
     return ops.conv2d_fwd(dz, conv.weight, None, conv.stride[0], conv.padding[0], -1.0, out_hw=x.shape[2:], wf=wf)

@@ -179,6 +179,61 @@ def _clws(ref):
     return ctypes.c_void_p(buf.data_ptr()), buf.numel()
 
 
+# ------------------------------------------------------------------------------------------------ weight gradients off the critical path
+# In a backward pass the weight gradient of a layer is a leaf: nothing but the optimizer waits for it, while the data gradient feeds the
+# next layer.  `forked()` enqueues the weight-gradient kernels on a child stream of the current stream (an event edge; inside a captured
+# step it becomes a graph dependency) so that they fill the SMs the HBM-bound BatchNorm / latency-bound conditioner kernels of the main
+# chain leave idle; `join_forks()` at the end of the module's backward makes the parent stream wait for them.
+use_wgrad_fork = True
+_fork_streams = {}
+_fork_keep = {}
+
+
+class forked:
+    def __init__(self, ref, *keep):
+        self.ref, self.keep, self.cm = ref, keep, None
+
+    def __enter__(self):
+        if not use_wgrad_fork:
+            return self
+        dev = self.ref.device
+        cur = torch.cuda.current_stream(dev)
+        key = (dev.index, cur.cuda_stream)
+        st = _fork_streams.get(key)
+        if st is None:
+            st = _fork_streams[key] = torch.cuda.Stream(device=dev)
+        st.wait_stream(cur)
+        # operands produced on the parent stream stay referenced until the join: the allocator must not hand their memory out again
+        # while the child stream still reads them
+        _fork_keep.setdefault(key, []).extend(self.keep)
+        self.cm = torch.cuda.stream(st)
+        self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+        return False
+
+
+def join_forks(ref):
+    dev = ref.device
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, cur.cuda_stream)
+    if key in _fork_keep:
+        cur.wait_stream(_fork_streams[key])
+        del _fork_keep[key]
+
+
+def _thin_ws(ref):
+    """Partial-sum workspace of the thin-layer weight gradient: the partial-tile area of the channels-last workspace (past its header)."""
+    ptr, n = _clws(ref)
+    if n == 0:
+        return ptr, 0
+    hdr = _lib.lib().pgv_conv_cl_workspace_bytes()
+    return ctypes.c_void_p(ptr.value + hdr), n - hdr
+
+
 def grad_out_of(param):
     """View into a flat gradient buffer registered on the parameter (TrainStep: `param._pgv_grad_out`): weight-gradient kernels that can
     write their result in the parameter's own layout store it there directly and the gradient needs no packing pass."""
@@ -302,7 +357,7 @@ def conv2d_wgrad(x, dy, w_shape, stride, pad, want_bias, db=None, out=None):
     dw = out if out is not None else _empty(x, *w_shape)
     assert tuple(dw.shape) == tuple(w_shape) and dw.is_contiguous()
     if route == 'thin':
-        _call('pgv_conv5x5s2_c1_wgrad', _f(to_nchw(x)), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, int(is_cl(dy)), _s(x), n=2,
+        _call('pgv_conv5x5s2_c1_wgrad', _f(to_nchw(x)), _f(dy), _f(dw), B, Cout, H, W, Ho, Wo, int(is_cl(dy)), *_thin_ws(x), _s(x), n=2,
               flops=flops, nbytes=4 * (x.numel() + dy.numel()))
         return dw, (db if db is not None else (channel_sum(dy) if want_bias else None))
     if route == 'cl':
@@ -583,9 +638,11 @@ def fc_bwd(dy, ctx, w, need_dx=True, out=None):
     dyr = round_copy(dy)
     dw = out if out is not None else _empty(dy, N, K)
     assert dw.shape == (N, K) and dw.is_contiguous()
-    _call('pgv_linear_cl_wgrad', _h(dy), _f(dyr), _f(xr), _f(dw), K, M, N, Kp, K, *_clws(dy), _s(dy), n=2,
-          flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    with forked(dy, dyr, xr, dw):                   # 120 MB of output, independent of the data gradient below
+        _call('pgv_linear_cl_wgrad', _h(dy), _f(dyr), _f(xr), _f(dw), K, M, N, Kp, K, *_clws(dy), _s(dy), n=2,
+              flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
     if not need_dx:
+        join_forks(dy)
         return None, dw, db
     if wr is not None:
         # dx^T [Kp, M] = W[N, Kp]^T dy^T[N, M] (reduction over N), then a small transpose back
@@ -594,10 +651,12 @@ def fc_bwd(dy, ctx, w, need_dx=True, out=None):
         _call('pgv_linear_cl_wgrad', _h(dy), _f(wr), _f(dyt), _f(dxt), M, N, Kp, M, M, *_clws(dy), _s(dy), n=2,
               flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
         _call('pgv_transpose_inner', _f(dxt), _f(dxp), 1, Kp, M, 0, _s(dy), nbytes=8 * dxp.numel())
+        join_forks(dy)
         return (dxp if Kp == K else dxp[:, :K].contiguous()), dw, db
     dx = _empty(dy, M, K)
     _call('pgv_linear_cl_dgrad', _h(dy), _f(dyr), _f(wt), _f(dx), M, N, K, *_clws(dy), _s(dy), n=2,
           flops=2 * M * N * K, nbytes=4 * (M * K + N * K + M * N))
+    join_forks(dy)
     return dx, dw, db
 
 

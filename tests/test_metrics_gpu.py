@@ -109,7 +109,8 @@ def test_flow_params_loss_and_inverse_flow_gradients(golden_dir, idx_helper):
         if r is not None and r.norm() > 1e-12:
             worst = max(worst, float((p.grad.cpu().double() - r).norm() / r.norm()))
     assert worst < 2e-3, worst
-    # eval-mode / no_grad inverse still runs without autograd, and undoes the forward map
+    # eval-mode inverse still runs without autograd, and undoes the forward map
+    mine.eval()
     with torch.no_grad():
         z = torch.randn(6, 610, device=DEV)
         y, ld = mine.ae_model.flow_transform(z)

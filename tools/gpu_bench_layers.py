@@ -13,6 +13,9 @@ ops.use_cl = not (len(sys.argv) > 2 and sys.argv[2] == 'nchw')
 if 'a0' in sys.argv:               # A operand by cp.async gathers instead of TMA (A/B)
     from preset_gen_vae_b200 import _lib
     _lib.check(_lib.lib().pgv_debug_set_conv_a_mode(0))
+if 'noa' in sys.argv:              # measurement aid: no A loads at all (results are garbage)
+    from preset_gen_vae_b200 import _lib
+    _lib.check(_lib.lib().pgv_debug_set_conv_a_mode(-2))
 if 'atomic' in sys.argv:           # round-1 split-K: fp32 atomics instead of the workspace
     ops.deterministic = False
 print('route:', 'channels-last' if ops.use_cl else 'NCHW register-staged', '| A operand:', 'cp.async' if 'a0' in sys.argv else 'TMA where possible',

@@ -27,6 +27,10 @@ def quad_case(cin, cout, H, W):
 cases = {'enc2 fwd (N=16, 4 k-blocks per tile)': fwd_case(8, 16, 129, 174), 'dec7 fwd (quad, N=32, 2 k-blocks per tile)': quad_case(8, 16, 129, 174),
          'enc3 fwd (N=32, 8 k-blocks)': fwd_case(16, 32, 65, 88), 'enc5 fwd (N=128, 32 k-blocks)': fwd_case(64, 128, 17, 23),
          'enc7 fwd (N=128, 128 k-blocks)': fwd_case(256, 512, 5, 7)}
+if 'a0' in sys.argv:
+    L.pgv_debug_set_conv_a_mode(0)
+if 'noa' in sys.argv:           # no A loads at all: what the tile period would be if the activation operand were free
+    L.pgv_debug_set_conv_a_mode(-2)
 for name, fn in cases.items():
     fn(); torch.cuda.synchronize()
     tr = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
@@ -36,7 +40,7 @@ for name, fn in cases.items():
     t = tr.view(3, 64, 8).cpu()
     t0 = int(t[0, 0, 0])
     print("==== %s   (cycles; start relative to the producer's first event)" % name)
-    for role, label in ((0, 'producer thread 0: wait_empty / issue+arrive'), (1, 'mma thread: wait_full / issue+commit'), (2, 'epilogue: wait_tfull / drain')):
+    for role, label in ((0, 'producer thread 0 (cp.async) / TMA warp: wait_empty / issue'), (1, 'mma thread: wait_full / issue+commit'), (2, 'epilogue: wait_tfull / drain')):
         print(' ' + label)
         prev = None
         for i in list(range(0, 10)) + list(range(24, 34)):
