@@ -8,6 +8,7 @@
 Workloads (BASELINE.json `configs`):
     train      (default) configs[2]: full ExtendedAE training step from audio - mel front end, conv VAE, latent flow,
                regression flow, losses, backward, Adam - C=1, per-GPU batch 160 (config.py:80); metric = samples/s
+    train_c6   configs[3]: the same step on multi-note input, 6 MIDI notes stacked as spectrogram channels (config.py:35-37)
     frontend   configs[1]: STFT + mel front end alone, 256 clips
     inference  configs[4]: audio -> latent -> preset parameters, batch 1024
 `value` is timed with inputs resident in HBM; `e2e` goes through the public API with pinned HOST buffers (H2D of
@@ -27,7 +28,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = {'train': 'train samples/sec', 'frontend': 'front-end clips/sec', 'inference': 'inference samples/sec'}
+METRIC = {'train': 'train samples/sec', 'train_c6': 'train samples/sec', 'frontend': 'front-end clips/sec', 'inference': 'inference samples/sec'}
+SIX_NOTES = ((40, 85), (50, 85), (60, 42), (60, 85), (60, 127), (70, 85))          # config.py:35 of the reference
 FRONTEND_FLOP_PER_CLIP = 820.63e6          # dense DFT (729.13 MFLOP) + dense mel (91.50 MFLOP)
 DFT_FLOP_PER_CLIP, MEL_FLOP_PER_CLIP = 729.13e6, 91.50e6
 
@@ -45,8 +47,8 @@ KERNEL_OF = {'pgv_conv_cl_fwd': 'conv_cl_kernel', 'pgv_conv_cl_dgrad': 'conv_cl_
 
 def measured_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of all launches of `kernel` in one training step, from the committed ncu
-    launch list of tools/run_train_once.py (profiles/traffic_r01.json, written by tools/summarize_launches.py); None if absent."""
-    path = os.path.join(ROOT, 'profiles', 'traffic_r01.json')
+    launch list of tools/run_train_once.py (profiles/traffic_r02.json, written by tools/summarize_launches.py); None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'traffic_r02.json')
     if not os.path.exists(path):
         return None
     rec = json.load(open(path)).get(kernel)
@@ -54,8 +56,8 @@ def measured_traffic(kernel):
 
 
 def ncu_kernel_times():
-    """{kernel: summed gpu__time_duration (us) of its launches in one training step} from profiles/traffic_r01.json, or {}."""
-    path = os.path.join(ROOT, 'profiles', 'traffic_r01.json')
+    """{kernel: summed gpu__time_duration (us) of its launches in one training step} from profiles/traffic_r02.json, or {}."""
+    path = os.path.join(ROOT, 'profiles', 'traffic_r02.json')
     if not os.path.exists(path):
         return {}
     return {k: float(v.get('us', 0.0)) for k, v in json.load(open(path)).items()}
@@ -80,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -113,7 +115,7 @@ def dist_env():
 
 
 def default_batch(workload):
-    return {'train': 160, 'frontend': 256, 'inference': 1024}[workload]
+    return {'train': 160, 'train_c6': 160, 'frontend': 256, 'inference': 1024}[workload]
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
@@ -121,12 +123,11 @@ def oracle_step_factory(workload, batch):
     """The reference algorithm on the host CPU (oracle port: nflows / librosa restated, see oracle/__init__.py).
     Returns (callable running ONE step on `batch` samples, description)."""
     from oracle import frontend as ofe, losses as oloss, model as omodel
-    from preset_gen_vae_b200 import config as pcfg, synthetic
-    from preset_gen_vae_b200.data.preset import DexedLearnableLayout
-    helper = DexedLearnableLayout().preset_indexes_helper
-    m_cfg, t_cfg = pcfg.make_default(minibatch_size=batch)
-    pcfg.apply_dataset_dims(m_cfg, helper)
-    audio = synthetic.make_audio(batch, 1, seed=0)
+    from preset_gen_vae_b200 import synthetic
+    helper, m_cfg, t_cfg = model_configs(workload, batch)
+    C = m_cfg.input_tensor_size[1]
+    audio = synthetic.make_audio(min(batch, 64), C, seed=0)
+    audio = audio.repeat((batch + audio.shape[0] - 1) // audio.shape[0], 1, 1)[:batch].contiguous()
     st = synthetic.SPEC_STATS
     if workload == 'frontend':
         def step():      # one clip at a time, as the reference DataLoader worker does (abstractbasedataset.py:124-134)
@@ -180,21 +181,43 @@ def main_reference(args):
     if rank != 0:
         return
     batch = args.batch_per_gpu or default_batch(args.workload)
-    cpu_batch = min(batch, args.cpu_batch)
+    cpu_batch = args.cpu_batch or batch                # the same per-GPU batch as our arm: same workload string, same config object
     budget = max(10.0, min(150.0, 12.0 * max(args.steps, 1)))
     cb, med = run_cpu(args.workload, cpu_batch, budget)
     line = {'impl': 'reference', 'metric': METRIC[args.workload], 'value': cb['value'], 'unit': 'samples/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.workload, cpu_batch), 'note': 'reference algorithm on the host CPU (no GPU)'},
+            'config': line_config(args.workload, cpu_batch, args.gpus, not args.no_graph),
+            'note': 'reference algorithm (oracle port) on the host CPU of rank 0: one replica of the per-GPU batch, no GPU',
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
 
 
+def model_configs(workload, batch):
+    from preset_gen_vae_b200 import config as pcfg
+    from preset_gen_vae_b200.data.preset import DexedLearnableLayout
+    helper = DexedLearnableLayout().preset_indexes_helper
+    if workload == 'train_c6':
+        m_cfg, t_cfg = pcfg.make_default(minibatch_size=batch, midi_notes=SIX_NOTES, stack_spectrograms=True)
+    else:
+        m_cfg, t_cfg = pcfg.make_default(minibatch_size=batch)
+    pcfg.apply_dataset_dims(m_cfg, helper)
+    return helper, m_cfg, t_cfg
+
+
+def line_config(workload, batch, gpus, cuda_graph):
+    """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {'workload': workload_name(workload, batch), 'global_batch': gpus * batch, 'parallelism': 'dp%d' % gpus,
+            'l2': 'per-step working set (activations + 241 MB of parameters, > 1 GB) exceeds the 126 MB L2; no flush needed',
+            'cuda_graph': bool(cuda_graph)}
+
+
 def workload_name(workload, batch):
     return {'train': 'full ExtendedAE train step from audio (mel front end + speccnn8l1_bn conv VAE + realnvp_6l300 latent flow + '
                      'flow_realnvp_6l300 regression + losses, fwd+bwd+Adam), C=1, dim_z=610, per-GPU batch %d' % batch,
+            'train_c6': 'full ExtendedAE train step from audio, 6 MIDI notes stacked as spectrogram channels (C=6: shared per-channel CNNs, '
+                        '4x4 mixer 1536->768, 67.1 M parameters), dim_z=610, per-GPU batch %d' % batch,
             'frontend': 'STFT + mel spectrogram front end alone, %d synthetic clips of 88576 samples (n_fft 1024, hop 256, 257 mel)' % batch,
             'inference': 'batched inference audio -> latent -> Dexed preset parameters, batch %d per GPU' % batch}[workload]
 
@@ -208,8 +231,8 @@ def main_ours(args):
     dev = torch.device('cuda', local_rank)
     pg = None
     if world > 1:
-        # NCCL prints its version banner to stdout when NCCL_DEBUG is set; keep stdout to the single JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/pgv_nccl_debug.%h.%p')
+        # (NCCL's debug output, if the environment asks for it, stays where the environment points it; stdout carries the JSON line only,
+        # see _guard_stdout)
         torch.distributed.init_process_group('nccl', device_id=dev)
         pg = torch.distributed.group.WORLD
     from preset_gen_vae_b200 import _lib, config as pcfg, synthetic
@@ -218,10 +241,9 @@ def main_ours(args):
     from preset_gen_vae_b200.train import TrainStep
     from preset_gen_vae_b200.utils.audio import MelSpectrogram
     B = args.batch_per_gpu or default_batch(args.workload)
-    helper = DexedLearnableLayout().preset_indexes_helper
-    m_cfg, t_cfg = pcfg.make_default(minibatch_size=B)
-    pcfg.apply_dataset_dims(m_cfg, helper)
-    audio_h = synthetic.make_audio(min(B, 64), 1, seed=rank)                 # CPU synthesis is slow: tile 64 distinct clips
+    helper, m_cfg, t_cfg = model_configs(args.workload, B)
+    C = m_cfg.input_tensor_size[1]
+    audio_h = synthetic.make_audio(min(B, 64), C, seed=rank)                 # CPU synthesis is slow: tile 64 distinct clips
     audio_h = audio_h.repeat((B + audio_h.shape[0] - 1) // audio_h.shape[0], 1, 1)[:B].contiguous().pin_memory()
     v_in_h = synthetic.make_preset_targets(helper, B, seed=rank).pin_memory()
     info_h = synthetic.make_sample_info(B).pin_memory()
@@ -242,7 +264,7 @@ def main_ours(args):
         h2d, d2h = audio_h.numel() * 4, B * 257 * 347 * 4
     else:
         trainer = TrainStep(m_cfg, t_cfg, helper, device=dev, process_group=pg, use_cuda_graph=not args.no_graph)
-        if args.workload == 'train':
+        if args.workload in ('train', 'train_c6'):
             def dev_step():
                 return trainer.step(audio, v_in, info)
 
@@ -319,7 +341,16 @@ def main_ours(args):
     if rank == 0:
         sampler.start()
     total_ms = timed(dev_step, args.steps)
+    if total_ms < 400.0:
+        # the timed region is too short for nvidia-smi's sampling period: keep the SAME step running (untimed) until the sampler has
+        # seen ~0.5 s of it, so that the clock / throttle record describes this load; every rank does the same number of steps
+        extra = int(min(5000, max(8, 500.0 / max(total_ms / args.steps, 1e-3))))
+        for _ in range(extra):
+            dev_step()
+        torch.cuda.synchronize(dev)
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None and total_ms < 400.0:
+        clocks['note'] = 'timed region %.0f ms: sampling continued over %d more untimed steps of the same workload' % (total_ms, extra)
     if launches is None:
         launches = getattr(trainer, 'launches_per_step', None) or (ops.launches - before) // max(args.steps, 1)
     ms_per_step = total_ms / args.steps
@@ -332,7 +363,7 @@ def main_ours(args):
     e2e_ms = timed(e2e_step, args.steps, e2e_fin) / args.steps
     e2e = {'value': world * B / e2e_ms * 1e3, 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
            'ms_per_step': e2e_ms}
-    if args.workload == 'train':
+    if args.workload in ('train', 'train_c6'):
         e2e['note'] = ('TrainStep.prefetch / step_prefetched: every timed step issues one pinned-host -> device copy of a full batch (the next '
                        "step's inputs, on a copy stream, overlapping the running step) and reads every step's three losses on the host (async copy to pinned "
                        "memory behind the step, fetched while the next step runs; the last step's are fetched before the region ends)")
@@ -379,11 +410,9 @@ def main_ours(args):
             for name, v in prof.items():
                 f = fam.setdefault(KERNEL_OF.get(name, name), dict(ms=0.0, flops=0, bytes=0, calls=0))
                 f['ms'] += v['ms']; f['flops'] += v['flops']; f['bytes'] += v['bytes']; f['calls'] += v['calls']
-            # Which kernel dominates the step: per-kernel device time of the committed ncu launch list of the same step when it is
-            # there (CUDA events around ~10 us launches also count the gaps between them and over-weight the small kernels), else
-            # the live event totals.  The achieved figure below is live either way.
-            ncu_us = ncu_kernel_times()
-            ranked = sorted(fam.items(), key=lambda kv: -(ncu_us.get(kv[0], 0.0) if ncu_us else kv[1]['ms']))
+            # Which kernel dominates the step: the live per-entry-point CUDA-event totals of THIS run (each call bracketed by its own
+            # pair of events while the GPU is kept busy, so launch gaps between calls are not counted).
+            ranked = sorted(fam.items(), key=lambda kv: -kv[1]['ms'])
             name, top = ranked[0]
             per_ms = top['ms'] / 2
             traffic = measured_traffic(name)
@@ -397,22 +426,19 @@ def main_ours(args):
                             'note': ('tcgen05 kind::tf32 kernel' if tensor else 'CUDA-core fp32 kernel (not on the tensor pipe)') +
                                     '; achieved = algorithmic flops of all its launches in one step / their summed CUDA-event time (events on '
                                     'the launching stream, GPU kept busy); peak = TF32 dense = half of the %s sustained bf16 figure; traffic = '
-                                    'dram bytes of the same launches under ncu (profiles/traffic_r01.json)' % pk['src']}
+                                    'dram bytes of the same launches under ncu (profiles/traffic_r02.json)' % pk['src']}
             else:
                 ach = top['bytes'] / 2 / (per_ms * 1e-3) / 1e9
                 roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
                             'traffic': traffic, 'share_of_step': top['ms'] / tot, 'note': 'peak = %s copy bandwidth' % pk['src']}
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:       # reported at N=1 only
-        cpu_baseline, _ = run_cpu(args.workload, min(B, args.cpu_batch), budget_s=args.cpu_budget)
+        cpu_baseline, _ = run_cpu(args.workload, args.cpu_batch or B, budget_s=args.cpu_budget)
     if rank == 0:
         line = {'metric': METRIC[args.workload], 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32 storage; tf32 tensor-core products where the layer runs on tcgen05, fp32 elsewhere',
-                'data': 'synthetic', 'config': {'workload': workload_name(args.workload, B), 'global_batch': world * B,
-                                                'parallelism': 'dp%d' % world,
-                                                'l2': 'per-step working set (activations + 241 MB of parameters, > 1 GB) exceeds the 126 MB L2; no flush needed',
-                                                'cuda_graph': bool(trainer is not None and trainer.use_graph)},
+                'data': 'synthetic', 'config': line_config(args.workload, B, world, not args.no_graph),
                 'e2e': e2e, 'gpu_launches': int(launches * args.steps), 'gpu_launches_per_step': int(launches), 'clocks': clocks,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline}
         if breakdown is not None:
@@ -448,9 +474,9 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='train', choices=['train', 'frontend', 'inference'])
+    ap.add_argument('--workload', default='train', choices=['train', 'train_c6', 'frontend', 'inference'])
     ap.add_argument('--batch-per-gpu', type=int, default=0)
-    ap.add_argument('--cpu-batch', type=int, default=160, help='batch of the bounded CPU sample')
+    ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the bounded CPU sample (0 = the per-GPU batch of the workload)')
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU baseline work')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')

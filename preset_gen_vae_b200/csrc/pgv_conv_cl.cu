@@ -46,11 +46,17 @@ constexpr int CL_A_BYTES = CL_BLOCK_M * 128;
 constexpr int CL_PRODUCER_WARPS = 8, CL_PRODUCERS = CL_PRODUCER_WARPS * 32;
 constexpr int CL_SLOTS = (CL_BLOCK_M * 8) / CL_PRODUCERS;          // 16-byte chunks of one operand tile per producer thread (4)
 constexpr int CL_ROWS_PER_PASS = CL_PRODUCERS / 8;               // GEMM mode: rows covered by one pass of the producers (32)
-constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/ + 32 /*weights by TMA*/;
+// 16 warps (the most that fit at 128 registers): 0-7 cp.async producers, 8 MMA issuer, 9-12 epilogue group 0, 13 TMA, 14-15 TMA helpers.
+// When the A operand comes through TMA (GEMM mode, a_mode 1 / 2) the producer warps have nothing to gather and become epilogue groups
+// 1 (warps 0-3) and 2 (warps 4-7): three accumulator tiles are drained concurrently, which is what the 8 / 16 / 32-channel layers need -
+// their tile period is the epilogue's instruction stream, one latency-bound warp per TMEM lane quarter (trace: 2 400 - 3 900 cycles
+// per tile against ~900 of MMA issue).
+constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/ + 32 /*TMA*/ + 64 /*TMA helpers*/;
+constexpr int CL_MAX_GROUPS = 3;
 // epilogue staging: per epilogue warp 32 rows x 32 columns (+4 pad) of fp32 and one 64-bit destination offset per row
 constexpr int CL_EPI_LD = 36, CL_EPI_WARP_BYTES = 32 * CL_EPI_LD * 4 + 32 * 8;
 constexpr int CL_SMEM = 232448;                                     // 227 KB: the per-block maximum of sm_100
-constexpr int CL_RING_BYTES = (CL_SMEM - 1024 - 256 - 4 * CL_EPI_WARP_BYTES) / 1024 * 1024;
+constexpr int CL_RING_BYTES = (CL_SMEM - 1024 - 256 - 4 * CL_MAX_GROUPS * CL_EPI_WARP_BYTES) / 1024 * 1024;
 
 struct ConvClParams {
     const float* a;      // GEMM: gathered activations [B, H, W, C]      WGRAD: x [B, H, W, C]
@@ -80,7 +86,7 @@ struct ConvClParams {
     float* ws;
     unsigned* ws_cnt;
     int wg_cin, wg_taps;           // WGRAD: if wg_taps > 0, out is the PyTorch weight layout [Cout][Cin][taps] (row m = tap * Cin + ci)
-    FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC;
+    FastDiv fd_HgWg, fd_Wg, fd_span /* KW*C */, fd_C, fd_bblocks, fd_qC, fd_splits, fd_ntiles;
     alignas(64) CUtensorMap tmap_b;      // GEMM mode: prepared weights [gemm_n][gemm_k], box 32 x n_tile, 128-byte swizzle
     alignas(64) CUtensorMap tmap_a;      // GEMM mode, a_mode 1: [gemm_m][C] tiled, box 32 x 128; a_mode 2: im2col map of the [B, H, W, C] activation
 };
@@ -108,11 +114,12 @@ __device__ __forceinline__ void cl_trace(const ConvClParams& p, int role, int& n
 struct ClItem { int tm, tn, kb0, kb1; };
 __device__ __forceinline__ ClItem cl_decode(const ConvClParams& p, int item) {
     ClItem wi;
-    const int split = item % p.k_splits;
-    int t = item / p.k_splits;
-    wi.tn = t % p.n_tiles;
-    wi.tm = t / p.n_tiles;
-    wi.kb0 = split * p.kb_per_split;
+    uint32_t t, split, tm, tn;
+    p.fd_splits.divmod(static_cast<uint32_t>(item), t, split);
+    p.fd_ntiles.divmod(t, tm, tn);
+    wi.tn = static_cast<int>(tn);
+    wi.tm = static_cast<int>(tm);
+    wi.kb0 = static_cast<int>(split) * p.kb_per_split;
     wi.kb1 = min(p.kb_total, wi.kb0 + p.kb_per_split);
     return wi;
 }
@@ -131,11 +138,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_ctl);
     uint64_t* bar_empty = bar_full + CL_MAX_STAGES;
     uint64_t* bar_tfull = bar_empty + CL_MAX_STAGES;
-    uint64_t* bar_tempty = bar_tfull + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + 2);
-    volatile uint32_t* ws_flag = tmem_ptr + 1;                              // split-K: "this CTA finishes the tile" (epilogue warps)
+    uint64_t* bar_tempty = bar_tfull + CL_MAX_GROUPS;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tempty + CL_MAX_GROUPS);
+    volatile uint32_t* ws_flags = tmem_ptr + 1;                             // split-K: "this CTA finishes the tile", one per epilogue group
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int MMA_WARP = CL_PRODUCER_WARPS, TMA_WARP = CL_PRODUCER_WARPS + 5;      // warps MMA_WARP + 1 .. + 4 are the epilogue
+    constexpr int MMA_WARP = CL_PRODUCER_WARPS, TMA_WARP = CL_PRODUCER_WARPS + 5;      // warps MMA_WARP + 1 .. + 4 are epilogue group 0
+    const bool a_by_tma = MODE == CL_GEMM && p.a_mode != 0;
+    // accumulator tiles in TMEM and epilogue groups: item j of this CTA uses accumulator j % n_acc and is drained by group j % n_groups
+    const int n_groups = a_by_tma ? CL_MAX_GROUPS : 1, n_acc = a_by_tma ? CL_MAX_GROUPS : 2;
     const bool with_stats = MODE == CL_GEMM && p.stats != nullptr;
 
     if (warp == MMA_WARP) {
@@ -144,11 +154,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             // TMA-fed A operand the TMA warp is the only producer
             const uint32_t full_count = MODE == CL_WGRAD ? CL_PRODUCERS : (p.a_mode != 0 ? 1 : CL_PRODUCERS + 1);
             for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&bar_full[s], full_count); mbar_init(&bar_empty[s], 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+            for (int a = 0; a < CL_MAX_GROUPS; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_ptr, 2 * CL_MAX_N);
+        tmem_alloc(tmem_ptr, 4 * CL_MAX_N);
         tmem_relinquish();
     }
     tc_fence_before_sync();
@@ -158,14 +168,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     const int n_items = p.m_tiles * p.n_tiles * p.k_splits;
     const uint32_t smem_base = smem_u32(smem);
 
-    if (warp < CL_PRODUCER_WARPS) {
+    const int epi_group = (warp > MMA_WARP && warp < TMA_WARP) ? 0 : ((a_by_tma && warp < CL_PRODUCER_WARPS) ? 1 + (warp >> 2) : -1);
+    if (warp < CL_PRODUCER_WARPS && !a_by_tma) {
         // ================================================================== producers
         const int t = threadIdx.x;
         int stage = 0; uint32_t phase = 0;
         int trace_n = 0;
-        if (MODE == CL_GEMM && p.a_mode != 0) {
-            // A operand through TMA (issued by the TMA warp): nothing to gather
-        } else if (MODE == CL_GEMM) {
+        if (MODE == CL_GEMM) {
             // A operand: thread = (row group r0 = t / 8, chunk j = t % 8): 8 consecutive lanes copy one 128-byte row; rows
             // r0 + CL_ROWS_PER_PASS * i.  B operand (prepared weights, a plain K-major matrix): ONE TMA box per k-block, issued by
             // thread 0, which also posts the expected byte count on the stage's barrier.
@@ -320,6 +329,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             int trace_n = 0;
             bool full_ready = false;
+            // A descriptors of the 8 / 16-channel im2col tiles: constant upper part and the byte offset of every K = 8 slice
+            const uint64_t a_desc_hi = umma_smem_desc_kmajor(0, p.a_sbo, p.a_layout);
+            uint32_t a_koff[CL_BLOCK_K / 8];
+            {
+                const uint32_t sub_bytes = CL_A_BYTES / (p.a_sub > 0 ? p.a_sub : 1), per_sub = (CL_BLOCK_K / 8) / (p.a_sub > 0 ? p.a_sub : 1);
+#pragma unroll
+                for (int k = 0; k < CL_BLOCK_K / 8; ++k) a_koff[k] = (static_cast<uint32_t>(k) / per_sub) * sub_bytes + (static_cast<uint32_t>(k) % per_sub) * 32;
+            }
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ClItem wi = cl_decode(p, item);
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
@@ -339,11 +356,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                         } else {
                             // im2col loads of C = 8 / 16 channels: the k-block holds 4 / 2 single-tap tiles of 128 rows x 32 / 64 bytes
                             // (SWIZZLE_32B / 64B), one K = 8 MMA per 32 bytes of a row; the weight tile keeps its 128-byte rows
-                            const uint32_t sub_bytes = CL_A_BYTES / p.a_sub, per_sub = (CL_BLOCK_K / 8) / p.a_sub;
 #pragma unroll
                             for (int k = 0; k < CL_BLOCK_K / 8; ++k) {
-                                const uint32_t sub = static_cast<uint32_t>(k) / per_sub, within = static_cast<uint32_t>(k) % per_sub;
-                                const uint64_t da = umma_smem_desc_kmajor(a_addr + sub * sub_bytes + within * 32, p.a_sbo, p.a_layout);
+                                const uint64_t da = a_desc_hi | static_cast<uint64_t>(((a_addr + a_koff[k]) >> 4) & 0x3FFF);
                                 umma_tf32(tmem_d, da, db + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
                             }
                         }
@@ -388,13 +403,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 }
                 if (elect_one()) umma_commit(&bar_tfull[acc]);
                 __syncwarp();
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp == TMA_WARP) {
-        // ================================================================== weights (GEMM mode): one TMA box per k-block
-        if (MODE == CL_GEMM) {
+    } else if (warp >= TMA_WARP) {
+        // ================================================================== TMA (GEMM mode): the weight box of every k-block and, with a
+        // TMA-fed A operand, the activation loads.  Issuing one cp.async.bulk.tensor costs its thread ~90 cycles, so the (up to four)
+        // im2col loads of a k-block are spread over the TMA warp and its two helper warps: role 0 = TMA warp (expect_tx, weights, A load 0),
+        // role 1 = A loads 1 and 3, role 2 = A load 2.  Bytes that land before the expect_tx is posted only drive the transaction count
+        // negative; the phase cannot complete before the TMA warp's arrival.
+        const int tma_role = warp - TMA_WARP;
+        if (MODE == CL_GEMM && (tma_role == 0 || (p.a_mode == 2 && tma_role < p.a_sub))) {
             // (a_mode 4 is a measurement aid: no A loads at all, the MMAs multiply whatever the stage holds)
             const uint32_t tx_bytes = static_cast<uint32_t>(p.n_tile) * 128u + ((p.a_mode == 1 || p.a_mode == 2) ? static_cast<uint32_t>(CL_A_BYTES) : 0u);
             int trace_n = 0;
@@ -420,19 +439,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     const long long tr_b = (p.trace && p.a_mode != 0) ? clock64() : 0;
                     if (elect_one()) {
                         uint8_t* st = smem + stage * CL_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
-                        tma_load_2d(st + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                        if (tma_role == 0) {
+                            mbar_arrive_expect_tx(&bar_full[stage], tx_bytes);
+                            tma_load_2d(st + CL_A_BYTES, &p.tmap_b, &bar_full[stage], kb * CL_BLOCK_K, wi.tn * p.n_tile);
+                        }
                         if (p.a_mode == 1) {
                             tma_load_2d(st, &p.tmap_a, &bar_full[stage], kb * CL_BLOCK_K, wi.tm * CL_BLOCK_M);
                         } else if (p.a_mode == 2) {
                             const uint32_t kw = p.fd_C.div(rem), c0 = rem - kw * static_cast<uint32_t>(p.C);
                             for (int sidx = 0; sidx < p.a_sub; ++sidx)
-                                tma_load_im2col_4d(smem_u32(st) + sidx * sub_bytes, &p.tmap_a, &bar_full[stage], static_cast<int>(c0), w0, h0, b0,
-                                                   static_cast<uint16_t>(kw + sidx), static_cast<uint16_t>(kh));
+                                if ((sidx == 3 ? 1 : sidx) == tma_role)                 // role 0: load 0, role 1: loads 1 and 3, role 2: load 2
+                                    tma_load_im2col_4d(smem_u32(st) + sidx * sub_bytes, &p.tmap_a, &bar_full[stage], static_cast<int>(c0), w0, h0,
+                                                       b0, static_cast<uint16_t>(kw + sidx), static_cast<uint16_t>(kh));
                         }
                     }
                     __syncwarp();
-                    if (p.trace && p.a_mode != 0 && lane == 0) cl_trace(p, 0, trace_n, tr_a, tr_b, clock64(), kb);
+                    if (p.trace && p.a_mode != 0 && lane == 0 && tma_role == 0) cl_trace(p, 0, trace_n, tr_a, tr_b, clock64(), kb);
                     if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
                     rem += CL_BLOCK_K;
                     if (rem >= span) { rem -= span; ++kh; }
@@ -446,10 +468,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         // per-warp shared-memory tile: thread = row on the way in, 8 lanes x float4 = 128 contiguous bytes of a row on the way out
         // (measured before: 16 k cycles to drain one 128 x 128 tile with row-strided float4 stores).
         const int quad = warp & 3, row = quad * 32 + lane;
-        float* stg = reinterpret_cast<float*>(smem_ctl + 256 + quad * CL_EPI_WARP_BYTES);
+        float* stg = reinterpret_cast<float*>(smem_ctl + 256 + (epi_group * 4 + quad) * CL_EPI_WARP_BYTES);
         long long* stg_dst = reinterpret_cast<long long*>(stg + 32 * CL_EPI_LD);     // per row: element offset of its destination, -1 = no row
-        int acc = 0; uint32_t acc_phase = 0;
+        volatile uint32_t* ws_flag = ws_flags + epi_group;
         int etrace_n = 0;
+        int j_local = -1;                                                            // index of the item among this CTA's items
         // BatchNorm statistics of the stored values (launches with one N tile only, so that a thread sees the same columns in
         // every tile): fp32 sums in registers over all tiles of the CTA, folded once at the end.  Direct epilogue: st_*[e] =
         // column e of the thread's rows; staged epilogue: st_*[4 * chunk + e] = column 32 * chunk + 4 * col4 + e of its 8 rows per tile.
@@ -462,6 +485,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
         int bias_tn = -1;
         const int col4 = lane & 7, rsub = lane >> 3;                         // staged read-back role: float4 column group, row within a group of 4
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            ++j_local;
+            if (j_local % n_groups != epi_group) continue;                           // another epilogue group drains this tile
+            const int acc = j_local % n_acc;
+            const uint32_t acc_phase = static_cast<uint32_t>(j_local / n_acc) & 1u;
             const ClItem wi = cl_decode(p, item);
             const uint32_t m = static_cast<uint32_t>(wi.tm) * CL_BLOCK_M + row;
             const bool row_ok = m < static_cast<uint32_t>(MODE == CL_WGRAD ? p.m_valid : p.gemm_m);
@@ -528,18 +555,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[acc]);                // the accumulator is free again
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
                 if (MODE == CL_WGRAD) continue;                              // summed and laid out by wgrad_finish_kernel
                 __threadfence();
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + epi_group, 128);
                 if (quad == 0 && lane == 0) {
                     const unsigned old = atomicAdd(p.ws_cnt + tile, 1u);
                     const bool last = old == static_cast<unsigned>(p.k_splits - 1);
                     if (last) p.ws_cnt[tile] = 0u;                           // every contributor has arrived: ready for the next launch
                     *ws_flag = last ? 1u : 0u;
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + epi_group, 128);
                 if (*ws_flag == 0u) continue;
                 __threadfence();
                 ws_tile = p.ws + static_cast<size_t>(tile) * p.k_splits * (static_cast<size_t>(p.n_tile) * CL_BLOCK_M) + row;
@@ -677,13 +702,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                     __syncwarp();
                 }
             }
-            if (p.trace && quad == 1 && lane == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item, tr_ld);
+            if (p.trace && quad == 1 && lane == 0 && epi_group == 0) cl_trace(p, 2, etrace_n, tr_a, tr_b, clock64(), item, tr_ld);
             if (ws_tile != nullptr) continue;                                // the accumulator was released when the partial was parked
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
         if (with_stats) {
             const bool direct = p.n_tile <= 16;
@@ -708,15 +731,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * CL_MAX_N);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 4 * CL_MAX_N);
     if (with_stats) {
         // fold the 4 epilogue warps (and, quad epilogue, the columns (class, c) of the 4 pixel classes) and add to the global sums
         const float* part = reinterpret_cast<const float*>(smem_ctl + 256);
         for (int i = threadIdx.x; i < 2 * p.stat_c; i += CL_THREADS) {
             double v = 0.0;
             for (int n = i >> 1; n < p.gemm_n; n += p.stat_c)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v += static_cast<double>(part[q * (CL_EPI_WARP_BYTES / 4) + 2 * n + (i & 1)]);
+                for (int q = 0; q < 4 * n_groups; ++q) v += static_cast<double>(part[q * (CL_EPI_WARP_BYTES / 4) + 2 * n + (i & 1)]);
             atomicAdd(p.stats + i, v);
         }
     }
@@ -778,6 +800,7 @@ extern long long* g_conv_trace_ptr;          // set by pgv_debug_set_conv_trace 
 template <int MODE>
 static int launch_conv_cl(const pgv_handle* h, ConvClParams& p, cudaStream_t stream) {
     p.trace = g_conv_trace_ptr;
+    p.fd_splits.init(p.k_splits);
     static bool configured = false;
     if (!configured) {
         PGV_CUDA(cudaFuncSetAttribute(conv_cl_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
@@ -869,7 +892,7 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     p.kb_total = ceil_div(p.gemm_k, CL_BLOCK_K); p.kb_per_split = p.kb_total; p.k_splits = 1;      // a K tail is zero-filled by the gather masks / TMA
     p.epi = epi; p.ldo = N; p.qH = qH; p.qW = qW; p.qC = qC;
     p.slope = slope; p.round_out = round_out;
-    p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1);
+    p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1); p.fd_ntiles.init(p.n_tiles);
     p.a_sub = 1; p.a_sbo = 1024; p.a_layout = 2;
     cl_set_ring(p);
     // ---- A operand: TMA where the geometry allows it
@@ -1087,7 +1110,7 @@ static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, co
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.k_splits = ceil_div(p.kb_total, p.kb_per_split);
     p.slope = -1.0f;
-    p.fd_HgWg.init(Ho * Wo); p.fd_Wg.init(Wo); p.fd_span.init(KW * Cin); p.fd_C.init(Cin); p.fd_bblocks.init(p.bblocks); p.fd_qC.init(1);
+    p.fd_HgWg.init(Ho * Wo); p.fd_Wg.init(Wo); p.fd_span.init(KW * Cin); p.fd_C.init(Cin); p.fd_bblocks.init(p.bblocks); p.fd_qC.init(1); p.fd_ntiles.init(p.n_tiles);
     if (p.k_splits > 1 && use_ws) {
         p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + CL_WS_HEADER);
         if (int rc = launch_conv_cl<CL_WGRAD>(h, p, stream)) return rc;
