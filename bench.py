@@ -389,6 +389,7 @@ def main_ours(args):
         # measure that kernel alone and not the time it shared the GPU with a concurrent branch.
         trainer_graph, trainer_side = trainer.use_graph, trainer._side
         trainer.use_graph, trainer._side = False, None
+        ops.use_wgrad_fork = False                      # same reason: weight gradients on the measuring stream, not on their child stream
         dev_step()
         torch.cuda.synchronize(dev)
         # keep the GPU busy while the CPU enqueues the instrumented steps, so that the CUDA events around each entry
@@ -402,6 +403,7 @@ def main_ours(args):
         prof = ops.stop_profile()
         del blocker
         trainer.use_graph, trainer._side = trainer_graph, trainer_side
+        ops.use_wgrad_fork = True
         if rank == 0:
             tot = sum(v['ms'] for v in prof.values())
             breakdown = {k: round(v['ms'] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:10]}

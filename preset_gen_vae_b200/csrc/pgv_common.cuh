@@ -25,6 +25,10 @@ struct pgv_handle {
 
 namespace pgv {
 
+// Hardtanh / clamp that lets NaN through like torch's (fminf / fmaxf would replace it by a bound and hide a diverged model from the
+// NaN guard of train.py:245)
+__device__ __forceinline__ float clamp_nan(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
 int set_error(int code, const char* fmt, ...);
 
 #define PGV_CHECK_ARG(cond, ...)                                   \

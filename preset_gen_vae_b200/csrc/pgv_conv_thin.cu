@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) thin_conv_quad_cl8_kernel(const float* __
 #pragma unroll
             for (int pw = 0; pw < 2; ++pw) {
                 const int ih = 2 * i + ph, iw = 2 * j + pw;
-                if (ih < H && iw < W) xb[ih * W + iw] = fminf(fmaxf(acc[ph][pw], lo), hi);
+                if (ih < H && iw < W) xb[ih * W + iw] = clamp_nan(acc[ph][pw], lo, hi);
             }
     }
 }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float* __res
                 }
             }
         }
-        x[i] = fminf(fmaxf(acc, lo), hi);
+        x[i] = clamp_nan(acc, lo, hi);
     }
 }
 

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(CPL_THREADS) coupling_bwd_kernel(const float* 
 
 __global__ void hardtanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float lo, float hi, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        y[i] = fminf(fmaxf(x[i], lo), hi);
+        y[i] = clamp_nan(x[i], lo, hi);
 }
 __global__ void hardtanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, float lo, float hi, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) preset_act_softmax_fwd_kernel(const float
     if (row >= B) return;
     const float* xr = x + static_cast<size_t>(row) * D;
     float* yr = y + static_cast<size_t>(row) * D;
-    for (int j = lane; j < n_num; j += 32) yr[num_cols[j]] = fminf(fmaxf(xr[num_cols[j]], 0.0f), 1.0f);
+    for (int j = lane; j < n_num; j += 32) yr[num_cols[j]] = clamp_nan(xr[num_cols[j]], 0.0f, 1.0f);
     for (int g = 0; g < n_grp; ++g) {
         const int s = grp_start[g], n = grp_len[g];
         float mx = -INFINITY;

@@ -254,8 +254,17 @@ def conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
     return 'tc' if _precision == 'tf32' else 'f32'
 
 
+def prepared_of(param):
+    """Operand copies made ahead of time for this parameter (`param._pgv_prepared`, set by TrainStep.prepare_operands and valid for
+    the current step only), or None."""
+    return getattr(param, '_pgv_prepared', None)
+
+
 def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True):
     """TF32-rounded operand matrices of the channels-last kernels for weight w [Cout, Cin, kh, kw]: (wf, wq)."""
+    ready = prepared_of(w)
+    if ready is not None:
+        return ready
     Cout, Cin, kh, kw = w.shape
     K = Cin * kh * kw
     wf = _empty(w, Cout, K) if fwd else None
@@ -612,7 +621,8 @@ def fc_fwd(x, w, bias, training=True):
     if fc_route(M, N, K) != 'cl':
         return linear_fwd(x, w, bias), (x, None, None, K, None)
     Kp = (K + 3) // 4 * 4
-    xr, wr = round_copy(x, Kp), round_copy(w, Kp)
+    ready = prepared_of(w)                       # rounded / re-pitched weight copy made ahead of the forward pass (TrainStep)
+    xr, wr = round_copy(x, Kp), (ready if ready is not None else round_copy(w, Kp))
     # Data gradient dx = dy @ W.  With M % 4 == 0 it runs on the weight-gradient form of the kernel, whose operands are both
     # "reduction index x contiguous output index": W [N, Kp] as stored (the rounded copy the forward already made) and dy^T [N, M].
     # Otherwise it needs the rounded transpose W^T [K, N], a second pass over the whole weight matrix.

@@ -172,10 +172,53 @@ class TrainStep:
                                              _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
         ops.launches += 1
 
+    # ------------------------------------------------------------------ operand copies of the weights, off the critical path
+    def _prepare_operands(self):
+        """The tensor-core kernels consume TF32-rounded, re-laid-out copies of the weights (forward / data-gradient matrices of every
+        convolution, 16-byte-pitched FC matrices: 0.3 ms of small copy kernels per step).  They only depend on the parameters, so they are
+        enqueued on a side stream at the very start of the step and run under the front end's DFT / mel contractions; the model picks
+        them up through `ops.prepared_of(param)`."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_prep_stream', None) is None:
+            self._prep_stream = torch.cuda.Stream(device=self.device)
+        self._prep_stream.wait_stream(main)
+        self._prepared_params = []
+        with torch.cuda.stream(self._prep_stream):
+            for m in self.model.modules():
+                if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                    w = m.weight
+                    cout, cin, kh, kw = w.shape                # (ConvTranspose2d: the convolution it is the data gradient of)
+                    if ops.cl_mode() and _lib.lib().pgv_conv_cl_supported(cin, cout, kh, kw, m.stride[0], m.padding[0]):
+                        w._pgv_prepared = ops.prep_conv_weights(w, m.stride[0], m.padding[0])
+                        self._prepared_params.append(w)
+            enc, dec = self.model.ae_model.encoder, self.model.ae_model.decoder
+            for lin in (enc.mlp[1], dec.mlp[0]):
+                N, K = lin.weight.shape
+                if ops.fc_route(self.tc.minibatch_size, N, K) == 'cl':
+                    lin.weight._pgv_prepared = ops.round_copy(lin.weight, (K + 3) // 4 * 4)
+                    self._prepared_params.append(lin.weight)
+
+    def _join_prepared(self):
+        torch.cuda.current_stream(self.device).wait_stream(self._prep_stream)
+
+    def _drop_prepared(self):
+        for w in self._prepared_params:
+            w._pgv_prepared = None
+        self._prepared_params = []
+
     # ------------------------------------------------------------------ one step, eager (also what gets captured)
     def _device_step(self, audio, v_in, sample_info, with_optimizer):
         B, C, L = audio.shape
+        self._prepare_operands()
+        try:
+            return self._device_step_body(audio, v_in, sample_info, with_optimizer)
+        finally:
+            self._drop_prepared()
+
+    def _device_step_body(self, audio, v_in, sample_info, with_optimizer):
+        B, C, L = audio.shape
         x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
+        self._join_prepared()
         ops.launches += _lib.lib().pgv_frontend_launch_count(self.mc.mel_bins)
         x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
         self.model.ae_model.decoder_stream = self._side

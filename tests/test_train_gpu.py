@@ -178,7 +178,7 @@ def test_dkl_regulariser_nan_guard_and_optimizer_state(idx_helper):
     tr.flat_params.copy_(tr2.flat_params)          # irrelevant for the gradient comparison below; keeps both models equal
     assert float((g_with - tr2.flat_grads).abs().max()) > 0.0
     # NaN guard
-    tr.model.ae_model.decoder.mlp[0].bias.data[3] = float('nan')        # (a NaN in the audio is swallowed by the dB floor's fmaxf)
+    tr.model.ae_model.decoder.mlp[0].bias.data[3] = float('nan')        # (a NaN in the audio would be swallowed by the dB floor, like np.maximum)
     tr.step(audio, v_in, info)
     handle = tr.losses_to_host_async()
     with pytest.raises(train_mod.ModelConvergenceError):
