@@ -332,6 +332,42 @@ def golden_metrics(ref_loss, ref_preset, ref_build, ref_config, fake, ref_helper
           % (qmse.item(), ql1.item(), float(acc), fpl.item(), len(g_names)))
 
 
+def golden_basic_vae(ref_config, ref_build, my_helper):
+    """BasicVAE (VAE.py:19-66; built when latent_flow_arch is None, build.py:45-47): reference vs oracle on the same seeds (eval forward and
+    Dkl latent loss; the training forward draws eps from the global generator, so it is compared in eval mode)."""
+    cfg = ref_config
+    _configure(cfg, 3)
+    cfg.model.latent_flow_arch = None
+    cfg.model.dim_z = 256
+    torch.manual_seed(0)
+    enc, dec, ae = ref_build.build_ae_model(cfg.model, cfg.train)
+    cfg.model.latent_flow_arch = 'realnvp_6l300'
+    assert type(ae).__name__ == 'BasicVAE'
+    from preset_gen_vae_b200 import config as pcfg
+    m_cfg, t_cfg = pcfg.make_default(minibatch_size=3, latent_flow_arch=None, params_regression_architecture='mlp_3l1024')
+    m_cfg.dim_z = 256
+    torch.manual_seed(0)
+    o_enc = omodel.Encoder(m_cfg.encoder_architecture, 256, m_cfg.input_tensor_size, t_cfg.fc_dropout,
+                           output_bn=(t_cfg.latent_flow_input_regularization.lower() == 'bn'), deepest_features_mix=False)
+    o_dec = omodel.Decoder(m_cfg.encoder_architecture, 256, m_cfg.input_tensor_size, t_cfg.fc_dropout)
+    o_ae = omodel.BasicVAE(o_enc, 256, o_dec, t_cfg.normalize_losses)
+    sd = ae.state_dict()
+    assert list(sd.keys()) == list(o_ae.state_dict().keys())
+    for k, v in o_ae.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    x = synthetic.make_spectrogram_like(3, 1, seed=2)
+    ae.eval(); o_ae.eval()
+    with torch.no_grad():
+        r, o = ae(x), o_ae(x)
+    for a, b in zip(o, r):
+        assert a.shape == b.shape and relerr(a, b) < 1e-6
+    lat = ae.latent_loss(r[0]).item()
+    assert abs(o_ae.latent_loss(o[0]).item() - lat) < 1e-6 * abs(lat)
+    np.savez_compressed(os.path.join(GOLDEN, 'basic_vae.npz'), z_mu_logvar=r[0].numpy(), x_out_sub=r[4].numpy()[:, :, ::4, ::4],
+                        x_out_sum=np.float64(r[4].double().sum().item()), latent_loss=np.float64(lat), n_state_entries=np.int64(len(sd)))
+    print("BasicVAE: oracle == reference (eval forward, Dkl latent loss %.6f, %d state entries)" % (lat, len(sd)))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -342,6 +378,7 @@ def main():
     six = ((40, 85), (50, 85), (60, 42), (60, 85), (60, 127), (70, 85))
     golden_model(ref_config, ref_build, ref_loss, ref_helper, my_helper, 'c6_b2', B=2, midi_notes=six, stack=True)
     golden_metrics(ref_loss, ref_preset, ref_build, ref_config, fake, ref_helper, my_helper)
+    golden_basic_vae(ref_config, ref_build, my_helper)
     print("golden fixtures written to", GOLDEN)
 
 

@@ -205,6 +205,28 @@ class FlowVAE(nn.Module):                                      # VAE.py:69-193
         return loss / z0.shape[1] if self.normalize_latent_loss else loss
 
 
+class BasicVAE(nn.Module):                                     # VAE.py:19-66
+    def __init__(self, encoder, dim_z, decoder, normalize_latent_loss, latent_loss_type='Dkl'):
+        super().__init__()
+        assert latent_loss_type.lower() == 'dkl'
+        self.encoder, self.dim_z, self.decoder = encoder, dim_z, decoder
+        self.normalize_latent_loss = normalize_latent_loss
+
+    def forward(self, x, noise=None):
+        ml = self.encoder(x, None if noise is None else noise['enc_fc_mask'])
+        mu, sigma = ml[:, 0, :], torch.exp(ml[:, 1, :] / 2.0)
+        if self.training:
+            eps = torch.randn(x.shape[0], self.dim_z, device=mu.device).to(mu.dtype) if noise is None else noise['eps'].to(mu.dtype)
+            z = mu + sigma * eps
+        else:
+            z = mu
+        x_out = self.decoder(z, None if noise is None else noise['dec_fc_mask'])
+        return ml, z, z, torch.zeros((z.shape[0], 1), device=x.device), x_out
+
+    def latent_loss(self, z_0_mu_logvar, **kwargs):
+        return gaussian_dkl(z_0_mu_logvar[:, 0, :], z_0_mu_logvar[:, 1, :], self.normalize_latent_loss)
+
+
 class CustomRealNVP(nf.CompositeTransform):                    # flows.py:42-90
     def __init__(self, features, hidden_features, num_layers, num_blocks_per_layer, dropout_probability=0.0,
                  batch_norm_within_layers=False, batch_norm_between_layers=False):

@@ -20,6 +20,7 @@ import copy
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import losses as oloss, model as omodel
 from preset_gen_vae_b200 import config as pcfg, synthetic
@@ -204,6 +205,79 @@ def test_midi_concat_and_softmax_head_config(idx_helper):
     res = run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, 'fp32', orc32)
     ops.set_precision('tf32')
     check(orc, mine, *res, out_tol=2e-4, loss_tol=2e-5, grad_tol=2e-3, min_cos=0.99999, orc32=orc32)
+
+
+def test_deepest_features_mix_layout(idx_helper):
+    """stack_specs_deepest_features_mix=True (encoder.py:55-58): the shared CNN keeps enc7 and the mixer is the single 1x1 convolution
+    512*C -> 1024; state_dict keys `single_ch_cnn.enc_nn.4x4conv.enc7conv.*` / `features_mixer_cnn.enc8conv.*`."""
+    B = 3
+    orc, mine, m_cfg, t_cfg = make_pair(idx_helper, B, SIX_NOTES, True, stack_specs_deepest_features_mix=True)
+    keys = list(orc.state_dict().keys())
+    assert keys == list(mine.state_dict().keys())
+    assert 'ae_model.encoder.single_ch_cnn.enc_nn.4x4conv.enc7conv.weight' in keys and 'ae_model.encoder.features_mixer_cnn.enc8conv.weight' in keys
+    assert mine.state_dict()['ae_model.encoder.features_mixer_cnn.enc8conv.weight'].shape == (1024, 512 * 6, 1, 1)
+    mine.load_state_dict(orc.state_dict())
+    mine.cuda()
+    orc32, orc = orc, copy.deepcopy(orc).double()
+    res = run_step(orc, mine, idx_helper, m_cfg, t_cfg, B, 'fp32', orc32)
+    ops.set_precision('tf32')
+    check(orc, mine, *res, out_tol=2e-4, loss_tol=2e-5, grad_tol=2e-3, min_cos=0.99999, orc32=orc32)
+
+
+def test_basic_vae(idx_helper):
+    """BasicVAE (VAE.py:19-66; latent_flow_arch=None, build.py:45-47): 5-tuple with z_K = z_0 and a zero [B, 1] log-det, Dkl latent loss;
+    forward and backward against the oracle with shared eps / dropout masks."""
+    B = 4
+    m_cfg, t_cfg = pcfg.make_default(minibatch_size=B, latent_flow_arch=None, params_regression_architecture='mlp_3l1024')
+    torch.manual_seed(0)
+    o_enc = omodel.Encoder(m_cfg.encoder_architecture, 256, m_cfg.input_tensor_size, t_cfg.fc_dropout, output_bn=True, deepest_features_mix=False)
+    o_dec = omodel.Decoder(m_cfg.encoder_architecture, 256, m_cfg.input_tensor_size, t_cfg.fc_dropout)
+    orc = omodel.BasicVAE(o_enc, 256, o_dec, t_cfg.normalize_losses).double().train()
+    torch.manual_seed(0)
+    _, _, mine = build.build_ae_model(m_cfg, t_cfg)
+    assert type(mine).__name__ == 'BasicVAE' and list(mine.state_dict().keys()) == list(orc.state_dict().keys())
+    mine.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in orc.state_dict().items()})
+    mine.cuda().train()
+    x = synthetic.make_spectrogram_like(B, 1, seed=4)
+    noise = synthetic.make_noise(B, 256, t_cfg.fc_dropout, 0.0, seed=2)
+    n64 = {k: v.double() for k, v in noise.items() if torch.is_tensor(v)}
+    o = orc(x.double(), n64)
+    (F.mse_loss(o[4], x.double()) + 0.2 * orc.latent_loss(o[0])).backward()
+    ops.set_precision('fp32')
+    try:
+        xm = x.cuda()
+        m = mine(xm, {k: v.cuda() for k, v in noise.items() if torch.is_tensor(v)})
+        lat = mine.latent_loss(m[0])
+        (ploss.MSELoss()(m[4], xm) + 0.2 * lat).backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision('tf32')
+    assert m[3].shape == (B, 1) and float(m[3].abs().max()) == 0.0 and torch.equal(m[1], m[2])
+    for a, b in zip((m[0], m[1], m[4]), (o[0], o[1], o[4])):
+        assert rel(a, b) < 1e-4
+    assert abs(lat.item() - orc.latent_loss(o[0]).item()) < 1e-5 * abs(orc.latent_loss(o[0]).item())
+    ref = dict(orc.named_parameters())
+    for n, p in mine.named_parameters():
+        r = ref[n].grad
+        if r.norm() > 1e-7:
+            assert rel(p.grad, r) < 5e-3, (n, rel(p.grad, r))
+
+
+def test_dataparallel_wrap_of_the_reference_train_script(idx_helper):
+    """train.py:95-97 wraps the model (and its regression head) in nn.DataParallel; with one device id that must be transparent."""
+    B = 3
+    _, mine, m_cfg, t_cfg = make_pair(idx_helper, B)
+    mine.cuda().eval()
+    ae_par = torch.nn.DataParallel(mine, device_ids=[0], output_device='cuda:0')
+    reg_par = torch.nn.DataParallel(mine.reg_model, device_ids=[0], output_device='cuda:0')
+    x, info = synthetic.make_spectrogram_like(B, 1, seed=3).cuda(), synthetic.make_sample_info(B).cuda()
+    with torch.no_grad():
+        a = ae_par(x, info)
+        b = mine(x, info)
+        va, vb = reg_par(a[2]), mine.reg_model(b[2])
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    assert torch.equal(va, vb) and va.shape == (B, 610)
 
 
 def test_mlp_regression_head_config(idx_helper):

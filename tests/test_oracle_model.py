@@ -118,3 +118,24 @@ def test_flow_logdet_equals_the_log_abs_determinant_of_the_autograd_jacobian(bet
         assert torch.allclose(torch.linalg.slogdet(J)[1], ld[i], atol=1e-9)
     zi, ldi = t.inverse(y)
     assert torch.allclose(zi, z, atol=1e-9) and torch.allclose(ldi, -ld, atol=1e-9)
+
+
+def test_basic_vae_matches_the_reference(golden_dir):
+    """BasicVAE (VAE.py:19-66), the model build.py:45-47 makes when latent_flow_arch is None: eval forward and Dkl latent loss of the
+    oracle against the reference's committed outputs (tests/golden/basic_vae.npz)."""
+    import os
+    import numpy as np
+    from preset_gen_vae_b200 import config as pcfg, synthetic
+    g = np.load(os.path.join(golden_dir, 'basic_vae.npz'))
+    m_cfg, t_cfg = pcfg.make_default(minibatch_size=3, latent_flow_arch=None, params_regression_architecture='mlp_3l1024')
+    torch.manual_seed(0)
+    enc = omodel.Encoder(m_cfg.encoder_architecture, 256, m_cfg.input_tensor_size, t_cfg.fc_dropout, output_bn=True, deepest_features_mix=False)
+    dec = omodel.Decoder(m_cfg.encoder_architecture, 256, m_cfg.input_tensor_size, t_cfg.fc_dropout)
+    ae = omodel.BasicVAE(enc, 256, dec, t_cfg.normalize_losses).eval()
+    assert len(ae.state_dict()) == int(g['n_state_entries'])
+    with torch.no_grad():
+        out = ae(synthetic.make_spectrogram_like(3, 1, seed=2))
+    assert out[3].shape == (3, 1) and torch.equal(out[1], out[2]) and torch.equal(out[1], out[0][:, 0, :])
+    assert np.allclose(out[0].numpy(), g['z_mu_logvar'], rtol=1e-5, atol=1e-6)
+    assert np.allclose(out[4].numpy()[:, :, ::4, ::4], g['x_out_sub'], rtol=1e-5, atol=1e-6)
+    assert abs(ae.latent_loss(out[0]).item() - float(g['latent_loss'])) < 1e-6 * abs(float(g['latent_loss'])) + 1e-9
