@@ -111,6 +111,8 @@ class TrainStep:
         self._static = None
         self.losses = None
         self.scalars = None
+        self._prepared_params = []
+        self._update_done = None
         self._nan_mask = torch.zeros(1, dtype=torch.int32, device=self.device)
         # Data parallel: SynthParamsLoss normalises every categorical group by its number of useful rows in the batch (loss.py:172) and the
         # reference evaluates it on the GATHERED batch.  The counts only depend on the targets: each step all-reduces the 54 counts
@@ -208,19 +210,24 @@ class TrainStep:
 
     # ------------------------------------------------------------------ one step, eager (also what gets captured)
     def _device_step(self, audio, v_in, sample_info, with_optimizer):
-        B, C, L = audio.shape
-        self._prepare_operands()
+        self._prepare_operands()                      # side stream: runs under the front end
         try:
-            return self._device_step_body(audio, v_in, sample_info, with_optimizer)
+            x_in = self._front_end(audio)
+            return self._model_step(x_in, v_in, sample_info, with_optimizer)
         finally:
             self._drop_prepared()
 
-    def _device_step_body(self, audio, v_in, sample_info, with_optimizer):
+    def _front_end(self, audio, out=None):
         B, C, L = audio.shape
-        x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']))
-        self._join_prepared()
+        x_in = self.frontend.compute(audio.view(B * C, L), normalize=(self.spec_stats['min'], self.spec_stats['max']), out=out)
         ops.launches += _lib.lib().pgv_frontend_launch_count(self.mc.mel_bins)
-        x_in = x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
+        return x_in.view(B, C, x_in.shape[-2], x_in.shape[-1])
+
+    def _model_step(self, x_in, v_in, sample_info, with_optimizer):
+        """Everything after the front end: forward, losses, backward, gradient packing (and Adam when with_optimizer)."""
+        if not self._prepared_params:                 # (two-graph mode: the copies are made inside the model graph)
+            self._prepare_operands()
+        self._join_prepared()
         self.model.ae_model.decoder_stream = self._side
         try:
             z0_ml, z0, zk, logdet, x_out = self.model(x_in, sample_info)
@@ -248,11 +255,14 @@ class TrainStep:
         return torch.stack([recons.detach(), lat.detach(), cont.detach(), metrics[0], metrics[1],
                             flow_in.detach() if flow_in is not None else zero, self._nan_mask[0].float()])
 
-    def _adam(self):
+    def _adam(self, lo=0, hi=None):
+        """Fused Adam on elements [lo, hi) of the flat buffers, on the current stream."""
         tc = self.tc
+        hi = self.flat_params.numel() if hi is None else hi
+        sl = slice(lo, hi)
         _lib.check(_lib.lib().pgv_adam_step_dev(
-            _lib.ptr(self.flat_params), _lib.ptr(self.flat_grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-            self.flat_params.numel(), _lib.ptr(self._hyper_dev), tc.adam_betas[0], tc.adam_betas[1], 1e-8, tc.weight_decay,
+            _lib.ptr(self.flat_params[sl]), _lib.ptr(self.flat_grads[sl]), _lib.ptr(self.exp_avg[sl]), _lib.ptr(self.exp_avg_sq[sl]),
+            hi - lo, _lib.ptr(self._hyper_dev), tc.adam_betas[0], tc.adam_betas[1], 1e-8, tc.weight_decay,
             _lib.stream_ptr(self.device)), 'pgv_adam_step_dev')
         ops.launches += 1
 
@@ -284,6 +294,9 @@ class TrainStep:
     def step(self, audio, v_in, sample_info):
         """audio [B, C, L] fp32, v_in [B, L_params] fp32, sample_info [B, 3] int32: CUDA tensors on this rank's device.
         Returns a device tensor (recons, latent, controls) of this rank's un-weighted losses."""
+        if self.world > 1 and self.use_graph and self._fc_ready is not None:
+            return self._step_overlapped(audio, v_in, sample_info)
+        self.finish_updates()
         self._refresh_hyper()
         fused_opt = self.world == 1
         if self._group_counts is not None:
@@ -305,6 +318,91 @@ class TrainStep:
         self.scalars = scalars                         # SCALAR_NAMES
         self.losses = scalars[:3]
         return self.losses
+
+    # ------------------------------------------------------------------ several ranks: exchange hidden behind compute
+    def _step_overlapped(self, audio, v_in, sample_info):
+        """Data-parallel step with the whole gradient exchange off the critical path.  Two captured graphs per step:
+            A = the mel front end of this step's audio (reads no parameter),   B = forward / losses / backward / packing.
+        A communication stream reduces the two FC weight-gradient slices (180 of 241 MB) as soon as graph B signals them (external
+        event) and applies Adam to exactly those slices right behind the reduction - under the encoder's convolution backward;
+        after B it reduces the rest and applies Adam there.  The NEXT step launches its graph A before it waits for that tail, so the
+        remaining exchange + update run under the next front end (0.65 ms of tensor-core work that touches no parameter)."""
+        main = torch.cuda.current_stream(self.device)
+        if self._graph is None:
+            self._group_counts.copy_(self.controls_criterion.useful_counts(v_in))      # sane values for the warm-up steps of the capture
+            self._capture_two(audio, v_in, sample_info)
+        st_audio, st_v, st_info = self._static[:3]
+        for dst, src in zip((st_audio, st_v, st_info), (audio, v_in, sample_info)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph_a.replay()                                   # front end -> static spectrogram batch
+        if self._update_done is not None:
+            main.wait_event(self._update_done)                   # previous step's parameters are final from here on
+        self._refresh_hyper()
+        counts = parallel.global_useful_counts(self.controls_criterion.useful_counts(st_v), self.pg)
+        self._group_counts.copy_(counts / self.world)
+        self._graph.replay()
+        scalars = self._static[3].clone()
+        end_b = torch.cuda.Event()
+        end_b.record(main)
+        comm = self._comm_stream
+        dist = torch.distributed
+        with torch.cuda.stream(comm):
+            comm.wait_event(self._fc_ready)
+            for lo, n in self._fc_slots:
+                dist.all_reduce(self.flat_grads[lo:lo + n], op=dist.ReduceOp.SUM, group=self.pg)
+            for lo, n in self._fc_slots:
+                self._adam(lo, lo + n)
+            comm.wait_event(end_b)
+            for lo, hi in self._rest_segments:
+                dist.all_reduce(self.flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            for lo, hi in self._rest_segments:
+                self._adam(lo, hi)
+            self._update_done = torch.cuda.Event()
+            self._update_done.record(comm)
+        self.scalars = scalars
+        self.losses = scalars[:3]
+        return self.losses
+
+    def finish_updates(self):
+        """Makes the current stream wait for the parameter update of the last overlapped step (before reading parameters / state)."""
+        if getattr(self, '_update_done', None) is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._update_done)
+
+    def _capture_two(self, audio, v_in, sample_info):
+        static_in = (audio.clone(), v_in.clone(), sample_info.clone())
+        backup = (self.flat_params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+        bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if 'running' in k}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                  # warm-up: lazy init, allocator pools, constants upload (no collective)
+                self._device_step(*static_in, with_optimizer=False)
+            x_static = self._front_end(static_in[0]).clone()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self.model.load_state_dict(bn_state, strict=False)
+        before = ops.launches
+        graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_a):
+            self._front_end(static_in[0], out=x_static.view(-1, x_static.shape[-2], x_static.shape[-1]))
+        graph_b = torch.cuda.CUDAGraph()
+        self.model.ae_model.encoder.fc_grads_ready_event = self._fc_ready
+        try:
+            with torch.cuda.graph(graph_b):
+                try:
+                    scalars = self._model_step(x_static, static_in[1], static_in[2], with_optimizer=False)
+                finally:
+                    self._drop_prepared()
+        finally:
+            self.model.ae_model.encoder.fc_grads_ready_event = None
+        self._rest_segments = parallel.complement_segments(self.flat_grads.numel(), self._fc_slots)
+        self.launches_per_step = ops.launches - before + len(self._fc_slots) + len(self._rest_segments)      # + the Adam launches on the communication stream
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self.model.load_state_dict(bn_state, strict=False)
+        self._graph_a, self._graph, self._static = graph_a, graph_b, (*static_in, scalars)
+        self._update_done = None
 
     # ------------------------------------------------------------------ host-fed steps with input prefetch
     def prefetch(self, audio_host, v_in_host, sample_info_host):
@@ -390,6 +488,7 @@ class TrainStep:
         is not needed for the parameters and is skipped.  full_presets: also run the learnable -> full VST preset conversion
         (data/preset.py:350-369) on the device and return [B, 155]."""
         was_training = self.model.training
+        self.finish_updates()
         self.model.eval()
         try:
             B, C, L = audio.shape
@@ -414,6 +513,7 @@ class TrainStep:
     def state_dict(self):
         """{'ae_model_state_dict', 'optimizer_state_dict'} in the spirit of the reference's checkpoint file: the optimizer part holds the
         flat Adam moments (one fp32 vector each, in `model.parameters()` order with 16-byte aligned slots) and the step count."""
+        self.finish_updates()
         return {'ae_model_state_dict': self.model.state_dict(),
                 'optimizer_state_dict': {'step': self.step_count, 'lr': self.lr, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
                                          'slot_offsets': [int(o) for o in self._offs], 'slot_sizes': list(self._sizes)}}
