@@ -363,6 +363,9 @@ PGV_API int pgv_nan_flags(const float* s0, const float* s1, const float* s2, con
 /* data/abstractbasedataset.py:348-391: per_item4[i] = (min, max, mean, unbiased variance) of spectrogram i (x [N, elems]); dataset4
  * (optional) = (min of mins, max of maxes, mean of means, sqrt(mean of variances)). */
 PGV_API int pgv_spectrogram_stats(const float* x, int N, size_t elems, float* per_item4, float* dataset4, pgv_stream_t stream);
+/* Hint: pull [p, p + bytes) into L2 (one prefetch per 128-byte line); used on a flow's 15 MB of conditioner weights right before the
+ * chain of small kernels that read them once each. */
+PGV_API int pgv_l2_prefetch(const void* p, size_t bytes, pgv_stream_t stream);
 /* Backward of the inverse direction of the affine coupling (pgv_coupling_fwd with inverse != 0), given its result x_out: needed by
  * FlowParamsLoss, which back-propagates through the inverse latent flow (model/VAE.py:128-131, regression.py:179-184). */
 PGV_API int pgv_coupling_inv_bwd(const float* dx_out, const float* dlogdet, const float* x_out, const float* params, const int* id_idx,

@@ -55,8 +55,11 @@ constexpr int CL_THREADS = CL_PRODUCERS + 32 /*mma*/ + 128 /*epilogue*/ + 32 /*T
 constexpr int CL_MAX_GROUPS = 3;
 // epilogue staging: per epilogue warp 32 rows x 32 columns (+4 pad) of fp32 and one 64-bit destination offset per row
 constexpr int CL_EPI_LD = 36, CL_EPI_WARP_BYTES = 32 * CL_EPI_LD * 4 + 32 * 8;
-constexpr int CL_SMEM = 232448;                                     // 227 KB: the per-block maximum of sm_100
-constexpr int CL_RING_BYTES = (CL_SMEM - 1024 - 256 - 4 * CL_MAX_GROUPS * CL_EPI_WARP_BYTES) / 1024 * 1024;
+// Shared-memory budget: 188 KB, NOT the 227 KB maximum - the kernel shares its SMs with the CTAs of concurrent kernels (NCCL's
+// all-reduce on the communication stream, the 27 KB conditioner kernels of the other branch), which need ~40 KB to be resident at all;
+// with nothing left, each of them would serialise with a persistent 148-CTA convolution.  (A deeper ring bought nothing: measured.)
+constexpr int CL_SMEM = 188 * 1024;
+__host__ __device__ constexpr int cl_ring_bytes(int groups) { return (CL_SMEM - 1024 - 256 - 4 * groups * CL_EPI_WARP_BYTES) / 1024 * 1024; }
 
 struct ConvClParams {
     const float* a;      // GEMM: gathered activations [B, H, W, C]      WGRAD: x [B, H, W, C]
@@ -67,6 +70,7 @@ struct ConvClParams {
     int gemm_m, gemm_n, gemm_k;
     int n_tile, n_tiles, m_tiles, kb_total, kb_per_split, k_splits;
     int stages, stage_bytes;       // ring geometry (cl_set_ring)
+    int n_groups;                  // epilogue groups (1 or CL_MAX_GROUPS): three only pay when a CTA drains many small tiles
     int epi, ldo;        // CL_EPI_ROWS: out[m * ldo + n]          WGRAD: out[n * ldo + m] for m < m_valid
     int m_valid;
     int qH, qW, qC;      // CL_EPI_QUAD: out is [B, qH, qW, qC]; row m = quad (b, i, j), column n = (2*ph + pw) * qC + c
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int CL_STAGES = p.stages, CL_STAGE_BYTES = p.stage_bytes;
-    uint8_t* smem_ctl = smem + CL_RING_BYTES;                                // barriers, then the epilogue staging tiles
+    uint8_t* smem_ctl = smem + cl_ring_bytes(p.n_groups);                    // barriers, then the epilogue staging tiles
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_ctl);
     uint64_t* bar_empty = bar_full + CL_MAX_STAGES;
     uint64_t* bar_tfull = bar_empty + CL_MAX_STAGES;
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     constexpr int MMA_WARP = CL_PRODUCER_WARPS, TMA_WARP = CL_PRODUCER_WARPS + 5;      // warps MMA_WARP + 1 .. + 4 are epilogue group 0
     const bool a_by_tma = MODE == CL_GEMM && p.a_mode != 0;
     // accumulator tiles in TMEM and epilogue groups: item j of this CTA uses accumulator j % n_acc and is drained by group j % n_groups
-    const int n_groups = a_by_tma ? CL_MAX_GROUPS : 1, n_acc = a_by_tma ? CL_MAX_GROUPS : 2;
+    const int n_groups = p.n_groups, n_acc = n_groups > 1 ? n_groups : 2;
     const bool with_stats = MODE == CL_GEMM && p.stats != nullptr;
 
     if (warp == MMA_WARP) {
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
     const int n_items = p.m_tiles * p.n_tiles * p.k_splits;
     const uint32_t smem_base = smem_u32(smem);
 
-    const int epi_group = (warp > MMA_WARP && warp < TMA_WARP) ? 0 : ((a_by_tma && warp < CL_PRODUCER_WARPS) ? 1 + (warp >> 2) : -1);
+    const int epi_group = (warp > MMA_WARP && warp < TMA_WARP) ? 0 : ((n_groups > 1 && warp < CL_PRODUCER_WARPS) ? 1 + (warp >> 2) : -1);
     if (warp < CL_PRODUCER_WARPS && !a_by_tma) {
         // ================================================================== producers
         const int t = threadIdx.x;
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                 }
             }
         }
-    } else {
+    } else if (epi_group >= 0) {
         // ================================================================== epilogue: TMEM -> registers -> (shared) -> global
         // A TMEM lane is an output row, so after tcgen05.ld a thread holds consecutive CHANNELS of one pixel while a coalesced
         // store wants consecutive lanes on consecutive channels.  GEMM mode therefore passes every 32-column chunk through a
@@ -822,9 +826,12 @@ static int cl_pick_n_tile(int n, int granule) {
     return t;
 }
 
-static void cl_set_ring(ConvClParams& p) {
+static void cl_set_ring(ConvClParams& p, int sm_count) {
+    // three epilogue groups (GEMM mode with a TMA-fed A operand only: the producer warps are free) when every CTA drains >= 6 tiles
+    const long long items = static_cast<long long>(p.m_tiles) * p.n_tiles * std::max(p.k_splits, 1);
+    p.n_groups = (p.a_mode != 0 && items >= 6LL * sm_count) ? CL_MAX_GROUPS : 1;
     p.stage_bytes = static_cast<int>(align_up(static_cast<size_t>(CL_A_BYTES) + static_cast<size_t>(p.n_tile) * 128, 1024));
-    p.stages = std::min(CL_MAX_STAGES, CL_RING_BYTES / p.stage_bytes);
+    p.stages = std::min(CL_MAX_STAGES, cl_ring_bytes(p.n_groups) / p.stage_bytes);
 }
 
 // Workspace of the deterministic split-K paths: [CL_WS_COUNTERS x u32 tile counters (zero on entry, self-resetting)][fp32 partial tiles].
@@ -894,7 +901,6 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     p.slope = slope; p.round_out = round_out;
     p.fd_HgWg.init(Hg * Wg); p.fd_Wg.init(Wg); p.fd_span.init(KW * C); p.fd_C.init(C); p.fd_bblocks.init(1); p.fd_qC.init(qC > 0 ? qC : 1); p.fd_ntiles.init(p.n_tiles);
     p.a_sub = 1; p.a_sbo = 1024; p.a_layout = 2;
-    cl_set_ring(p);
     // ---- A operand: TMA where the geometry allows it
     const bool one_by_one = KH == 1 && KW == 1 && stride == 1 && pad == 0 && H == Hg && W == Wg;
     if (g_conv_a_mode == -2) {
@@ -952,6 +958,7 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     const uint64_t bd[2] = {static_cast<uint64_t>(p.gemm_k), static_cast<uint64_t>(N)}, bs[1] = {static_cast<uint64_t>(p.gemm_k) * 4};
     const uint32_t bbox[2] = {CL_BLOCK_K, static_cast<uint32_t>(p.n_tile)};
     if (int rc = make_tmap_f32(h, &p.tmap_b, bw, 2, bd, bs, bbox)) return rc;
+    cl_set_ring(p, h->sm_count);
     return launch_conv_cl<CL_GEMM>(h, p, stream);
 }
 
@@ -1094,7 +1101,8 @@ static int conv_cl_wgrad_impl(pgv_handle* h, const char* who, const float* x, co
     p.n_tile = cl_pick_n_tile(Cout, 32); p.n_tiles = ceil_div(Cout, p.n_tile);
     if (p.n_tile != 32 && p.n_tile != 64 && p.n_tile != 128) { p.n_tile = p.n_tile <= 64 ? 64 : 128; p.n_tiles = ceil_div(Cout, p.n_tile); }
     p.m_tiles = ceil_div(p.gemm_m, CL_BLOCK_M);
-    cl_set_ring(p);
+    p.k_splits = 1;
+    cl_set_ring(p, h->sm_count);
     p.bblocks = ceil_div(B, 32);
     p.kb_total = Ho * Wo * p.bblocks;
     const int tiles = p.m_tiles * p.n_tiles;

@@ -283,6 +283,9 @@ class CompositeTransform(Transform):
         """extra: None, or a list (one entry per coupling) of per-block dropout masks."""
         x = inputs[0].contiguous()
         B = x.shape[0]
+        rng = getattr(self, '_pgv_param_range', None)    # TrainStep: this flow's parameters as one contiguous slice of the flat buffer
+        if rng is not None and training:
+            ops.l2_prefetch(rng)
         logdet = None                                    # the first coupling starts the sum (NULL logdet_in)
         ctxs, c_i = [], 0
         for t in self._transforms:
@@ -300,11 +303,16 @@ class CompositeTransform(Transform):
                     x, ld = ops.flowbn_eval(x, t)
                     ctxs.append(None)
                 logdet = _add_scalar_to_rows(logdet, ld, B)
+        if rng is not None and training:
+            ops.join_forks(x)
         return (x, logdet), ctxs
 
     def prog_bwd(self, douts, ctxs, grads, needs):
         dy, dld = douts
         B = ctxs[0][0].shape[0]
+        rng = getattr(self, '_pgv_param_range', None)
+        if rng is not None:
+            ops.l2_prefetch(rng)
         if dy is None:
             dy = torch.zeros_like(ctxs[0][0])
         if dld is None:

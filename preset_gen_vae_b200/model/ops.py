@@ -260,15 +260,19 @@ def prepared_of(param):
     return getattr(param, '_pgv_prepared', None)
 
 
-def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True):
-    """TF32-rounded operand matrices of the channels-last kernels for weight w [Cout, Cin, kh, kw]: (wf, wq)."""
+def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True, out=None):
+    """TF32-rounded operand matrices of the channels-last kernels for weight w [Cout, Cin, kh, kw]: (wf, wq).
+    out: (wf, wq) buffers to refresh in place (persistent operand copies)."""
     ready = prepared_of(w)
-    if ready is not None:
+    if ready is not None and out is None:
         return ready
     Cout, Cin, kh, kw = w.shape
     K = Cin * kh * kw
-    wf = _empty(w, Cout, K) if fwd else None
-    wq = (_empty(w, 4 * Cin, 4 * Cout) if kh == 4 else _empty(w, Cin, Cout)) if dgrad else None
+    if out is not None:
+        wf, wq = out
+    else:
+        wf = _empty(w, Cout, K) if fwd else None
+        wq = (_empty(w, 4 * Cin, 4 * Cout) if kh == 4 else _empty(w, Cin, Cout)) if dgrad else None
     _call('pgv_conv_cl_prep_weights', _f(w), _f(wf), _f(wq), Cout, Cin, kh, kw, stride, pad, _s(w), nbytes=12 * w.numel())
     return wf, wq
 
@@ -600,11 +604,12 @@ def linear_wgrad(dy, x, want_bias=True, out=None):
 use_fc_cl = True
 
 
-def round_copy(x, ld=None):
+def round_copy(x, ld=None, out=None):
     """TF32-rounded copy of the 2-D tensor x with row pitch `ld` (>= columns, zero padded): [rows, ld]."""
     rows, cols = x.shape
     ld = cols if ld is None else ld
-    y = _empty(x, rows, ld)
+    y = out if out is not None else _empty(x, rows, ld)
+    assert y.shape == (rows, ld) and y.is_contiguous()
     _call('pgv_round_copy', _f(x), x.stride(0), _f(y), ld, rows, cols, _s(x), nbytes=4 * (x.numel() + y.numel()))
     return y
 
@@ -928,3 +933,9 @@ def coupling_inv_bwd(dx_out, dlogdet, x_out, params, id_idx, tr_idx):
     _call('pgv_coupling_inv_bwd', _f(dx_out), _f(dlogdet), _f(x_out), _f(params), _f(id_idx), _f(tr_idx), _f(dy), _f(dp), B, D, id_idx.numel(),
           tr_idx.numel(), _s(x_out))
     return dy, dp
+
+
+def l2_prefetch(t):
+    """Hint (no result): pull the contiguous tensor `t` into L2 from a child stream of the current stream."""
+    with forked(t, t):
+        _call('pgv_l2_prefetch', _f(t), t.numel() * t.element_size(), _s(t))

@@ -112,6 +112,7 @@ class TrainStep:
         self.losses = None
         self.scalars = None
         self._prepared_params = []
+        self._persistent_operands = False
         self._update_done = None
         self._nan_mask = torch.zeros(1, dtype=torch.int32, device=self.device)
         # Data parallel: SynthParamsLoss normalises every categorical group by its number of useful rows in the batch (loss.py:172) and the
@@ -158,6 +159,13 @@ class TrainStep:
                     idx = index_of[id(m.weight)]
                     m.weight._pgv_grad_out = views[idx]
                     self._direct[idx] = views[idx]
+        # each flow's parameters are one contiguous slice of the flat buffer: registered for the L2 prefetch ahead of its kernel chain
+        for flow in (self.model.ae_model.flow_transform, getattr(self.model.reg_model, '_forward_flow_transform', None)):
+            if flow is not None:
+                idxs = [index_of[id(p)] for p in flow.parameters()]
+                lo, hi = min(idxs), max(idxs)
+                if hi - lo + 1 == len(idxs):
+                    flow._pgv_param_range = flat[int(self._offs[lo]):int(self._offs[hi]) + sizes[hi]]
         self._packed = [i for i in range(len(params)) if i not in self._direct]
         self._direct_slots = self._fc_slots                                             # (offset, size) of the early all-reduce slices
         self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
@@ -180,30 +188,59 @@ class TrainStep:
         convolution, 16-byte-pitched FC matrices: 0.3 ms of small copy kernels per step).  They only depend on the parameters, so they are
         enqueued on a side stream at the very start of the step and run under the front end's DFT / mel contractions; the model picks
         them up through `ops.prepared_of(param)`."""
+        if self._persistent_operands:
+            return                                             # refreshed behind the optimizer instead (_refresh_operands)
         main = torch.cuda.current_stream(self.device)
         if getattr(self, '_prep_stream', None) is None:
             self._prep_stream = torch.cuda.Stream(device=self.device)
         self._prep_stream.wait_stream(main)
         self._prepared_params = []
         with torch.cuda.stream(self._prep_stream):
-            for m in self.model.modules():
-                if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
-                    w = m.weight
-                    cout, cin, kh, kw = w.shape                # (ConvTranspose2d: the convolution it is the data gradient of)
-                    if ops.cl_mode() and _lib.lib().pgv_conv_cl_supported(cin, cout, kh, kw, m.stride[0], m.padding[0]):
-                        w._pgv_prepared = ops.prep_conv_weights(w, m.stride[0], m.padding[0])
-                        self._prepared_params.append(w)
-            enc, dec = self.model.ae_model.encoder, self.model.ae_model.decoder
-            for lin in (enc.mlp[1], dec.mlp[0]):
-                N, K = lin.weight.shape
-                if ops.fc_route(self.tc.minibatch_size, N, K) == 'cl':
-                    lin.weight._pgv_prepared = ops.round_copy(lin.weight, (K + 3) // 4 * 4)
-                    self._prepared_params.append(lin.weight)
+            self._refresh_operands(conv=True, fc=True, persistent=False)
+
+    def _operand_modules(self):
+        convs = []
+        for m in self.model.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                cout, cin, kh, kw = m.weight.shape            # (ConvTranspose2d: the convolution it is the data gradient of)
+                if ops.cl_mode() and _lib.lib().pgv_conv_cl_supported(cin, cout, kh, kw, m.stride[0], m.padding[0]):
+                    convs.append(m)
+        enc, dec = self.model.ae_model.encoder, self.model.ae_model.decoder
+        fcs = [lin for lin in (enc.mlp[1], dec.mlp[0]) if ops.fc_route(self.tc.minibatch_size, *lin.weight.shape) == 'cl']
+        return convs, fcs
+
+    def _refresh_operands(self, conv, fc, persistent):
+        """(Re)computes the operand copies on the current stream; persistent: in place, into the buffers the captured graph reads."""
+        convs, fcs = self._operand_modules()
+        if conv:
+            for m in convs:
+                w = m.weight
+                w._pgv_prepared = ops.prep_conv_weights(w, m.stride[0], m.padding[0], out=w._pgv_prepared if persistent else None)
+                if not persistent:
+                    self._prepared_params.append(w)
+        if fc:
+            for lin in fcs:
+                w = lin.weight
+                w._pgv_prepared = ops.round_copy(w, (w.shape[1] + 3) // 4 * 4, out=w._pgv_prepared if persistent else None)
+                if not persistent:
+                    self._prepared_params.append(w)
+
+    def _make_operands_persistent(self):
+        """Several ranks: the copies live in fixed buffers that the model graph reads and that are refreshed on the communication
+        stream right behind the Adam launch of their parameters (FC copies under the encoder backward, the rest under the next step's
+        front end)."""
+        self._drop_prepared()
+        self._refresh_operands(conv=True, fc=True, persistent=False)      # allocates; from now on refreshed in place
+        self._prepared_params = []
+        self._persistent_operands = True
 
     def _join_prepared(self):
-        torch.cuda.current_stream(self.device).wait_stream(self._prep_stream)
+        if not self._persistent_operands:
+            torch.cuda.current_stream(self.device).wait_stream(self._prep_stream)
 
     def _drop_prepared(self):
+        if self._persistent_operands:
+            return
         for w in self._prepared_params:
             w._pgv_prepared = None
         self._prepared_params = []
@@ -225,7 +262,7 @@ class TrainStep:
 
     def _model_step(self, x_in, v_in, sample_info, with_optimizer):
         """Everything after the front end: forward, losses, backward, gradient packing (and Adam when with_optimizer)."""
-        if not self._prepared_params:                 # (two-graph mode: the copies are made inside the model graph)
+        if not self._prepared_params:                 # (not reached through _device_step)
             self._prepare_operands()
         self._join_prepared()
         self.model.ae_model.decoder_stream = self._side
@@ -315,6 +352,8 @@ class TrainStep:
         if not fused_opt:
             self._allreduce(overlapped=self.use_graph and self._fc_ready is not None)
             self._adam()
+            if self._persistent_operands:
+                self._refresh_operands(conv=True, fc=True, persistent=True)
         self.scalars = scalars                         # SCALAR_NAMES
         self.losses = scalars[:3]
         return self.losses
@@ -353,11 +392,13 @@ class TrainStep:
                 dist.all_reduce(self.flat_grads[lo:lo + n], op=dist.ReduceOp.SUM, group=self.pg)
             for lo, n in self._fc_slots:
                 self._adam(lo, lo + n)
+            self._refresh_operands(conv=False, fc=True, persistent=True)
             comm.wait_event(end_b)
             for lo, hi in self._rest_segments:
                 dist.all_reduce(self.flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             for lo, hi in self._rest_segments:
                 self._adam(lo, hi)
+            self._refresh_operands(conv=True, fc=False, persistent=True)
             self._update_done = torch.cuda.Event()
             self._update_done.record(comm)
         self.scalars = scalars
@@ -373,6 +414,7 @@ class TrainStep:
         static_in = (audio.clone(), v_in.clone(), sample_info.clone())
         backup = (self.flat_params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if 'running' in k}
+        self._make_operands_persistent()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -519,7 +561,10 @@ class TrainStep:
                                          'slot_offsets': [int(o) for o in self._offs], 'slot_sizes': list(self._sizes)}}
 
     def load_state_dict(self, state):
+        self.finish_updates()
         self.model.load_state_dict(state['ae_model_state_dict'])
+        if self._persistent_operands:
+            self._refresh_operands(conv=True, fc=True, persistent=True)
         opt = state.get('optimizer_state_dict')
         if opt is not None:
             if list(opt['slot_sizes']) != list(self._sizes):
