@@ -209,6 +209,8 @@ def model_configs(workload, batch):
 def line_config(workload, batch, gpus, cuda_graph):
     """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
     return {'workload': workload_name(workload, batch), 'global_batch': gpus * batch, 'parallelism': 'dp%d' % gpus,
+            'step': 'one timed step = one front end + one forward/backward/Adam over a batch; on one GPU the front end of batch i+1 runs '
+                    'inside the step of batch i (software pipeline), on several GPUs between the steps under the gradient exchange',
             'l2': 'per-step working set (activations + 241 MB of parameters, > 1 GB) exceeds the 126 MB L2; no flush needed',
             'cuda_graph': bool(cuda_graph)}
 
@@ -263,7 +265,8 @@ def main_ours(args):
             return mel.compute_host(audio_h.view(B, -1), normalize=(st['min'], st['max']), device=dev)
         h2d, d2h = audio_h.numel() * 4, B * 257 * 347 * 4
     else:
-        trainer = TrainStep(m_cfg, t_cfg, helper, device=dev, process_group=pg, use_cuda_graph=not args.no_graph)
+        trainer = TrainStep(m_cfg, t_cfg, helper, device=dev, process_group=pg, use_cuda_graph=not args.no_graph,
+                            pipeline_frontend=not args.no_pipeline)
         if args.workload in ('train', 'train_c6'):
             def dev_step():
                 return trainer.step(audio, v_in, info)
@@ -279,7 +282,8 @@ def main_ours(args):
                 # (the usual non-blocking loss logging); the last ones are fetched by e2e_finish() inside the timed region.
                 trainer.step_prefetched()
                 trainer.prefetch(audio_h, v_in_h, info_h)
-                pending.append(trainer.losses_to_host_async())
+                if trainer.scalars is not None:
+                    pending.append(trainer.losses_to_host_async())
                 return pending.pop(0).get() if len(pending) > 1 else None
 
             def e2e_finish():
@@ -387,8 +391,8 @@ def main_ours(args):
         # EVERY rank runs the instrumented eager steps (they contain the gradient all-reduce); rank 0 reports.
         # The instrumented pass is eager and single-stream (no decoder side stream), so that the events around each entry point
         # measure that kernel alone and not the time it shared the GPU with a concurrent branch.
-        trainer_graph, trainer_side = trainer.use_graph, trainer._side
-        trainer.use_graph, trainer._side = False, None
+        trainer_graph, trainer_side, trainer_pipe = trainer.use_graph, trainer._side, trainer.pipeline_frontend
+        trainer.use_graph, trainer._side, trainer.pipeline_frontend = False, None, False
         ops.use_wgrad_fork = False                      # same reason: weight gradients on the measuring stream, not on their child stream
         dev_step()
         torch.cuda.synchronize(dev)
@@ -402,7 +406,7 @@ def main_ours(args):
             dev_step()
         prof = ops.stop_profile()
         del blocker
-        trainer.use_graph, trainer._side = trainer_graph, trainer_side
+        trainer.use_graph, trainer._side, trainer.pipeline_frontend = trainer_graph, trainer_side, trainer_pipe
         ops.use_wgrad_fork = True
         if rank == 0:
             tot = sum(v['ms'] for v in prof.values())
@@ -482,6 +486,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU baseline work')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true', help='one GPU: do not software-pipeline the front end (TrainStep(pipeline_frontend=False))')
     args = ap.parse_args()
     if args.impl == 'reference':
         main_reference(args)

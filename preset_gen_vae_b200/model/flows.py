@@ -310,6 +310,9 @@ class CompositeTransform(Transform):
     def prog_bwd(self, douts, ctxs, grads, needs):
         dy, dld = douts
         B = ctxs[0][0].shape[0]
+        hook = getattr(self, 'on_backward_start', None)      # TrainStep: independent work that fills this latency-bound stretch
+        if hook is not None:
+            hook()
         rng = getattr(self, '_pgv_param_range', None)
         if rng is not None:
             ops.l2_prefetch(rng)

@@ -257,7 +257,12 @@ def conv_route(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
 def prepared_of(param):
     """Operand copies made ahead of time for this parameter (`param._pgv_prepared`, set by TrainStep.prepare_operands and valid for
     the current step only), or None."""
-    return getattr(param, '_pgv_prepared', None)
+    ready = getattr(param, '_pgv_prepared', None)
+    if ready is not None:
+        ev = getattr(param, '_pgv_prepared_event', None)      # recorded on the stream that made the copies: wait for it lazily, per
+        if ev is not None:                                     # parameter, so that the copies of later layers run under earlier layers
+            torch.cuda.current_stream(param.device).wait_event(ev)
+    return ready
 
 
 def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True, out=None):

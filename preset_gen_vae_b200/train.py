@@ -56,7 +56,7 @@ class _HostLosses:
 
 class TrainStep:
     def __init__(self, model_config, train_config, idx_helper, device=None, process_group=None, use_cuda_graph=True,
-                 spec_stats=None, beta=None, seed=0, overlap_branches=True, overlap_allreduce=True):
+                 spec_stats=None, beta=None, seed=0, overlap_branches=True, overlap_allreduce=True, pipeline_frontend=False):
         self.mc, self.tc, self.idx_helper = model_config, train_config, idx_helper
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         if self.device.index is None:
@@ -64,6 +64,11 @@ class TrainStep:
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.use_graph = use_cuda_graph
+        # One GPU: software-pipeline the front end.  step(batch i) then runs the model step of batch i-1 and, on a side branch forked
+        # where the latent flow's backward starts (300 launches of 5-10 us that leave the SMs idle), the front end of batch i; it
+        # returns the losses of batch i-1 (None on the first call).  flush_pipeline() runs the last staged batch.
+        self.pipeline_frontend = bool(pipeline_frontend) and process_group is None and use_cuda_graph
+        self._pgraph = None
         self.spec_stats = spec_stats or synthetic.SPEC_STATS
         self.beta = train_config.beta if beta is None else beta
         torch.manual_seed(seed)                       # same initial weights on every rank
@@ -212,18 +217,22 @@ class TrainStep:
     def _refresh_operands(self, conv, fc, persistent):
         """(Re)computes the operand copies on the current stream; persistent: in place, into the buffers the captured graph reads."""
         convs, fcs = self._operand_modules()
-        if conv:
-            for m in convs:
-                w = m.weight
+        cur = torch.cuda.current_stream(self.device)
+
+        def done(w):
+            if not persistent:                                 # consumers wait for THIS parameter's copies only (ops.prepared_of)
+                w._pgv_prepared_event = torch.cuda.Event()
+                w._pgv_prepared_event.record(cur)
+                self._prepared_params.append(w)
+        enc_params = {id(p) for p in self.model.ae_model.encoder.parameters()}
+        jobs = [(m.weight, m) for m in convs] * bool(conv) + [(lin.weight, None) for lin in fcs] * bool(fc)
+        jobs.sort(key=lambda j: (id(j[0]) not in enc_params, j[1] is None))      # encoder first (convolutions, then its FC), then the decoder
+        for w, m in jobs:
+            if m is not None:
                 w._pgv_prepared = ops.prep_conv_weights(w, m.stride[0], m.padding[0], out=w._pgv_prepared if persistent else None)
-                if not persistent:
-                    self._prepared_params.append(w)
-        if fc:
-            for lin in fcs:
-                w = lin.weight
+            else:
                 w._pgv_prepared = ops.round_copy(w, (w.shape[1] + 3) // 4 * 4, out=w._pgv_prepared if persistent else None)
-                if not persistent:
-                    self._prepared_params.append(w)
+            done(w)
 
     def _make_operands_persistent(self):
         """Several ranks: the copies live in fixed buffers that the model graph reads and that are refreshed on the communication
@@ -235,7 +244,8 @@ class TrainStep:
         self._persistent_operands = True
 
     def _join_prepared(self):
-        if not self._persistent_operands:
+        """End of the step: the side stream has nothing pending that the main stream has not waited for, except copies nobody used."""
+        if not self._persistent_operands and getattr(self, '_prep_stream', None) is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._prep_stream)
 
     def _drop_prepared(self):
@@ -243,6 +253,7 @@ class TrainStep:
             return
         for w in self._prepared_params:
             w._pgv_prepared = None
+            w._pgv_prepared_event = None
         self._prepared_params = []
 
     # ------------------------------------------------------------------ one step, eager (also what gets captured)
@@ -264,7 +275,6 @@ class TrainStep:
         """Everything after the front end: forward, losses, backward, gradient packing (and Adam when with_optimizer)."""
         if not self._prepared_params:                 # (not reached through _device_step)
             self._prepare_operands()
-        self._join_prepared()
         self.model.ae_model.decoder_stream = self._side
         try:
             z0_ml, z0, zk, logdet, x_out = self.model(x_in, sample_info)
@@ -286,6 +296,7 @@ class TrainStep:
             p.grad = None
         total.backward()
         self._pack_grads(1.0)
+        self._join_prepared()
         if with_optimizer:
             self._adam()
         zero = torch.zeros((), device=self.device)
@@ -333,6 +344,8 @@ class TrainStep:
         Returns a device tensor (recons, latent, controls) of this rank's un-weighted losses."""
         if self.world > 1 and self.use_graph and self._fc_ready is not None:
             return self._step_overlapped(audio, v_in, sample_info)
+        if self.pipeline_frontend:
+            return self._step_pipelined(audio, v_in, sample_info)
         self.finish_updates()
         self._refresh_hyper()
         fused_opt = self.world == 1
@@ -357,6 +370,69 @@ class TrainStep:
         self.scalars = scalars                         # SCALAR_NAMES
         self.losses = scalars[:3]
         return self.losses
+
+    # ------------------------------------------------------------------ one GPU: front end of the next batch inside the current step
+    def _step_pipelined(self, audio, v_in, sample_info):
+        if self._pgraph is None:
+            self._capture_pipelined(audio, v_in, sample_info)           # stages this batch; nothing to report yet
+            return None
+        for dst, src in zip(self._pstatic[:3], (audio, v_in, sample_info)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._refresh_hyper()
+        self._pgraph.replay()
+        self.scalars = self._pstatic[3].clone()
+        self.losses = self.scalars[:3]
+        return self.losses
+
+    def flush_pipeline(self):
+        """Runs the model step of the batch staged by the last step() call (its front end is already done); returns its losses."""
+        assert self._pgraph is not None
+        return self._step_pipelined(*self._pstatic[:3])
+
+    def _capture_pipelined(self, audio, v_in, sample_info):
+        nxt = (audio.clone(), v_in.clone(), sample_info.clone())           # static inputs: the batch whose front end runs in the replay
+        backup = (self.flat_params.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+        bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if 'running' in k}
+        main = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for _ in range(2):                                              # warm-up (lazy init, allocator pools, constants upload)
+                self._device_step(*nxt, with_optimizer=True)
+            x_cur = self._front_end(nxt[0]).clone()                        # the batch the first replay trains on
+            x_next = torch.empty_like(x_cur)
+        main.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self.model.load_state_dict(bn_state, strict=False)
+        cur = (x_cur, nxt[1].clone(), nxt[2].clone())
+        fe_stream = torch.cuda.Stream(device=self.device)
+        flow = self.model.ae_model.flow_transform
+
+        def launch_next_front_end():
+            here = torch.cuda.current_stream(self.device)
+            fe_stream.wait_stream(here)
+            with torch.cuda.stream(fe_stream):
+                self._front_end(nxt[0], out=x_next.view(-1, x_next.shape[-2], x_next.shape[-1]))
+
+        graph = torch.cuda.CUDAGraph()
+        before = ops.launches
+        flow.on_backward_start = launch_next_front_end
+        try:
+            with torch.cuda.graph(graph):
+                try:
+                    scalars = self._model_step(*cur, with_optimizer=True)
+                finally:
+                    self._drop_prepared()
+                torch.cuda.current_stream(self.device).wait_stream(fe_stream)
+                cur[0].copy_(x_next); cur[1].copy_(nxt[1]); cur[2].copy_(nxt[2])      # the staged batch becomes the current one
+        finally:
+            flow.on_backward_start = None
+        self.launches_per_step = ops.launches - before
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self.model.load_state_dict(bn_state, strict=False)
+        self._pgraph, self._pstatic = graph, (*nxt, scalars, cur)
 
     # ------------------------------------------------------------------ several ranks: exchange hidden behind compute
     def _step_overlapped(self, audio, v_in, sample_info):
@@ -390,15 +466,11 @@ class TrainStep:
             comm.wait_event(self._fc_ready)
             for lo, n in self._fc_slots:
                 dist.all_reduce(self.flat_grads[lo:lo + n], op=dist.ReduceOp.SUM, group=self.pg)
-            for lo, n in self._fc_slots:
-                self._adam(lo, lo + n)
-            self._refresh_operands(conv=False, fc=True, persistent=True)
+            self._update_graphs[0].replay()                      # Adam on the FC slices + their rounded operand copies
             comm.wait_event(end_b)
             for lo, hi in self._rest_segments:
                 dist.all_reduce(self.flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-            for lo, hi in self._rest_segments:
-                self._adam(lo, hi)
-            self._refresh_operands(conv=True, fc=False, persistent=True)
+            self._update_graphs[1].replay()                      # Adam on the rest + the convolutions' operand matrices
             self._update_done = torch.cuda.Event()
             self._update_done.record(comm)
         self.scalars = scalars
@@ -443,6 +515,24 @@ class TrainStep:
         self.launches_per_step = ops.launches - before + len(self._fc_slots) + len(self._rest_segments)      # + the Adam launches on the communication stream
         self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
         self.model.load_state_dict(bn_state, strict=False)
+        # the update kernels behind each reduction (Adam per segment + the refresh of the operand copies: ~25 small launches) are
+        # captured too, so that a step costs the host a handful of calls - with 8 ranks per host the Python threads are the scarce resource
+        self._update_graphs = []
+        for part in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if part == 0:
+                    for lo, n in self._fc_slots:
+                        self._adam(lo, lo + n)
+                    self._refresh_operands(conv=False, fc=True, persistent=True)
+                else:
+                    for lo, hi in self._rest_segments:
+                        self._adam(lo, hi)
+                    self._refresh_operands(conv=True, fc=False, persistent=True)
+            self._update_graphs.append(g)
+        # (capturing executed nothing, but be explicit about the state the first real step starts from)
+        self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
+        self._refresh_operands(conv=True, fc=True, persistent=True)
         self._graph_a, self._graph, self._static = graph_a, graph_b, (*static_in, scalars)
         self._update_done = None
 
@@ -471,11 +561,12 @@ class TrainStep:
         main.wait_event(self._staged_ready)
         self._staged_ready = None
         self._staged_free = torch.cuda.Event()
-        if self.use_graph and self._graph is not None:
-            for dst, src in zip(self._static[:3], self._staged):      # device to device, then the staging buffers are free again
+        static = self._pstatic if (self.pipeline_frontend and self._pgraph is not None) else (self._static if self._graph is not None else None)
+        if self.use_graph and static is not None:
+            for dst, src in zip(static[:3], self._staged):            # device to device, then the staging buffers are free again
                 dst.copy_(src, non_blocking=True)
             self._staged_free.record(main)
-            return self.step(*self._static[:3])
+            return self.step(*static[:3])
         out = self.step(*self._staged)
         self._staged_free.record(main)
         return out

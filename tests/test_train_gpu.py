@@ -184,3 +184,36 @@ def test_dkl_regulariser_nan_guard_and_optimizer_state(idx_helper):
     with pytest.raises(train_mod.ModelConvergenceError):
         handle.get()
     assert int(handle.scalars()['nan_mask']) & 1                          # the reconstruction loss is the NaN one
+
+
+def test_pipelined_front_end_is_the_same_training(idx_helper):
+    """pipeline_frontend=True: step(batch i) runs the model step of batch i-1 with the front end of batch i on a side branch inside the
+    same captured graph.  Same seeds => the same losses, one call later, and the same parameters after the last flush."""
+    B = 8
+    m, t = pcfg.make_default(minibatch_size=B)
+    pcfg.apply_dataset_dims(m, idx_helper)
+    plain = TrainStep(m, t, idx_helper, use_cuda_graph=True, seed=0)
+    piped = TrainStep(m, t, idx_helper, use_cuda_graph=True, seed=0, pipeline_frontend=True)
+    assert piped.pipeline_frontend and torch.equal(plain.flat_params, piped.flat_params)
+    batches = [(synthetic.make_audio(B, 1, seed=40 + i).cuda(), synthetic.make_preset_targets(idx_helper, B, seed=40 + i).cuda(),
+                synthetic.make_sample_info(B).cuda()) for i in range(3)]
+    init = piped.flat_params.clone()
+    plain.step(*batches[0])                                  # captures the graph (and trains one step): rewind to the initial state
+    torch.cuda.synchronize()
+    plain.flat_params.copy_(init); plain.exp_avg.zero_(); plain.exp_avg_sq.zero_(); plain.step_count = 0
+    want = []
+    for i, b in enumerate(batches):
+        torch.cuda.manual_seed(1000 + i)
+        want.append(plain.step(*b).clone())
+    torch.cuda.synchronize()
+    got = []
+    assert piped.step(*batches[0]) is None                  # staged only
+    for i in range(3):
+        torch.cuda.manual_seed(1000 + i)
+        out = piped.step(*batches[i + 1]) if i + 1 < 3 else piped.flush_pipeline()
+        got.append(out.clone())
+    torch.cuda.synchronize()
+    assert piped.step_count == 3
+    for w, g in zip(want, got):
+        assert torch.isfinite(g).all()
+        assert float((w - g).abs().max()) <= 2e-3 * float(w.abs().max()), (w.tolist(), g.tolist())
