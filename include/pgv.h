@@ -226,6 +226,9 @@ PGV_API int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, 
                                 void* ws, size_t ws_bytes, pgv_stream_t stream);
 /* Bytes of the zero-filled header at the start of a channels-last workspace. */
 PGV_API int pgv_conv_cl_workspace_bytes(void);
+/* Debug / A-B switch: programmatic dependent launch of the flow kernels (gather / column-slice GEMMs / couplings / scatter): 1 (default)
+ * lets each of them become resident and prefetch its weights while its predecessor drains; 0 launches them fully serialised. */
+PGV_API int pgv_debug_set_pdl(int on);
 /* Debug / A-B switch: 0 forces the cp.async gather of the activation operand, -1 (default) lets the library choose TMA where it can. */
 PGV_API int pgv_debug_set_conv_a_mode(int mode);
 /* dst [rows, ldd] = TF32-rounded src [rows, lds] (first `cols` columns), zero in columns cols..ldd-1. */

@@ -6,6 +6,7 @@
 namespace pgv {
 
 static thread_local char g_last_error[512] = "";
+int g_use_pdl = 1;
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -82,5 +83,7 @@ int pgv_init(pgv_handle** out, int device) {
 void pgv_destroy(pgv_handle* h) { delete h; }
 
 int pgv_sm_count(const pgv_handle* h) { return h ? h->sm_count : 0; }
+
+int pgv_debug_set_pdl(int on) { pgv::g_use_pdl = on ? 1 : 0; return 0; }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/pgv.h"
 
@@ -50,6 +51,23 @@ int set_error(int code, const char* fmt, ...);
 // rank-1 entries (dimension 0 is implicitly 4 bytes).  box[0] must be 32 (128 bytes).
 int make_tmap_f32(const pgv_handle* h, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box);
+
+extern int g_use_pdl;        // pgv_debug_set_pdl: programmatic dependent launch of the PDL-aware kernels (default on)
+
+// Launch of a PDL-aware kernel (one that starts with griddepcontrol.launch_dependents and executes griddepcontrol.wait before its
+// first dependent access): lets it overlap its launch and prologue with the tail of its predecessor in the stream.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -3,6 +3,7 @@
 // conditioner network, Hardtanh (decoder.py:98, regression.py:22,51-52) and the per-group softmax activation
 // (regression.py:47-50).  One warp per row where a row reduction (log|det J|) is needed.
 #include "pgv_common.cuh"
+#include "pgv_tc.cuh"
 
 namespace pgv {
 
@@ -45,12 +46,16 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
 }
 
 __global__ void gather_cols_kernel(const float* __restrict__ x, const int* __restrict__ idx, float* __restrict__ out, int B, int D, int n) {
+    griddep_launch_dependents();
+    griddep_wait();
     const size_t total = static_cast<size_t>(B) * n;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
         out[i] = x[(i / n) * D + idx[i % n]];
 }
 // dst[b, idx[j]] += src[b, j]   (idx has no duplicates)
 __global__ void scatter_add_cols_kernel(float* __restrict__ dst, const int* __restrict__ idx, const float* __restrict__ src, int B, int D, int n) {
+    griddep_launch_dependents();
+    griddep_wait();
     const size_t total = static_cast<size_t>(B) * n;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
         dst[(i / n) * D + idx[i % n]] += src[i];
@@ -64,6 +69,8 @@ __global__ void __launch_bounds__(CPL_THREADS) coupling_fwd_kernel(const float* 
                                                            float* __restrict__ y, const float* __restrict__ ld_in, float* __restrict__ ld_out,
                                                            int B, int D, int n_id, int n_t, int inverse) {
     __shared__ float red[CPL_THREADS / 32];
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x, tid = threadIdx.x;
     const float* xr = x + static_cast<size_t>(row) * D;
     float* yr = y + static_cast<size_t>(row) * D;
@@ -92,6 +99,8 @@ __global__ void __launch_bounds__(CPL_THREADS) coupling_bwd_kernel(const float* 
                                                            const float* __restrict__ x, const float* __restrict__ params,
                                                            const int* __restrict__ id_idx, const int* __restrict__ tr_idx,
                                                            float* __restrict__ dx, float* __restrict__ dparams, int B, int D, int n_id, int n_t) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x, tid = threadIdx.x;
     const size_t ro = static_cast<size_t>(row) * D;
     const float* pr = params + static_cast<size_t>(row) * 2 * n_t;
@@ -216,14 +225,14 @@ int pgv_reparam_bwd(const float* dz0, const float* mu_logvar, const float* eps, 
 
 int pgv_gather_cols(const float* x, const int* idx, float* out, int B, int D, int n, pgv_stream_t stream) {
     PGV_CHECK_ARG(x && idx && out && B > 0 && D > 0 && n > 0, "pgv_gather_cols: bad argument");
-    gather_cols_kernel<<<grid1d(static_cast<size_t>(B) * n), 256, 0, PGV_STREAM(stream)>>>(x, idx, out, B, D, n);
+    PGV_CUDA(launch_pdl(gather_cols_kernel, dim3(grid1d(static_cast<size_t>(B) * n)), dim3(256), 0, PGV_STREAM(stream), x, idx, out, B, D, n));
     PGV_LAUNCH_CHECK();
     return 0;
 }
 
 int pgv_scatter_add_cols(float* dst, const int* idx, const float* src, int B, int D, int n, pgv_stream_t stream) {
     PGV_CHECK_ARG(dst && idx && src && B > 0 && D > 0 && n > 0, "pgv_scatter_add_cols: bad argument");
-    scatter_add_cols_kernel<<<grid1d(static_cast<size_t>(B) * n), 256, 0, PGV_STREAM(stream)>>>(dst, idx, src, B, D, n);
+    PGV_CUDA(launch_pdl(scatter_add_cols_kernel, dim3(grid1d(static_cast<size_t>(B) * n)), dim3(256), 0, PGV_STREAM(stream), dst, idx, src, B, D, n));
     PGV_LAUNCH_CHECK();
     return 0;
 }
@@ -233,8 +242,8 @@ int pgv_coupling_fwd(const float* x, const float* params, const int* identity_id
                      pgv_stream_t stream) {
     PGV_CHECK_ARG(x && params && identity_idx && transform_idx && y && logdet_out, "pgv_coupling_fwd: NULL argument");
     PGV_CHECK_ARG(n_identity + n_transform == D && B > 0, "pgv_coupling_fwd: index lists must partition the %d features", D);
-    coupling_fwd_kernel<<<B, CPL_THREADS, 0, PGV_STREAM(stream)>>>(x, params, identity_idx, transform_idx, y, logdet_in, logdet_out, B, D,
-                                                                       n_identity, n_transform, inverse);
+    PGV_CUDA(launch_pdl(coupling_fwd_kernel, dim3(B), dim3(CPL_THREADS), 0, PGV_STREAM(stream), x, params, identity_idx, transform_idx, y,
+                        logdet_in, logdet_out, B, D, n_identity, n_transform, inverse));
     PGV_LAUNCH_CHECK();
     return 0;
 }
@@ -244,8 +253,8 @@ int pgv_coupling_bwd(const float* dy, const float* dlogdet, const float* x, cons
                      pgv_stream_t stream) {
     PGV_CHECK_ARG(dy && x && params && identity_idx && transform_idx && dx && dparams, "pgv_coupling_bwd: NULL argument");
     PGV_CHECK_ARG(n_identity + n_transform == D && B > 0, "pgv_coupling_bwd: index lists must partition the features");
-    coupling_bwd_kernel<<<B, CPL_THREADS, 0, PGV_STREAM(stream)>>>(dy, dlogdet, x, params, identity_idx, transform_idx, dx, dparams, B, D,
-                                                                       n_identity, n_transform);
+    PGV_CUDA(launch_pdl(coupling_bwd_kernel, dim3(B), dim3(CPL_THREADS), 0, PGV_STREAM(stream), dy, dlogdet, x, params, identity_idx,
+                        transform_idx, dx, dparams, B, D, n_identity, n_transform));
     PGV_LAUNCH_CHECK();
     return 0;
 }

@@ -95,11 +95,13 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
     const uint32_t stage0_u32 = smem_u32(stage0);
     const int n_chunks = (p.Kd + CS_BK - 1) / CS_BK;
 
-    auto issue = [&](int ch) {
+    // parts: bit 0 = the A (activation) tile, bit 1 = the B (weight) tile of chunk ch; `commit` closes the chunk's cp.async group
+    auto issue = [&](int ch, int parts, bool commit) {
         if (ch < n_chunks) {
             const int k0 = ch * CS_BK;
             const uint32_t sA = stage0_u32 + (ch % CS_STAGES) * CS_STAGE_FLOATS * 4, sB = sA + CS_ROWS * CS_LD * 4;
-            if (p.a_vec) {                                  // 32 rows x 8 float4: one per thread
+            if (!(parts & 1)) {
+            } else if (p.a_vec) {                           // 32 rows x 8 float4: one per thread
                 const int row = t >> 3, c4 = t & 7, k = k0 + 4 * c4;
                 const bool ok = m0 + row < p.M && k < p.Kd;
                 cp_async16_cg(sA + (row * CS_LD + 4 * c4) * 4, ok ? p.a + static_cast<size_t>(m0 + row) * p.lda + k : p.a, ok ? 16u : 0u);
@@ -111,7 +113,8 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
                     cp_async4(sA + (row * CS_LD + kk) * 4, ok ? p.a + static_cast<size_t>(m0 + row) * p.lda + k : p.a, ok ? 4u : 0u);
                 }
             }
-            if (TB == 0) {                                  // B[n0 + c][k0 + kk], contiguous along k
+            if (!(parts & 2)) {
+            } else if (TB == 0) {                           // B[n0 + c][k0 + kk], contiguous along k
                 if (p.b_vec) {
                     if (t < CS_COLS * 8) {
                         const int c = t >> 3, c4 = t & 7, k = k0 + 4 * c4;
@@ -135,16 +138,22 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
                 }
             }
         }
-        cp_async_commit();                                  // one group per chunk slot, empty past the end
+        if (commit) cp_async_commit();                      // one group per chunk slot, empty past the end
     };
 
+    // Programmatic dependent launch: the weights do not depend on the kernel in front, so their first tiles are fetched while that
+    // kernel is still draining; everything else (activations, every store) comes after griddepcontrol.wait.
+    griddep_launch_dependents();
     float acc[2] = {0.0f, 0.0f};
 #pragma unroll
-    for (int s = 0; s < CS_STAGES - 1; ++s) issue(s);
+    for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 2, false);
+    griddep_wait();
+#pragma unroll
+    for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 1, true);
     for (int ch = 0; ch < n_chunks; ++ch) {
         cp_async_wait<CS_STAGES - 2>();                     // chunk ch has landed (this thread's copies) ...
         __syncthreads();                                    // ... and everybody's; everybody is also done with chunk ch - 1
-        issue(ch + CS_STAGES - 1);                          // refill the slot chunk ch - 1 used
+        issue(ch + CS_STAGES - 1, 3, true);                 // refill the slot chunk ch - 1 used
         const float* sA = stage0 + (ch % CS_STAGES) * CS_STAGE_FLOATS;
         const float* sB = sA + CS_ROWS * CS_LD;
 #pragma unroll
@@ -256,13 +265,15 @@ static int cs_launch(CsParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(CS_THREADS, 1, 1);
     cfg.dynamicSmemBytes = CS_SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = (EPI == EPI_PLAIN) ? 1 : row_ctas;       // the row CTAs of one column slice exchange BatchNorm partial sums
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // see the prologue of the kernel
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
     PGV_CUDA(cudaLaunchKernelEx(&cfg, colslice_gemm_kernel<TB, EPI>, p));
     return 0;
 }

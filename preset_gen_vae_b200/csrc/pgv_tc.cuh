@@ -102,6 +102,14 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident
+// as soon as every CTA of its predecessor in the stream has executed griddepcontrol.launch_dependents (or exited); it must execute
+// griddepcontrol.wait before it reads anything the predecessor wrote or writes anything the predecessor may still read - the wait
+// returns once the predecessor has completed and its memory is visible.  Used by the chains of 5-10 us flow kernels, whose time is
+// mostly launch latency and a cold fetch of weights that do not depend on the predecessor.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // named barrier among `count` threads of the CTA (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
