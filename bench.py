@@ -42,7 +42,8 @@ KERNEL_OF = {'pgv_conv_cl_fwd': 'conv_cl_kernel', 'pgv_conv_cl_dgrad': 'conv_cl_
              'pgv_linear_cl_fwd': 'conv_cl_kernel', 'pgv_linear_cl_dgrad': 'conv_cl_kernel', 'pgv_linear_cl_wgrad': 'conv_cl_kernel',
              'pgv_linear_cs_fwd': 'colslice_gemm_kernel', 'pgv_linear_cs_dgrad': 'colslice_gemm_kernel', 'pgv_linear_bn_fwd': 'colslice_gemm_kernel',
              'pgv_linear_dgrad_bn_bwd': 'colslice_gemm_kernel',
-             'pgv_gemm_f32': 'gemm_f32_small_kernel', 'pgv_linear_wgrad_f32': 'gemm_f32_small_kernel'}
+             'pgv_gemm_f32': 'gemm_f32_small_kernel', 'pgv_linear_wgrad_f32': 'gemm_f32_small_kernel',
+             'pgv_flow_program': 'flow_program_kernel'}
 
 
 def measured_traffic(kernel):

@@ -226,8 +226,9 @@ PGV_API int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, 
                                 void* ws, size_t ws_bytes, pgv_stream_t stream);
 /* Bytes of the zero-filled header at the start of a channels-last workspace. */
 PGV_API int pgv_conv_cl_workspace_bytes(void);
-/* Debug / A-B switch: programmatic dependent launch of the flow kernels (gather / column-slice GEMMs / couplings / scatter): 1 (default)
- * lets each of them become resident and prefetch its weights while its predecessor drains; 0 launches them fully serialised. */
+/* Debug / A-B switch: programmatic dependent launch of the stand-alone flow kernels (gather / column-slice GEMMs / couplings / scatter):
+ * 1 lets each of them become resident and prefetch its weights while its predecessor drains; 0 (default: measured faster on B200)
+ * launches them fully serialised. */
 PGV_API int pgv_debug_set_pdl(int on);
 /* Debug / A-B switch: 0 forces the cp.async gather of the activation operand, -1 (default) lets the library choose TMA where it can. */
 PGV_API int pgv_debug_set_conv_a_mode(int mode);
@@ -366,6 +367,14 @@ PGV_API int pgv_nan_flags(const float* s0, const float* s1, const float* s2, con
 /* data/abstractbasedataset.py:348-391: per_item4[i] = (min, max, mean, unbiased variance) of spectrogram i (x [N, elems]); dataset4
  * (optional) = (min of mins, max of maxes, mean of means, sqrt(mean of variances)). */
 PGV_API int pgv_spectrogram_stats(const float* x, int N, size_t elems, float* per_item4, float* dataset4, pgv_stream_t stream);
+/* A recorded chain of flow ops (gather / column-slice Linear with fused BatchNorm forward or backward / coupling / scatter / small
+ * weight gradients) as ONE persistent launch with grid barriers between dependent ops: `ops` = host array of n_ops records of
+ * pgv_flow_program_op_bytes() bytes each (kind, barrier_after, the parameter block of the stand-alone kernel: see csrc/pgv_flow_fused.cu
+ * and model/ops.py), at most pgv_flow_program_max_ops(); M = batch rows (<= pgv_colslice_max_rows()); counter = one device word.
+ * Replaces ~50 (forward) / ~90 (backward) launches of 5-10 us per RealNVP flow (model/flows.py:42-90, VAE.py:118-125). */
+PGV_API int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned* counter, pgv_stream_t stream);
+PGV_API int pgv_flow_program_op_bytes(void);
+PGV_API int pgv_flow_program_max_ops(void);
 /* Hint: pull [p, p + bytes) into L2 (one prefetch per 128-byte line); used on a flow's 15 MB of conditioner weights right before the
  * chain of small kernels that read them once each. */
 PGV_API int pgv_l2_prefetch(const void* p, size_t bytes, pgv_stream_t stream);

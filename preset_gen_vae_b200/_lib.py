@@ -66,8 +66,8 @@ def lib():
             if cdll.pgv_version() != _header_version():
                 raise PgvError("libpgv.so version %d does not match include/pgv.h (%d): rebuild" %
                                (cdll.pgv_version(), _header_version()))
-            if os.environ.get('PGV_PDL') == '0':          # A/B switch (tools / bench): flow kernels without programmatic dependent launch
-                cdll.pgv_debug_set_pdl(0)
+            if os.environ.get('PGV_PDL') == '1':          # A/B switch (tools / bench): flow kernels WITH programmatic dependent launch
+                cdll.pgv_debug_set_pdl(1)
             _lib = cdll
     return _lib
 

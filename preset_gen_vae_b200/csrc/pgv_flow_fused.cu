@@ -14,6 +14,8 @@
 // 4-stage shared-memory ring (27 KB, so a CTA fits next to a resident 194 KB convolution CTA of the concurrent decoder
 // branch); each thread owns 1 row x 2 columns and reads shared memory with 128-bit loads along k.
 #include <cooperative_groups.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "pgv_common.cuh"
@@ -83,14 +85,23 @@ __device__ __forceinline__ void cs_cluster_col_reduce(double (&s)[2], double (&q
     cluster.sync();                                       // nobody leaves (or overwrites `part`) while a peer still reads it
 }
 
+struct CsShared {
+    double wred[8][CS_COLS][2];
+    double part[CS_COLS][2], tot[CS_COLS][2];
+    float stat[CS_COLS][2];
+};
+
+// One 32-row x 16-column tile: column slice `slice`, row block `rblock` of `cluster_size`.  PDL: the stand-alone kernels prefetch their
+// weights before griddepcontrol.wait; inside the flow program kernel (pdl = false) the grid barrier has already ordered everything.
 template <int TB, int EPI>
-__global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParams p) {
-    extern __shared__ __align__(16) uint8_t cs_smem[];
-    __shared__ double wred[8][CS_COLS][2];
-    __shared__ double part[CS_COLS][2], tot[CS_COLS][2];
-    __shared__ float stat[CS_COLS][2];
+__device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int rblock, int cluster_size, uint8_t* cs_smem, CsShared& sh,
+                                              bool pdl) {
+    double (&wred)[8][CS_COLS][2] = sh.wred;
+    double (&part)[CS_COLS][2] = sh.part;
+    double (&tot)[CS_COLS][2] = sh.tot;
+    float (&stat)[CS_COLS][2] = sh.stat;
     const int t = threadIdx.x, tx = t & 7, ty = t >> 3;           // row ty of this CTA's 32; columns tx, tx + 8
-    const int n0 = blockIdx.x * CS_COLS, m0 = blockIdx.y * CS_ROWS;
+    const int n0 = slice * CS_COLS, m0 = rblock * CS_ROWS;
     float* const stage0 = reinterpret_cast<float*>(cs_smem);
     const uint32_t stage0_u32 = smem_u32(stage0);
     const int n_chunks = (p.Kd + CS_BK - 1) / CS_BK;
@@ -143,13 +154,18 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
 
     // Programmatic dependent launch: the weights do not depend on the kernel in front, so their first tiles are fetched while that
     // kernel is still draining; everything else (activations, every store) comes after griddepcontrol.wait.
-    griddep_launch_dependents();
     float acc[2] = {0.0f, 0.0f};
+    if (pdl) {
+        griddep_launch_dependents();
 #pragma unroll
-    for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 2, false);
-    griddep_wait();
+        for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 2, false);
+        griddep_wait();
 #pragma unroll
-    for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 1, true);
+        for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 1, true);
+    } else {
+#pragma unroll
+        for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 3, true);
+    }
     for (int ch = 0; ch < n_chunks; ++ch) {
         cp_async_wait<CS_STAGES - 2>();                     // chunk ch has landed (this thread's copies) ...
         __syncthreads();                                    // ... and everybody's; everybody is also done with chunk ch - 1
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
     for (int j = 0; j < 2; ++j)
         if (ok[j]) {
             if (p.bias != nullptr) acc[j] += __ldg(p.bias + col[j]);
-            if (p.add_pre != nullptr) acc[j] += __ldg(p.add_pre + static_cast<size_t>(row) * p.N + col[j]);
+            if (p.add_pre != nullptr) acc[j] += p.add_pre[static_cast<size_t>(row) * p.N + col[j]];
         }
     if (EPI == EPI_PLAIN) {
 #pragma unroll
@@ -184,7 +200,6 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
             if (ok[j]) p.out[static_cast<size_t>(row) * p.N + col[j]] = p.relu ? fmaxf(acc[j], 0.0f) : acc[j];
         return;
     }
-    const int cluster_size = gridDim.y;
     if (EPI == EPI_BN_FWD) {
         double s[2] = {0.0, 0.0}, q[2] = {0.0, 0.0};
 #pragma unroll
@@ -202,7 +217,7 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
             if (var < 0.0) var = 0.0;
             const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps))), fm = static_cast<float>(mean);
             stat[t][0] = fm; stat[t][1] = rstd;
-            if (c < p.N && blockIdx.y == 0) {
+            if (c < p.N && rblock == 0) {
                 p.save_mean[c] = fm; p.save_rstd[c] = rstd;
                 if (p.running_mean != nullptr) {
                     const double unbiased = p.M > 1 ? var * p.M / (p.M - 1.0) : var;
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
                 const float g = __ldg(p.gamma + col[j]) * stat[tx + 8 * j][1], sh = __ldg(p.beta + col[j]) - stat[tx + 8 * j][0] * g;
                 const size_t o = static_cast<size_t>(row) * p.N + col[j];
                 float v = fmaxf(fmaf(acc[j], g, sh), 0.0f);
-                if (p.mask != nullptr) v *= __ldg(p.mask + o);
+                if (p.mask != nullptr) v *= p.mask[o];
                 p.out[o] = v;
             }
         return;
@@ -230,28 +245,35 @@ __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParam
     for (int j = 0; j < 2; ++j)
         if (ok[j]) {
             const size_t o = static_cast<size_t>(row) * p.N + col[j];
-            const float h = (__ldg(p.bn_x + o) - __ldg(p.mean + col[j])) * __ldg(p.rstd + col[j]);
+            const float h = (p.bn_x[o] - p.mean[col[j]]) * p.rstd[col[j]];
             float d = acc[j];
-            if (p.mask != nullptr) d *= __ldg(p.mask + o);
+            if (p.mask != nullptr) d *= p.mask[o];
             if (!(fmaf(__ldg(p.gamma + col[j]), h, __ldg(p.beta + col[j])) > 0.0f)) d = 0.0f;
             acc[j] = d; xh[j] = h;
             s[j] = d; q[j] = static_cast<double>(d) * h;
         }
     cs_cluster_col_reduce(s, q, wred, part, tot, cluster_size);
-    if (t < CS_COLS && n0 + t < p.N && blockIdx.y == 0) {
+    if (t < CS_COLS && n0 + t < p.N && rblock == 0) {
         p.dbeta[n0 + t] = static_cast<float>(tot[t][0]);
         p.dgamma[n0 + t] = static_cast<float>(tot[t][1]);
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
         if (ok[j]) {
-            const float gr = __ldg(p.gamma + col[j]) * __ldg(p.rstd + col[j]);
+            const float gr = __ldg(p.gamma + col[j]) * p.rstd[col[j]];
             const float mean_d = static_cast<float>(tot[tx + 8 * j][0] / p.M), mean_dx = static_cast<float>(tot[tx + 8 * j][1] / p.M);
             const size_t o = static_cast<size_t>(row) * p.N + col[j];
             float v = gr * (acc[j] - mean_d - xh[j] * mean_dx);
-            if (p.add_post != nullptr) v += __ldg(p.add_post + o);
+            if (p.add_post != nullptr) v += p.add_post[o];
             p.out[o] = v;
         }
+}
+
+template <int TB, int EPI>
+__global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParams p) {
+    extern __shared__ __align__(16) uint8_t cs_smem_k[];
+    __shared__ CsShared sh;
+    colslice_tile<TB, EPI>(p, blockIdx.x, blockIdx.y, gridDim.y, cs_smem_k, sh, true);
 }
 
 template <int TB, int EPI>
@@ -278,11 +300,240 @@ static int cs_launch(CsParams& p, cudaStream_t stream) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ flow program kernel
+// A RealNVP flow is a chain of ~50 (forward) / ~90 (backward) of the small kernels above and in pgv_flow.cu, each 5-10 us of mostly
+// launch / drain / cold-start latency: on the training step's critical path the two flows took 3.6 of 7.4 ms.  The program kernel runs
+// such a chain as ONE persistent launch: the host records the calls into a table (passed by value as a kernel parameter, up to 32 KB),
+// every CTA walks the table and executes its share of each op - the same tile code as the stand-alone kernels - with a grid-wide
+// barrier between dependent ops (release: bar.sync + fence + atomic; acquire: spin on ld.acquire + fence, which also invalidates L1).
+// Grid = G clusters of `row_ctas` CTAs (the cluster that reduces BatchNorm statistics through DSMEM); all CTAs are co-resident
+// (<= 1 per SM; 31 KB of shared memory each, so they fit beside a 188 KB convolution CTA of the concurrent decoder branch).
+enum { MOP_GATHER = 0, MOP_CS_FWD = 1, MOP_CS_BN_FWD = 2, MOP_CS_DGRAD = 3, MOP_CS_BN_BWD = 4, MOP_COUPLING_FWD = 5, MOP_COUPLING_BWD = 6,
+       MOP_SCATTER_ADD = 7, MOP_WGRAD = 8 };
+struct MegaOp {
+    int kind, barrier_after;
+    CsParams cs;          // column-slice kinds: as for the stand-alone kernels; other kinds reuse the fields (see pgv_flow_program)
+};
+constexpr int MEGA_MAX_OPS = 150;
+struct MegaProgram {
+    int n_ops, row_ctas;
+    unsigned* counter;    // grid barrier: zero on entry
+    MegaOp ops[MEGA_MAX_OPS];
+};
+static_assert(sizeof(MegaProgram) <= 32000, "the program must fit the kernel parameter space");
+
+__device__ __forceinline__ void mega_grid_barrier(unsigned* counter, unsigned& target, unsigned n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += n_ctas;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v, spins = 0;
+        uint64_t t0 = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v < target && (++spins & 4095u) == 0) {       // never wedge the device: a barrier that has not opened after 4 s traps
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) __trap();
+            }
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float mega_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// dw[n][k] = sum_m dy[m][n] * x[m][k] (32 x 32 tile, 2 x 2 outputs per thread); db[n] = sum_m dy[m][n] from the k-tile-0 tiles
+__device__ __forceinline__ void mega_wgrad_tile(const CsParams& p, int tile_k, int tile_n, float (*sa)[33], float (*sb)[33]) {
+    const float* dy = p.a; const float* x = p.b; float* dw = p.out; float* db = p.out_pre;
+    const int M = p.M, N = p.N, K = p.Kd, t = threadIdx.x, tx = t & 15, ty = t >> 4, n0 = tile_n * 32, k0 = tile_k * 32;
+    float acc[2][2] = {};
+    float cs0 = 0.0f, cs1 = 0.0f;
+    const bool do_colsum = db != nullptr && tile_k == 0 && tx == 0;
+    for (int m0 = 0; m0 < M; m0 += 32) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int id = t + q * 256, c = id & 31, r = id >> 5, m = m0 + r;
+            sa[r][c] = (m < M && n0 + c < N) ? dy[static_cast<size_t>(m) * N + n0 + c] : 0.0f;
+            sb[r][c] = (m < M && k0 + c < K) ? x[static_cast<size_t>(m) * K + k0 + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < 32; ++mm) {
+            const float a0 = sa[mm][ty * 2], a1 = sa[mm][ty * 2 + 1], b0 = sb[mm][tx * 2], b1 = sb[mm][tx * 2 + 1];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+            if (do_colsum) { cs0 += a0; cs1 += a1; }
+        }
+    }
+    if (do_colsum) {
+        if (n0 + ty * 2 < N) db[n0 + ty * 2] = cs0;
+        if (n0 + ty * 2 + 1 < N) db[n0 + ty * 2 + 1] = cs1;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + ty * 2 + i, k = k0 + tx * 2 + j;
+            if (n < N && k < K) dw[static_cast<size_t>(n) * K + k] = acc[i][j];
+        }
+}
+
+__global__ void __launch_bounds__(CS_THREADS) flow_program_kernel(const __grid_constant__ MegaProgram prog) {
+    extern __shared__ __align__(16) uint8_t cs_smem_m[];
+    __shared__ CsShared sh;
+    __shared__ float red[8];
+    const int row_ctas = prog.row_ctas, rblock = blockIdx.y, cl = blockIdx.z, n_clusters = gridDim.z;
+    const unsigned n_ctas = gridDim.y * gridDim.z;
+    const int cta = cl * row_ctas + rblock, t = threadIdx.x;
+    unsigned target = 0;
+    for (int oi = 0; oi < prog.n_ops; ++oi) {
+        const MegaOp& op = prog.ops[oi];
+        const CsParams& p = op.cs;
+        switch (op.kind) {
+        case MOP_CS_FWD: case MOP_CS_BN_FWD: case MOP_CS_DGRAD: case MOP_CS_BN_BWD: {
+            const int slices = (p.N + CS_COLS - 1) / CS_COLS;
+            for (int sl = cl; sl < slices; sl += n_clusters) {
+                __syncthreads();                               // the previous tile's readers are done with the ring and the statistics
+                if (op.kind == MOP_CS_FWD) colslice_tile<0, EPI_PLAIN>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
+                else if (op.kind == MOP_CS_BN_FWD) colslice_tile<0, EPI_BN_FWD>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
+                else if (op.kind == MOP_CS_DGRAD) colslice_tile<1, EPI_PLAIN>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
+                else colslice_tile<1, EPI_BN_BWD>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
+            }
+            break;
+        }
+        case MOP_GATHER: {                                     // out[b, j] = x[b, idx[j]]: a = x, b = idx, M = B, N = D, Kd = n
+            const int* idx = reinterpret_cast<const int*>(p.b);
+            const size_t total = static_cast<size_t>(p.M) * p.Kd;
+            for (size_t i = static_cast<size_t>(cta) * CS_THREADS + t; i < total; i += static_cast<size_t>(n_ctas) * CS_THREADS)
+                p.out[i] = p.a[(i / p.Kd) * p.N + idx[i % p.Kd]];
+            break;
+        }
+        case MOP_SCATTER_ADD: {                                // dst[b, idx[j]] += src[b, j]: out = dst, b = idx, a = src
+            const int* idx = reinterpret_cast<const int*>(p.b);
+            const size_t total = static_cast<size_t>(p.M) * p.Kd;
+            for (size_t i = static_cast<size_t>(cta) * CS_THREADS + t; i < total; i += static_cast<size_t>(n_ctas) * CS_THREADS)
+                p.out[(i / p.Kd) * p.N + idx[i % p.Kd]] += p.a[i];
+            break;
+        }
+        case MOP_COUPLING_FWD: {       // a = x, b = params, bias = id_idx, add_pre = tr_idx, out = y, out_pre = ld_out, gamma = ld_in; Kd = n_id, lda = n_t
+            const int* id_idx = reinterpret_cast<const int*>(p.bias);
+            const int* tr_idx = reinterpret_cast<const int*>(p.add_pre);
+            const int D = p.N, n_id = p.Kd, n_t = p.lda, inverse = p.relu;
+            for (int row = cta; row < p.M; row += static_cast<int>(n_ctas)) {
+                const float* xr = p.a + static_cast<size_t>(row) * D;
+                float* yr = p.out + static_cast<size_t>(row) * D;
+                const float* pr = p.b + static_cast<size_t>(row) * 2 * n_t;
+                for (int j = t; j < n_id; j += CS_THREADS) yr[id_idx[j]] = xr[id_idx[j]];
+                float ld = 0.0f;
+                for (int j = t; j < n_t; j += CS_THREADS) {
+                    const float sc = mega_sigmoid(pr[n_t + j] + 2.0f) + 1e-3f, sf = pr[j];
+                    const int c = tr_idx[j];
+                    yr[c] = inverse ? (xr[c] - sf) / sc : fmaf(xr[c], sc, sf);
+                    ld += logf(sc);
+                }
+                for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+                __syncthreads();
+                if ((t & 31) == 0) red[t >> 5] = ld;
+                __syncthreads();
+                if (t == 0) {
+                    float tot = 0.0f;
+                    for (int w = 0; w < CS_THREADS / 32; ++w) tot += red[w];
+                    p.out_pre[row] = (p.gamma != nullptr ? p.gamma[row] : 0.0f) + (inverse ? -tot : tot);
+                }
+            }
+            break;
+        }
+        case MOP_COUPLING_BWD: {       // a = dy, b = dld, bias = x, add_pre = params, gamma = id_idx, beta = tr_idx, out = dx, out_pre = dparams
+            const int* id_idx = reinterpret_cast<const int*>(p.gamma);
+            const int* tr_idx = reinterpret_cast<const int*>(p.beta);
+            const int D = p.N, n_id = p.Kd, n_t = p.lda;
+            for (int row = cta; row < p.M; row += static_cast<int>(n_ctas)) {
+                const size_t ro = static_cast<size_t>(row) * D;
+                const float* pr = p.add_pre + static_cast<size_t>(row) * 2 * n_t;
+                float* dpr = p.out_pre + static_cast<size_t>(row) * 2 * n_t;
+                const float gl = p.b != nullptr ? p.b[row] : 0.0f;
+                for (int j = t; j < n_id; j += CS_THREADS) p.out[ro + id_idx[j]] = p.a[ro + id_idx[j]];
+                for (int j = t; j < n_t; j += CS_THREADS) {
+                    const int c = tr_idx[j];
+                    const float sg = mega_sigmoid(pr[n_t + j] + 2.0f), sc = sg + 1e-3f, g = p.a[ro + c];
+                    p.out[ro + c] = g * sc;
+                    dpr[j] = g;
+                    dpr[n_t + j] = (g * p.bias[ro + c] + gl / sc) * sg * (1.0f - sg);
+                }
+            }
+            break;
+        }
+        case MOP_WGRAD: {              // a = dy [M, N], b = x [M, Kd], out = dw [N, Kd], out_pre = db
+            const int tk = (p.Kd + 31) / 32, tn = (p.N + 31) / 32;
+            float (*sa)[33] = reinterpret_cast<float (*)[33]>(cs_smem_m);
+            float (*sb)[33] = sa + 32;
+            for (int tile = cta; tile < tk * tn; tile += static_cast<int>(n_ctas)) mega_wgrad_tile(p, tile % tk, tile / tk, sa, sb);
+            break;
+        }
+        default: break;
+        }
+        if (op.barrier_after) mega_grid_barrier(prog.counter, target, n_ctas);
+    }
+}
+
 }  // namespace pgv
 
 using namespace pgv;
 
 extern "C" {
+
+/* Runs a recorded chain of flow ops as one persistent launch.  `ops` is a HOST array of n_ops records {int kind; int barrier_after;
+ * CsParams} (layout as in this file; the Python side builds it with ctypes), `counter` a zero-filled device word (zeroed again by this
+ * call), M the batch rows shared by the column-slice ops. */
+int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned* counter, pgv_stream_t stream_) {
+    PGV_CHECK_ARG(h && ops && counter && n_ops > 0 && n_ops <= MEGA_MAX_OPS && M > 0 && M <= CS_MAXM, "pgv_flow_program: bad argument (%d ops)", n_ops);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    static MegaProgram prog;                                  // 30 KB: not on the stack; copied into the launch by cudaLaunchKernelEx
+    prog.n_ops = n_ops;
+    prog.row_ctas = ceil_div(M, CS_ROWS);
+    prog.counter = counter;
+    memcpy(prog.ops, ops, sizeof(MegaOp) * n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        CsParams& p = prog.ops[i].cs;
+        const int k = prog.ops[i].kind;
+        if (k == MOP_CS_FWD || k == MOP_CS_BN_FWD || k == MOP_CS_DGRAD || k == MOP_CS_BN_BWD) {
+            const bool tb0 = k == MOP_CS_FWD || k == MOP_CS_BN_FWD;
+            p.a_vec = (p.Kd % 4 == 0 && p.lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p.a) & 15) == 0) ? 1 : 0;
+            p.b_vec = (tb0 && p.Kd % 4 == 0 && p.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(p.b) & 15) == 0) ? 1 : 0;
+            if (p.M != M) return set_error(-1, "pgv_flow_program: op %d has %d rows, the program %d", i, p.M, M);
+        }
+    }
+    prog.ops[n_ops - 1].barrier_after = 0;
+    static bool configured = false;
+    if (!configured) {
+        PGV_CUDA(cudaFuncSetAttribute(flow_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+        configured = true;
+    }
+    PGV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+    const int clusters = std::max(1, std::min(39, (h->sm_count - 8) / prog.row_ctas));       // co-resident: at most one CTA per SM
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(1, prog.row_ctas, clusters);
+    cfg.blockDim = dim3(CS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = CS_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = prog.row_ctas;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PGV_CUDA(cudaLaunchKernelEx(&cfg, flow_program_kernel, prog));
+    return 0;
+}
+
+int pgv_flow_program_op_bytes(void) { return static_cast<int>(sizeof(MegaOp)); }
+int pgv_flow_program_max_ops(void) { return MEGA_MAX_OPS; }
 
 int pgv_colslice_max_rows(void) { return CS_MAXM; }
 

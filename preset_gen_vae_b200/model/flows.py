@@ -286,6 +286,14 @@ class CompositeTransform(Transform):
         rng = getattr(self, '_pgv_param_range', None)    # TrainStep: this flow's parameters as one contiguous slice of the flat buffer
         if rng is not None and training:
             ops.l2_prefetch(rng)
+        if training:
+            ops.mega_begin(x, B)                         # the whole chain as one persistent launch (ops.py, pgv_flow_program)
+        try:
+            return self._prog_fwd_body(x, B, training, extra, rng)
+        finally:
+            ops.mega_end()
+
+    def _prog_fwd_body(self, x, B, training, extra, rng):
         logdet = None                                    # the first coupling starts the sum (NULL logdet_in)
         ctxs, c_i = [], 0
         for t in self._transforms:
@@ -320,6 +328,13 @@ class CompositeTransform(Transform):
             dy = torch.zeros_like(ctxs[0][0])
         if dld is None:
             dld = torch.zeros(B, device=dy.device)
+        ops.mega_begin(dy, B)
+        try:
+            return self._prog_bwd_body(dy, dld, B, ctxs, grads)
+        finally:
+            ops.mega_end()
+
+    def _prog_bwd_body(self, dy, dld, B, ctxs, grads):
         for t, c in zip(reversed(list(self._transforms)), reversed(ctxs)):
             if isinstance(t, AffineCouplingTransform):
                 dy, dld = t.bwd(dy, dld, c, grads)

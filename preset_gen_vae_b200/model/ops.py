@@ -35,6 +35,8 @@ def get_precision():
 def _f(t):
     if t is None:
         return ctypes.c_void_p(0)
+    if _mega is not None:
+        _mega_keep.append(t)          # recorded ops run later: nothing they touch may be recycled by the allocator before the flush
     if not t.is_cuda:
         raise _lib.PgvError("pgv kernels need CUDA tensors (got %s): there is no CPU path" % t.device)
     assert t.dtype in (torch.float32, torch.int32, torch.float64, torch.uint8), t.dtype
@@ -119,6 +121,11 @@ def stop_profile():
 
 def _call(name, *args, n=1, flops=0, nbytes=0):
     global launches
+    if _mega is not None:
+        if name in _MEGA_BUILDERS and len(_mega) < _mega_max_ops():
+            _mega.append(_MEGA_BUILDERS[name](*args))
+            return
+        mega_flush()                  # an op the program kernel does not know: run what is pending first, then this one on its own
     launches += n
     if profile is None:
         _lib.check(getattr(_lib.lib(), name)(*args), name)
@@ -136,6 +143,120 @@ def _call(name, *args, n=1, flops=0, nbytes=0):
 
 def _s(t):
     return _lib.stream_ptr(t.device)
+
+
+# ------------------------------------------------------------------------------------------------ flow program (one launch per chain)
+# A RealNVP flow is a chain of ~50 (forward) / ~90 (backward) latency-bound kernels; between mega_begin() and mega_end() the calls
+# that the program kernel knows are RECORDED instead of launched and then run as one persistent launch with grid barriers between
+# dependent ops (csrc/pgv_flow_fused.cu, pgv_flow_program).  Everything else flushes the pending program first, so order is preserved.
+use_flow_program = True
+_mega = None
+_mega_keep = []
+_mega_ref = None
+
+
+class _CsParams(ctypes.Structure):
+    _fields_ = [('a', ctypes.c_void_p), ('lda', ctypes.c_int), ('b', ctypes.c_void_p), ('ldb', ctypes.c_int), ('M', ctypes.c_int),
+                ('N', ctypes.c_int), ('Kd', ctypes.c_int), ('bias', ctypes.c_void_p), ('add_pre', ctypes.c_void_p), ('out_pre', ctypes.c_void_p),
+                ('out', ctypes.c_void_p), ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p), ('mask', ctypes.c_void_p),
+                ('save_mean', ctypes.c_void_p), ('save_rstd', ctypes.c_void_p), ('running_mean', ctypes.c_void_p),
+                ('running_var', ctypes.c_void_p), ('momentum', ctypes.c_float), ('eps', ctypes.c_float), ('bn_x', ctypes.c_void_p),
+                ('mean', ctypes.c_void_p), ('rstd', ctypes.c_void_p), ('add_post', ctypes.c_void_p), ('dgamma', ctypes.c_void_p),
+                ('dbeta', ctypes.c_void_p), ('relu', ctypes.c_int), ('a_vec', ctypes.c_int), ('b_vec', ctypes.c_int)]
+
+
+class _MegaOp(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int), ('barrier_after', ctypes.c_int), ('cs', _CsParams)]
+
+
+(_MOP_GATHER, _MOP_CS_FWD, _MOP_CS_BN_FWD, _MOP_CS_DGRAD, _MOP_CS_BN_BWD, _MOP_COUPLING_FWD, _MOP_COUPLING_BWD, _MOP_SCATTER_ADD,
+ _MOP_WGRAD) = range(9)
+
+
+def _v(p):
+    return p.value if isinstance(p, ctypes.c_void_p) else p
+
+
+def _mop(kind, barrier=1, **kw):
+    op = _MegaOp()
+    op.kind, op.barrier_after = kind, barrier
+    for k, val in kw.items():
+        setattr(op.cs, k, _v(val))
+    return op
+
+
+# argument order = the C signatures in include/pgv.h
+_MEGA_BUILDERS = {
+    'pgv_gather_cols': lambda x, idx, out, B, D, n, st: _mop(_MOP_GATHER, a=x, b=idx, out=out, M=B, N=D, Kd=n),
+    'pgv_scatter_add_cols': lambda dst, idx, src, B, D, n, st: _mop(_MOP_SCATTER_ADD, out=dst, b=idx, a=src, M=B, N=D, Kd=n),
+    'pgv_coupling_fwd': lambda x, prm, ii, ti, y, ld_in, ld_out, B, D, n_id, n_t, inv, st:
+        _mop(_MOP_COUPLING_FWD, a=x, b=prm, bias=ii, add_pre=ti, out=y, out_pre=ld_out, gamma=ld_in, M=B, N=D, Kd=n_id, lda=n_t, relu=inv),
+    'pgv_coupling_bwd': lambda dy, dld, x, prm, ii, ti, dx, dprm, B, D, n_id, n_t, st:
+        _mop(_MOP_COUPLING_BWD, a=dy, b=dld, bias=x, add_pre=prm, gamma=ii, beta=ti, out=dx, out_pre=dprm, M=B, N=D, Kd=n_id, lda=n_t),
+    'pgv_linear_cs_fwd': lambda x, w, bias, res, y, M, N, K, relu, st:
+        _mop(_MOP_CS_FWD, a=x, lda=K, b=w, ldb=K, M=M, N=N, Kd=K, bias=bias, add_pre=res, out=y, relu=relu),
+    'pgv_linear_cs_dgrad': lambda dy, w, dx, M, N, K, st: _mop(_MOP_CS_DGRAD, a=dy, lda=N, b=w, ldb=K, M=M, N=K, Kd=N, out=dx),
+    'pgv_linear_bn_fwd': lambda x, w, bias, res, y_pre, out, g, be, mask, sm, sr, rm, rv, mom, eps, M, N, K, st:
+        _mop(_MOP_CS_BN_FWD, a=x, lda=K, b=w, ldb=K, M=M, N=N, Kd=K, bias=bias, add_pre=res, out_pre=y_pre, out=out, gamma=g, beta=be, mask=mask,
+             save_mean=sm, save_rstd=sr, running_mean=rm, running_var=rv, momentum=mom, eps=eps),
+    'pgv_linear_dgrad_bn_bwd': lambda dy, w, bn_x, g, be, mean, rstd, mask, add_post, dx, dg, db, M, N, K, st:
+        _mop(_MOP_CS_BN_BWD, a=dy, lda=N, b=w, ldb=K, M=M, N=K, Kd=N, out=dx, gamma=g, beta=be, mask=mask, bn_x=bn_x, mean=mean, rstd=rstd,
+             add_post=add_post, dgamma=dg, dbeta=db),
+    # weight gradients have no consumer inside the chain: no barrier behind them, they run beside the data-gradient op that follows
+    'pgv_linear_wgrad_f32': lambda h, dy, x, dw, db, M, N, K, st: _mop(_MOP_WGRAD, barrier=0, a=dy, b=x, out=dw, out_pre=db, M=M, N=N, Kd=K),
+}
+_mega_limits = {}
+
+
+def _mega_max_ops():
+    if 'max' not in _mega_limits:
+        L = _lib.lib()
+        assert L.pgv_flow_program_op_bytes() == ctypes.sizeof(_MegaOp), "MegaOp layout differs between pgv_flow_fused.cu and ops.py"
+        _mega_limits['max'] = L.pgv_flow_program_max_ops()
+    return _mega_limits['max']
+
+
+def mega_begin(ref, rows):
+    """Start recording (no-op when disabled or the batch does not fit the column-slice kernels)."""
+    global _mega, _mega_ref
+    if use_flow_program and _mega is None and colslice_ok(rows):
+        _mega_max_ops()
+        _mega, _mega_ref = [], (ref, rows)
+
+
+def mega_flush():
+    """Launch what has been recorded so far (recording continues)."""
+    global _mega, launches
+    if not _mega:
+        del _mega_keep[:]
+        return
+    ops_, (ref, rows) = _mega, _mega_ref
+    _mega = None                                  # (the launch itself goes through _call)
+    try:
+        arr = (_MegaOp * len(ops_))(*ops_)
+        counter = _mega_counter(ref)
+        _call('pgv_flow_program', _h(ref), ctypes.cast(arr, ctypes.c_void_p), len(ops_), rows, _f(counter), _s(ref), n=2)
+    finally:
+        _mega = []
+        del _mega_keep[:]
+
+
+def mega_end():
+    global _mega
+    if _mega is not None:
+        mega_flush()
+        _mega = None
+        del _mega_keep[:]
+
+
+_mega_counters = {}
+
+
+def _mega_counter(ref):
+    key = (ref.device.index, torch.cuda.current_stream(ref.device).cuda_stream)
+    if key not in _mega_counters:
+        _mega_counters[key] = torch.zeros(4, dtype=torch.int32, device=ref.device)
+    return _mega_counters[key]
 
 
 def _h(t):
@@ -194,7 +315,7 @@ class forked:
         self.ref, self.keep, self.cm = ref, keep, None
 
     def __enter__(self):
-        if not use_wgrad_fork:
+        if not use_wgrad_fork or _mega is not None:      # (recording a flow program: the op goes into the program, no stream switch)
             return self
         dev = self.ref.device
         cur = torch.cuda.current_stream(dev)

@@ -86,3 +86,43 @@ def test_fused_residual_net_matches_unfused_sequence():
         assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-6
     for k in res[True][3]:
         assert rel(res[True][3][k], res[False][3][k]) < 1e-5
+
+
+def test_flow_program_kernel_equals_the_separate_launches():
+    """A whole RealNVP forward + backward recorded into ONE persistent launch (pgv_flow_program: the same tile code behind grid barriers)
+    against the chain of stand-alone kernels: outputs, log-determinants and every parameter gradient, for the latent flow (couplings
+    only) and the regression flow (dropout masks + flow BatchNorm transforms, which flush the recording)."""
+    from preset_gen_vae_b200.model import flows
+    torch.manual_seed(3)
+    for reg in (False, True):
+        for B in (160, 5):
+            if reg:
+                flow = flows.CustomRealNVP(610, 300, 6, 2, dropout_probability=0.4, batch_norm_within_layers=True, batch_norm_between_layers=True).cuda().train()
+            else:
+                flow = flows.SimpleRealNVP(610, 300, 6, 2, batch_norm_within_layers=True)._transform.cuda().train()
+            for prm in flow.parameters():                       # the conditioners' last layers are initialised near zero: make them matter
+                if prm.dim() == 2:
+                    prm.data.mul_(3.0)
+            x = torch.randn(B, 610, device='cuda')
+            masks = flow._draw_masks(x)
+            gy, gld = torch.randn(B, 610, device='cuda'), torch.randn(B, device='cuda')
+            res = {}
+            for on in (True, False):
+                ops.use_flow_program = on
+                try:
+                    flow.zero_grad()
+                    xi = x.clone().requires_grad_()
+                    before = ops.launches
+                    y, ld = flow(xi, dropout_masks=masks)
+                    n_fwd = ops.launches - before
+                    ((y * gy).sum() + (ld * gld).sum()).backward()
+                    torch.cuda.synchronize()
+                    res[on] = (y.detach(), ld.detach(), xi.grad.clone(), [p.grad.clone() for p in flow.parameters()], n_fwd)
+                finally:
+                    ops.use_flow_program = True
+            a, b = res[True], res[False]
+            assert a[4] < b[4] / 4, (a[4], b[4])                  # e.g. 3 launches instead of 49
+            for u, v in zip(a[:3], b[:3]):
+                assert float((u - v).abs().max()) <= 2e-6 * float(v.abs().max()) + 1e-7
+            for u, v in zip(a[3], b[3]):
+                assert float((u - v).abs().max()) <= 1e-5 * float(v.abs().max()) + 1e-9
