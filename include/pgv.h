@@ -373,6 +373,10 @@ PGV_API int pgv_spectrogram_stats(const float* x, int N, size_t elems, float* pe
  * and model/ops.py), at most pgv_flow_program_max_ops(); M = batch rows (<= pgv_colslice_max_rows()); counter = one device word.
  * Replaces ~50 (forward) / ~90 (backward) launches of 5-10 us per RealNVP flow (model/flows.py:42-90, VAE.py:118-125). */
 PGV_API int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned* counter, pgv_stream_t stream);
+/* Debug (tools/gpu_flow_trace.py): subsequent pgv_flow_program launches write, per op, 4 words {start ns, end of CTA 0's share ns, barrier open ns, kind} */
+PGV_API int pgv_debug_set_flow_trace(void* trace_dev);
+/* Debug: 6 words of pinned host memory that a timed-out grid barrier fills with {0xdead, cta, op, counter, target, n_ctas} before it traps. */
+PGV_API int pgv_debug_set_flow_diag(void* pinned_host);
 PGV_API int pgv_flow_program_op_bytes(void);
 PGV_API int pgv_flow_program_max_ops(void);
 /* Hint: pull [p, p + bytes) into L2 (one prefetch per 128-byte line); used on a flow's 15 MB of conditioner weights right before the

@@ -25,7 +25,9 @@ namespace cg = cooperative_groups;
 
 namespace pgv {
 
-constexpr int CS_COLS = 16, CS_ROWS = 32, CS_BK = 32, CS_LD = 36, CS_MAXM = 256, CS_THREADS = 256, CS_STAGES = 4;
+// 10 stages = the whole reduction of a 300-wide layer in flight at once: the K loop of such a tile is one L2 round trip plus the FMAs
+// (measured with 4 stages: 0.6 us per 32-wide chunk, i.e. one exposed L2 latency per chunk, 6.1 us per tile).
+constexpr int CS_COLS = 16, CS_ROWS = 32, CS_BK = 32, CS_LD = 36, CS_MAXM = 256, CS_THREADS = 256, CS_STAGES = 10;
 constexpr int CS_STAGE_FLOATS = (CS_ROWS + CS_COLS) * CS_LD;
 constexpr int CS_SMEM = CS_STAGES * CS_STAGE_FLOATS * 4;
 enum { EPI_PLAIN = 0, EPI_BN_FWD = 1, EPI_BN_BWD = 2 };
@@ -51,53 +53,56 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+struct CsShared {
+    double wred[8][CS_COLS][2];
+    double gather[2][8][CS_COLS][2];    // [reduction parity][cluster rank]: every CTA of the cluster PUSHES its partial totals here
+    double tot[CS_COLS][2];
+    float stat[CS_COLS][2];
+};
+
 // Column totals over ALL rows of the batch of two per-thread quantities (thread = 1 row x columns tx, tx + 8):
 // warp shuffle over the 4 rows of a warp, shared memory over the 8 warps, distributed shared memory over the cluster.
-// On return tot[c][0..1] holds the totals of column c in every CTA of the cluster.
-__device__ __forceinline__ void cs_cluster_col_reduce(double (&s)[2], double (&q)[2], double (*wred)[CS_COLS][2], double (*part)[2],
-                                                      double (*tot)[2], int cluster_size) {
+// On return tot[c][0..1] holds the totals of column c in every CTA of the cluster (summed in rank order everywhere: bit-identical).
+// Each CTA stores its partial into every peer's `gather` slot (remote stores do not wait for a round trip, remote loads do) and ONE
+// cluster barrier publishes them; the slots alternate with `phase` (the count of reductions this CTA has done, the same in every CTA
+// of a cluster), so a CTA that races ahead to its next reduction writes the other buffer and needs no second barrier: to reach the
+// reduction after that it has to pass a barrier its peers only arrive at once they have read the first one.
+__device__ __forceinline__ void cs_cluster_col_reduce(double (&s)[2], double (&q)[2], CsShared& sh, int cluster_size, unsigned& phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tx = threadIdx.x & 7;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);  q[j] += __shfl_xor_sync(0xffffffffu, q[j], 8);
         s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16); q[j] += __shfl_xor_sync(0xffffffffu, q[j], 16);
-        if (lane < 8) { wred[warp][tx + 8 * j][0] = s[j]; wred[warp][tx + 8 * j][1] = q[j]; }
+        if (lane < 8) { sh.wred[warp][tx + 8 * j][0] = s[j]; sh.wred[warp][tx + 8 * j][1] = q[j]; }
     }
     __syncthreads();
+    cg::cluster_group cluster = cg::this_cluster();
+    double (*slot)[CS_COLS][2] = sh.gather[phase & 1u];
     if (threadIdx.x < 2 * CS_COLS) {
         const int c = threadIdx.x >> 1, w = threadIdx.x & 1;
         double t = 0.0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) t += wred[g][c][w];
-        part[c][w] = t;
+        for (int g = 0; g < 8; ++g) t += sh.wred[g][c][w];
+        double* mine = &slot[cluster.block_rank()][c][w];
+        for (int r = 0; r < cluster_size; ++r) *cluster.map_shared_rank(mine, r) = t;
     }
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();                                       // every CTA's `part` is complete and visible cluster-wide
+    cluster.sync();                                       // (release / acquire) every CTA's partial has landed in every CTA
     if (threadIdx.x < 2 * CS_COLS) {
         const int c = threadIdx.x >> 1, w = threadIdx.x & 1;
         double t = 0.0;
-        for (int r = 0; r < cluster_size; ++r) {
-            const double (*remote)[2] = cluster.map_shared_rank(part, r);
-            t += remote[c][w];
-        }
-        tot[c][w] = t;
+        for (int r = 0; r < cluster_size; ++r) t += slot[r][c][w];
+        sh.tot[c][w] = t;
     }
-    cluster.sync();                                       // nobody leaves (or overwrites `part`) while a peer still reads it
+    __syncthreads();
+    ++phase;
 }
-
-struct CsShared {
-    double wred[8][CS_COLS][2];
-    double part[CS_COLS][2], tot[CS_COLS][2];
-    float stat[CS_COLS][2];
-};
 
 // One 32-row x 16-column tile: column slice `slice`, row block `rblock` of `cluster_size`.  PDL: the stand-alone kernels prefetch their
 // weights before griddepcontrol.wait; inside the flow program kernel (pdl = false) the grid barrier has already ordered everything.
 template <int TB, int EPI>
 __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int rblock, int cluster_size, uint8_t* cs_smem, CsShared& sh,
-                                              bool pdl) {
-    double (&wred)[8][CS_COLS][2] = sh.wred;
-    double (&part)[CS_COLS][2] = sh.part;
+                                              bool pdl, unsigned& phase, unsigned long long* dbg = nullptr) {
+    if (dbg != nullptr) dbg[0] = global_timer_ns();
     double (&tot)[CS_COLS][2] = sh.tot;
     float (&stat)[CS_COLS][2] = sh.stat;
     const int t = threadIdx.x, tx = t & 7, ty = t >> 3;           // row ty of this CTA's 32; columns tx, tx + 8
@@ -106,46 +111,61 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
     const uint32_t stage0_u32 = smem_u32(stage0);
     const int n_chunks = (p.Kd + CS_BK - 1) / CS_BK;
 
+    // Per-thread copy plan, computed once (everything but k0 is loop invariant; recomputing it per chunk made the copy issue as long
+    // as the arithmetic).  A: one 16-byte copy (row t / 8, floats 4 (t % 8) ..) or four 4-byte copies (rows t / 32 + 8 e, float t % 32).
+    // B, [N, Kd]: the same shapes over 16 columns;  B, [Kd, N]: two 4-byte copies (k = t / 16 + 16 e, column t % 16), transposed on the way in.
+    const int a_kk = p.a_vec ? 4 * (t & 7) : (t & 31), a_row = p.a_vec ? (t >> 3) : (t >> 5);
+    const float* const a_src = p.a + static_cast<size_t>(m0 + a_row) * p.lda + a_kk;
+    const uint32_t a_dst = (a_row * CS_LD + a_kk) * 4;
+    uint32_t a_ok = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a_ok |= (m0 + a_row + 8 * e < p.M ? 1u : 0u) << e;
+    const size_t a_step = static_cast<size_t>(8) * p.lda;
+    const bool b_v = TB == 0 && p.b_vec;
+    const int b_kk = TB == 1 ? (t >> 4) : (b_v ? 4 * (t & 7) : (t & 31)), b_c = TB == 1 ? (t & 15) : (b_v ? (t >> 3) : (t >> 5));
+    const float* const b_src = TB == 1 ? p.b + static_cast<size_t>(b_kk) * p.ldb + n0 + b_c : p.b + static_cast<size_t>(n0 + b_c) * p.ldb + b_kk;
+    const uint32_t b_dst = (b_c * CS_LD + b_kk) * 4;
+    const uint32_t b_ok = TB == 1 ? (n0 + b_c < p.N ? 3u : 0u)
+                                  : (b_v ? (t < CS_COLS * 8 && n0 + b_c < p.N ? 1u : 0u) : ((n0 + b_c < p.N ? 1u : 0u) | (n0 + b_c + 8 < p.N ? 2u : 0u)));
+    const size_t b_step = TB == 1 ? static_cast<size_t>(16) * p.ldb : static_cast<size_t>(8) * p.ldb;
+    const size_t b_kstride = TB == 1 ? static_cast<size_t>(p.ldb) : 1;
+
     // parts: bit 0 = the A (activation) tile, bit 1 = the B (weight) tile of chunk ch; `commit` closes the chunk's cp.async group
     auto issue = [&](int ch, int parts, bool commit) {
         if (ch < n_chunks) {
             const int k0 = ch * CS_BK;
             const uint32_t sA = stage0_u32 + (ch % CS_STAGES) * CS_STAGE_FLOATS * 4, sB = sA + CS_ROWS * CS_LD * 4;
-            if (!(parts & 1)) {
-            } else if (p.a_vec) {                           // 32 rows x 8 float4: one per thread
-                const int row = t >> 3, c4 = t & 7, k = k0 + 4 * c4;
-                const bool ok = m0 + row < p.M && k < p.Kd;
-                cp_async16_cg(sA + (row * CS_LD + 4 * c4) * 4, ok ? p.a + static_cast<size_t>(m0 + row) * p.lda + k : p.a, ok ? 16u : 0u);
-            } else {
+            if (parts & 1) {
+                const bool kin = k0 + a_kk < p.Kd;
+                if (p.a_vec) {
+                    const bool ok = kin && (a_ok & 1u);
+                    cp_async16_cg(sA + a_dst, ok ? a_src + k0 : p.a, ok ? 16u : 0u);
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int id = t + e * CS_THREADS, row = id >> 5, kk = id & 31, k = k0 + kk;
-                    const bool ok = m0 + row < p.M && k < p.Kd;
-                    cp_async4(sA + (row * CS_LD + kk) * 4, ok ? p.a + static_cast<size_t>(m0 + row) * p.lda + k : p.a, ok ? 4u : 0u);
+                    for (int e = 0; e < 4; ++e) {
+                        const bool ok = kin && ((a_ok >> e) & 1u);
+                        cp_async4(sA + a_dst + e * 8 * CS_LD * 4, ok ? a_src + e * a_step + k0 : p.a, ok ? 4u : 0u);
+                    }
                 }
             }
-            if (!(parts & 2)) {
-            } else if (TB == 0) {                           // B[n0 + c][k0 + kk], contiguous along k
-                if (p.b_vec) {
+            if (parts & 2) {
+                if (TB == 1) {                              // B[k0 + kk][n0 + c], contiguous along c
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const bool ok = (b_ok & 1u) && k0 + b_kk + 16 * e < p.Kd;
+                        cp_async4(sB + b_dst + e * 16 * 4, ok ? b_src + e * b_step + k0 * b_kstride : p.b, ok ? 4u : 0u);
+                    }
+                } else if (b_v) {                           // B[n0 + c][k0 + kk], contiguous along k
                     if (t < CS_COLS * 8) {
-                        const int c = t >> 3, c4 = t & 7, k = k0 + 4 * c4;
-                        const bool ok = n0 + c < p.N && k < p.Kd;
-                        cp_async16_cg(sB + (c * CS_LD + 4 * c4) * 4, ok ? p.b + static_cast<size_t>(n0 + c) * p.ldb + k : p.b, ok ? 16u : 0u);
+                        const bool ok = (b_ok & 1u) && k0 + b_kk < p.Kd;
+                        cp_async16_cg(sB + b_dst, ok ? b_src + k0 : p.b, ok ? 16u : 0u);
                     }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int id = t + e * CS_THREADS, c = id >> 5, kk = id & 31, k = k0 + kk;
-                        const bool ok = n0 + c < p.N && k < p.Kd;
-                        cp_async4(sB + (c * CS_LD + kk) * 4, ok ? p.b + static_cast<size_t>(n0 + c) * p.ldb + k : p.b, ok ? 4u : 0u);
+                        const bool ok = ((b_ok >> e) & 1u) && k0 + b_kk < p.Kd;
+                        cp_async4(sB + b_dst + e * 8 * CS_LD * 4, ok ? b_src + e * b_step + k0 : p.b, ok ? 4u : 0u);
                     }
-                }
-            } else {                                        // B[k0 + kk][n0 + c], contiguous along c: transposed on the way in
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int id = t + e * CS_THREADS, kk = id >> 4, c = id & 15, k = k0 + kk;
-                    const bool ok = n0 + c < p.N && k < p.Kd;
-                    cp_async4(sB + (c * CS_LD + kk) * 4, ok ? p.b + static_cast<size_t>(k) * p.ldb + n0 + c : p.b, ok ? 4u : 0u);
                 }
             }
         }
@@ -166,34 +186,77 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
 #pragma unroll
         for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 3, true);
     }
-    for (int ch = 0; ch < n_chunks; ++ch) {
-        cp_async_wait<CS_STAGES - 2>();                     // chunk ch has landed (this thread's copies) ...
-        __syncthreads();                                    // ... and everybody's; everybody is also done with chunk ch - 1
-        issue(ch + CS_STAGES - 1, 3, true);                 // refill the slot chunk ch - 1 used
-        const float* sA = stage0 + (ch % CS_STAGES) * CS_STAGE_FLOATS;
-        const float* sB = sA + CS_ROWS * CS_LD;
-#pragma unroll
-        for (int k4 = 0; k4 < CS_BK / 4; ++k4) {
-            const float4 a = *reinterpret_cast<const float4*>(sA + ty * CS_LD + 4 * k4);
-            const float4 b0 = *reinterpret_cast<const float4*>(sB + tx * CS_LD + 4 * k4);
-            const float4 b1 = *reinterpret_cast<const float4*>(sB + (tx + 8) * CS_LD + 4 * k4);
-            acc[0] = fmaf(a.x, b0.x, fmaf(a.y, b0.y, fmaf(a.z, b0.z, fmaf(a.w, b0.w, acc[0]))));
-            acc[1] = fmaf(a.x, b1.x, fmaf(a.y, b1.y, fmaf(a.z, b1.z, fmaf(a.w, b1.w, acc[1]))));
-        }
-    }
-    cp_async_wait<0>();
-
-    // ---------------------------------------------------------------- epilogue
+    // The epilogue's operands are independent of the product: fetch them now so their latency hides behind the K loop.
     const int row = m0 + ty;
     const bool row_ok = row < p.M;
     const int col[2] = {n0 + tx, n0 + tx + 8};
     const bool ok[2] = {row_ok && col[0] < p.N, row_ok && col[1] < p.N};
+    float e_bias[2] = {0.0f, 0.0f}, e_add[2] = {0.0f, 0.0f}, e_gamma[2] = {0.0f, 0.0f}, e_beta[2] = {0.0f, 0.0f}, e_mask[2] = {1.0f, 1.0f};
+    float e_x[2] = {0.0f, 0.0f}, e_mean[2] = {0.0f, 0.0f}, e_rstd[2] = {0.0f, 0.0f}, e_post[2] = {0.0f, 0.0f};
 #pragma unroll
     for (int j = 0; j < 2; ++j)
         if (ok[j]) {
-            if (p.bias != nullptr) acc[j] += __ldg(p.bias + col[j]);
-            if (p.add_pre != nullptr) acc[j] += p.add_pre[static_cast<size_t>(row) * p.N + col[j]];
+            const size_t o = static_cast<size_t>(row) * p.N + col[j];
+            if (p.bias != nullptr) e_bias[j] = __ldg(p.bias + col[j]);
+            if (p.add_pre != nullptr) e_add[j] = p.add_pre[o];
+            if (EPI != EPI_PLAIN) {
+                e_gamma[j] = __ldg(p.gamma + col[j]); e_beta[j] = __ldg(p.beta + col[j]);
+                if (p.mask != nullptr) e_mask[j] = p.mask[o];
+            }
+            if (EPI == EPI_BN_BWD) {
+                e_x[j] = p.bn_x[o]; e_mean[j] = p.mean[col[j]]; e_rstd[j] = p.rstd[col[j]];
+                if (p.add_post != nullptr) e_post[j] = p.add_post[o];
+            }
         }
+    // The K loop is split over the 8 warps: warp w multiplies the w-th group of 4 k values of every 32-wide chunk for the WHOLE 32 x 16
+    // tile, each lane rows r4 + 8 i x columns c4 + 4 j (interleaved so that the 36-float row pitch spreads a quarter warp's float4 loads
+    // over distinct banks; 8 LDS.128 per 64 FMAs; with 1 row x 2 columns per thread the loop was bound by shared-memory
+    // wavefronts: 0.6 us per chunk), and the eight partial tiles are added through shared memory in warp order afterwards.
+    const int lane_ = t & 31, warp_ = t >> 5, r4 = lane_ >> 2, c4 = lane_ & 3;
+    float part16[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part16[i][j] = 0.0f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        cp_async_wait<CS_STAGES - 2>();                     // chunk ch has landed (this thread's copies) ...
+        __syncthreads();                                    // ... and everybody's; everybody is also done with chunk ch - 1
+        issue(ch + CS_STAGES - 1, 3, true);                 // refill the slot chunk ch - 1 used
+        const float* sA = stage0 + (ch % CS_STAGES) * CS_STAGE_FLOATS + 4 * warp_;
+        const float* sB = stage0 + (ch % CS_STAGES) * CS_STAGE_FLOATS + CS_ROWS * CS_LD + 4 * warp_;
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(sA + (r4 + 8 * i) * CS_LD);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sB + (c4 + 4 * j) * CS_LD);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                part16[i][j] = fmaf(av[i].x, bv[j].x, fmaf(av[i].y, bv[j].y, fmaf(av[i].z, bv[j].z, fmaf(av[i].w, bv[j].w, part16[i][j]))));
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                        // every warp is done with the ring: reuse it for the partial tiles
+    {
+        float* red = stage0;                                // [warp][32 rows][16 columns]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(warp_ * CS_ROWS + r4 + 8 * i) * CS_COLS + c4 + 4 * j] = part16[i][j];
+        __syncthreads();
+#pragma unroll
+        for (int w8 = 0; w8 < CS_THREADS / 32; ++w8) {
+            acc[0] += red[(w8 * CS_ROWS + ty) * CS_COLS + tx];
+            acc[1] += red[(w8 * CS_ROWS + ty) * CS_COLS + tx + 8];
+        }
+        __syncthreads();                                    // (the next tile of a program refills the ring)
+    }
+    if (dbg != nullptr) dbg[1] = global_timer_ns();
+
+    // ---------------------------------------------------------------- epilogue (operands were fetched before the K loop)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        if (ok[j]) acc[j] = (acc[j] + e_bias[j]) + e_add[j];
     if (EPI == EPI_PLAIN) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -209,7 +272,8 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
                 s[j] = v; q[j] = v * v;
                 if (p.out_pre != nullptr) p.out_pre[static_cast<size_t>(row) * p.N + col[j]] = acc[j];
             }
-        cs_cluster_col_reduce(s, q, wred, part, tot, cluster_size);
+        cs_cluster_col_reduce(s, q, sh, cluster_size, phase);
+        if (dbg != nullptr) dbg[2] = global_timer_ns();
         if (t < CS_COLS) {
             const int c = n0 + t;
             const double mean = tot[t][0] / p.M;
@@ -230,11 +294,8 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
 #pragma unroll
         for (int j = 0; j < 2; ++j)
             if (ok[j]) {
-                const float g = __ldg(p.gamma + col[j]) * stat[tx + 8 * j][1], sh = __ldg(p.beta + col[j]) - stat[tx + 8 * j][0] * g;
-                const size_t o = static_cast<size_t>(row) * p.N + col[j];
-                float v = fmaxf(fmaf(acc[j], g, sh), 0.0f);
-                if (p.mask != nullptr) v *= p.mask[o];
-                p.out[o] = v;
+                const float g = e_gamma[j] * stat[tx + 8 * j][1], sh_ = e_beta[j] - stat[tx + 8 * j][0] * g;
+                p.out[static_cast<size_t>(row) * p.N + col[j]] = fmaxf(fmaf(acc[j], g, sh_), 0.0f) * e_mask[j];
             }
         return;
     }
@@ -244,15 +305,13 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
 #pragma unroll
     for (int j = 0; j < 2; ++j)
         if (ok[j]) {
-            const size_t o = static_cast<size_t>(row) * p.N + col[j];
-            const float h = (p.bn_x[o] - p.mean[col[j]]) * p.rstd[col[j]];
-            float d = acc[j];
-            if (p.mask != nullptr) d *= p.mask[o];
-            if (!(fmaf(__ldg(p.gamma + col[j]), h, __ldg(p.beta + col[j])) > 0.0f)) d = 0.0f;
+            const float h = (e_x[j] - e_mean[j]) * e_rstd[j];
+            float d = acc[j] * e_mask[j];
+            if (!(fmaf(e_gamma[j], h, e_beta[j]) > 0.0f)) d = 0.0f;
             acc[j] = d; xh[j] = h;
             s[j] = d; q[j] = static_cast<double>(d) * h;
         }
-    cs_cluster_col_reduce(s, q, wred, part, tot, cluster_size);
+    cs_cluster_col_reduce(s, q, sh, cluster_size, phase);
     if (t < CS_COLS && n0 + t < p.N && rblock == 0) {
         p.dbeta[n0 + t] = static_cast<float>(tot[t][0]);
         p.dgamma[n0 + t] = static_cast<float>(tot[t][1]);
@@ -260,12 +319,9 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
 #pragma unroll
     for (int j = 0; j < 2; ++j)
         if (ok[j]) {
-            const float gr = __ldg(p.gamma + col[j]) * p.rstd[col[j]];
+            const float gr = e_gamma[j] * e_rstd[j];
             const float mean_d = static_cast<float>(tot[tx + 8 * j][0] / p.M), mean_dx = static_cast<float>(tot[tx + 8 * j][1] / p.M);
-            const size_t o = static_cast<size_t>(row) * p.N + col[j];
-            float v = gr * (acc[j] - mean_d - xh[j] * mean_dx);
-            if (p.add_post != nullptr) v += p.add_post[o];
-            p.out[o] = v;
+            p.out[static_cast<size_t>(row) * p.N + col[j]] = gr * (acc[j] - mean_d - xh[j] * mean_dx) + e_post[j];
         }
 }
 
@@ -273,7 +329,8 @@ template <int TB, int EPI>
 __global__ void __launch_bounds__(CS_THREADS) colslice_gemm_kernel(const CsParams p) {
     extern __shared__ __align__(16) uint8_t cs_smem_k[];
     __shared__ CsShared sh;
-    colslice_tile<TB, EPI>(p, blockIdx.x, blockIdx.y, gridDim.y, cs_smem_k, sh, true);
+    unsigned phase = 0;
+    colslice_tile<TB, EPI>(p, blockIdx.x, blockIdx.y, gridDim.y, cs_smem_k, sh, true, phase);
 }
 
 template <int TB, int EPI>
@@ -296,6 +353,11 @@ static int cs_launch(CsParams& p, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 2 : 1;
+    static bool configured = false;
+    if (!configured) {
+        PGV_CUDA(cudaFuncSetAttribute(colslice_gemm_kernel<TB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+        configured = true;
+    }
     PGV_CUDA(cudaLaunchKernelEx(&cfg, colslice_gemm_kernel<TB, EPI>, p));
     return 0;
 }
@@ -318,11 +380,14 @@ constexpr int MEGA_MAX_OPS = 150;
 struct MegaProgram {
     int n_ops, row_ctas;
     unsigned* counter;    // grid barrier: zero on entry
+    unsigned long long* trace;   // debug (pgv_debug_set_flow_trace): per op, globaltimer of CTA 0 at start / after the body / after the barrier
     MegaOp ops[MEGA_MAX_OPS];
 };
 static_assert(sizeof(MegaProgram) <= 32000, "the program must fit the kernel parameter space");
 
-__device__ __forceinline__ void mega_grid_barrier(unsigned* counter, unsigned& target, unsigned n_ctas) {
+__device__ unsigned long long* g_mega_diag = nullptr;      // pinned host memory (pgv_debug_set_flow_diag): what a timed-out barrier saw
+
+__device__ __forceinline__ void mega_grid_barrier(unsigned* counter, unsigned& target, unsigned n_ctas, int op_index) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += n_ctas;
@@ -335,7 +400,14 @@ __device__ __forceinline__ void mega_grid_barrier(unsigned* counter, unsigned& t
             if (v < target && (++spins & 4095u) == 0) {       // never wedge the device: a barrier that has not opened after 4 s traps
                 const uint64_t now = global_timer_ns();
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > 4000000000ull) __trap();
+                else if (now - t0 > 4000000000ull) {
+                    if (g_mega_diag != nullptr) {
+                        g_mega_diag[0] = 0xdeadull; g_mega_diag[1] = blockIdx.z * gridDim.y + blockIdx.y; g_mega_diag[2] = op_index;
+                        g_mega_diag[3] = v; g_mega_diag[4] = target; g_mega_diag[5] = n_ctas;
+                        __threadfence_system();
+                    }
+                    __trap();
+                }
             }
         } while (v < target);
         __threadfence();
@@ -390,18 +462,22 @@ __global__ void __launch_bounds__(CS_THREADS) flow_program_kernel(const __grid_c
     const unsigned n_ctas = gridDim.y * gridDim.z;
     const int cta = cl * row_ctas + rblock, t = threadIdx.x;
     unsigned target = 0;
+    const bool tracing = prog.trace != nullptr && cta == 0 && t == 0;
+    unsigned bn_phase = 0;                                  // BatchNorm reductions done so far (the same in every CTA of a cluster)
     for (int oi = 0; oi < prog.n_ops; ++oi) {
         const MegaOp& op = prog.ops[oi];
         const CsParams& p = op.cs;
+        if (tracing) { prog.trace[4 * oi] = global_timer_ns(); prog.trace[4 * oi + 3] = static_cast<unsigned long long>(op.kind); }
         switch (op.kind) {
         case MOP_CS_FWD: case MOP_CS_BN_FWD: case MOP_CS_DGRAD: case MOP_CS_BN_BWD: {
             const int slices = (p.N + CS_COLS - 1) / CS_COLS;
             for (int sl = cl; sl < slices; sl += n_clusters) {
                 __syncthreads();                               // the previous tile's readers are done with the ring and the statistics
-                if (op.kind == MOP_CS_FWD) colslice_tile<0, EPI_PLAIN>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
-                else if (op.kind == MOP_CS_BN_FWD) colslice_tile<0, EPI_BN_FWD>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
-                else if (op.kind == MOP_CS_DGRAD) colslice_tile<1, EPI_PLAIN>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
-                else colslice_tile<1, EPI_BN_BWD>(p, sl, rblock, row_ctas, cs_smem_m, sh, false);
+                unsigned long long* dbg = (tracing && sl == cl) ? prog.trace + 4 * MEGA_MAX_OPS + 4 * oi : nullptr;
+                if (op.kind == MOP_CS_FWD) colslice_tile<0, EPI_PLAIN>(p, sl, rblock, row_ctas, cs_smem_m, sh, false, bn_phase, dbg);
+                else if (op.kind == MOP_CS_BN_FWD) colslice_tile<0, EPI_BN_FWD>(p, sl, rblock, row_ctas, cs_smem_m, sh, false, bn_phase, dbg);
+                else if (op.kind == MOP_CS_DGRAD) colslice_tile<1, EPI_PLAIN>(p, sl, rblock, row_ctas, cs_smem_m, sh, false, bn_phase);
+                else colslice_tile<1, EPI_BN_BWD>(p, sl, rblock, row_ctas, cs_smem_m, sh, false, bn_phase);
             }
             break;
         }
@@ -476,9 +552,14 @@ __global__ void __launch_bounds__(CS_THREADS) flow_program_kernel(const __grid_c
         }
         default: break;
         }
-        if (op.barrier_after) mega_grid_barrier(prog.counter, target, n_ctas);
+        if (prog.trace != nullptr) __syncthreads();        // (uniform condition) the body time of CTA 0 = its slowest thread
+        if (tracing) prog.trace[4 * oi + 1] = global_timer_ns();
+        if (op.barrier_after) mega_grid_barrier(prog.counter, target, n_ctas, oi);
+        if (tracing) prog.trace[4 * oi + 2] = global_timer_ns();
     }
 }
+
+unsigned long long* g_flow_trace = nullptr;
 
 }  // namespace pgv
 
@@ -496,6 +577,7 @@ int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned*
     prog.n_ops = n_ops;
     prog.row_ctas = ceil_div(M, CS_ROWS);
     prog.counter = counter;
+    prog.trace = g_flow_trace;
     memcpy(prog.ops, ops, sizeof(MegaOp) * n_ops);
     for (int i = 0; i < n_ops; ++i) {
         CsParams& p = prog.ops[i].cs;
@@ -531,6 +613,14 @@ int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned*
     PGV_CUDA(cudaLaunchKernelEx(&cfg, flow_program_kernel, prog));
     return 0;
 }
+
+int pgv_debug_set_flow_diag(void* pinned_host) {
+    unsigned long long* p = static_cast<unsigned long long*>(pinned_host);
+    PGV_CUDA(cudaMemcpyToSymbol(g_mega_diag, &p, sizeof(p)));
+    return 0;
+}
+
+int pgv_debug_set_flow_trace(void* trace_dev) { g_flow_trace = static_cast<unsigned long long*>(trace_dev); return 0; }
 
 int pgv_flow_program_op_bytes(void) { return static_cast<int>(sizeof(MegaOp)); }
 int pgv_flow_program_max_ops(void) { return MEGA_MAX_OPS; }

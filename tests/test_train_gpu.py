@@ -85,7 +85,7 @@ def test_cuda_graph_steps_train(idx_helper):
     torch.cuda.synchronize()
     hist = torch.stack(hist).cpu()
     assert torch.isfinite(hist).all()
-    assert tr._graph is not None and tr.launches_per_step > 300
+    assert tr._graph is not None and tr.launches_per_step > 150
     assert not torch.equal(before, tr.flat_params)         # every replay applies an optimizer step
     assert tr.step_count == 6
     assert hist[-1, 0] < hist[0, 0] and hist[-1, 2] < hist[0, 2]      # reconstruction and controls losses go down on a fixed batch
