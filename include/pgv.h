@@ -370,7 +370,7 @@ PGV_API int pgv_spectrogram_stats(const float* x, int N, size_t elems, float* pe
 /* A recorded chain of flow ops (gather / column-slice Linear with fused BatchNorm forward or backward / coupling / scatter / small
  * weight gradients) as ONE persistent launch with grid barriers between dependent ops: `ops` = host array of n_ops records of
  * pgv_flow_program_op_bytes() bytes each (kind, barrier_after, the parameter block of the stand-alone kernel: see csrc/pgv_flow_fused.cu
- * and model/ops.py), at most pgv_flow_program_max_ops(); M = batch rows (<= pgv_colslice_max_rows()); counter = one device word.
+ * and model/ops.py), at most pgv_flow_program_max_ops(); M = batch rows (<= pgv_colslice_max_rows()); counter = pgv_flow_program_max_ops() + 1 device words (the grid barrier and one tile counter per weight-gradient op; zeroed by the call).
  * Replaces ~50 (forward) / ~90 (backward) launches of 5-10 us per RealNVP flow (model/flows.py:42-90, VAE.py:118-125). */
 PGV_API int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned* counter, pgv_stream_t stream);
 /* Debug (tools/gpu_flow_trace.py): subsequent pgv_flow_program launches write, per op, 4 words {start ns, end of CTA 0's share ns, barrier open ns, kind} */

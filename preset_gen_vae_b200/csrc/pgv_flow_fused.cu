@@ -27,7 +27,7 @@ namespace pgv {
 
 // 10 stages = the whole reduction of a 300-wide layer in flight at once: the K loop of such a tile is one L2 round trip plus the FMAs
 // (measured with 4 stages: 0.6 us per 32-wide chunk, i.e. one exposed L2 latency per chunk, 6.1 us per tile).
-constexpr int CS_COLS = 16, CS_ROWS = 32, CS_BK = 32, CS_LD = 36, CS_MAXM = 256, CS_THREADS = 256, CS_STAGES = 10;
+constexpr int CS_COLS = 16, CS_ROWS = 32, CS_BK = 32, CS_LD = 36, CS_MAXM = 256, CS_THREADS = 256, CS_GROUP = 2, CS_NG = 5, CS_STAGES = CS_NG * CS_GROUP;
 constexpr int CS_STAGE_FLOATS = (CS_ROWS + CS_COLS) * CS_LD;
 constexpr int CS_SMEM = CS_STAGES * CS_STAGE_FLOATS * 4;
 enum { EPI_PLAIN = 0, EPI_BN_FWD = 1, EPI_BN_BWD = 2 };
@@ -175,16 +175,18 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
     // Programmatic dependent launch: the weights do not depend on the kernel in front, so their first tiles are fetched while that
     // kernel is still draining; everything else (activations, every store) comes after griddepcontrol.wait.
     float acc[2] = {0.0f, 0.0f};
+    // The ring holds CS_NG GROUPS of CS_GROUP chunks; one cp.async group and one pair of CTA barriers per chunk group (a barrier per
+    // chunk put every warp's shared-memory loads and then every warp's FMAs in lock step).
     if (pdl) {
         griddep_launch_dependents();
 #pragma unroll
-        for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 2, false);
+        for (int s = 0; s < CS_STAGES; ++s) issue(s, 2, false);
         griddep_wait();
 #pragma unroll
-        for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 1, true);
+        for (int s = 0; s < CS_STAGES; ++s) issue(s, 1, s % CS_GROUP == CS_GROUP - 1);
     } else {
 #pragma unroll
-        for (int s = 0; s < CS_STAGES - 1; ++s) issue(s, 3, true);
+        for (int s = 0; s < CS_STAGES; ++s) issue(s, 3, s % CS_GROUP == CS_GROUP - 1);
     }
     // The epilogue's operands are independent of the product: fetch them now so their latency hides behind the K loop.
     const int row = m0 + ty;
@@ -218,22 +220,35 @@ __device__ __forceinline__ void colslice_tile(const CsParams& p, int slice, int 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) part16[i][j] = 0.0f;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-        cp_async_wait<CS_STAGES - 2>();                     // chunk ch has landed (this thread's copies) ...
-        __syncthreads();                                    // ... and everybody's; everybody is also done with chunk ch - 1
-        issue(ch + CS_STAGES - 1, 3, true);                 // refill the slot chunk ch - 1 used
-        const float* sA = stage0 + (ch % CS_STAGES) * CS_STAGE_FLOATS + 4 * warp_;
-        const float* sB = stage0 + (ch % CS_STAGES) * CS_STAGE_FLOATS + CS_ROWS * CS_LD + 4 * warp_;
-        float4 av[4], bv[4];
+    const int n_groups = (n_chunks + CS_GROUP - 1) / CS_GROUP;
+    for (int g = 0; g < n_groups; ++g) {
+        cp_async_wait<CS_NG - 1>();                         // group g has landed (this thread's copies) ...
+        __syncthreads();                                    // ... and everybody's
+        if (dbg != nullptr && g == 0) dbg[3] = global_timer_ns();
+        const float* const ring = stage0 + (g % CS_NG) * CS_GROUP * CS_STAGE_FLOATS + 4 * warp_;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(sA + (r4 + 8 * i) * CS_LD);
+        for (int c = 0; c < CS_GROUP; ++c) {
+            if (g * CS_GROUP + c < n_chunks) {
+                const float* sA = ring + c * CS_STAGE_FLOATS;
+                const float* sB = sA + CS_ROWS * CS_LD;
+                float4 av[4], bv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sB + (c4 + 4 * j) * CS_LD);
+                for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(sA + (r4 + 8 * i) * CS_LD);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sB + (c4 + 4 * j) * CS_LD);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                part16[i][j] = fmaf(av[i].x, bv[j].x, fmaf(av[i].y, bv[j].y, fmaf(av[i].z, bv[j].z, fmaf(av[i].w, bv[j].w, part16[i][j]))));
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        part16[i][j] = fmaf(av[i].x, bv[j].x, fmaf(av[i].y, bv[j].y, fmaf(av[i].z, bv[j].z, fmaf(av[i].w, bv[j].w, part16[i][j]))));
+            }
+        }
+        if (g + CS_NG < n_groups) {                         // (uniform) refill this part of the ring once everybody has left it
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < CS_GROUP; ++c) issue((g + CS_NG) * CS_GROUP + c, 3, false);
+        }
+        cp_async_commit();
     }
     cp_async_wait<0>();
     __syncthreads();                                        // every warp is done with the ring: reuse it for the partial tiles
@@ -383,6 +398,7 @@ struct MegaProgram {
     unsigned long long* trace;   // debug (pgv_debug_set_flow_trace): per op, globaltimer of CTA 0 at start / after the body / after the barrier
     MegaOp ops[MEGA_MAX_OPS];
 };
+static_assert(CS_SMEM >= 2 * CS_MAXM * 32 * 4, "the weight-gradient tile keeps two [CS_MAXM][32] panels in the ring");
 static_assert(sizeof(MegaProgram) <= 32000, "the program must fit the kernel parameter space");
 
 __device__ unsigned long long* g_mega_diag = nullptr;      // pinned host memory (pgv_debug_set_flow_diag): what a timed-out barrier saw
@@ -417,47 +433,99 @@ __device__ __forceinline__ void mega_grid_barrier(unsigned* counter, unsigned& t
 
 __device__ __forceinline__ float mega_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// dw[n][k] = sum_m dy[m][n] * x[m][k] (32 x 32 tile, 2 x 2 outputs per thread); db[n] = sum_m dy[m][n] from the k-tile-0 tiles
-__device__ __forceinline__ void mega_wgrad_tile(const CsParams& p, int tile_k, int tile_n, float (*sa)[33], float (*sb)[33]) {
+// One 32 x 32 tile of dW[N, Kd] = dy^T x (and the bias gradient, the column sums of dy, on the tiles of the first k column).
+// Both operand panels ([M, 32] each, M <= CS_MAXM) are fetched in ONE round of cp.async (the batch loop used to pay a global-memory
+// round trip per 32 rows); the batch rows are then split over the 8 warps, each lane a 4 (n) x 8 (k) register block (3 LDS.128 per 32
+// FMAs), and the eight partial tiles are added through shared memory in warp order (deterministic).
+__device__ __forceinline__ void mega_wgrad_tile(const CsParams& p, int tile_k, int tile_n, float* smem) {
     const float* dy = p.a; const float* x = p.b; float* dw = p.out; float* db = p.out_pre;
-    const int M = p.M, N = p.N, K = p.Kd, t = threadIdx.x, tx = t & 15, ty = t >> 4, n0 = tile_n * 32, k0 = tile_k * 32;
-    float acc[2][2] = {};
-    float cs0 = 0.0f, cs1 = 0.0f;
-    const bool do_colsum = db != nullptr && tile_k == 0 && tx == 0;
-    for (int m0 = 0; m0 < M; m0 += 32) {
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int id = t + q * 256, c = id & 31, r = id >> 5, m = m0 + r;
-            sa[r][c] = (m < M && n0 + c < N) ? dy[static_cast<size_t>(m) * N + n0 + c] : 0.0f;
-            sb[r][c] = (m < M && k0 + c < K) ? x[static_cast<size_t>(m) * K + k0 + c] : 0.0f;
+    const int M = p.M, N = p.N, K = p.Kd, t = threadIdx.x, lane = t & 31, warp = t >> 5, n0 = tile_n * 32, k0 = tile_k * 32;
+    float* sa = smem;                                         // dy panel [M][32]; afterwards the partial tiles [8][32][32]
+    float* sb = smem + CS_MAXM * 32;                          // x panel  [M][32]; afterwards the partial column sums [8][32]
+    const uint32_t sa_u = smem_u32(sa), sb_u = smem_u32(sb);
+    if (N % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+        for (int id = t; id < M * 8; id += CS_THREADS) {
+            const int r = id >> 3, c = 4 * (id & 7);
+            const bool ok = n0 + c < N;
+            cp_async16_cg(sa_u + (r * 32 + c) * 4, ok ? dy + static_cast<size_t>(r) * N + n0 + c : dy, ok ? 16u : 0u);
         }
-        __syncthreads();
-#pragma unroll
-        for (int mm = 0; mm < 32; ++mm) {
-            const float a0 = sa[mm][ty * 2], a1 = sa[mm][ty * 2 + 1], b0 = sb[mm][tx * 2], b1 = sb[mm][tx * 2 + 1];
-            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
-            if (do_colsum) { cs0 += a0; cs1 += a1; }
+    } else {
+        for (int id = t; id < M * 32; id += CS_THREADS) {
+            const int r = id >> 5, c = id & 31;
+            const bool ok = n0 + c < N;
+            cp_async4(sa_u + (r * 32 + c) * 4, ok ? dy + static_cast<size_t>(r) * N + n0 + c : dy, ok ? 4u : 0u);
         }
     }
-    if (do_colsum) {
-        if (n0 + ty * 2 < N) db[n0 + ty * 2] = cs0;
-        if (n0 + ty * 2 + 1 < N) db[n0 + ty * 2 + 1] = cs1;
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int n = n0 + ty * 2 + i, k = k0 + tx * 2 + j;
-            if (n < N && k < K) dw[static_cast<size_t>(n) * K + k] = acc[i][j];
+    if (K % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        for (int id = t; id < M * 8; id += CS_THREADS) {
+            const int r = id >> 3, c = 4 * (id & 7);
+            const bool ok = k0 + c < K;
+            cp_async16_cg(sb_u + (r * 32 + c) * 4, ok ? x + static_cast<size_t>(r) * K + k0 + c : x, ok ? 16u : 0u);
         }
+    } else {
+        for (int id = t; id < M * 32; id += CS_THREADS) {
+            const int r = id >> 5, c = id & 31;
+            const bool ok = k0 + c < K;
+            cp_async4(sb_u + (r * 32 + c) * 4, ok ? x + static_cast<size_t>(r) * K + k0 + c : x, ok ? 4u : 0u);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int n4 = lane >> 2, k8 = lane & 3;
+    float acc[4][8], cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+#pragma unroll 2
+    for (int m = warp; m < M; m += CS_THREADS / 32) {
+        const float4 a4 = *reinterpret_cast<const float4*>(sa + m * 32 + 4 * n4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + m * 32 + 8 * k8), b1 = *reinterpret_cast<const float4*>(sb + m * 32 + 8 * k8 + 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cs[i] += av[i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    __syncthreads();                                          // every warp is done with the panels
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float* dst = sa + warp * 1024 + (4 * n4 + i) * 32 + 8 * k8;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        if (k8 == 0) sb[warp * 32 + 4 * n4 + i] = cs[i];
+    }
+    __syncthreads();
+    float4 tot = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int w = 0; w < CS_THREADS / 32; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(sa + w * 1024 + 4 * t);
+        tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+    }
+    const int n = n0 + (t >> 3), k = k0 + 4 * (t & 7);
+    if (n < N) {
+        float* o = dw + static_cast<size_t>(n) * K + k;
+        if (k < K) o[0] = tot.x;
+        if (k + 1 < K) o[1] = tot.y;
+        if (k + 2 < K) o[2] = tot.z;
+        if (k + 3 < K) o[3] = tot.w;
+    }
+    if (db != nullptr && tile_k == 0 && t < 32 && n0 + t < N) {
+        float c = 0.0f;
+#pragma unroll
+        for (int w = 0; w < CS_THREADS / 32; ++w) c += sb[w * 32 + t];
+        db[n0 + t] = c;
+    }
 }
 
 __global__ void __launch_bounds__(CS_THREADS) flow_program_kernel(const __grid_constant__ MegaProgram prog) {
     extern __shared__ __align__(16) uint8_t cs_smem_m[];
     __shared__ CsShared sh;
     __shared__ float red[8];
+    __shared__ int wg_tile[2];
     const int row_ctas = prog.row_ctas, rblock = blockIdx.y, cl = blockIdx.z, n_clusters = gridDim.z;
     const unsigned n_ctas = gridDim.y * gridDim.z;
     const int cta = cl * row_ctas + rblock, t = threadIdx.x;
@@ -543,11 +611,23 @@ __global__ void __launch_bounds__(CS_THREADS) flow_program_kernel(const __grid_c
             }
             break;
         }
-        case MOP_WGRAD: {              // a = dy [M, N], b = x [M, Kd], out = dw [N, Kd], out_pre = db
+        case MOP_WGRAD: {              // a = dy [M, N], b = x [M, Kd], out = dw [N, Kd], out_pre = db, relu = index of this op's tile counter
+            // Tiles are handed out through an atomic counter: a weight gradient sits BEHIND the data-gradient op of its barrier
+            // interval (pgv_flow_program orders them so), so the CTAs that op leaves idle start on the tiles at once and the busy
+            // ones join when they are through.  Which CTA computes a tile does not change its value.
             const int tk = (p.Kd + 31) / 32, tn = (p.N + 31) / 32;
-            float (*sa)[33] = reinterpret_cast<float (*)[33]>(cs_smem_m);
-            float (*sb)[33] = sa + 32;
-            for (int tile = cta; tile < tk * tn; tile += static_cast<int>(n_ctas)) mega_wgrad_tile(p, tile % tk, tile / tk, sa, sb);
+            unsigned* const ctr = prog.counter + 1 + p.relu;
+            __syncthreads();                                   // the previous op is done with wg_tile
+            if (t == 0) wg_tile[0] = static_cast<int>(atomicAdd(ctr, 1u));
+            for (int it = 0;; ++it) {
+                __syncthreads();                               // wg_tile[it & 1] is set; the previous tile is done with shared memory
+                const int tile = wg_tile[it & 1];
+                if (tile >= tk * tn) break;
+                int next = 0;
+                if (t == 0) next = static_cast<int>(atomicAdd(ctr, 1u));       // the next ticket travels while this tile is computed
+                mega_wgrad_tile(p, tile % tk, tile / tk, reinterpret_cast<float*>(cs_smem_m));
+                if (t == 0) wg_tile[(it + 1) & 1] = next;
+            }
             break;
         }
         default: break;
@@ -589,13 +669,26 @@ int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned*
             if (p.M != M) return set_error(-1, "pgv_flow_program: op %d has %d rows, the program %d", i, p.M, M);
         }
     }
+    // Inside a barrier interval the ops are independent by construction: put the weight gradients last (see MOP_WGRAD) and give
+    // each one a tile counter; counter[0] is the grid barrier's.
+    int n_wgrad = 0;
+    for (int lo = 0; lo < n_ops;) {
+        int hi = lo;
+        while (hi < n_ops - 1 && !prog.ops[hi].barrier_after) ++hi;
+        std::stable_partition(prog.ops + lo, prog.ops + hi + 1, [](const MegaOp& o) { return o.kind != MOP_WGRAD; });
+        for (int i = lo; i <= hi; ++i) {
+            prog.ops[i].barrier_after = i == hi ? 1 : 0;
+            if (prog.ops[i].kind == MOP_WGRAD) prog.ops[i].cs.relu = n_wgrad++;
+        }
+        lo = hi + 1;
+    }
     prog.ops[n_ops - 1].barrier_after = 0;
     static bool configured = false;
     if (!configured) {
         PGV_CUDA(cudaFuncSetAttribute(flow_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
         configured = true;
     }
-    PGV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+    PGV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned) * (1 + n_wgrad), stream));
     const int clusters = std::max(1, std::min(39, (h->sm_count - 8) / prog.row_ctas));       // co-resident: at most one CTA per SM
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

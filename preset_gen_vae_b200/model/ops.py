@@ -255,7 +255,7 @@ _mega_counters = {}
 def _mega_counter(ref):
     key = (ref.device.index, torch.cuda.current_stream(ref.device).cuda_stream)
     if key not in _mega_counters:
-        _mega_counters[key] = torch.zeros(4, dtype=torch.int32, device=ref.device)
+        _mega_counters[key] = torch.zeros(_mega_max_ops() + 1, dtype=torch.int32, device=ref.device)   # grid barrier + one tile counter per wgrad op
     return _mega_counters[key]
 
 

@@ -124,5 +124,8 @@ def test_flow_program_kernel_equals_the_separate_launches():
             assert a[4] < b[4] / 2, (a[4], b[4])                  # 2 launches instead of 48 (latent flow); the flow BatchNorms flush the recording
             for u, v in zip(a[:3], b[:3]):
                 assert float((u - v).abs().max()) <= 2e-6 * float(v.abs().max()) + 1e-7
+            # the program kernel's weight-gradient tile adds the batch rows in a different order; a bias in front of a BatchNorm has a
+            # mathematically zero gradient (rounding noise ~1e-4 of the weight gradients' scale), hence the common absolute term
+            scale = max(float(v.abs().max()) for v in b[3])
             for u, v in zip(a[3], b[3]):
-                assert float((u - v).abs().max()) <= 1e-5 * float(v.abs().max()) + 1e-9
+                assert float((u - v).abs().max()) <= 1e-5 * float(v.abs().max()) + 1e-5 * scale

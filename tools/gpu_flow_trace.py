@@ -45,8 +45,9 @@ for name, t in (('forward', fwd), ('backward', bwd)):
 
 print("==== inside the column-slice tile (forward, thread 0 of CTA 0): K loop / BatchNorm cluster reduction / rest")
 for i in range(1, 8):
-    a, b, c, _ = inner[i].tolist()
+    a, b, c, g0 = inner[i].tolist()
     if a:
         end = fwd[i][1].item()
+        print("  op %d  first chunk group landed after %.1f us" % (i, (g0 - a) / 1e3), end='')
         print("  op %d  k-loop %.1f us  reduce %.1f us  rest %.1f us" % (i, (b - a) / 1e3, ((c - b) / 1e3) if c else 0.0, (end - (c or b)) / 1e3))
 
