@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "pgv_common.cuh"
+#include "pgv_tc.cuh"
 
 namespace pgv {
 
@@ -249,60 +250,107 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const float* __res
     }
 }
 
-// Channels-last, C == 8 variant: lane = tap (25 of 32 lanes), 8 channel accumulators per lane, warp w walks row w of the 8 x 32
-// pixel tile.  Per pixel a lane reads its patch element (1 LDS) and the pixel's 8 dy values (2 broadcast LDS.128) for 8 FMAs:
-// 0.4 shared-memory reads per FMA instead of 2, which is what bounds the generic kernel above.
-__global__ void __launch_bounds__(256) thin_conv_wgrad_cl8_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                  float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
-                                                                  int tiles_per_block, float* __restrict__ partial) {
-    __shared__ float4 sdy[TW_TH * TW_TW * 2];            // [pixel][2] : 8 channels
-    __shared__ float sx[TW_PH * TW_PW];
-    __shared__ float sred[8][THIN_TAPS][THIN_MAXC];
-    const int tiles_h = (Ho + TW_TH - 1) / TW_TH, tiles_w = (Wo + TW_TW - 1) / TW_TW, tiles_img = tiles_h * tiles_w;
-    const long long n_tiles = static_cast<long long>(B) * tiles_img;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool worker = lane < THIN_TAPS;
-    const int r = lane / THIN_K, s = lane % THIN_K;
-    float acc[THIN_MAXC] = {};
-    const long long t0 = static_cast<long long>(blockIdx.x) * tiles_per_block;
-    for (long long t = t0; t < t0 + tiles_per_block && t < n_tiles; ++t) {
-        const int b = static_cast<int>(t / tiles_img), ti = static_cast<int>(t % tiles_img), oh0 = (ti / tiles_w) * TW_TH,
-                  ow0 = (ti % tiles_w) * TW_TW;
-        const float* xb = x + static_cast<size_t>(b) * H * W;
-        const float4* dyb = reinterpret_cast<const float4*>(dy) + static_cast<size_t>(b) * Ho * Wo * 2;
-        __syncthreads();
-        for (int i = threadIdx.x; i < TW_PH * TW_PW; i += 256) {
-            const int ih = 2 * oh0 - 2 + i / TW_PW, iw = 2 * ow0 - 2 + i % TW_PW;
-            sx[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.0f;
-        }
-        for (int i = threadIdx.x; i < TW_TH * TW_TW * 2; i += 256) {
-            const int p = i >> 1, oh = oh0 + p / TW_TW, ow = ow0 + p % TW_TW;
-            sdy[i] = (oh < Ho && ow < Wo) ? __ldg(dyb + (static_cast<size_t>(oh) * Wo + ow) * 2 + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        if (worker) {
-            const float* px = sx + (2 * warp + r) * TW_PW + s;
-            const float4* pd = sdy + warp * TW_TW * 2;
-#pragma unroll 8
-            for (int qx = 0; qx < TW_TW; ++qx) {
-                const float xv = px[2 * qx];
-                const float4 d0 = pd[2 * qx], d1 = pd[2 * qx + 1];
-                acc[0] = fmaf(d0.x, xv, acc[0]); acc[1] = fmaf(d0.y, xv, acc[1]); acc[2] = fmaf(d0.z, xv, acc[2]); acc[3] = fmaf(d0.w, xv, acc[3]);
-                acc[4] = fmaf(d1.x, xv, acc[4]); acc[5] = fmaf(d1.y, xv, acc[5]); acc[6] = fmaf(d1.z, xv, acc[6]); acc[7] = fmaf(d1.w, xv, acc[7]);
-            }
-        }
+// Channels-last, C == 8: thread = (output pixel, channel half), 25 taps x 4 channels = 100 accumulators in registers,
+// so a pixel costs 25 conflict-free LDS.32 (its patch) + 1 LDS.128 (its 4 dy values) for 100 FMAs: the FMA pipe, not shared memory,
+// is the on-chip bound (a lane = tap mapping needs 3 shared-memory reads per 8 FMAs and idles 7 of 32 lanes), and below both sits
+// the HBM stream (x once with a 1.4x halo, dy once).  Tile = 4 rows x 32 pixels; warp w: row w % 4, channel half w / 4.  The patch is
+// stored split into even and odd columns so that lanes (consecutive pixels, input columns 2 px + s) read consecutive words.  Tiles are
+// fetched WG_STAGES - 1 ahead with cp.async (zero fill outside the image; a 7 KB tile computes in ~0.2 us but takes ~1.5 us to arrive, so
+// one tile in flight per CTA is latency bound at 1.4 TB/s) and dealt round-robin to a fixed grid: per-CTA sums in a fixed order.
+constexpr int WG_STAGES = 6, WG_TH = 4, WG_TW = 32, WG_PH = 2 * WG_TH + 3, WG_PW = 2 * WG_TW + 3, WG_PITCH = 36, WG_PIX = WG_TH * WG_TW;
+struct WgStage {
+    float xe[WG_PH][WG_PITCH], xo[WG_PH][WG_PITCH];
+    float4 dy[2][WG_PIX];
+};
+
+__global__ void __launch_bounds__(256, 2) thin_conv_wgrad_cl8_reg_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                         float* __restrict__ dw, int B, int H, int W, int Ho, int Wo,
+                                                                         FastDiv div_img, FastDiv div_w, int n_tiles,
+                                                                         float* __restrict__ partial) {
+    __shared__ __align__(16) WgStage st[WG_STAGES];
+    __shared__ float sred[8][THIN_TAPS * 4];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, half = warp >> 2, py = warp & 3;
+
+    // Per-thread copy plan, fixed for all tiles (the copy issue must stay well below the 126 instructions of the tile's arithmetic):
+    // patch elements t, t + 256, t + 512 (row, column -> offset in the image relative to the patch corner, offset in the stage) and
+    // the 16-byte half of dy pixel t / 2.
+    int x_row[3], x_col[3], x_src[3];
+    uint32_t x_dst[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = t + 256 * k, row = i / WG_PW, col = i - row * WG_PW;
+        x_row[k] = i < WG_PH * WG_PW ? row : -100000;        // (never inside the image)
+        x_col[k] = col;
+        x_src[k] = row * W + col;
+        x_dst[k] = static_cast<uint32_t>(((col & 1) ? offsetof(WgStage, xo) : offsetof(WgStage, xe)) + (row * WG_PITCH + (col >> 1)) * 4);
     }
-    if (worker)
+    const int d_pix = t >> 1, d_h = t & 1, d_oh = d_pix / WG_TW, d_ow = d_pix % WG_TW;
+    const uint32_t d_dst = static_cast<uint32_t>(offsetof(WgStage, dy) + (d_h * WG_PIX + d_pix) * 16);
+    const uint32_t st_u32 = smem_u32(&st[0]);
+
+    auto issue = [&](int tile, int s) {
+        if (tile < n_tiles) {
+            uint32_t b, ti, th, tw;
+            div_img.divmod(static_cast<uint32_t>(tile), b, ti);
+            div_w.divmod(ti, th, tw);
+            const int oh0 = static_cast<int>(th) * WG_TH, ow0 = static_cast<int>(tw) * WG_TW, ih0 = 2 * oh0 - 2, iw0 = 2 * ow0 - 2;
+            const float* xc = x + static_cast<size_t>(b) * H * W + ih0 * W + iw0;          // patch corner (may lie outside: never dereferenced there)
+            const uint32_t base = st_u32 + s * static_cast<uint32_t>(sizeof(WgStage));
 #pragma unroll
-        for (int c = 0; c < THIN_MAXC; ++c) sred[warp][lane][c] = acc[c];
+            for (int k = 0; k < 3; ++k) {
+                const bool ok = static_cast<unsigned>(ih0 + x_row[k]) < static_cast<unsigned>(H) && static_cast<unsigned>(iw0 + x_col[k]) < static_cast<unsigned>(W);
+                if (k < 2 || t + 512 < WG_PH * WG_PW) cp_async4(base + x_dst[k], ok ? xc + x_src[k] : x, ok ? 4u : 0u);
+            }
+            const int oh = oh0 + d_oh, ow = ow0 + d_ow;
+            const bool ok = oh < Ho && ow < Wo;
+            cp_async16_cg(base + d_dst, ok ? dy + ((static_cast<size_t>(b) * Ho + oh) * Wo + ow) * THIN_MAXC + 4 * d_h : dy, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+    };
+
+    float acc[THIN_TAPS][4];
+#pragma unroll
+    for (int k = 0; k < THIN_TAPS; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[k][i] = 0.0f;
+    int tile = blockIdx.x, s = 0, s_in = WG_STAGES - 1;
+    const int grid = gridDim.x;
+#pragma unroll 1
+    for (int k = 0; k < WG_STAGES - 1; ++k) issue(tile + k * grid, k);
+#pragma unroll 1
+    for (; tile < n_tiles; tile += grid) {
+        issue(tile + (WG_STAGES - 1) * grid, s_in);          // (that buffer was released by the last tile's barrier)
+        cp_async_wait<WG_STAGES - 1>();
+        __syncthreads();
+        const float4 d = st[s].dy[half][py * WG_TW + lane];
+#pragma unroll
+        for (int r = 0; r < THIN_K; ++r)
+#pragma unroll
+            for (int q = 0; q < THIN_K; ++q) {
+                const float xv = (q & 1) ? st[s].xo[2 * py + r][lane + (q >> 1)] : st[s].xe[2 * py + r][lane + (q >> 1)];
+                float* a = acc[r * THIN_K + q];
+                a[0] = fmaf(d.x, xv, a[0]); a[1] = fmaf(d.y, xv, a[1]); a[2] = fmaf(d.z, xv, a[2]); a[3] = fmaf(d.w, xv, a[3]);
+            }
+        __syncthreads();
+        s = s + 1 == WG_STAGES ? 0 : s + 1;
+        s_in = s_in + 1 == WG_STAGES ? 0 : s_in + 1;
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int k = 0; k < THIN_TAPS; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v = acc[k][i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sred[warp][k * 4 + i] = v;
+        }
     __syncthreads();
-    if (threadIdx.x < THIN_TAPS * THIN_MAXC) {
-        const int c = threadIdx.x / THIN_TAPS, tap = threadIdx.x % THIN_TAPS;
-        float v = 0.0f;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) v += sred[w8][tap][c];
-        if (partial != nullptr) partial[static_cast<size_t>(blockIdx.x) * (THIN_MAXC * THIN_TAPS) + c * THIN_TAPS + tap] = v;
-        else atomicAdd(dw + c * THIN_TAPS + tap, v);
+    if (t < THIN_TAPS * THIN_MAXC) {
+        const int c = t / THIN_TAPS, tap = t % THIN_TAPS, h = c >> 2, i = c & 3;
+        const float v = ((sred[4 * h][tap * 4 + i] + sred[4 * h + 1][tap * 4 + i]) + sred[4 * h + 2][tap * 4 + i]) + sred[4 * h + 3][tap * 4 + i];
+        if (partial != nullptr) partial[static_cast<size_t>(blockIdx.x) * (THIN_MAXC * THIN_TAPS) + t] = v;
+        else atomicAdd(dw + t, v);
     }
 }
 
@@ -395,15 +443,26 @@ int pgv_conv5x5s2_c1_wgrad(const float* x, const float* dy, float* dw, int B, in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PGV_CHECK_ARG(x && dy && dw, "pgv_conv5x5s2_c1_wgrad: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_wgrad: unsupported geometry");
-    const long long n_tiles = static_cast<long long>(B) * ((Ho + TW_TH - 1) / TW_TH) * ((Wo + TW_TW - 1) / TW_TW);
+    const bool reg_form = channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
+    long long n_tiles = static_cast<long long>(B) * ((Ho + TW_TH - 1) / TW_TH) * ((Wo + TW_TW - 1) / TW_TW);
     int per_block = static_cast<int>((n_tiles + 148 * 4 - 1) / (148 * 4));
     if (per_block < 1) per_block = 1;
-    const int grid = static_cast<int>((n_tiles + per_block - 1) / per_block);
+    int grid = static_cast<int>((n_tiles + per_block - 1) / per_block);
+    if (reg_form) {                                   // persistent: two CTAs per SM, tiles dealt round-robin
+        n_tiles = static_cast<long long>(B) * ((Ho + WG_TH - 1) / WG_TH) * ((Wo + WG_TW - 1) / WG_TW);
+        PGV_CHECK_ARG(n_tiles < (1LL << 30) && static_cast<long long>(B) * H * W < (1LL << 31), "pgv_conv5x5s2_c1_wgrad: too many tiles");
+        grid = static_cast<int>(std::min<long long>(n_tiles, 2LL * 148));
+    }
     // with a workspace (>= grid x 200 floats) the per-block sums are combined in a fixed order (deterministic); else fp32 atomics
     float* partial = (ws != nullptr && ws_bytes >= static_cast<size_t>(grid) * THIN_MAXC * THIN_TAPS * sizeof(float)) ? static_cast<float*>(ws) : nullptr;
     if (partial == nullptr) PGV_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C * THIN_TAPS, stream));
-    if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)
-        thin_conv_wgrad_cl8_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, H, W, Ho, Wo, per_block, partial);
+    if (reg_form)
+    {
+        FastDiv div_img, div_w;
+        div_img.init(static_cast<uint32_t>(((Ho + WG_TH - 1) / WG_TH) * ((Wo + WG_TW - 1) / WG_TW)));
+        div_w.init(static_cast<uint32_t>((Wo + WG_TW - 1) / WG_TW));
+        thin_conv_wgrad_cl8_reg_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, H, W, Ho, Wo, div_img, div_w, static_cast<int>(n_tiles), partial);
+    }
     else
         thin_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dy, dw, B, C, H, W, Ho, Wo, per_block, channels_last, partial);
     PGV_LAUNCH_CHECK();

@@ -47,12 +47,6 @@ struct CsParams {
     int a_vec, b_vec;                   // operand rows are 16-byte aligned and Kd % 4 == 0: 16-byte cp.async
 };
 
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 struct CsShared {
     double wred[8][CS_COLS][2];
     double gather[2][8][CS_COLS][2];    // [reduction parity][cluster rank]: every CTA of the cluster PUSHES its partial totals here

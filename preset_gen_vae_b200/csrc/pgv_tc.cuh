@@ -200,6 +200,12 @@ __device__ __forceinline__ void cp_async16_ca(uint32_t smem_dst, const void* src
 __device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
 }
+// 4-byte variant (`bytes` 0 or 4) and plain commit / wait groups for kernels that do not use mbarriers
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // The mbarrier receives ONE arrival (counted in its expected-arrival count) once all cp.async issued so far by this thread have landed.
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
