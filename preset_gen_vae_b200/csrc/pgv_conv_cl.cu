@@ -1018,6 +1018,42 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
     }
 }
 
+// Tiled form of cl_prep_weights_kernel for up to 16 taps: a CTA moves a 16 (co) x 32 (ci) x taps block through shared memory, so
+// the source is read in contiguous runs (32 ci x taps floats per co) and both destinations are written in 64..128-byte rows
+// (wf: 32 ci per (co, tap); wq: 16 co per (ci, tap)); the one-element-per-thread kernel above writes wq with a 4 Cout stride.
+constexpr int PW_TCO = 16, PW_TCI = 32, PW_MAXT = 16, PW_ROW = PW_TCI * (PW_MAXT + 1) + 1;
+__global__ void __launch_bounds__(256) cl_prep_weights_tiled_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wq,
+                                                                   int Cout, int Cin, int KH, int KW, int quad) {
+    __shared__ float s[PW_TCO][PW_ROW];
+    const int taps = KH * KW, tp = taps + 1, co0 = blockIdx.y * PW_TCO, ci0 = blockIdx.x * PW_TCI;
+    const int nco = min(PW_TCO, Cout - co0), nci = min(PW_TCI, Cin - ci0), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int co = warp; co < nco; co += 8) {
+        const float* src = w + (static_cast<size_t>(co0 + co) * Cin + ci0) * taps;
+        for (int e = lane; e < nci * taps; e += 32) s[co][(e / taps) * tp + e % taps] = to_tf32_rna(__ldg(src + e));
+    }
+    __syncthreads();
+    if (wf != nullptr)
+        for (int row = warp; row < nco * taps; row += 8) {
+            const int co = row / taps, tap = row - co * taps;
+            if (lane < nci) wf[(static_cast<size_t>(co0 + co) * taps + tap) * Cin + ci0 + lane] = s[co][lane * tp + tap];
+        }
+    if (wq != nullptr) {
+        const int co = lane & 15;
+        for (int row = warp * 2 + (lane >> 4); row < nci * taps; row += 16) {
+            const int ci = row / taps, tap = row - ci * taps;
+            if (co >= nco) continue;
+            const float v = s[co][ci * tp + tap];
+            if (quad) {
+                const int kh = tap / KW, kw = tap % KW;
+                const int ph = kh & 1, a = 1 - (kh >> 1), pw = kw & 1, bb = 1 - (kw >> 1);
+                wq[(static_cast<size_t>((ph * 2 + pw) * Cin + ci0 + ci)) * (4 * static_cast<size_t>(Cout)) + (a * 2 + bb) * Cout + co0 + co] = v;
+            } else {
+                wq[static_cast<size_t>(ci0 + ci) * Cout + co0 + co] = v;
+            }
+        }
+    }
+}
+
 }  // namespace pgv
 
 using namespace pgv;
@@ -1029,9 +1065,14 @@ int pgv_conv_cl_prep_weights(const float* w, float* wf, float* wq, int Cout, int
     const int quad = (KH == 4 && KW == 4 && stride == 2 && pad == 2) ? 1 : 0;
     PGV_CHECK_ARG(wq == nullptr || quad || (KH == 1 && KW == 1 && stride == 1 && pad == 0),
                   "pgv_conv_cl_prep_weights: the data-gradient matrix exists for 4x4/stride 2/pad 2 and 1x1/stride 1 only");
-    const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
-    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
-    cl_prep_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wf, wq, Cout, Cin, KH, KW, quad);
+    if (KH * KW <= PW_MAXT && ceil_div(Cout, PW_TCO) <= 65535) {
+        const dim3 grid(ceil_div(Cin, PW_TCI), ceil_div(Cout, PW_TCO));
+        cl_prep_weights_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wf, wq, Cout, Cin, KH, KW, quad);
+    } else {
+        const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+        const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+        cl_prep_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wf, wq, Cout, Cin, KH, KW, quad);
+    }
     PGV_LAUNCH_CHECK();
     return 0;
 }

@@ -200,7 +200,10 @@ class SpectrogramEncoder(nn.Module):
         direct = getattr(self, 'fc_weight_grad_out', None)
         dflat, dw, db = ops.fc_bwd(dy, fc_ctx, lin.weight, True, out=direct)
         ready = getattr(self, 'fc_grads_ready_event', None)
-        if ready is not None:       # train.py: both FC weight gradients (the decoder's backward has already joined) are final here
+        if ready is not None:       # train.py: both FC weight gradients (the decoder's backward has already joined) are final here,
+            hook = getattr(self, 'before_fc_grads_ready', None)      # and so is every gradient outside the encoder
+            if hook is not None:
+                hook()
             ready.record()
         grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
         if drop_mask is not None:

@@ -61,6 +61,20 @@ def complement_segments(total: int, excluded: Sequence[Sequence[int]]):
     return out
 
 
+def merged_slot_ranges(offsets: Sequence[int], total: int, chosen: Sequence[int]):
+    """[lo, hi) ranges covering the slots `chosen` (indices into `offsets`) of a flat buffer; a slot extends to the next slot's
+    offset (its alignment padding belongs to it), so that neighbouring slots merge into one range - one collective per range."""
+    bounds = [int(o) for o in offsets] + [int(total)]
+    out = []
+    for i in sorted(set(int(c) for c in chosen)):
+        lo, hi = bounds[i], bounds[i + 1]
+        if out and out[-1][1] == lo:
+            out[-1] = (out[-1][0], hi)
+        else:
+            out.append((lo, hi))
+    return out
+
+
 def allreduce_segments_(flat: torch.Tensor, slots: Sequence[Sequence[int]], group=None, early_stream=None, early_event=None):
     """Sum over ranks of `flat`, issued as one collective per excluded slot followed by one per complement range (same order on
     every rank).  With `early_stream` / `early_event` (CUDA) the slot collectives are enqueued from that stream once the event

@@ -9,6 +9,7 @@ NVLink on that buffer, one fused Adam kernel over the flat buffers, and the whol
 CUDA graph.  BatchNorm statistics are per-rank, as with the reference's nn.DataParallel replicas (train.py:95-97).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -16,6 +17,8 @@ import torch
 from . import _lib, parallel, synthetic
 from .model import build, loss as ploss, ops
 from .utils import audio as paudio
+
+_DEBUG_SKIP_AR = os.environ.get('PGV_DEBUG_SKIP_ALLREDUCE') == '1'      # measurement only (tools/): isolates what the exchange costs the step
 
 
 class ModelConvergenceError(ValueError):
@@ -105,6 +108,7 @@ class TrainStep:
         if self.world > 1 and use_cuda_graph and overlap_allreduce:
             self._fc_ready = torch.cuda.Event(external=True)
             self._comm_stream = torch.cuda.Stream(device=self.device)
+            self._aux_stream = torch.cuda.Stream(device=self.device)
         self.step_count = 0
         self.lr = train_config.initial_learning_rate
         # lr, bias corrections, grad scale, beta: staged through a ring of pinned buffers because the host runs ahead of the device
@@ -132,7 +136,9 @@ class TrainStep:
     def _flatten_parameters(self):
         params = [p for p in self.model.parameters() if p.requires_grad]
         sizes = [p.numel() for p in params]
-        self.layout = parallel.FlatLayout(sizes)                                         # 16-byte aligned slots
+        # 16-byte aligned slots; with several ranks every slot is a multiple of 4 x world elements, so that any run of whole slots
+        # splits into `world` equal, 16-byte aligned shards (reduce-scatter / sharded Adam / all-gather in _step_overlapped)
+        self.layout = parallel.FlatLayout(sizes, align_elems=4 * max(1, self.world))
         flat = torch.zeros(self.layout.total, dtype=torch.float32, device=self.device)
         for p, view in zip(params, self.layout.views(flat, [p.shape for p in params])):
             view.copy_(p.data)
@@ -173,19 +179,45 @@ class TrainStep:
                     flow._pgv_param_range = flat[int(self._offs[lo]):int(self._offs[hi]) + sizes[hi]]
         self._packed = [i for i in range(len(params)) if i not in self._direct]
         self._direct_slots = self._fc_slots                                             # (offset, size) of the early all-reduce slices
-        self._table_host = torch.zeros(len(self._packed) * 3, dtype=torch.int64).pin_memory()
-        self._table_dev = torch.zeros(len(self._packed) * 3, dtype=torch.int64, device=self.device)
-        self._table_host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in self._packed], dtype=np.int64))
-        self._table_host[2::3] = torch.tensor([sizes[i] for i in self._packed], dtype=torch.int64)
+        enc_ids = {id(p) for p in enc.parameters()}
+        self._in_encoder = [id(p) in enc_ids for p in params]
+        self._pack_tables = {}                          # key -> (indices, pinned host table, device table)
+        self._early_packed = None                       # indices packed by _pack_early in this step (overlapped data-parallel step)
+
+    def _pack_subset(self, key, idx, scale=1.0):
+        """Copies the gradients of parameters `idx` into their flat slots (one launch; the pointer table is re-read from pinned host
+        memory by the captured copy node, and is the same every step because the captured allocations are)."""
+        if not idx:
+            return
+        tab = self._pack_tables.get(key)
+        if tab is None or tab[0] != idx:
+            host = torch.zeros(len(idx) * 3, dtype=torch.int64).pin_memory()
+            host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in idx], dtype=np.int64))
+            host[2::3] = torch.tensor([self._sizes[i] for i in idx], dtype=torch.int64)
+            tab = self._pack_tables[key] = (list(idx), host, torch.zeros(len(idx) * 3, dtype=torch.int64, device=self.device))
+        _, host, dev = tab
+        host[0::3] = torch.tensor([self.params[i].grad.data_ptr() for i in idx], dtype=torch.int64)
+        dev.copy_(host, non_blocking=True)
+        _lib.check(_lib.lib().pgv_multi_pack(_lib.ptr(dev), len(idx), max(self._sizes[i] for i in idx),
+                                             _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
+        ops.launches += 1
+
+    def _pack_early(self):
+        """Called from the encoder's backward right before it records `_fc_ready`: every gradient outside the encoder is final
+        there (decoder, both flows, regression head: their backward nodes have run and accumulated), so it is packed now and its
+        exchange + Adam run under the encoder's convolution backward instead of after the step."""
+        idx = [i for i in self._packed if not self._in_encoder[i] and self.params[i].grad is not None]
+        self._pack_subset('early', idx)
+        self._early_packed = idx
 
     def _pack_grads(self, scale=1.0):
         for i, view in self._direct.items():           # already in place; expose them like every other gradient
             self.params[i].grad = view
-        self._table_host[0::3] = torch.tensor([self.params[i].grad.data_ptr() for i in self._packed], dtype=torch.int64)
-        self._table_dev.copy_(self._table_host, non_blocking=True)
-        _lib.check(_lib.lib().pgv_multi_pack(_lib.ptr(self._table_dev), len(self._packed), max(self._sizes[i] for i in self._packed),
-                                             _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
-        ops.launches += 1
+        if self._early_packed is not None:
+            done = set(self._early_packed)
+            self._pack_subset('late', [i for i in self._packed if i not in done], scale)
+        else:
+            self._pack_subset('all', self._packed, scale)
 
     # ------------------------------------------------------------------ operand copies of the weights, off the critical path
     def _prepare_operands(self):
@@ -225,6 +257,8 @@ class TrainStep:
                 w._pgv_prepared_event.record(cur)
                 self._prepared_params.append(w)
         enc_params = {id(p) for p in self.model.ae_model.encoder.parameters()}
+        if conv in ('enc', 'dec'):                             # one side's convolutions only
+            convs = [m for m in convs if (id(m.weight) in enc_params) == (conv == 'enc')]
         jobs = [(m.weight, m) for m in convs] * bool(conv) + [(lin.weight, None) for lin in fcs] * bool(fc)
         jobs.sort(key=lambda j: (id(j[0]) not in enc_params, j[1] is None))      # encoder first (convolutions, then its FC), then the decoder
         for w, m in jobs:
@@ -240,6 +274,9 @@ class TrainStep:
         front end)."""
         self._drop_prepared()
         self._refresh_operands(conv=True, fc=True, persistent=False)      # allocates; from now on refreshed in place
+        torch.cuda.current_stream(self.device).synchronize()
+        for w in self._prepared_params:                                   # ordered by the graphs from now on, not by per-parameter events
+            w._pgv_prepared_event = None
         self._prepared_params = []
         self._persistent_operands = True
 
@@ -294,6 +331,7 @@ class TrainStep:
         ops.nan_flags_(self._nan_mask, recons, lat, flow_in if flow_in is not None else recons, cont)               # train.py:245
         for p in self.params:
             p.grad = None
+        self._early_packed = None
         total.backward()
         self._pack_grads(1.0)
         self._join_prepared()
@@ -438,10 +476,13 @@ class TrainStep:
     def _step_overlapped(self, audio, v_in, sample_info):
         """Data-parallel step with the whole gradient exchange off the critical path.  Two captured graphs per step:
             A = the mel front end of this step's audio (reads no parameter),   B = forward / losses / backward / packing.
-        A communication stream reduces the two FC weight-gradient slices (180 of 241 MB) as soon as graph B signals them (external
-        event) and applies Adam to exactly those slices right behind the reduction - under the encoder's convolution backward;
-        after B it reduces the rest and applies Adam there.  The NEXT step launches its graph A before it waits for that tail, so the
-        remaining exchange + update run under the next front end (0.65 ms of tensor-core work that touches no parameter)."""
+        When the encoder's backward has passed its FC layer, every gradient outside the encoder's convolution stack is final (both
+        FC weights, decoder, both flows, regression head: 94 % of the 241 MB).  Graph B packs those there and signals an external
+        event; a communication stream reduce-scatters them, applies Adam to this rank's 1/world share, all-gathers the updated
+        parameters and refreshes the operand copies of those weights (_exchange_and_update) - under the encoder's convolution
+        backward.  After B it does the same for the encoder's stack (15 MB).  The NEXT step launches its graph A before it waits
+        for that tail, so what is left of the exchange + update runs under the next front end (0.8 ms of tensor-core work that
+        touches no parameter).  Measured at 2 ranks (tools/gpu_timeline_ddp.py): the step is 0.3 ms longer than on one GPU."""
         main = torch.cuda.current_stream(self.device)
         if self._graph is None:
             self._group_counts.copy_(self.controls_criterion.useful_counts(v_in))      # sane values for the warm-up steps of the capture
@@ -450,32 +491,83 @@ class TrainStep:
         for dst, src in zip((st_audio, st_v, st_info), (audio, v_in, sample_info)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        self._mark('step start')
+        # the categorical normaliser of the gathered batch (54 counts, targets only): exchanged on a side stream under the front end
+        aux = self._aux_stream
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            counts = parallel.global_useful_counts(self.controls_criterion.useful_counts(st_v), self.pg)
+            counts.div_(self.world)
+            counts_ready = torch.cuda.Event()
+            counts_ready.record(aux)
         self._graph_a.replay()                                   # front end -> static spectrogram batch
+        self._mark('front end done')
         if self._update_done is not None:
             main.wait_event(self._update_done)                   # previous step's parameters are final from here on
         self._refresh_hyper()
-        counts = parallel.global_useful_counts(self.controls_criterion.useful_counts(st_v), self.pg)
-        self._group_counts.copy_(counts / self.world)
+        main.wait_event(counts_ready)
+        self._group_counts.copy_(counts)
+        counts.record_stream(main)
+        self._mark('graph B start (previous update waited for)')
         self._graph.replay()
         scalars = self._static[3].clone()
         end_b = torch.cuda.Event()
         end_b.record(main)
+        self._mark('graph B end')
         comm = self._comm_stream
         dist = torch.distributed
         with torch.cuda.stream(comm):
             comm.wait_event(self._fc_ready)
-            for lo, n in self._fc_slots:
-                dist.all_reduce(self.flat_grads[lo:lo + n], op=dist.ReduceOp.SUM, group=self.pg)
-            self._update_graphs[0].replay()                      # Adam on the FC slices + their rounded operand copies
+            self._mark('comm: early gradients ready')
+            self._exchange_and_update(0)
+            self._mark('comm: early exchange + Adam + operand refresh done')
             comm.wait_event(end_b)
-            for lo, hi in self._rest_segments:
-                dist.all_reduce(self.flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-            self._update_graphs[1].replay()                      # Adam on the rest + the convolutions' operand matrices
+            self._exchange_and_update(1)
+            self._mark('comm: late exchange + Adam + operand refresh done')
             self._update_done = torch.cuda.Event()
             self._update_done.record(comm)
         self.scalars = scalars
         self.losses = scalars[:3]
         return self.losses
+
+    def _shards(self, part):
+        """[(lo, hi, my_lo, my_hi)] for the segments of phase `part` (0 early, 1 late): this rank's equal share of each segment."""
+        out = []
+        for lo, hi in (self._early_segments, self._rest_segments)[part]:
+            c = (hi - lo) // self.world
+            assert c * self.world == hi - lo and c % 4 == 0
+            out.append((lo, hi, lo + self.rank * c, lo + (self.rank + 1) * c))
+        return out
+
+    def _exchange_and_update(self, part):
+        """Current stream = the communication stream.  Reduce-scatter of the phase's gradient segments (each rank receives the sum of
+        its 1/world share), Adam on that share only (1/world of the optimizer's 28 bytes per parameter of HBM traffic, which would
+        otherwise compete with the backward pass running beside it), all-gather of the updated parameters, operand copies."""
+        dist = torch.distributed
+        if not _DEBUG_SKIP_AR:
+            for lo, hi, mlo, mhi in self._shards(part):
+                dist.reduce_scatter_tensor(self.flat_grads[mlo:mhi], self.flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+        self._update_graphs[part][0].replay()                    # Adam on the shards
+        if not _DEBUG_SKIP_AR:
+            for lo, hi, mlo, mhi in self._shards(part):
+                dist.all_gather_into_tensor(self.flat_params[lo:hi], self.flat_params[mlo:mhi], group=self.pg)
+        self._update_graphs[part][1].replay()                    # operand copies of the weights that just changed
+
+    def gather_sharded(self, flat):
+        """Completes a flat buffer of which every rank holds its shards only (the reduced gradients, the Adam moments) on all ranks."""
+        if getattr(self, '_sharded', False):
+            self.finish_updates()
+            for part in (0, 1):
+                for lo, hi, mlo, mhi in self._shards(part):
+                    torch.distributed.all_gather_into_tensor(flat[lo:hi], flat[mlo:mhi].clone(), group=self.pg)
+        return flat
+
+    def _mark(self, name):
+        """tools/gpu_timeline_ddp.py: timing events on the current stream while `self._trace` is a list."""
+        if getattr(self, '_trace', None) is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self._trace.append((name, ev))
 
     def finish_updates(self):
         """Makes the current stream wait for the parameter update of the last overlapped step (before reading parameters / state)."""
@@ -502,7 +594,8 @@ class TrainStep:
         with torch.cuda.graph(graph_a):
             self._front_end(static_in[0], out=x_static.view(-1, x_static.shape[-2], x_static.shape[-1]))
         graph_b = torch.cuda.CUDAGraph()
-        self.model.ae_model.encoder.fc_grads_ready_event = self._fc_ready
+        enc = self.model.ae_model.encoder
+        enc.fc_grads_ready_event, enc.before_fc_grads_ready = self._fc_ready, self._pack_early
         try:
             with torch.cuda.graph(graph_b):
                 try:
@@ -510,26 +603,34 @@ class TrainStep:
                 finally:
                     self._drop_prepared()
         finally:
-            self.model.ae_model.encoder.fc_grads_ready_event = None
-        self._rest_segments = parallel.complement_segments(self.flat_grads.numel(), self._fc_slots)
-        self.launches_per_step = ops.launches - before + len(self._fc_slots) + len(self._rest_segments)      # + the Adam launches on the communication stream
+            enc.fc_grads_ready_event, enc.before_fc_grads_ready = None, None
+        # early = final when `_fc_ready` fires: what _pack_early packed, the direct views outside the encoder and the encoder's own
+        # FC weight; late = the encoder's convolution stack and its few small vectors (6 % of the bytes)
+        fc_idx = {i for i in self._direct if (int(self._offs[i]), self._sizes[i]) in self._fc_slots}
+        early = set(self._early_packed or []) | fc_idx | {i for i in self._direct if not self._in_encoder[i]}
+        late = [i for i in range(len(self.params)) if i not in early]
+        self._early_segments = parallel.merged_slot_ranges(self._offs, self.flat_grads.numel(), early)
+        self._rest_segments = parallel.merged_slot_ranges(self._offs, self.flat_grads.numel(), late)
+        self.early_fraction = sum(hi - lo for lo, hi in self._early_segments) / float(self.flat_grads.numel())
+        self.launches_per_step = ops.launches - before + len(self._early_segments) + len(self._rest_segments)      # + the Adam launches on the communication stream
         self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
         self.model.load_state_dict(bn_state, strict=False)
         # the update kernels behind each reduction (Adam per segment + the refresh of the operand copies: ~25 small launches) are
         # captured too, so that a step costs the host a handful of calls - with 8 ranks per host the Python threads are the scarce resource
         self._update_graphs = []
         for part in (0, 1):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                if part == 0:
-                    for lo, n in self._fc_slots:
-                        self._adam(lo, lo + n)
-                    self._refresh_operands(conv=False, fc=True, persistent=True)
-                else:
-                    for lo, hi in self._rest_segments:
-                        self._adam(lo, hi)
-                    self._refresh_operands(conv=True, fc=False, persistent=True)
-            self._update_graphs.append(g)
+            pair = []
+            for what in ('adam', 'refresh'):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    if what == 'adam':
+                        for lo, hi, mlo, mhi in self._shards(part):
+                            self._adam(mlo, mhi)
+                    else:
+                        self._refresh_operands(conv=('dec', 'enc')[part], fc=(part == 0), persistent=True)
+                pair.append(g)
+            self._update_graphs.append(pair)
+        self._sharded = True
         # (capturing executed nothing, but be explicit about the state the first real step starts from)
         self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
         self._refresh_operands(conv=True, fc=True, persistent=True)
@@ -648,7 +749,8 @@ class TrainStep:
         flat Adam moments (one fp32 vector each, in `model.parameters()` order with 16-byte aligned slots) and the step count."""
         self.finish_updates()
         return {'ae_model_state_dict': self.model.state_dict(),
-                'optimizer_state_dict': {'step': self.step_count, 'lr': self.lr, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
+                'optimizer_state_dict': {'step': self.step_count, 'lr': self.lr, 'exp_avg': self.gather_sharded(self.exp_avg).clone(),
+                                         'exp_avg_sq': self.gather_sharded(self.exp_avg_sq).clone(),
                                          'slot_offsets': [int(o) for o in self._offs], 'slot_sizes': list(self._sizes)}}
 
     def load_state_dict(self, state):

@@ -64,6 +64,16 @@ def test_two_rank_gradient_allreduce_equals_full_batch():
             assert all(o % 4 == 0 for o in offsets)              # 16-byte aligned slots
 
 
+def test_merged_slot_ranges_cover_padding_and_merge_neighbours():
+    layout = parallel.FlatLayout([5, 8, 3, 4])                 # offsets 0, 8, 16, 20; total 24
+    total = layout.total
+    assert parallel.merged_slot_ranges(layout.offsets, total, [0, 1, 3]) == [(0, 16), (20, 24)]
+    assert parallel.merged_slot_ranges(layout.offsets, total, [2]) == [(16, 20)]
+    early, late = [1, 2], [0, 3]
+    cover = sorted(parallel.merged_slot_ranges(layout.offsets, total, early) + parallel.merged_slot_ranges(layout.offsets, total, late))
+    assert cover[0][0] == 0 and cover[-1][1] == total and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
+
 def test_complement_segments():
     assert parallel.complement_segments(40, [(24, 8), (4, 12)]) == [(0, 4), (16, 24), (32, 40)]
     assert parallel.complement_segments(10, [(0, 10)]) == [] and parallel.complement_segments(10, []) == [(0, 10)]

@@ -32,7 +32,7 @@ for t in trainers:
         torch.manual_seed(5)                        # same eps / dropout masks for both trainers
         t.step(audio, v_in, info)
         torch.cuda.synchronize()
-    res.append(t.flat_grads.clone())
+    res.append(t.gather_sharded(t.flat_grads).clone())     # (the overlapped step leaves every rank with its reduce-scatter shards)
 a, b = res
 rel = float((a.double() - b.double()).norm() / b.double().norm())
 fc = [float((ta.double() - tb.double()).norm() / tb.double().norm()) for ta, tb in

@@ -1,0 +1,6 @@
+set -x
+timeout 600 python -m pytest tests/test_conv_cl_gpu.py tests/test_model_gpu.py -x -q -m gpu 2>&1 | tail -2
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_train_2gpu_r02c.json 2> gpurun_out/bench2.err; echo rc=$?
+python -c "
+import json; d=json.loads([l for l in open('gpurun_out/bench_train_2gpu_r02c.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e'].get('ms_per_step'))"
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r02m.json 2> gpurun_out/bench_r02m.err; echo bench=$?; cut -c1-200 gpurun_out/bench_r02m.json
