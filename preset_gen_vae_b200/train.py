@@ -107,6 +107,7 @@ class TrainStep:
         self._fc_ready = None
         if self.world > 1 and use_cuda_graph and overlap_allreduce:
             self._fc_ready = torch.cuda.Event(external=True)
+            self._dec_ready = torch.cuda.Event(external=True)
             self._comm_stream = torch.cuda.Stream(device=self.device)
             self._aux_stream = torch.cuda.Stream(device=self.device)
         self.step_count = 0
@@ -182,7 +183,7 @@ class TrainStep:
         enc_ids = {id(p) for p in enc.parameters()}
         self._in_encoder = [id(p) in enc_ids for p in params]
         self._pack_tables = {}                          # key -> (indices, pinned host table, device table)
-        self._early_packed = None                       # indices packed by _pack_early in this step (overlapped data-parallel step)
+        self._early_packed = []                         # per phase: indices packed by _pack_early in this step (overlapped data-parallel step)
 
     def _pack_subset(self, key, idx, scale=1.0):
         """Copies the gradients of parameters `idx` into their flat slots (one launch; the pointer table is re-read from pinned host
@@ -202,19 +203,24 @@ class TrainStep:
                                              _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
         ops.launches += 1
 
-    def _pack_early(self):
-        """Called from the encoder's backward right before it records `_fc_ready`: every gradient outside the encoder is final
-        there (decoder, both flows, regression head: their backward nodes have run and accumulated), so it is packed now and its
-        exchange + Adam run under the encoder's convolution backward instead of after the step."""
-        idx = [i for i in self._packed if not self._in_encoder[i] and self.params[i].grad is not None]
-        self._pack_subset('early', idx)
-        self._early_packed = idx
+    def _pack_early(self, phase):
+        """Overlapped data-parallel step: packs the gradients that are final at one of two points of the backward pass, so that their
+        exchange + Adam run under the rest of it instead of after the step.
+          phase 0  from the latent flow's backward start: the decoder, the regression flow and everything else whose backward node
+                   has already run and accumulated;
+          phase 1  from the encoder's backward right before it records `_fc_ready`: what became final since (the latent flow)."""
+        done = {i for ph in self._early_packed for i in ph}
+        idx = [i for i in self._packed if i not in done and not self._in_encoder[i] and self.params[i].grad is not None]
+        self._pack_subset('early%d' % phase, idx)
+        while len(self._early_packed) <= phase:
+            self._early_packed.append([])
+        self._early_packed[phase] = idx
 
     def _pack_grads(self, scale=1.0):
         for i, view in self._direct.items():           # already in place; expose them like every other gradient
             self.params[i].grad = view
-        if self._early_packed is not None:
-            done = set(self._early_packed)
+        if self._early_packed:
+            done = {i for ph in self._early_packed for i in ph}
             self._pack_subset('late', [i for i in self._packed if i not in done], scale)
         else:
             self._pack_subset('all', self._packed, scale)
@@ -259,6 +265,8 @@ class TrainStep:
         enc_params = {id(p) for p in self.model.ae_model.encoder.parameters()}
         if conv in ('enc', 'dec'):                             # one side's convolutions only
             convs = [m for m in convs if (id(m.weight) in enc_params) == (conv == 'enc')]
+        if fc in ('enc', 'dec'):
+            fcs = [lin for lin in fcs if (id(lin.weight) in enc_params) == (fc == 'enc')]
         jobs = [(m.weight, m) for m in convs] * bool(conv) + [(lin.weight, None) for lin in fcs] * bool(fc)
         jobs.sort(key=lambda j: (id(j[0]) not in enc_params, j[1] is None))      # encoder first (convolutions, then its FC), then the decoder
         for w, m in jobs:
@@ -331,7 +339,7 @@ class TrainStep:
         ops.nan_flags_(self._nan_mask, recons, lat, flow_in if flow_in is not None else recons, cont)               # train.py:245
         for p in self.params:
             p.grad = None
-        self._early_packed = None
+        self._early_packed = []
         total.backward()
         self._pack_grads(1.0)
         self._join_prepared()
@@ -517,13 +525,11 @@ class TrainStep:
         comm = self._comm_stream
         dist = torch.distributed
         with torch.cuda.stream(comm):
-            comm.wait_event(self._fc_ready)
-            self._mark('comm: early gradients ready')
-            self._exchange_and_update(0)
-            self._mark('comm: early exchange + Adam + operand refresh done')
-            comm.wait_event(end_b)
-            self._exchange_and_update(1)
-            self._mark('comm: late exchange + Adam + operand refresh done')
+            for part, ready in enumerate((self._dec_ready, self._fc_ready, end_b)):
+                comm.wait_event(ready)
+                self._mark('comm: phase %d gradients ready' % part)
+                self._exchange_and_update(part)
+                self._mark('comm: phase %d exchange + Adam + operand refresh done' % part)
             self._update_done = torch.cuda.Event()
             self._update_done.record(comm)
         self.scalars = scalars
@@ -531,9 +537,9 @@ class TrainStep:
         return self.losses
 
     def _shards(self, part):
-        """[(lo, hi, my_lo, my_hi)] for the segments of phase `part` (0 early, 1 late): this rank's equal share of each segment."""
+        """[(lo, hi, my_lo, my_hi)] for the segments of phase `part`: this rank's equal share of each segment."""
         out = []
-        for lo, hi in (self._early_segments, self._rest_segments)[part]:
+        for lo, hi in self._phase_segments[part]:
             c = (hi - lo) // self.world
             assert c * self.world == hi - lo and c % 4 == 0
             out.append((lo, hi, lo + self.rank * c, lo + (self.rank + 1) * c))
@@ -557,7 +563,7 @@ class TrainStep:
         """Completes a flat buffer of which every rank holds its shards only (the reduced gradients, the Adam moments) on all ranks."""
         if getattr(self, '_sharded', False):
             self.finish_updates()
-            for part in (0, 1):
+            for part in range(3):
                 for lo, hi, mlo, mhi in self._shards(part):
                     torch.distributed.all_gather_into_tensor(flat[lo:hi], flat[mlo:mhi].clone(), group=self.pg)
         return flat
@@ -594,8 +600,14 @@ class TrainStep:
         with torch.cuda.graph(graph_a):
             self._front_end(static_in[0], out=x_static.view(-1, x_static.shape[-2], x_static.shape[-1]))
         graph_b = torch.cuda.CUDAGraph()
-        enc = self.model.ae_model.encoder
-        enc.fc_grads_ready_event, enc.before_fc_grads_ready = self._fc_ready, self._pack_early
+        enc, flow = self.model.ae_model.encoder, self.model.ae_model.flow_transform
+
+        def phase0():
+            self._pack_early(0)
+            self._dec_ready.record()
+
+        enc.fc_grads_ready_event, enc.before_fc_grads_ready = self._fc_ready, lambda: self._pack_early(1)
+        flow.on_backward_start = phase0
         try:
             with torch.cuda.graph(graph_b):
                 try:
@@ -603,22 +615,24 @@ class TrainStep:
                 finally:
                     self._drop_prepared()
         finally:
-            enc.fc_grads_ready_event, enc.before_fc_grads_ready = None, None
-        # early = final when `_fc_ready` fires: what _pack_early packed, the direct views outside the encoder and the encoder's own
-        # FC weight; late = the encoder's convolution stack and its few small vectors (6 % of the bytes)
-        fc_idx = {i for i in self._direct if (int(self._offs[i]), self._sizes[i]) in self._fc_slots}
-        early = set(self._early_packed or []) | fc_idx | {i for i in self._direct if not self._in_encoder[i]}
-        late = [i for i in range(len(self.params)) if i not in early]
-        self._early_segments = parallel.merged_slot_ranges(self._offs, self.flat_grads.numel(), early)
-        self._rest_segments = parallel.merged_slot_ranges(self._offs, self.flat_grads.numel(), late)
-        self.early_fraction = sum(hi - lo for lo, hi in self._early_segments) / float(self.flat_grads.numel())
-        self.launches_per_step = ops.launches - before + len(self._early_segments) + len(self._rest_segments)      # + the Adam launches on the communication stream
+            enc.fc_grads_ready_event, enc.before_fc_grads_ready, flow.on_backward_start = None, None, None
+        # Three phases.  0: final when the latent flow's backward starts (decoder incl. its FC weight, regression flow);  1: final when
+        # `_fc_ready` fires (latent flow, the encoder's FC weight);  2: the encoder's convolution stack and its few small vectors (6 %).
+        slot_index = {(int(self._offs[i]), self._sizes[i]): i for i in self._direct}
+        enc_fc = {slot_index[sl] for sl in self._fc_slots if self._in_encoder[slot_index[sl]]}
+        packed = self._early_packed + [[]] * (2 - len(self._early_packed))
+        phases = [set(packed[0]) | {i for i in self._direct if not self._in_encoder[i]}, set(packed[1]) | enc_fc]
+        phases.append(set(range(len(self.params))) - phases[0] - phases[1])
+        total = self.flat_grads.numel()
+        self._phase_segments = [parallel.merged_slot_ranges(self._offs, total, ph) for ph in phases]
+        self.phase_fractions = [sum(hi - lo for lo, hi in seg) / float(total) for seg in self._phase_segments]
+        self.launches_per_step = ops.launches - before + sum(len(seg) for seg in self._phase_segments)      # + the Adam launches on the communication stream
         self.flat_params.copy_(backup[0]); self.exp_avg.copy_(backup[1]); self.exp_avg_sq.copy_(backup[2])
         self.model.load_state_dict(bn_state, strict=False)
         # the update kernels behind each reduction (Adam per segment + the refresh of the operand copies: ~25 small launches) are
         # captured too, so that a step costs the host a handful of calls - with 8 ranks per host the Python threads are the scarce resource
         self._update_graphs = []
-        for part in (0, 1):
+        for part in range(3):
             pair = []
             for what in ('adam', 'refresh'):
                 g = torch.cuda.CUDAGraph()
@@ -627,7 +641,7 @@ class TrainStep:
                         for lo, hi, mlo, mhi in self._shards(part):
                             self._adam(mlo, mhi)
                     else:
-                        self._refresh_operands(conv=('dec', 'enc')[part], fc=(part == 0), persistent=True)
+                        self._refresh_operands(conv=('dec', False, 'enc')[part], fc=('dec', 'enc', False)[part], persistent=True)
                 pair.append(g)
             self._update_graphs.append(pair)
         self._sharded = True

@@ -32,7 +32,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 if rank == 0:
     t0 = t._trace[0][1]
-    print("early segments %s (%.1f %% of the gradient bytes), late segments %s" % (t._early_segments, 100 * t.early_fraction, t._rest_segments))
+    print("phase segments %s; fractions of the gradient bytes %s" % (t._phase_segments, ['%.3f' % f for f in t.phase_fractions]))
     for name, ev in sorted(t._trace, key=lambda ne: t0.elapsed_time(ne[1])):
         print("  %8.3f ms  %s" % (t0.elapsed_time(ev), name))
 dist.destroy_process_group()
