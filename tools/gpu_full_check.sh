@@ -1,18 +1,26 @@
-# Round-end verification on one B200 (run through gpurun): GPU tests, smoke, ncu launch list + traffic, the four bench lines,
-# one ncu --set full capture of conv_cl_kernel, per-layer / small-kernel / pipeline-trace logs.  Outputs land in gpurun_out/.
+# Round-end verification on one B200 (run through gpurun): GPU tests, smoke, ncu launch list + traffic, the bench lines, ncu --set full
+# captures (conv_cl thin / deep, flow program kernel, front-end GEMMs), per-layer / pipeline-trace / timeline logs.  Outputs land in gpurun_out/.
+R=r02
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytestZ.log 2>&1; echo pytest=$?; tail -2 gpurun_out/pytestZ.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smokeZ.log 2>&1; echo smoke=$?; tail -1 gpurun_out/smokeZ.log
-timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 2200 --csv --log-file gpurun_out/launches_train_r01.csv python tools/run_train_once.py 160 2 > gpurun_out/ncu_l.log 2>&1; echo ncu=$?
-python tools/summarize_launches.py gpurun_out/launches_train_r01.csv profiles/traffic_r01.json > gpurun_out/launches_train_r01.md
-timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_train_r01.json 2> gpurun_out/bench_train.err; echo bench=$?
-timeout 300 python bench.py --workload frontend --steps 20 --warmup 5 > gpurun_out/bench_frontend_r01.json 2>> gpurun_out/bench_train.err; echo benchf=$?
-timeout 300 python bench.py --workload inference --steps 20 --warmup 5 > gpurun_out/bench_inference_r01.json 2>> gpurun_out/bench_train.err; echo benchi=$?
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_r01.json 2>> gpurun_out/bench_train.err; echo benchr=$?
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_cl_kernel -c 4 -f -o gpurun_out/conv_cl_r01 python tools/ncu_conv_probe.py > gpurun_out/ncu_f.log 2>&1; echo ncufull=$?
-timeout 300 python tools/gpu_bench_layers.py 160 > gpurun_out/layers_M.log 2>&1
-timeout 300 python tools/gpu_bench_small.py 160 > gpurun_out/small_M.log 2>&1
-timeout 200 python tools/gpu_trace_conv.py > gpurun_out/trace_cl.log 2>&1
-cp profiles/traffic_r01.json gpurun_out/traffic_r01.json
-for f in gpurun_out/bench_train_r01.json gpurun_out/bench_frontend_r01.json gpurun_out/bench_inference_r01.json gpurun_out/bench_reference_r01.json; do python -c "
-import json,sys; d=json.load(open('$f')); print('$f', d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('value'), (d.get('roofline') or {}).get('kernel'), (d.get('roofline') or {}).get('frac'))"; done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$R.log 2>&1; echo pytest=$?; tail -2 gpurun_out/pytest_$R.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$R.log 2>&1; echo smoke=$?; tail -1 gpurun_out/smoke_$R.log
+timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 2200 --csv --log-file gpurun_out/launches_train_$R.csv python tools/run_train_once.py 160 2 > gpurun_out/ncu_l.log 2>&1; echo ncu=$?
+python tools/summarize_launches.py gpurun_out/launches_train_$R.csv profiles/traffic_$R.json > gpurun_out/launches_train_$R.md
+cp profiles/traffic_$R.json gpurun_out/traffic_$R.json
+timeout 400 python bench.py > gpurun_out/bench_train_$R.json 2> gpurun_out/bench_train.err; echo bench=$?
+timeout 300 python bench.py --workload frontend --steps 20 --warmup 5 > gpurun_out/bench_frontend_$R.json 2>> gpurun_out/bench_train.err; echo benchf=$?
+timeout 300 python bench.py --workload inference --steps 20 --warmup 5 > gpurun_out/bench_inference_$R.json 2>> gpurun_out/bench_train.err; echo benchi=$?
+timeout 300 python bench.py --workload train_c6 --steps 10 --warmup 3 > gpurun_out/bench_train_c6_$R.json 2>> gpurun_out/bench_train.err; echo benchc6=$?
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_$R.json 2>> gpurun_out/bench_train.err; echo benchr=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_cl_kernel -c 4 -f -o gpurun_out/conv_cl_$R python tools/ncu_conv_probe.py > gpurun_out/ncu_f.log 2>&1; echo ncufull=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_cl_kernel -c 3 -f -o gpurun_out/conv_cl_thin_$R python tools/ncu_conv_thin_probe.py > gpurun_out/ncu_f2.log 2>&1; echo ncuthin=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:flow_program_kernel -s 4 -c 2 -f -o gpurun_out/flow_program_$R python tools/gpu_flow_ncu.py program > gpurun_out/ncu_f3.log 2>&1; echo ncuflow=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32_kernel -s 2 -c 2 -f -o gpurun_out/frontend_gemm_$R python tools/run_frontend_once.py 160 2 > gpurun_out/ncu_f4.log 2>&1; echo ncufe=$?
+timeout 300 python tools/gpu_bench_layers.py 160 > gpurun_out/layers_$R.log 2>&1
+timeout 200 python tools/gpu_trace_conv.py > gpurun_out/trace_cl_$R.log 2>&1
+timeout 200 python tools/gpu_timeline.py 160 > gpurun_out/timeline_$R.log 2>&1
+timeout 200 python tools/gpu_step_breakdown.py 160 > gpurun_out/breakdown_$R.log 2>&1
+timeout 200 python tools/gpu_flow_trace.py 160 > gpurun_out/flow_trace_$R.log 2>&1
+timeout 200 python tools/gpu_determinism.py 16 > gpurun_out/determinism_$R.log 2>&1
+for f in train frontend inference train_c6 reference; do python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_${f}_$R.json')); print('$f', d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('value'), (d.get('roofline') or {}).get('kernel'), (d.get('roofline') or {}).get('frac'), (d.get('clocks') or {}).get('reasons'))"; done
