@@ -422,18 +422,23 @@ def main_ours(args):
             ranked = sorted(fam.items(), key=lambda kv: -kv[1]['ms'])
             name, top = ranked[0]
             per_ms = top['ms'] / 2
-            traffic = measured_traffic(name)
+            # (the ncu launch list is one B=160 training step: its DRAM bytes only describe that workload)
+            traffic = measured_traffic(name) if args.workload == 'train' else None
+            n_launch = max(1, top['calls'] // 2)
             if top['flops'] > 0:
                 ach = top['flops'] / 2 / (per_ms * 1e-3) / 1e12
                 tensor = name in ('conv_cl_kernel', 'conv_tc_kernel')
                 peak = pk['bf16_sustained'] / 2
                 roofline = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                            'traffic': traffic, 'launches_per_step': top['calls'] // 2, 'ms_per_step': per_ms, 'share_of_step': top['ms'] / tot,
-                            'algorithmic_bytes_per_step': top['bytes'] // 2,
+                            'traffic': None if traffic is None else traffic / n_launch, 'traffic_per_step': traffic,
+                            'launches_per_step': n_launch, 'ms_per_step': per_ms, 'us_per_launch': per_ms * 1e3 / n_launch,
+                            'share_of_step': top['ms'] / tot, 'algorithmic_bytes_per_step': top['bytes'] // 2,
+                            'algorithmic_bytes_per_launch': top['bytes'] // 2 // n_launch, 'algorithmic_flops_per_launch': top['flops'] // 2 // n_launch,
                             'note': ('tcgen05 kind::tf32 kernel' if tensor else 'CUDA-core fp32 kernel (not on the tensor pipe)') +
                                     '; achieved = algorithmic flops of all its launches in one step / their summed CUDA-event time (events on '
-                                    'the launching stream, GPU kept busy); peak = TF32 dense = half of the %s sustained bf16 figure; traffic = '
-                                    'dram bytes of the same launches under ncu (profiles/traffic_r02.json)' % pk['src']}
+                                    'the launching stream, GPU kept busy) = per-launch average flops / per-launch average duration; peak = TF32 dense = half of '
+                                    'the %s sustained bf16 figure; traffic = dram bytes per launch (average over the same launches of one step under '
+                                    'ncu, profiles/traffic_r02.json)' % pk['src']}
             else:
                 ach = top['bytes'] / 2 / (per_ms * 1e-3) / 1e9
                 roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],

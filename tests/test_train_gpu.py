@@ -54,19 +54,17 @@ def test_eager_step_matches_manual_forward_backward_and_torch_adam(idx_helper):
     assert abs(sc['controls_accuracy'] - ploss.CategoricalParamsAccuracy(idx_helper)(v_out, v_in).item()) < 0.5
     assert sc['nan_mask'] == 0.0 and sc['flow_input'] == 0.0
     for a, b in zip(got, (rec.item(), lat.item(), con.item())):
-        assert abs(a - b) <= 2e-5 * abs(b) + 1e-6       # atomics in wgrad / split-K make runs non bit-identical
-    # Gradients landed in the flat buffer.  Two runs of the same kernels are not bit-identical (fp32 atomics in the split-K /
-    # weight-gradient kernels: ~1e-6 relative noise on activations) and this network amplifies such noise strongly: the fp64
-    # CPU oracle itself changes its decoder weight gradients by 1e-2 relative-L2 when the input is perturbed by 1e-6
-    # (branch flips of LeakyReLU / Hardtanh elements near their kinks).  tools/gpu_determinism.py measures
-    # 4e-2 (decoder) / 4e-3 (encoder) run to run at B=16.  Hence a consistency bound here, not a precision test; precision is
-    # tested against the fp64 oracle in test_model_gpu.py.
+        assert abs(a - b) <= 2e-6 * abs(b) + 1e-7
+    # Gradients landed in the flat buffer.  Both paths run the same kernels and every reduction is order-fixed since round 2
+    # (workspace split-K, finish kernels, per-warp partials), so they agree to rounding: tools/gpu_determinism.py
+    # measures 7e-9 run to run (round 1, with fp32 atomics: 4e-2 on the decoder, because this network amplifies 1e-6 activation
+    # noise into percent-level gradient differences).  Precision is tested against the fp64 oracle in test_model_gpu.py.
     num = den = dot = 0.0
     for p, q in zip(tr.params, ref_model.parameters()):
         num += float(((p.grad - q.grad) ** 2).sum()); den += float((q.grad ** 2).sum()); dot += float((p.grad * q.grad).sum())
-    assert num ** 0.5 <= 2e-2 * den ** 0.5
+    assert num ** 0.5 <= 1e-4 * den ** 0.5
     for p, q in list(zip(tr.params, ref_model.parameters()))[::17]:
-        assert float((p.grad - q.grad).norm()) <= 1.5e-1 * float(q.grad.norm()) + 1e-7
+        assert float((p.grad - q.grad).norm()) <= 1e-3 * float(q.grad.norm()) + 1e-7
     # the fused Adam on the flat buffers against torch.optim.Adam fed with the SAME gradients
     for p, q in zip(tr.params, ref_model.parameters()):
         q.grad = p.grad.clone()
