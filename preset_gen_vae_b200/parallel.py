@@ -75,6 +75,50 @@ def merged_slot_ranges(offsets: Sequence[int], total: int, chosen: Sequence[int]
     return out
 
 
+def shard_of_segment(lo: int, hi: int, rank: int, world: int):
+    """This rank's equal share [my_lo, my_hi) of the flat range [lo, hi); the length must divide by `world` (FlatLayout pads every
+    slot to 4 x world elements for that) and shards stay 16-byte aligned."""
+    n = hi - lo
+    if n % world:
+        raise ValueError("segment of %d elements does not split into %d equal shards" % (n, world))
+    c = n // world
+    return lo + rank * c, lo + (rank + 1) * c
+
+
+def _native_shard_collectives(group) -> bool:
+    return dist.get_backend(group) == 'nccl'
+
+
+def reduce_scatter_segments_(flat: torch.Tensor, segments: Sequence[Sequence[int]], group=None):
+    """In place, per segment [lo, hi): afterwards this rank's shard of the segment holds the SUM over ranks of that shard (the rest of
+    the segment is unspecified).  NCCL: reduce_scatter_tensor with the output aliasing its slice of the input; other backends (gloo in
+    the CPU tests) emulate it with an all-reduce."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    for lo, hi in segments:
+        mlo, mhi = shard_of_segment(lo, hi, rank, world)
+        if _native_shard_collectives(group):
+            dist.reduce_scatter_tensor(flat[mlo:mhi], flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+        else:
+            total = flat[lo:hi].clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+            flat[mlo:mhi].copy_(total[mlo - lo:mhi - lo])
+    return flat
+
+
+def all_gather_segments_(flat: torch.Tensor, segments: Sequence[Sequence[int]], group=None):
+    """In place, per segment: every rank's shard is copied to all ranks (the counterpart of reduce_scatter_segments_)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    for lo, hi in segments:
+        mlo, mhi = shard_of_segment(lo, hi, rank, world)
+        if _native_shard_collectives(group):
+            dist.all_gather_into_tensor(flat[lo:hi], flat[mlo:mhi], group=group)
+        else:
+            parts = [torch.empty_like(flat[mlo:mhi]) for _ in range(world)]
+            dist.all_gather(parts, flat[mlo:mhi].clone(), group=group)
+            flat[lo:hi].copy_(torch.cat(parts))
+    return flat
+
+
 def allreduce_segments_(flat: torch.Tensor, slots: Sequence[Sequence[int]], group=None, early_stream=None, early_event=None):
     """Sum over ranks of `flat`, issued as one collective per excluded slot followed by one per complement range (same order on
     every rank).  With `early_stream` / `early_event` (CUDA) the slot collectives are enqueued from that stream once the event

@@ -538,34 +538,25 @@ class TrainStep:
 
     def _shards(self, part):
         """[(lo, hi, my_lo, my_hi)] for the segments of phase `part`: this rank's equal share of each segment."""
-        out = []
-        for lo, hi in self._phase_segments[part]:
-            c = (hi - lo) // self.world
-            assert c * self.world == hi - lo and c % 4 == 0
-            out.append((lo, hi, lo + self.rank * c, lo + (self.rank + 1) * c))
-        return out
+        return [(lo, hi) + parallel.shard_of_segment(lo, hi, self.rank, self.world) for lo, hi in self._phase_segments[part]]
 
     def _exchange_and_update(self, part):
         """Current stream = the communication stream.  Reduce-scatter of the phase's gradient segments (each rank receives the sum of
         its 1/world share), Adam on that share only (1/world of the optimizer's 28 bytes per parameter of HBM traffic, which would
         otherwise compete with the backward pass running beside it), all-gather of the updated parameters, operand copies."""
-        dist = torch.distributed
         if not _DEBUG_SKIP_AR:
-            for lo, hi, mlo, mhi in self._shards(part):
-                dist.reduce_scatter_tensor(self.flat_grads[mlo:mhi], self.flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            parallel.reduce_scatter_segments_(self.flat_grads, self._phase_segments[part], self.pg)
         self._update_graphs[part][0].replay()                    # Adam on the shards
         if not _DEBUG_SKIP_AR:
-            for lo, hi, mlo, mhi in self._shards(part):
-                dist.all_gather_into_tensor(self.flat_params[lo:hi], self.flat_params[mlo:mhi], group=self.pg)
+            parallel.all_gather_segments_(self.flat_params, self._phase_segments[part], self.pg)
         self._update_graphs[part][1].replay()                    # operand copies of the weights that just changed
 
     def gather_sharded(self, flat):
         """Completes a flat buffer of which every rank holds its shards only (the reduced gradients, the Adam moments) on all ranks."""
         if getattr(self, '_sharded', False):
             self.finish_updates()
-            for part in range(3):
-                for lo, hi, mlo, mhi in self._shards(part):
-                    torch.distributed.all_gather_into_tensor(flat[lo:hi], flat[mlo:mhi].clone(), group=self.pg)
+            for seg in self._phase_segments:
+                parallel.all_gather_segments_(flat, seg, self.pg)
         return flat
 
     def _mark(self, name):

@@ -43,9 +43,26 @@ def _worker(rank, world, port, ret):
         seg = torch.arange(40.0) * (rank + 1)
         parallel.allreduce_segments_(seg, [(24, 8), (4, 12)])
         seg_err = float((seg - torch.arange(40.0) * 3).abs().max())
+        # reduce-scatter -> update of this rank's shard only -> all-gather == all-reduce -> full update (TrainStep._exchange_and_update)
+        lay = parallel.FlatLayout([5, 9, 3, 6], align_elems=4 * world)
+        segs = parallel.merged_slot_ranges(lay.offsets, lay.total, [0, 1]) + parallel.merged_slot_ranges(lay.offsets, lay.total, [3])
+        g1 = torch.Generator().manual_seed(10 + rank)
+        grads, params = torch.randn(lay.total, generator=g1), torch.arange(float(lay.total))
+        want = grads.clone()
+        dist.all_reduce(want)
+        want_p = params - 0.1 * want
+        parallel.reduce_scatter_segments_(grads, segs)
+        for lo, hi in segs:
+            mlo, mhi = parallel.shard_of_segment(lo, hi, rank, world)
+            params[mlo:mhi] -= 0.1 * grads[mlo:mhi]              # "Adam" on the shard
+        parallel.all_gather_segments_(params, segs)
+        covered = torch.zeros(lay.total, dtype=torch.bool)
+        for lo, hi in segs:
+            covered[lo:hi] = True
+        shard_err = float((params - want_p)[covered].abs().max()) + float((params - torch.arange(float(lay.total)))[~covered].abs().max())
         counts = parallel.global_useful_counts(torch.tensor([3.0 + rank, 4.0]))
         slow = parallel.max_over_ranks(1.0 + rank, 'cpu')
-        ret[rank] = (err, counts.tolist(), slow, layout.offsets.tolist(), seg_err)
+        ret[rank] = (err, counts.tolist(), slow, layout.offsets.tolist(), seg_err, shard_err)
     finally:
         dist.destroy_process_group()
 
@@ -57,8 +74,8 @@ def test_two_rank_gradient_allreduce_equals_full_batch():
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert len(ret) == 2
         for rank in range(world):
-            err, counts, slow, offsets, seg_err = ret[rank]
-            assert seg_err == 0.0
+            err, counts, slow, offsets, seg_err, shard_err = ret[rank]
+            assert seg_err == 0.0 and shard_err < 1e-6
             assert err < 1e-6                                    # equal shards: mean of shard means == full-batch mean
             assert counts == [7.0, 8.0] and slow == 2.0
             assert all(o % 4 == 0 for o in offsets)              # 16-byte aligned slots
