@@ -19,9 +19,14 @@ static ClMap cl_map(int C) {
     while (tcb < tc && tcb < 256) tcb <<= 1;
     return {tcb, 256 / tcb};
 }
+// Rows each thread walks before the grid is capped (pgv_debug_set_bn_rows_per_lane).  Swept on the captured training step at B = 160
+// (tools/gpu_sweep_bn.py): 1: 6.74, 2: 6.78, 4: 6.64, 8: 6.57, 16: 6.49, 32: 6.59, 64: 7.03 ms - small grids win on the layers with few pixels
+// because every CTA ends in 2C fp64 atomics on the same addresses and a sub-wave tail.
+static int g_cl_rows_per_lane = 16;
 static int cl_grid_rows(size_t P, int rl_count) {
-    const size_t want = (P + static_cast<size_t>(rl_count) * 8 - 1) / (static_cast<size_t>(rl_count) * 8);
-    // 4 blocks per SM: measured faster for the whole step than 8 (more blocks only add atomics and tail effects)
+    const size_t per = static_cast<size_t>(rl_count) * static_cast<size_t>(g_cl_rows_per_lane);
+    const size_t want = (P + per - 1) / per;
+    // cap: 4 blocks per SM, measured faster for the whole step than 8 (more blocks only add atomics and tail effects)
     return static_cast<int>(std::max<size_t>(1, std::min<size_t>(want, 148 * 4)));
 }
 
@@ -245,6 +250,8 @@ __global__ void __launch_bounds__(256) transpose_inner_kernel(const float* __res
 using namespace pgv;
 
 extern "C" {
+
+int pgv_debug_set_bn_rows_per_lane(int rows) { g_cl_rows_per_lane = rows < 1 ? 1 : rows; return 0; }
 
 int pgv_bn_cl_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_rstd, float* running_mean,
                         float* running_var, float momentum, float eps, size_t P, int C, int round_out, void* workspace, pgv_stream_t stream) {

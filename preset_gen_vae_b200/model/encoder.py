@@ -199,11 +199,13 @@ class SpectrogramEncoder(nn.Module):
         # buffer instead of a temporary that would be copied there; autograd then gets no tensor for it
         direct = getattr(self, 'fc_weight_grad_out', None)
         dflat, dw, db = ops.fc_bwd(dy, fc_ctx, lin.weight, True, out=direct)
+        # TrainStep: both FC weight gradients (the decoder's backward has already joined) are final here, and so is every gradient
+        # outside the encoder: a hook packs / updates them under the rest of this backward, an event releases their exchange
+        hook = getattr(self, 'before_fc_grads_ready', None)
+        if hook is not None:
+            hook()
         ready = getattr(self, 'fc_grads_ready_event', None)
-        if ready is not None:       # train.py: both FC weight gradients (the decoder's backward has already joined) are final here,
-            hook = getattr(self, 'before_fc_grads_ready', None)      # and so is every gradient outside the encoder
-            if hook is not None:
-                hook()
+        if ready is not None:
             ready.record()
         grads[id(lin.weight)], grads[id(lin.bias)] = (None if direct is not None else dw), db
         if drop_mask is not None:

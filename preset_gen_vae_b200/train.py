@@ -184,6 +184,7 @@ class TrainStep:
         self._in_encoder = [id(p) in enc_ids for p in params]
         self._pack_tables = {}                          # key -> (indices, pinned host table, device table)
         self._early_packed = []                         # per phase: indices packed by _pack_early in this step (overlapped data-parallel step)
+        self.early_adam = False                         # one GPU: Adam on everything outside the encoder stack under the encoder backward
 
     def _pack_subset(self, key, idx, scale=1.0):
         """Copies the gradients of parameters `idx` into their flat slots (one launch; the pointer table is re-read from pinned host
@@ -215,6 +216,25 @@ class TrainStep:
         while len(self._early_packed) <= phase:
             self._early_packed.append([])
         self._early_packed[phase] = idx
+
+    def _early_update(self):
+        """One GPU: called from the encoder's backward once it has passed its FC layer.  Every gradient outside the encoder's
+        convolution stack is final (94 % of the parameters): they are packed and Adam runs on their slots on a side stream, under the
+        encoder's convolution backward, instead of 0.3 ms at the end of the step (nothing that is still to run reads those
+        parameters)."""
+        main = torch.cuda.current_stream(self.device)
+        self._pack_early(0)
+        slot_index = {(int(self._offs[i]), self._sizes[i]): i for i in self._direct}
+        enc_fc = {slot_index[sl] for sl in self._fc_slots if self._in_encoder[slot_index[sl]]}
+        early = set(self._early_packed[0]) | enc_fc | {i for i in self._direct if not self._in_encoder[i]}
+        segs = parallel.merged_slot_ranges(self._offs, self.flat_grads.numel(), early)
+        if getattr(self, '_update_stream', None) is None:
+            self._update_stream = torch.cuda.Stream(device=self.device)
+        self._update_stream.wait_stream(main)
+        with torch.cuda.stream(self._update_stream):
+            for lo, hi in segs:
+                self._adam(lo, hi)
+        self._early_adam_segments = segs
 
     def _pack_grads(self, scale=1.0):
         for i, view in self._direct.items():           # already in place; expose them like every other gradient
@@ -340,11 +360,26 @@ class TrainStep:
         for p in self.params:
             p.grad = None
         self._early_packed = []
-        total.backward()
+        enc = self.model.ae_model.encoder
+        early_adam = with_optimizer and self.world == 1 and self.early_adam and getattr(enc, 'before_fc_grads_ready', None) is None
+        self._early_adam_segments = None
+        if early_adam:
+            enc.before_fc_grads_ready = self._early_update
+        try:
+            total.backward()
+        finally:
+            if early_adam:
+                enc.before_fc_grads_ready = None
         self._pack_grads(1.0)
         self._join_prepared()
         if with_optimizer:
-            self._adam()
+            if self._early_adam_segments is not None:          # the rest: the encoder's stack (6 % of the parameters)
+                n = self.flat_grads.numel()
+                for lo, hi in parallel.complement_segments(n, [(lo, hi - lo) for lo, hi in self._early_adam_segments]):
+                    self._adam(lo, hi)
+                torch.cuda.current_stream(self.device).wait_stream(self._update_stream)
+            else:
+                self._adam()
         zero = torch.zeros((), device=self.device)
         return torch.stack([recons.detach(), lat.detach(), cont.detach(), metrics[0], metrics[1],
                             flow_in.detach() if flow_in is not None else zero, self._nan_mask[0].float()])
