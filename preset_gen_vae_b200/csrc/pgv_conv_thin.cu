@@ -386,6 +386,9 @@ static int thin_load_constants(const Sym& symbol, const float* w, const float* b
     return 0;
 }
 
+// CTAs per SM the one-thread-per-pixel forward / transposed kernels are capped at (pgv_debug_set_thin_grid_mult)
+static int g_thin_grid_mult = 32;
+
 static bool thin_geometry(int C, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo) {
     return C >= 1 && C <= THIN_MAXC && kh == 5 && kw == 5 && stride == 2 && pad == 2 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1;
 }
@@ -396,6 +399,8 @@ using namespace pgv;
 
 extern "C" {
 
+int pgv_debug_set_thin_grid_mult(int m) { g_thin_grid_mult = m < 1 ? 1 : m; return 0; }
+
 int pgv_conv5x5s2_c1_supported(int Cin, int Cout, int kh, int kw, int stride, int pad, int H, int W, int Ho, int Wo) {
     return Cin == 1 && thin_geometry(Cout, kh, kw, stride, pad, H, W, Ho, Wo);
 }
@@ -405,7 +410,7 @@ int pgv_conv5x5s2_c1_fwd(const float* x, const float* w, const float* bias, floa
     PGV_CHECK_ARG(x && w && y, "pgv_conv5x5s2_c1_fwd: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_fwd: unsupported geometry");
     const long long total = static_cast<long long>(B) * Ho * Wo;
-    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * g_thin_grid_mult));
     if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (int rc = thin_load_constants(c_thin_fwd_w, w, bias, THIN_MAXC, st)) return rc;
@@ -423,12 +428,12 @@ int pgv_conv5x5s2_c1_dgrad(const float* y, const float* w, const float* bias, fl
     PGV_CHECK_ARG(y && w && x, "pgv_conv5x5s2_c1_dgrad: NULL argument");
     PGV_CHECK_ARG(thin_geometry(C, 5, 5, 2, 2, H, W, Ho, Wo) && B > 0, "pgv_conv5x5s2_c1_dgrad: unsupported geometry");
     const long long total = static_cast<long long>(B) * H * W;
-    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * g_thin_grid_mult));
     if (channels_last && C == THIN_MAXC && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (int rc = thin_load_constants(c_thin_quad_w, w, bias, 1, st)) return rc;
         const long long quads = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
-        const int qgrid = static_cast<int>(std::min<long long>((quads + 255) / 256, 148LL * 32));
+        const int qgrid = static_cast<int>(std::min<long long>((quads + 255) / 256, 148LL * g_thin_grid_mult));
         thin_conv_quad_cl8_kernel<<<qgrid, 256, 0, st>>>(y, x, B, H, W, Ho, Wo, clamp_lo, clamp_hi);
     } else if (channels_last)
         thin_conv_dgrad_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, bias, x, B, C, H, W, Ho, Wo, clamp_lo, clamp_hi);

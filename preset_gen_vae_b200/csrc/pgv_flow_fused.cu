@@ -634,6 +634,7 @@ __global__ void __launch_bounds__(CS_THREADS) flow_program_kernel(const __grid_c
 }
 
 unsigned long long* g_flow_trace = nullptr;
+int g_flow_clusters = 0;
 
 }  // namespace pgv
 
@@ -683,7 +684,8 @@ int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned*
         configured = true;
     }
     PGV_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned) * (1 + n_wgrad), stream));
-    const int clusters = std::max(1, std::min(39, (h->sm_count - 8) / prog.row_ctas));       // co-resident: at most one CTA per SM
+    // co-resident: at most one CTA per SM (pgv_debug_set_flow_clusters overrides the count for sweeps)
+    const int clusters = std::max(1, std::min(g_flow_clusters > 0 ? g_flow_clusters : 39, (h->sm_count - 8) / prog.row_ctas));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(1, prog.row_ctas, clusters);
@@ -707,6 +709,7 @@ int pgv_debug_set_flow_diag(void* pinned_host) {
     return 0;
 }
 
+int pgv_debug_set_flow_clusters(int clusters) { g_flow_clusters = clusters; return 0; }
 int pgv_debug_set_flow_trace(void* trace_dev) { g_flow_trace = static_cast<unsigned long long*>(trace_dev); return 0; }
 
 int pgv_flow_program_op_bytes(void) { return static_cast<int>(sizeof(MegaOp)); }

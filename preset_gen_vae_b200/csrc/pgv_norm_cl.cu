@@ -20,7 +20,7 @@ static ClMap cl_map(int C) {
     return {tcb, 256 / tcb};
 }
 // Rows each thread walks before the grid is capped (pgv_debug_set_bn_rows_per_lane).  Swept on the captured training step at B = 160
-// (tools/gpu_sweep_bn.py): 1: 6.74, 2: 6.78, 4: 6.64, 8: 6.57, 16: 6.49, 32: 6.59, 64: 7.03 ms - small grids win on the layers with few pixels
+// (tools/gpu_sweep_knob.py): 1: 6.74, 2: 6.78, 4: 6.64, 8: 6.57, 16: 6.49, 32: 6.59, 64: 7.03 ms - small grids win on the layers with few pixels
 // because every CTA ends in 2C fp64 atomics on the same addresses and a sub-wave tail.
 static int g_cl_rows_per_lane = 16;
 static int cl_grid_rows(size_t P, int rl_count) {

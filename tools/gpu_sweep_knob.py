@@ -1,4 +1,5 @@
-"""Sweep of the channels-last BatchNorm grid sizing knob: captured training step time at B = 160 for several rows-per-thread values."""
+"""Sweep of an integer debug knob of the kernel library (pgv_debug_set_<knob>): captured training step time at B = 160 per value.
+Usage: gpu_sweep_knob.py bn_rows_per_lane 8 16 32"""
 import sys
 
 import torch
@@ -13,8 +14,9 @@ h = DexedLearnableLayout().preset_indexes_helper
 audio = synthetic.make_audio(B, 1, seed=3).cuda()
 v = synthetic.make_preset_targets(h, B, seed=3).cuda()
 info = synthetic.make_sample_info(B).cuda()
-for rows in [int(a) for a in sys.argv[1:]] or [8, 4, 2, 1]:
-    _lib.lib().pgv_debug_set_bn_rows_per_lane(rows)
+knob = sys.argv[1]                      # name of a pgv_debug_set_* entry point taking one int, e.g. bn_rows_per_lane, flow_clusters
+for rows in [int(a) for a in sys.argv[2:]]:
+    getattr(_lib.lib(), 'pgv_debug_set_' + knob)(rows)
     m, t = pcfg.make_default(minibatch_size=B)
     pcfg.apply_dataset_dims(m, h)
     tr = TrainStep(m, t, h, pipeline_frontend=True)
@@ -30,6 +32,6 @@ for rows in [int(a) for a in sys.argv[1:]] or [8, 4, 2, 1]:
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) / 20)
-    print("rows per thread %2d: %.3f ms per step" % (rows, best), flush=True)
+    print("%s = %3d: %.3f ms per step" % (knob, rows, best), flush=True)
     del tr
     torch.cuda.empty_cache()
