@@ -426,19 +426,28 @@ def main_ours(args):
             traffic = measured_traffic(name) if args.workload == 'train' else None
             n_launch = max(1, top['calls'] // 2)
             if top['flops'] > 0:
-                ach = top['flops'] / 2 / (per_ms * 1e-3) / 1e12
                 tensor = name in ('conv_cl_kernel', 'conv_tc_kernel')
-                peak = pk['bf16_sustained'] / 2
-                roofline = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                peak_t = pk['bf16_sustained'] / 2
+                ach_t = top['flops'] / 2 / (per_ms * 1e-3) / 1e12
+                ach_h = top['bytes'] / 2 / (per_ms * 1e-3) / 1e9
+                frac_t, frac_h = ach_t / peak_t, ach_h / pk['hbm_gbs']
+                # the binding roofline of the kernel's launches taken together is the larger of its two floors (flops / tensor peak,
+                # algorithmic bytes / HBM peak): the 8..32-channel layers make conv_cl_kernel HBM-class in aggregate
+                hbm_bound = tensor and frac_h > frac_t
+                roofline = {'kernel': name, 'bound': 'hbm' if hbm_bound else 'tensor', 'achieved': ach_h if hbm_bound else ach_t,
+                            'peak': pk['hbm_gbs'] if hbm_bound else peak_t, 'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
+                            'frac': frac_h if hbm_bound else frac_t, 'frac_tensor': frac_t, 'frac_hbm': frac_h,
+                            'achieved_tflops': ach_t, 'achieved_algorithmic_gbs': ach_h,
                             'traffic': None if traffic is None else traffic / n_launch, 'traffic_per_step': traffic,
                             'launches_per_step': n_launch, 'ms_per_step': per_ms, 'us_per_launch': per_ms * 1e3 / n_launch,
                             'share_of_step': top['ms'] / tot, 'algorithmic_bytes_per_step': top['bytes'] // 2,
                             'algorithmic_bytes_per_launch': top['bytes'] // 2 // n_launch, 'algorithmic_flops_per_launch': top['flops'] // 2 // n_launch,
                             'note': ('tcgen05 kind::tf32 kernel' if tensor else 'CUDA-core fp32 kernel (not on the tensor pipe)') +
-                                    '; achieved = algorithmic flops of all its launches in one step / their summed CUDA-event time (events on '
-                                    'the launching stream, GPU kept busy) = per-launch average flops / per-launch average duration; peak = TF32 dense = half of '
-                                    'the %s sustained bf16 figure; traffic = dram bytes per launch (average over the same launches of one step under '
-                                    'ncu, profiles/traffic_r02.json)' % pk['src']}
+                                    '; achieved = algorithmic bytes (or flops) of all its launches in one step / their summed CUDA-event time '
+                                    '(events on the launching stream, GPU kept busy) = per-launch average / per-launch average duration; bound = the '
+                                    'larger of the two floors; tensor peak = TF32 dense = half of the %s sustained bf16 figure, HBM peak = the %s copy '
+                                    'bandwidth; traffic = dram bytes per launch (average over the same launches of one step under ncu, '
+                                    'profiles/traffic_r02.json)' % (pk['src'], pk['src'])}
             else:
                 ach = top['bytes'] / 2 / (per_ms * 1e-3) / 1e9
                 roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],

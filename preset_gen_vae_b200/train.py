@@ -197,9 +197,16 @@ class TrainStep:
             host[1::3] = torch.from_numpy(np.asarray([self._offs[i] for i in idx], dtype=np.int64))
             host[2::3] = torch.tensor([self._sizes[i] for i in idx], dtype=torch.int64)
             tab = self._pack_tables[key] = (list(idx), host, torch.zeros(len(idx) * 3, dtype=torch.int64, device=self.device))
-        _, host, dev = tab
+        _, host, dev = tab[:3]
+        capturing = torch.cuda.is_current_stream_capturing()
+        if len(tab) > 3 and tab[3] is not None and not capturing:
+            tab[3].synchronize()                     # eager mode: the host runs ahead; the previous copy must have read the table
         host[0::3] = torch.tensor([self.params[i].grad.data_ptr() for i in idx], dtype=torch.int64)
         dev.copy_(host, non_blocking=True)
+        if not capturing:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pack_tables[key] = tab[:3] + (ev,)
         _lib.check(_lib.lib().pgv_multi_pack(_lib.ptr(dev), len(idx), max(self._sizes[i] for i in idx),
                                              _lib.ptr(self.flat_grads), float(scale), _lib.stream_ptr(self.device)), 'pgv_multi_pack')
         ops.launches += 1
