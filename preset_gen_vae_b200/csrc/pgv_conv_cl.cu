@@ -1018,10 +1018,12 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
     }
 }
 
-// Tiled form of cl_prep_weights_kernel for up to 16 taps: a CTA moves a 16 (co) x 32 (ci) x taps block through shared memory, so
-// the source is read in contiguous runs (32 ci x taps floats per co) and both destinations are written in 64..128-byte rows
-// (wf: 32 ci per (co, tap); wq: 16 co per (ci, tap)); the one-element-per-thread kernel above writes wq with a 4 Cout stride.
-constexpr int PW_TCO = 16, PW_TCI = 32, PW_MAXT = 16, PW_ROW = PW_TCI * (PW_MAXT + 1) + 1;
+// Tiled form of cl_prep_weights_kernel for up to 16 taps: a CTA moves an 8 (co) x 32 (ci) x taps block through shared memory, so
+// the source is read in contiguous runs (32 ci x taps floats per co) and both destinations are written in whole sectors
+// (wf: 32 ci per (co, tap); wq: 8 co per (ci, tap)); the one-element-per-thread kernel above writes wq with a 4 Cout stride.
+// 17 KB of shared memory on purpose: these launches run on a side stream UNDER the front end, whose persistent DFT GEMM CTAs hold
+// 198 KB per SM - with a 35 KB tile nothing co-resided and the copies queued up behind the front end (encoder forward +0.15 ms).
+constexpr int PW_TCO = 8, PW_TCI = 32, PW_MAXT = 16, PW_ROW = PW_TCI * (PW_MAXT + 1) + 1;
 __global__ void __launch_bounds__(256) cl_prep_weights_tiled_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wq,
                                                                    int Cout, int Cin, int KH, int KW, int quad) {
     __shared__ float s[PW_TCO][PW_ROW];
@@ -1038,8 +1040,8 @@ __global__ void __launch_bounds__(256) cl_prep_weights_tiled_kernel(const float*
             if (lane < nci) wf[(static_cast<size_t>(co0 + co) * taps + tap) * Cin + ci0 + lane] = s[co][lane * tp + tap];
         }
     if (wq != nullptr) {
-        const int co = lane & 15;
-        for (int row = warp * 2 + (lane >> 4); row < nci * taps; row += 16) {
+        const int co = lane & 7;
+        for (int row = warp * 4 + (lane >> 3); row < nci * taps; row += 32) {
             const int ci = row / taps, tap = row - ci * taps;
             if (co >= nco) continue;
             const float v = s[co][ci * tp + tap];
