@@ -244,6 +244,8 @@ def main_ours(args):
     from preset_gen_vae_b200.train import TrainStep
     from preset_gen_vae_b200.utils.audio import MelSpectrogram
     B = args.batch_per_gpu or default_batch(args.workload)
+    if args.strong_scaling:                          # the fixed global batch of the workload split over the ranks
+        B = max(4, B // world // 4 * 4)
     helper, m_cfg, t_cfg = model_configs(args.workload, B)
     C = m_cfg.input_tensor_size[1]
     audio_h = synthetic.make_audio(min(B, 64), C, seed=rank)                 # CPU synthesis is slow: tile 64 distinct clips
@@ -457,7 +459,8 @@ def main_ours(args):
         cpu_baseline, _ = run_cpu(args.workload, args.cpu_batch or B, budget_s=args.cpu_budget)
     if rank == 0:
         line = {'metric': METRIC[args.workload], 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+                'scaling': 'strong' if args.strong_scaling else 'weak', 'vs_baseline': None,
                 'dtype': 'f32 storage; tf32 tensor-core products where the layer runs on tcgen05, fp32 elsewhere',
                 'data': 'synthetic', 'config': line_config(args.workload, B, world, not args.no_graph),
                 'e2e': e2e, 'gpu_launches': int(launches * args.steps), 'gpu_launches_per_step': int(launches), 'clocks': clocks,
@@ -500,6 +503,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the bounded CPU sample (0 = the per-GPU batch of the workload)')
     ap.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU baseline work')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--strong-scaling', action='store_true', help='split the workload\'s per-GPU batch over the ranks (fixed global batch) instead of weak scaling')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-pipeline', action='store_true', help='one GPU: do not software-pipeline the front end (TrainStep(pipeline_frontend=False))')
     args = ap.parse_args()
