@@ -375,6 +375,8 @@ PGV_API int pgv_spectrogram_stats(const float* x, int N, size_t elems, float* pe
 PGV_API int pgv_flow_program(pgv_handle* h, const void* ops, int n_ops, int M, unsigned* counter, pgv_stream_t stream);
 /* Debug (tools/gpu_flow_trace.py): subsequent pgv_flow_program launches write, per op, 4 words {start ns, end of CTA 0's share ns, barrier open ns, kind} */
 PGV_API int pgv_debug_set_flow_trace(void* trace_dev);
+/* Experiment knob: epilogue groups of the channels-last conv kernel: 0 = choose (default), 1 = always one, 2 = three for the quad epilogue only. */
+PGV_API int pgv_debug_set_conv_groups(int mode);
 /* Experiment knob: CTAs per SM at which the grids of the thin 5x5 forward / transposed kernels are capped (default 32). */
 PGV_API int pgv_debug_set_thin_grid_mult(int m);
 /* Experiment knob: number of clusters (of ceil(M / 32) CTAs) of the flow program kernel; 0 = as many as fit (default). */

@@ -826,10 +826,13 @@ static int cl_pick_n_tile(int n, int granule) {
     return t;
 }
 
+int g_conv_groups = 0;        // debug: 0 = choose, 1 = one epilogue group everywhere, 2 = three groups for the quad epilogue only
+
 static void cl_set_ring(ConvClParams& p, int sm_count) {
     // three epilogue groups (GEMM mode with a TMA-fed A operand only: the producer warps are free) when every CTA drains >= 6 tiles
     const long long items = static_cast<long long>(p.m_tiles) * p.n_tiles * std::max(p.k_splits, 1);
     p.n_groups = (p.a_mode != 0 && items >= 6LL * sm_count) ? CL_MAX_GROUPS : 1;
+    if (g_conv_groups == 1 || (g_conv_groups == 2 && p.epi != CL_EPI_QUAD)) p.n_groups = 1;      // (pgv_debug_set_conv_groups)
     p.stage_bytes = static_cast<int>(align_up(static_cast<size_t>(CL_A_BYTES) + static_cast<size_t>(p.n_tile) * 128, 1024));
     p.stages = std::min(CL_MAX_STAGES, cl_ring_bytes(p.n_groups) / p.stage_bytes);
 }
@@ -1078,6 +1081,8 @@ int pgv_conv_cl_prep_weights(const float* w, float* wf, float* wq, int Cout, int
     PGV_LAUNCH_CHECK();
     return 0;
 }
+
+int pgv_debug_set_conv_groups(int mode) { g_conv_groups = mode; return 0; }
 
 int pgv_conv_cl_supported(int Cin, int Cout, int KH, int KW, int stride, int pad) {
     if (Cin % 4 != 0 || Cout % 4 != 0 || (KH * KW * Cin) % 32 != 0) return 0;

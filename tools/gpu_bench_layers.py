@@ -6,7 +6,7 @@ import torch
 sys.path.insert(0, '.')
 from preset_gen_vae_b200.model import ops  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 160
+B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 160)
 dev = 'cuda'
 ops.set_precision('tf32')
 ops.use_cl = not (len(sys.argv) > 2 and sys.argv[2] == 'nchw')
@@ -51,6 +51,10 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / (3 * reps)
 
 
+for a in sys.argv:
+    if a.startswith('groups='):
+        from preset_gen_vae_b200 import _lib as _l
+        _l.lib().pgv_debug_set_conv_groups(int(a.split('=')[1]))
 tot = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
 print("layer        flops(G)  fwd ms (TF/s)      dgrad ms (TF/s)    wgrad ms (TF/s)   act MB")
 for name, cin, cout, k, H, W in ENC + DEC:
