@@ -182,12 +182,14 @@ def main_reference(args):
     if rank != 0:
         return
     batch = args.batch_per_gpu or default_batch(args.workload)
+    if args.strong_scaling:
+        batch = max(4, batch // max(args.gpus, 1) // 4 * 4)
     cpu_batch = args.cpu_batch or batch                # the same per-GPU batch as our arm: same workload string, same config object
     budget = max(10.0, min(150.0, 12.0 * max(args.steps, 1)))
     cb, med = run_cpu(args.workload, cpu_batch, budget)
     line = {'impl': 'reference', 'metric': METRIC[args.workload], 'value': cb['value'], 'unit': 'samples/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True,
+            'scaling': 'strong' if args.strong_scaling else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': line_config(args.workload, cpu_batch, args.gpus, not args.no_graph),
             'note': 'reference algorithm (oracle port) on the host CPU of rank 0: one replica of the per-GPU batch, no GPU',
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
