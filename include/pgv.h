@@ -198,6 +198,10 @@ PGV_API int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, c
  * also accumulates the batch statistics of what it stores, bn_sums[2c] = sum and bn_sums[2c + 1] = sum of squares of channel c
  * (zero-filled by the call; only for launches with one N tile: Cout <= 128, or 4 * Cin <= 128 for the 4x4 data gradient), which
  * pgv_bn_cl_train_apply then turns into the normalisation; bn_sums may be NULL.
+ * bn_bwd_x (optional, needs bn_sums; a tensor of the output's shape and layout): the second statistic becomes the sum of
+ * stored value * bn_bwd_x instead of the sum of squares.  In the backward pass the stored values are the gradient flowing into the
+ * BatchNorm2d whose input bn_bwd_x was, so bn_sums then holds exactly what that BatchNorm's backward has to reduce over the batch
+ * (pgv_bn_cl_train_bwd, raw_sums): its reduction pass over two activation-sized tensors disappears.
  * ws / ws_bytes (optional, 16-byte aligned, ws_bytes >= pgv_conv_cl_workspace_bytes() of ZERO-FILLED header + room for partial tiles;
  * the header is left zero by every call): with it, launches whose tiles do not fill the GPU split the reduction over several CTAs and
  * combine the partial accumulators in a fixed order (deterministic; no atomics).  One workspace per stream.
@@ -205,10 +209,10 @@ PGV_API int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, c
  * stride 2 and for the 2x2 window of the data gradient when the channel count is 8, 16 or a multiple of 32; cp.async gathers otherwise. */
 PGV_API int pgv_conv_cl_fwd_bn(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin,
                                int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
-                               double* bn_sums, void* ws, size_t ws_bytes, pgv_stream_t stream);
+                               double* bn_sums, const float* bn_bwd_x, void* ws, size_t ws_bytes, pgv_stream_t stream);
 PGV_API int pgv_conv_cl_dgrad_bn(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin,
                                  int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out,
-                                 double* bn_sums, void* ws, size_t ws_bytes, pgv_stream_t stream);
+                                 double* bn_sums, const float* bn_bwd_x, void* ws, size_t ws_bytes, pgv_stream_t stream);
 /* Weight gradient of the convolution: sum over pixels of dy x patch(x), split over CTAs.  oihw_layout != 0: dw is the PyTorch tensor
  * [Cout, Cin, KH, KW] (e.g. a slice of a flat gradient buffer); else the forward-operand matrix [Cout][(kh, kw, ci)].
  * With a workspace the partial sums are combined in a fixed order by a finish kernel (deterministic); without one, fp32 atomics into
@@ -245,9 +249,11 @@ PGV_API int pgv_bn_cl_train_apply(const float* x, const double* sums, const floa
                                   int round_out, pgv_stream_t stream);
 PGV_API int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                                float* y, float eps, size_t P, int C, int round_out, pgv_stream_t stream);
+/* raw_sums (optional): raw_sums[2c] = sum(dy), raw_sums[2c + 1] = sum(dy * x) of channel c over the P rows, as accumulated by the
+ * convolution that produced dy (pgv_conv_cl_fwd_bn / pgv_conv_cl_dgrad_bn with bn_bwd_x = x): the reduction pass is skipped. */
 PGV_API int pgv_bn_cl_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd,
                                 float* dx, float* dgamma, float* dbeta, float* dx_colsum, float lrelu_slope, size_t P, int C, int round_out,
-                                void* workspace, pgv_stream_t stream);
+                                const double* raw_sums, void* workspace, pgv_stream_t stream);
 /* out[c] = sum over rows of x [P, C] (bias gradient).  workspace: 16*C bytes. */
 PGV_API int pgv_colsum_cl(const float* x, float* out, size_t P, int C, void* workspace, pgv_stream_t stream);
 /* dx = dy * (a > 0 ? 1 : slope), flat arrays of n elements (n % 4 == 0), optionally rounded to TF32. */

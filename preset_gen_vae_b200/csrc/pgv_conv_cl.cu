@@ -77,6 +77,8 @@ struct ConvClParams {
     int bblocks;         // WGRAD: ceil(B / 32) k-blocks per output position
     int round_out, atomic_out;
     double* stats;       // GEMM: if not NULL, stats[2c] += sum, stats[2c + 1] += sum of squares of the stored values of channel c
+    const float* stat_x; // GEMM + stats: if not NULL (same layout as out), stats[2c + 1] += sum of stored value * stat_x instead of squares:
+                         // the raw sums of the BatchNorm BACKWARD in front of this launch's output (pgv_bn_cl_train_bwd, raw_sums)
     int stat_c;          // number of channels (gemm_n, or qC with the quad epilogue)
     long long* trace;    // debug (tools/gpu_trace_conv.py): clock64 timestamps of CTA 0, [role][64 events][8]; NULL in production
     float slope;
@@ -638,9 +640,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                             r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
                             r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
                             *reinterpret_cast<float4*>(o) = r;
+                            // second statistic: squares (BatchNorm forward) or products with the activation at the same place (backward)
+                            const float4 xq = p.stat_x != nullptr ? __ldg(reinterpret_cast<const float4*>(p.stat_x + (o - p.out))) : r;
                             st_s[4 * g] += r.x; st_s[4 * g + 1] += r.y; st_s[4 * g + 2] += r.z; st_s[4 * g + 3] += r.w;
-                            st_q[4 * g] = fmaf(r.x, r.x, st_q[4 * g]); st_q[4 * g + 1] = fmaf(r.y, r.y, st_q[4 * g + 1]);
-                            st_q[4 * g + 2] = fmaf(r.z, r.z, st_q[4 * g + 2]); st_q[4 * g + 3] = fmaf(r.w, r.w, st_q[4 * g + 3]);
+                            st_q[4 * g] = fmaf(r.x, xq.x, st_q[4 * g]); st_q[4 * g + 1] = fmaf(r.y, xq.y, st_q[4 * g + 1]);
+                            st_q[4 * g + 2] = fmaf(r.z, xq.z, st_q[4 * g + 2]); st_q[4 * g + 3] = fmaf(r.w, xq.w, st_q[4 * g + 3]);
                         }
                     }
                 }
@@ -697,9 +701,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_cl_kernel(const __grid_con
                                 r.x = cl_act(r.x, p.slope, p.round_out); r.y = cl_act(r.y, p.slope, p.round_out);
                                 r.z = cl_act(r.z, p.slope, p.round_out); r.w = cl_act(r.w, p.slope, p.round_out);
                                 *reinterpret_cast<float4*>(o) = r;
+                                const float4 xq = p.stat_x != nullptr ? __ldg(reinterpret_cast<const float4*>(p.stat_x + (o - p.out))) : r;
                                 st_s[4 * ci] += r.x; st_s[4 * ci + 1] += r.y; st_s[4 * ci + 2] += r.z; st_s[4 * ci + 3] += r.w;
-                                st_q[4 * ci] = fmaf(r.x, r.x, st_q[4 * ci]); st_q[4 * ci + 1] = fmaf(r.y, r.y, st_q[4 * ci + 1]);
-                                st_q[4 * ci + 2] = fmaf(r.z, r.z, st_q[4 * ci + 2]); st_q[4 * ci + 3] = fmaf(r.w, r.w, st_q[4 * ci + 3]);
+                                st_q[4 * ci] = fmaf(r.x, xq.x, st_q[4 * ci]); st_q[4 * ci + 1] = fmaf(r.y, xq.y, st_q[4 * ci + 1]);
+                                st_q[4 * ci + 2] = fmaf(r.z, xq.z, st_q[4 * ci + 2]); st_q[4 * ci + 3] = fmaf(r.w, xq.w, st_q[4 * ci + 3]);
                             }
                         }
                     }
@@ -881,7 +886,9 @@ static int cl_pick_splits(int tiles, int kb_total, int sm_count, int max_splits)
 // Shared by forward and data gradient: out = act(bias + gather(in) * Bw^T).
 static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, const float* bw, const float* bias, float* out, int B, int H,
                         int W, int C, int KH, int KW, int stride, int pad, int Hg, int Wg, int N, int epi, int qH, int qW, int qC, float slope,
-                        int round_out, size_t out_elems, double* stats, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                        int round_out, size_t out_elems, double* stats, const float* stat_x, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (stat_x != nullptr && (stats == nullptr || (reinterpret_cast<uintptr_t>(stat_x) & 15)))
+        return set_error(-1, "%s: the BatchNorm-backward sums need a statistics buffer and a 16-byte aligned activation", who);
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || N <= 0 || Hg <= 0 || Wg <= 0 || KH <= 0 || KH > 8 || KW <= 0 || KW > 8 || stride <= 0 || pad < 0)
         return set_error(-1, "%s: bad geometry", who);
     const bool unaligned_n = N % 4 != 0;           // only the atomic (scalar) epilogue can write rows whose pitch is not 16-byte aligned
@@ -952,6 +959,7 @@ static int conv_cl_gemm(const pgv_handle* h, const char* who, const float* in, c
     if (unaligned_n) p.atomic_out = 1;
     if (stats != nullptr) {
         p.stats = stats;
+        p.stat_x = stat_x;
         p.stat_c = epi == CL_EPI_QUAD ? qC : N;
         if (p.atomic_out || p.n_tiles != 1 || p.stat_c % 4 != 0)
             return set_error(-1, "%s: output statistics need a non-atomic launch with one N tile (N=%d <= %d)", who, N, CL_MAX_N);
@@ -1092,42 +1100,42 @@ int pgv_conv_cl_supported(int Cin, int Cout, int KH, int KW, int stride, int pad
 }
 
 int pgv_conv_cl_fwd_bn(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
-                       int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, void* ws, size_t ws_bytes,
-                       pgv_stream_t stream) {
+                       int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, const float* bn_bwd_x, void* ws,
+                       size_t ws_bytes, pgv_stream_t stream) {
     PGV_CHECK_ARG(h && x && wf && y, "pgv_conv_cl_fwd: NULL argument");
     PGV_CHECK_ARG((Ho - 1) * stride - 2 * pad + KH <= H + stride && (Wo - 1) * stride - 2 * pad + KW <= W + stride,
                   "pgv_conv_cl_fwd: output %dx%d does not fit input %dx%d", Ho, Wo, H, W);
     return conv_cl_gemm(h, "pgv_conv_cl_fwd", x, wf, bias, y, B, H, W, Cin, KH, KW, stride, pad, Ho, Wo, Cout, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
-                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, bn_sums, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+                        round_out, static_cast<size_t>(B) * Ho * Wo * Cout, bn_sums, bn_bwd_x, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int pgv_conv_cl_fwd(pgv_handle* h, const float* x, const float* wf, const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int KH,
                     int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
-    return pgv_conv_cl_fwd_bn(h, x, wf, bias, y, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, nullptr, 0, stream);
+    return pgv_conv_cl_fwd_bn(h, x, wf, bias, y, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int pgv_conv_cl_dgrad_bn(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
-                         int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, void* ws,
-                         size_t ws_bytes, pgv_stream_t stream) {
+                         int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, double* bn_sums, const float* bn_bwd_x,
+                         void* ws, size_t ws_bytes, pgv_stream_t stream) {
     PGV_CHECK_ARG(h && dy && wq && dx, "pgv_conv_cl_dgrad: NULL argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t out_elems = static_cast<size_t>(B) * H * W * Cin;
     if (KH == 1 && KW == 1 && stride == 1 && pad == 0) {
         PGV_CHECK_ARG(H == Ho && W == Wo, "pgv_conv_cl_dgrad: 1x1 geometry mismatch");
         return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 1, 1, 1, 0, Ho, Wo, Cin, CL_EPI_ROWS, 0, 0, 0, lrelu_slope,
-                            round_out, out_elems, bn_sums, ws, ws_bytes, s);
+                            round_out, out_elems, bn_sums, bn_bwd_x, ws, ws_bytes, s);
     }
     PGV_CHECK_ARG(KH == 4 && KW == 4 && stride == 2, "pgv_conv_cl_dgrad: only 4x4/stride 2/pad 2 and 1x1/stride 1");
     // pad = 2: the four pixels (2i + ph, 2j + pw) of a quad all read the 2x2 patch of dy whose corner is (i, j)
     PGV_CHECK_ARG(pad == 2, "pgv_conv_cl_dgrad: pad %d not implemented", pad);
     const int Hq = (H + 1) / 2, Wq = (W + 1) / 2;
     return conv_cl_gemm(h, "pgv_conv_cl_dgrad", dy, wq, bias, dx, B, Ho, Wo, Cout, 2, 2, 1, 0, Hq, Wq, 4 * Cin, CL_EPI_QUAD, H, W, Cin, lrelu_slope,
-                        round_out, out_elems, bn_sums, ws, ws_bytes, s);
+                        round_out, out_elems, bn_sums, bn_bwd_x, ws, ws_bytes, s);
 }
 
 int pgv_conv_cl_dgrad(pgv_handle* h, const float* dy, const float* wq, const float* bias, float* dx, int B, int H, int W, int Cin, int Cout,
                       int KH, int KW, int stride, int pad, int Ho, int Wo, float lrelu_slope, int round_out, pgv_stream_t stream) {
-    return pgv_conv_cl_dgrad_bn(h, dy, wq, bias, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, nullptr, 0,
+    return pgv_conv_cl_dgrad_bn(h, dy, wq, bias, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, lrelu_slope, round_out, nullptr, nullptr, nullptr, 0,
                                 stream);
 }
 
@@ -1203,14 +1211,14 @@ int pgv_linear_cl_fwd(pgv_handle* h, const float* x, const float* wr, const floa
                       pgv_stream_t stream) {
     PGV_CHECK_ARG(h && x && wr && y && M > 0 && N > 0 && K > 0, "pgv_linear_cl_fwd: bad argument");
     return conv_cl_gemm(h, "pgv_linear_cl_fwd", x, wr, bias, y, M, 1, 1, K, 1, 1, 1, 0, 1, 1, N, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
-                        static_cast<size_t>(M) * N, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+                        static_cast<size_t>(M) * N, nullptr, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int pgv_linear_cl_dgrad(pgv_handle* h, const float* dy, const float* wt, float* dx, int M, int N, int K, void* ws, size_t ws_bytes,
                         pgv_stream_t stream) {
     PGV_CHECK_ARG(h && dy && wt && dx && M > 0 && N > 0 && K > 0, "pgv_linear_cl_dgrad: bad argument");
     return conv_cl_gemm(h, "pgv_linear_cl_dgrad", dy, wt, nullptr, dx, M, 1, 1, N, 1, 1, 1, 0, 1, 1, K, CL_EPI_ROWS, 0, 0, 0, -1.0f, 0,
-                        static_cast<size_t>(M) * K, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+                        static_cast<size_t>(M) * K, nullptr, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int pgv_linear_cl_wgrad(pgv_handle* h, const float* dy, const float* x, float* dw, int lddw, int M, int N, int K, int k_valid, void* ws,

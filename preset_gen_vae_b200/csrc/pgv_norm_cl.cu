@@ -212,6 +212,19 @@ __global__ void __launch_bounds__(256) cl_bn_bwd_apply_kernel(const float* __res
     }
 }
 
+// ws[2c] = sum(dy), ws[2c + 1] = sum(dy * xhat) from the raw sums (sum(dy), sum(dy * x)) a convolution epilogue accumulated:
+// sum(dy * (x - mean) * rstd) = rstd * (sum(dy * x) - mean * sum(dy)), in fp64; ws[2C + c] = 0 (the apply kernel's dx column sums).
+__global__ void __launch_bounds__(256) cl_bnbwd_sums_kernel(const double* __restrict__ raw, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, double* __restrict__ ws, int C) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < C) {
+        const double s = raw[2 * c];
+        ws[2 * c] = s;
+        ws[2 * c + 1] = static_cast<double>(rstd[c]) * (raw[2 * c + 1] - static_cast<double>(mean[c]) * s);
+        ws[2 * C + c] = 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(256) cl_sum_finish_kernel(const double* __restrict__ ws, float* __restrict__ out, int C, int stride) {
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c < C) out[c] = static_cast<float>(ws[stride * c]);
@@ -297,16 +310,21 @@ int pgv_bn_cl_eval_fwd(const float* x, const float* gamma, const float* beta, co
 }
 
 int pgv_bn_cl_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_rstd, float* dx,
-                        float* dgamma, float* dbeta, float* dx_colsum, float lrelu_slope, size_t P, int C, int round_out, void* workspace,
-                        pgv_stream_t stream) {
+                        float* dgamma, float* dbeta, float* dx_colsum, float lrelu_slope, size_t P, int C, int round_out, const double* raw_sums,
+                        void* workspace, pgv_stream_t stream) {
     PGV_CHECK_ARG(dy && x && gamma && save_mean && save_rstd && dx && dgamma && dbeta && workspace, "pgv_bn_cl_train_bwd: NULL argument");
     PGV_CHECK_ARG(P > 0 && C > 0 && C % 4 == 0, "pgv_bn_cl_train_bwd: needs C %% 4 == 0 (C=%d)", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     double* ws = static_cast<double*>(workspace);
-    PGV_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, s));
     const ClMap mp = cl_map(C);
     const dim3 grid(cl_grid_rows(P, mp.rl_count), ceil_div(C / 4, mp.tcb));
-    cl_reduce_kernel<1><<<grid, 256, 256 * 8 * sizeof(double), s>>>(x, dy, save_mean, save_rstd, ws, P, C, mp.tcb);
+    if (raw_sums != nullptr) {
+        // the convolution that produced dy already summed it: raw_sums[2c] = sum(dy), raw_sums[2c + 1] = sum(dy * x) (pgv_conv_cl_*_bn, bn_bwd_x)
+        cl_bnbwd_sums_kernel<<<ceil_div(C, 256), 256, 0, s>>>(raw_sums, save_mean, save_rstd, ws, C);
+    } else {
+        PGV_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, s));
+        cl_reduce_kernel<1><<<grid, 256, 256 * 8 * sizeof(double), s>>>(x, dy, save_mean, save_rstd, ws, P, C, mp.tcb);
+    }
     PGV_LAUNCH_CHECK();
     cl_bn_bwd_apply_kernel<<<grid, 256, dx_colsum ? 256 * 4 * sizeof(double) : 0, s>>>(dy, x, gamma, save_mean, save_rstd, ws, dx, dgamma, dbeta,
                                                                                        lrelu_slope, P, C, mp.tcb, round_out,

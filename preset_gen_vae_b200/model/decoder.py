@@ -65,10 +65,7 @@ class SpectrogramCNN(nn.Module):
         ctxs, h_last, pre = ctx
         d = ops.hardtanh_bwd(dy, pre, self.out_act.min_val, self.out_act.max_val)
         d = layer.tconv_bwd(d, h_last, self.last_tconv, grads, True)
-        blocks = self.blocks()
-        for i in range(len(blocks) - 1, -1, -1):
-            d = blocks[i].bwd(d, ctxs[i], grads, True)
-        return d
+        return layer.chain_bwd(self.blocks(), ctxs, d, grads, True)
 
     def forward(self, x_spectrogram):
         raise NotImplementedError("the per-channel CNN runs inside SpectrogramDecoder's fused program")

@@ -211,8 +211,7 @@ class SpectrogramEncoder(nn.Module):
         if drop_mask is not None:
             dflat = ops.mul(dflat, drop_mask)
         dh = dflat.view(cnn_shape)
-        for blk, c in zip(reversed(self._mixer_blocks()), reversed(mix_ctx)):
-            dh = blk.bwd(dh, c, grads, True)
+        dh = layer.chain_bwd(self._mixer_blocks(), mix_ctx, dh, grads, True)
         need_dx = bool(needs[0])
         dxs = []
         per = dh.shape[1] // C
@@ -220,8 +219,7 @@ class SpectrogramEncoder(nn.Module):
         for ch in range(C):
             d = dh if C == 1 else ops.slice_channels(dh, ch * per, (ch + 1) * per)
             local = {}
-            for i in range(len(blocks) - 1, -1, -1):
-                d = blocks[i].bwd(d, ch_ctx[ch][i], local, need_dx or i > 0)
+            d = layer.chain_bwd(blocks, ch_ctx[ch], d, local, need_dx)
             if C > 1:
                 ops.join_forks(dout)                       # the sums below read gradients produced on the child stream
             for k, v in local.items():                   # the CNN is shared: sum parameter gradients over channels

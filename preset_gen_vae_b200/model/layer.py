@@ -66,11 +66,12 @@ class _BlockBase(nn.Sequential):
             return y, mean, rstd
         return ops.bn2d_eval_fwd(a, self.bn), None, None
 
-    def _pre_bwd(self, dy, a, mean, rstd, grads):
-        """Returns (dz, bias gradient of the convolution or None if it still has to be computed from dz)."""
+    def _pre_bwd(self, dy, a, mean, rstd, grads, raw_sums=None):
+        """Returns (dz, bias gradient of the convolution or None if it still has to be computed from dz).  raw_sums: the BatchNorm
+        backward's batch sums if the kernel that produced dy accumulated them (chain_bwd)."""
         if self.bn is None:
             return ops.lrelu_bwd(dy, a, self.slope), None
-        dz, dg, db, dbias = ops.bn2d_train_bwd(dy, a, self.bn.weight, mean, rstd, self.slope, want_colsum=True)
+        dz, dg, db, dbias = ops.bn2d_train_bwd(dy, a, self.bn.weight, mean, rstd, self.slope, want_colsum=True, raw_sums=raw_sums)
         grads[id(self.bn.weight)] = dg
         grads[id(self.bn.bias)] = db
         return dz, dbias
@@ -129,17 +130,18 @@ class Conv2D(_BlockBase):
         y, mean, rstd = self._post(a, training, sums)
         return y, (x, a, mean, rstd, wq)
 
-    def bwd(self, dy, ctx, grads, need_dx=True):
+    def bwd(self, dy, ctx, grads, need_dx=True, sums=None, prev_a=None):
+        """sums / prev_a: see chain_bwd; with prev_a the result is (dx, sums of the previous block's BatchNorm backward or None)."""
         x, a, mean, rstd, wq = ctx
         c = self.conv
-        dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads)
+        dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads, sums)
         direct = ops.grad_out_of(c.weight)          # written in place into the flat gradient buffer: autograd gets no tensor for it
         with ops.forked(x, x, dz):                   # joined by the owning module at the end of its backward
             dw, db = ops.conv2d_wgrad(x, dz, c.weight.shape, c.stride[0], c.padding[0], want_bias=True, db=dbias, out=direct)
         grads[id(c.weight)], grads[id(c.bias)] = (None if direct is not None else dw), db
         if not need_dx:
             return None
-        return ops.conv2d_dgrad(dz, c.weight, x.shape[2:], c.stride[0], c.padding[0], wq=wq)
+        return ops.conv2d_dgrad(dz, c.weight, x.shape[2:], c.stride[0], c.padding[0], wq=wq, bn_bwd_x=prev_a)
 
 
 class TConv2D(_BlockBase):
@@ -170,10 +172,10 @@ class TConv2D(_BlockBase):
         y, mean, rstd = self._post(a, training, sums)
         return y, (x, a, mean, rstd, wf)
 
-    def bwd(self, dy, ctx, grads, need_dx=True):
+    def bwd(self, dy, ctx, grads, need_dx=True, sums=None, prev_a=None):
         x, a, mean, rstd, wf = ctx
-        dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads)
-        return tconv_bwd(dz, x, self.conv, grads, need_dx, wf=wf, dbias=dbias)
+        dz, dbias = self._pre_bwd(dy, a, mean, rstd, grads, sums)
+        return tconv_bwd(dz, x, self.conv, grads, need_dx, wf=wf, dbias=dbias, bn_bwd_x=prev_a)
 
 
 def tconv_out_hw(conv, h, w):
@@ -201,8 +203,9 @@ def tconv_clamp_fusable(x, conv):
     return ops.use_thin and ops._thin(cout_t, cin_t, kh, kw, conv.stride[0], conv.padding[0], H, W, x.shape[2], x.shape[3])
 
 
-def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None, dbias=None):
-    """dz: gradient w.r.t. the transposed convolution's (pre-activation) output; dbias: its per-channel sums if already known."""
+def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None, dbias=None, bn_bwd_x=None):
+    """dz: gradient w.r.t. the transposed convolution's (pre-activation) output; dbias: its per-channel sums if already known.
+    bn_bwd_x: as in ops.conv2d_fwd (the result is then (dx, sums))."""
     direct = ops.grad_out_of(conv.weight)
     with ops.forked(x, x, dz):
         dw, _ = ops.conv2d_wgrad(dz, x, conv.weight.shape, conv.stride[0], conv.padding[0], want_bias=False, out=direct)
@@ -210,4 +213,18 @@ def tconv_bwd(dz, x, conv, grads, need_dx=True, wf=None, dbias=None):
     grads[id(conv.weight)] = None if direct is not None else dw
     if not need_dx:
         return None
-    return ops.conv2d_fwd(dz, conv.weight, None, conv.stride[0], conv.padding[0], -1.0, out_hw=x.shape[2:], wf=wf)
+    return ops.conv2d_fwd(dz, conv.weight, None, conv.stride[0], conv.padding[0], -1.0, out_hw=x.shape[2:], wf=wf, bn_bwd_x=bn_bwd_x)
+
+
+def chain_bwd(blocks, ctxs, d, grads, need_first_dx=True):
+    """Backward through a sequential chain of Conv2D / TConv2D blocks (block i's input is block i - 1's output).  The gradient that
+    block i's data-gradient kernel writes is the gradient flowing into block i - 1's BatchNorm2d, so that kernel's epilogue also
+    accumulates the two batch sums that BatchNorm backward needs (ops.conv2d_fwd / conv2d_dgrad, bn_bwd_x) and block i - 1 skips its
+    reduction pass over two activation-sized tensors.  Launches that cannot (several N tiles, other kernel families) return no sums
+    and the block falls back to its own reduction."""
+    sums = None
+    for i in range(len(blocks) - 1, -1, -1):
+        prev_a = ctxs[i - 1][1] if (i > 0 and ops.fuse_bn_bwd and blocks[i - 1].bn is not None and ctxs[i - 1][2] is not None) else None
+        out = blocks[i].bwd(d, ctxs[i], grads, need_first_dx or i > 0, sums=sums, prev_a=prev_a)
+        d, sums = out if prev_a is not None else (out, None)
+    return d

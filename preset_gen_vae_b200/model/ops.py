@@ -403,6 +403,10 @@ def prep_conv_weights(w, stride, pad, fwd=True, dgrad=True, out=None):
     return wf, wq
 
 
+# Data-gradient kernels can also accumulate the BatchNorm-backward sums of the block in front (layer.chain_bwd): correct and tested, but
+# OFF: the extra activation read in the epilogue of the 16/32-channel data-gradient launches (already bound by their epilogue and by
+# 32-byte requests) costs more than the six reduction launches it removes - captured step 6.52 -> 6.64 ms at B = 160.
+fuse_bn_bwd = False
 BN_SUMS_MAX_N = 128     # the conv epilogue accumulates statistics in registers, which needs a single N tile (CL_MAX_N)
 use_bn_sums = True
 
@@ -414,9 +418,12 @@ def _bn_sums(ref, C, gemm_n, route):
     return None
 
 
-def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_out=False, bn_sums=False):
+def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_out=False, bn_sums=False, bn_bwd_x=None):
     """round_out: round the result to TF32 (set when it feeds a channels-last tensor-core kernel directly).
-    bn_sums: return (y, sums) where sums holds the batch statistics of y for ops.bn2d_train_fwd (None if the route has no such by-product)."""
+    bn_sums: return (y, sums) where sums holds the batch statistics of y for ops.bn2d_train_fwd (None if the route has no such by-product).
+    bn_bwd_x (backward pass; implies bn_sums): the activation that went into the BatchNorm2d whose output gradient this call computes;
+    sums then holds (sum y, sum y * bn_bwd_x), the raw sums of that BatchNorm's backward (ops.bn2d_train_bwd, raw_sums)."""
+    bn_sums = bn_sums or bn_bwd_x is not None
     B, Cin, H, W = x.shape
     Cout, _, kh, kw = w.shape
     Ho, Wo = out_hw if out_hw is not None else (conv_out_size(H, kh, stride, pad), conv_out_size(W, kw, stride, pad))
@@ -434,8 +441,10 @@ def conv2d_fwd(x, w, bias, stride, pad, slope=-1.0, out_hw=None, wf=None, round_
             wf, _ = prep_conv_weights(w, stride, pad, dgrad=False)
         y = _empty_cl(x, B, Cout, Ho, Wo)
         sums = _bn_sums(x, Cout, Cout, route) if bn_sums else None
+        if sums is not None and bn_bwd_x is not None:
+            assert is_cl(bn_bwd_x) and tuple(bn_bwd_x.shape) == tuple(y.shape)
         _call('pgv_conv_cl_fwd_bn', _h(x), _f(x), _f(wf), _f(bias), _f(y), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope, int(round_out),
-              _f(sums), *_clws(x), _s(x), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
+              _f(sums), _f(bn_bwd_x if sums is not None else None), *_clws(x), _s(x), n=2 if sums is not None else 1, flops=flops, nbytes=4 * (x.numel() + y.numel() + w.numel()))
         return (y, sums) if bn_sums else y
     x = to_nchw(x)
     y = _empty(x, B, Cout, Ho, Wo)
@@ -448,10 +457,11 @@ def _thin(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo):
     return bool(_lib.lib().pgv_conv5x5s2_c1_supported(Cin, Cout, kh, kw, stride, pad, H, W, Ho, Wo))
 
 
-def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, wq=None, round_out=False, bn_sums=False):
+def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, wq=None, round_out=False, bn_sums=False, bn_bwd_x=None):
     """dx of the convolution with weight w [Cout, Cin, kh, kw]; also the forward of ConvTranspose2d(weight=w).
     clamp=(lo, hi) fuses a Hardtanh (only available on the thin-layer kernel; callers check `tconv_clamp_fusable`).
-    bn_sums: as in conv2d_fwd, returns (dx, sums)."""
+    bn_sums / bn_bwd_x: as in conv2d_fwd, returns (dx, sums)."""
+    bn_sums = bn_sums or bn_bwd_x is not None
     B, Cout, Ho, Wo = dy.shape
     _, Cin, kh, kw = w.shape
     H, W = in_hw
@@ -470,8 +480,10 @@ def conv2d_dgrad(dy, w, in_hw, stride, pad, bias=None, slope=-1.0, clamp=None, w
             _, wq = prep_conv_weights(w, stride, pad, fwd=False)
         dx = _empty_cl(dy, B, Cin, H, W)
         sums = _bn_sums(dy, Cin, (4 if kh == 4 else 1) * Cin, route) if bn_sums else None
+        if sums is not None and bn_bwd_x is not None:
+            assert is_cl(bn_bwd_x) and tuple(bn_bwd_x.shape) == tuple(dx.shape)
         _call('pgv_conv_cl_dgrad_bn', _h(dy), _f(dy), _f(wq), _f(bias), _f(dx), B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo, slope,
-              int(round_out), _f(sums), *_clws(dy), _s(dy), n=2 if sums is not None else 1, flops=flops,
+              int(round_out), _f(sums), _f(bn_bwd_x if sums is not None else None), *_clws(dy), _s(dy), n=2 if sums is not None else 1, flops=flops,
               nbytes=4 * (dx.numel() + dy.numel() + w.numel()))
         return (dx, sums) if bn_sums else dx
     dy = to_nchw(dy)
@@ -558,16 +570,18 @@ def bn2d_eval_fwd(x, bn):
     return y
 
 
-def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope, want_colsum=False):
+def bn2d_train_bwd(dy, x, gamma, mean, rstd, slope, want_colsum=False, raw_sums=None):
     """(dx, dgamma, dbeta[, colsum(dx)]): colsum(dx) is the bias gradient of the convolution in front of the block; the
-    channels-last kernel produces it while writing dx."""
+    channels-last kernel produces it while writing dx.  raw_sums: (sum dy, sum dy * x) per channel if the convolution that produced dy
+    accumulated them (conv2d_fwd / conv2d_dgrad, bn_bwd_x=x): the reduction pass over dy and x is skipped."""
     B, C = x.shape[:2]
     dy = same_layout(dy, x)
     dx, dg, db = torch.empty_like(x), _empty(x, C), _empty(x, C)
     if is_cl(x):
         cs = _empty(x, C) if want_colsum else None
+        assert raw_sums is None or raw_sums.numel() == 2 * C
         _call('pgv_bn_cl_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), _f(cs), slope, B * x[0, 0].numel(), C,
-              1, _f(_ws(x, 24 * C)), _s(x), n=4 if want_colsum else 3, nbytes=4 * 5 * x.numel())
+              1, _f(raw_sums), _f(_ws(x, 24 * C)), _s(x), n=4 if want_colsum else 3, nbytes=4 * (5 if raw_sums is None else 3) * x.numel())
         return (dx, dg, db, cs) if want_colsum else (dx, dg, db)
     _call('pgv_bn2d_train_bwd', _f(dy), _f(x), _f(gamma), _f(mean), _f(rstd), _f(dx), _f(dg), _f(db), slope, B, C, x[0, 0].numel(),
           _f(_ws(x, 16 * C)), _s(x), n=3, nbytes=4 * 5 * x.numel())

@@ -180,6 +180,84 @@ def test_conv_epilogue_accumulates_the_batchnorm_statistics(cin, cout, H, W):
     assert float(((tsums - want).abs() / scale).max()) < 2e-6
 
 
+@pytest.mark.parametrize("transposed", [False, True])
+def test_chain_backward_with_fused_batchnorm_sums_equals_the_unfused_chain(transposed):
+    """layer.chain_bwd with ops.fuse_bn_bwd on (each data-gradient kernel hands the BatchNorm-backward sums to the block in front) and off
+    (every block reduces for itself): same input gradient, same parameter gradients, for a Conv2D chain and a TConv2D chain."""
+    torch.manual_seed(7)
+    B = 4
+    act = torch.nn.LeakyReLU(0.1)
+    if transposed:
+        blocks = [layer.TConv2D(64, 32, [4, 4], [2, 2], 2, output_padding=[1, 1], activation=act, name_prefix='a').to(DEV),
+                  layer.TConv2D(32, 16, [4, 4], [2, 2], 2, output_padding=[1, 0], activation=act, name_prefix='b').to(DEV),
+                  layer.TConv2D(16, 8, [4, 4], [2, 2], 2, output_padding=[1, 0], activation=act, name_prefix='c').to(DEV)]
+        x = rnd(B, 64, 17, 23, seed=1)
+    else:
+        blocks = [layer.Conv2D(8, 16, [4, 4], [2, 2], 2, [1, 1], activation=act, name_prefix='a').to(DEV),
+                  layer.Conv2D(16, 32, [4, 4], [2, 2], 2, [1, 1], activation=act, name_prefix='b').to(DEV),
+                  layer.Conv2D(32, 64, [4, 4], [2, 2], 2, [1, 1], activation=act, name_prefix='c').to(DEV)]
+        x = rnd(B, 8, 129, 174, seed=1)
+    ctxs, h = [], ops.to_cl(x, True)
+    for blk in blocks:
+        h, c = blk.fwd(h, True)
+        ctxs.append(c)
+    dy = ops.to_cl(rnd(*h.shape, seed=2))
+    res = {}
+    for fused in (True, False):
+        ops.fuse_bn_bwd = fused
+        try:
+            grads = {}
+            dx = layer.chain_bwd(blocks, ctxs, dy, grads, True)
+            ops.join_forks(dy)
+            torch.cuda.synchronize()
+            res[fused] = (dx.clone(), {k: v.clone() for k, v in grads.items() if v is not None})
+        finally:
+            ops.fuse_bn_bwd = False
+    assert rel(res[True][0], res[False][0]) < 2e-5
+    assert res[True][1].keys() == res[False][1].keys() and len(res[True][1]) >= 10
+    for k, v in res[False][1].items():
+        assert rel(res[True][1][k], v) < 5e-5
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 129, 174), (16, 32, 65, 88), (32, 64, 33, 45), (64, 128, 17, 23)])
+def test_data_gradient_epilogue_accumulates_the_batchnorm_backward_sums(cin, cout, H, W):
+    """bn_bwd_x: the kernel that writes the gradient flowing into a BatchNorm2d also accumulates (sum dy, sum dy * x) with x that
+    BatchNorm's input; BatchNorm backward from these raw sums equals BatchNorm backward with its own reduction pass.  Both forms of the
+    data gradient: the quad GEMM of a Conv2D block (odd sizes: partial quads) and the forward-conv form of a TConv2D block."""
+    B = 3
+    w = rnd(cout, cin, 4, 4, seed=81, scale=0.1)
+    Ho, Wo = (H + 4 - 4) // 2 + 1, (W + 4 - 4) // 2 + 1
+    for form in ('quad', 'conv'):
+        if form == 'quad':              # dx [B, cin, H, W] of a convolution; the block in front normalised a [B, cin, H, W] activation
+            g_in, act_shape = rnd(B, cout, Ho, Wo, seed=82), (B, cin, H, W)
+            run = lambda xa: ops.conv2d_dgrad(g_in, w, (H, W), 2, 2, bn_bwd_x=xa)
+            plain = lambda: ops.conv2d_dgrad(g_in, w, (H, W), 2, 2)
+            eligible = 4 * cin <= 128
+        else:                           # data gradient of a transposed convolution = forward convolution: [B, cin, H, W] -> [B, cout, Ho, Wo]
+            g_in, act_shape = rnd(B, cin, H, W, seed=83), (B, cout, Ho, Wo)
+            run = lambda xa: ops.conv2d_fwd(g_in, w, None, 2, 2, bn_bwd_x=xa)
+            plain = lambda: ops.conv2d_fwd(g_in, w, None, 2, 2)
+            eligible = cout <= 128
+        a = ops.to_cl(rnd(*act_shape, seed=84) + 0.3)
+        dy, sums = run(a)
+        assert torch.equal(dy, plain())
+        if not eligible:
+            assert sums is None
+            continue
+        d, ad = dy.double(), a.double()
+        want = torch.stack([d.sum((0, 2, 3)), (d * ad).sum((0, 2, 3))], 1).reshape(-1)
+        scale = torch.stack([d.abs().sum((0, 2, 3)), (d * ad).abs().sum((0, 2, 3))], 1).reshape(-1)
+        assert float(((sums - want).abs() / scale).max()) < 2e-6
+        C = act_shape[1]
+        gamma = rnd(C, seed=85) * 0.2 + 1.0
+        mean = a.double().mean((0, 2, 3)).float()
+        rstd = (1.0 / (a.double().var((0, 2, 3), unbiased=False) + 1e-5).sqrt()).float()
+        r1 = ops.bn2d_train_bwd(dy, a, gamma, mean, rstd, 0.1, want_colsum=True)
+        r2 = ops.bn2d_train_bwd(dy, a, gamma, mean, rstd, 0.1, want_colsum=True, raw_sums=sums)
+        for u, v in zip(r2, r1):
+            assert rel(u, v) < 2e-5, form
+
+
 @pytest.mark.parametrize("m,n,k", [(160, 1220, 24576), (160, 24576, 610), (64, 1024, 1030), (62, 1024, 1030), (5, 36, 26)])
 def test_big_linear_layers_on_the_channels_last_kernel(m, n, k):
     """encoder / decoder FC (and a padded-K case) through fc_fwd / fc_bwd: rounded + re-pitched operand copies, weights by TMA,
