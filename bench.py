@@ -4,6 +4,7 @@
     python bench.py --gpus 1 --steps K --warmup W                       # this repo's CUDA path, one JSON line
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      # N ranks, NCCL, weak scaling
     python bench.py --impl reference ...                                # the reference algorithm on the host CPU
+    ... --strong-scaling                                                # fixed global batch split over the ranks (default: weak scaling)
 
 Workloads (BASELINE.json `configs`):
     train      (default) configs[2]: full ExtendedAE training step from audio - mel front end, conv VAE, latent flow,
@@ -12,7 +13,8 @@ Workloads (BASELINE.json `configs`):
     frontend   configs[1]: STFT + mel front end alone, 256 clips
     inference  configs[4]: audio -> latent -> preset parameters, batch 1024
 `value` is timed with inputs resident in HBM; `e2e` goes through the public API with pinned HOST buffers (H2D of
-the step's audio / targets and D2H of the losses inside the timed region).
+the step's audio / targets and D2H of the losses inside the timed region).  `roofline` describes the kernel that dominates the
+live run and reports the larger of its two floors (algorithmic flops / tensor peak, algorithmic bytes / HBM peak) as the bound.
 """
 import argparse
 import json
